@@ -1,0 +1,200 @@
+/* sidm_b200.h - C ABI of libsidm_b200.so: the B200 (sm_100a) implementation of the
+ * per-step hot path of junkoda/sidm-nbody ("sidm-gadget"): Barnes-Hut tree gravity
+ * (gravity_tree / force_treebuild / force_treeevaluate) and the SIDM scatter step
+ * (sidm / ngb_treefind_variable / sidm_ensure_neighbours).
+ *
+ * The reference has no plugin API: its driver (run.c, accel.c, init.c) calls plain C
+ * functions that work on the globals of allvars.h.  The drop-in therefore has two
+ * layers:
+ *   1. this coarse C ABI (plain pointers and sizes, no torch/CUDA types), one call per
+ *      reference entry point; and
+ *   2. sidm-nbody_b200/shim/b200_shim.c, which re-implements the reference's own symbols
+ *      (gravity_tree(), sidm(), sidm_ensure_neighbours(), force_treebuild(), ...) on top
+ *      of it and is linked with the unmodified driver instead of gravtree.c /
+ *      forcetree.c / sidm.c.  INTEGRATION.md shows the link line.
+ *
+ * Conventions (mirroring the reference):
+ *   - every function returns 0 on success, else an error code.  Where the reference has
+ *     an endrun() code for the same condition the same number is returned (1 tree nodes
+ *     exhausted forcetree.c:233-239, 3 allocation failure forcetree.c:1805-1809, 78
+ *     neighbour list overflow forcetree.c:2184-2188, 1155 smoothing-length iteration
+ *     failed sidm.c:936-939); CUDA failures return B200_ERR_CUDA (+ cudaError in
+ *     b200_last_cuda_error()).  The library never calls exit().
+ *   - particle indices are 0-based positions in the bound particle array (the
+ *     reference's P[i+1]).
+ *   - one CUDA device per process; calls are blocking; not thread-safe (the reference is
+ *     single-threaded per rank with static state, forcetree.c:54,1991-1994).
+ *   - the library owns all device memory; the host particle array stays owned by the
+ *     caller and is the source of truth between calls.
+ *   - there is NO CPU fallback: without a CUDA device b200_init() fails with
+ *     B200_ERR_NODEVICE and nothing else works.
+ */
+#ifndef SIDM_B200_H
+#define SIDM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK             0
+#define B200_ERR_NODES      1     /* forcetree.c:233-239  endrun(1)  */
+#define B200_ERR_ALLOC      3     /* forcetree.c:1805-1809 endrun(3) */
+#define B200_ERR_NGBOVERFLOW 78   /* forcetree.c:2184-2188 endrun(78) */
+#define B200_ERR_HSML       1155  /* sidm.c:936-939 endrun(1155)     */
+#define B200_ERR_CUDA       9001
+#define B200_ERR_NODEVICE   9002
+#define B200_ERR_ARG        9003
+#define B200_ERR_STATE      9004
+#define B200_ERR_COINCIDENT 9005  /* >1 particle at one position to 42 octree levels;
+                                     the reference randomises such pairs with rand()
+                                     (forcetree.c:320-326), which cannot be reproduced */
+#define B200_ERR_TYPES      9006  /* more than one collisionless particle type present */
+
+/* The `All` fields the path reads (allvars.h:164-420).  Filled by the shim from `All`. */
+typedef struct b200_params {
+  int    device;                   /* CUDA device ordinal (rank-local)                 */
+  int    MaxPart;                  /* capacity in particles   (All.MaxPart)            */
+  double TreeAllocFactor;          /* node capacity = factor*MaxPart (All.TreeAllocFactor) */
+  /* gravity */
+  double ErrTolTheta;              /* BH opening angle          forcetree.c:967        */
+  double ErrTolForceAcc;           /* relative criterion alpha  forcetree.c:1129       */
+  int    TypeOfOpeningCriterion;   /* 0 BH, 1 relative          forcetree.c:801        */
+  int    ComovingIntegrationOn;    /* gravtree.c:42-49,252-298                         */
+  double G;                        /* gravtree.c:318                                   */
+  double SofteningTable[6];        /* Plummer-equivalent eps per type forcetree.c:800  */
+  double BoxSize;                  /* >0 with PeriodicBoundariesOn: Ewald path         */
+  int    PeriodicBoundariesOn;
+  double Omega0, OmegaLambda, Hubble;
+  /* SIDM */
+  int    DesNumNgb;                /* sidm.c:512                                       */
+  int    MaxNumNgbDeviation;
+  double CrossSectionInternal;     /* sidm.c:278-280,372                               */
+  int    CrossSectionType;         /* compile-time CROSS_SECTION_TYPE of the reference;
+                                      0 (hard sphere) .. 3 supported                    */
+  double YukawaVelocity, CrossSectionPowLaw, CrossSectionVelScale;
+  unsigned long long Seed;         /* All.Seed1 + All.Seed2*ThisTask  begrun.c:44      */
+  int    BunchSizeSidm;            /* slots per sidm() bunch (allocate.c:64); <=0: one
+                                      bunch holds every active particle                */
+  int    ReferenceNgbOrder;        /* 1: scan neighbours in the reference's list order
+                                      (tree order + next[] chains + swap-remove filter,
+                                      forcetree.c:2163-2297); 0: ascending tree order   */
+} b200_params;
+
+/* Byte layout of the caller's array-of-structs (struct particle_data, allvars.h:422-460,
+ * depends on the reference's -D flags, so offsets are passed, not assumed). */
+typedef struct b200_layout {
+  int stride;
+  int Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc;
+  int Left, Right, NgbVelDisp, HsmlVelDisp, dVel;
+} b200_layout;
+
+/* Optional replay of the reference's random numbers: the
+ * uniform each buffered particle consumed at sidm.c:341 and the unit vector
+ * random_direction() returned for it (sidm_rand.h:24-37), both indexed by buffer slot. */
+typedef struct b200_replay {
+  const double *rand;              /* [nslot]            */
+  const double *dir;               /* [nslot][3], used only where a scatter happens */
+} b200_replay;
+
+typedef struct b200_scatlog {      /* struct scatlog, sidm.h:1-10 */
+  float time; int id1, id2; float Hsml1, Hsml2;
+  float x1[3], x2[3], v1[3], v2[3], dv[3];
+} b200_scatlog;
+
+typedef struct b200_counters {
+  /* tree */
+  int       num_nodes;             /* internal nodes (numnodestree, forcetree.c:60)   */
+  int       max_level;
+  /* last gravity call: the reference's -DDIAG quantities (forcetree.c:65-66) */
+  long long part_interactions;     /* treecost        */
+  long long node_interactions;     /* treecost_quadru */
+  long long list_nodes;            /* node records a 32-target warp streamed (I_n sum) */
+  long long list_parts;            /* particle records a warp streamed       (I_p sum) */
+  long long num_targets;
+  /* last sidm() call: the SCT line (sidm.c:614-620) */
+  int       sct_ntot, sct_pass1, sct_scattered, sct_rejected;
+  long long ngb_candidates;        /* cube candidates examined (C in SURVEY 8d)       */
+  int       ensure_iterations;     /* passes of the last sidm_ensure_neighbours       */
+  /* device milliseconds of the last calls (CUDA events) */
+  float     ms_upload, ms_predict, ms_build, ms_walk, ms_sidm, ms_ensure, ms_download;
+  long long kernel_launches;       /* cumulative launches of this library's kernels   */
+} b200_counters;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+int  b200_init(const b200_params *p);          /* allocate.c / force_treeallocate():1797 */
+int  b200_set_params(const b200_params *p);    /* re-read All (time-dependent softenings) */
+void b200_finalize(void);
+int  b200_last_cuda_error(void);
+/* run on the caller's CUDA stream (a cudaStream_t); default is the legacy default stream */
+int  b200_set_stream(void *cuda_stream);
+const char *b200_version(void);
+
+/* ---- particle state -------------------------------------------------------------- */
+/* Bind the host AoS (the reference's &P[1]).  pin!=0 page-locks it for async DMA. */
+int  b200_bind_particles(void *base, int num_part, const b200_layout *layout, int pin);
+int  b200_upload(void);                        /* host AoS -> device (all fields)        */
+int  b200_download(void);                      /* device -> host AoS (fields the path writes:
+                                                  PosPred VelPred Accel GravCost OldAcc Left
+                                                  Right NgbVelDisp HsmlVelDisp dVel)      */
+/* Structure-of-arrays alternative used by the tests / bench (host pointers, float32/int32;
+ * any pointer may be NULL = keep current).  pos/vel are [n][3]. */
+int  b200_set_soa(int num_part, const float *pos, const float *vel, const float *mass,
+                  const int *id, const float *curtime, const float *accel, const float *oldacc,
+                  const float *hsml, const float *dvel);
+int  b200_get_soa(float *pospred, float *velpred, float *accel, float *oldacc, float *gravcost,
+                  float *hsml, int *ngb, float *dvel, float *left, float *right);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+/* predict_collisionless_only(time), predict.c:106: PosPred, VelPred for all particles. */
+int  b200_predict(double time);
+/* force_treebuild(), forcetree.c:90: octree over PosPred + multipole moments.        */
+int  b200_tree_build(void);
+/* gravity_tree(), gravtree.c:127-324 for the given active list (NULL = all, in index
+ * order): walk, Accel (pre-G) -> OldAcc, Accel*G (+ Lambda / comoving terms). */
+int  b200_gravity(const int *active, int nactive, double time);
+/* sidm(), sidm.c:57-627, for the active list, in list order. */
+int  b200_sidm(const int *active, int nactive, double time, double vmax,
+               const b200_replay *replay);
+/* setup_nbr_sidm(), sidm.c:630-805: neighbour counts only. */
+int  b200_setup_nbr_sidm(const int *active, int nactive);
+/* sidm_ensure_neighbours(mode), sidm.c:814-968 (repair loop; calls the sidm pass on the
+ * repaired set; replay arrays are indexed by [pass][slot] flattened, may be NULL). */
+int  b200_sidm_ensure_neighbours(int mode, double time, double vmax, const b200_replay *replay);
+/* setup_smoothinglengths_sidm(desngb), init.c:431-512. */
+int  b200_setup_smoothinglengths_sidm(int desired_ngb);
+/* compute_accelerations(mode), accel.c:27-132: predict + build + gravity
+ * (+ sidm + ensure_neighbours when mode==0). */
+int  b200_compute_accelerations(int mode, const int *active, int nactive, double time, double vmax);
+/* getvmax(), sidm.c:970-990. */
+int  b200_getvmax(double *vmax);
+/* ngb_treefind(xyz, desngb, 0, type), forcetree.c:2311: exact k-th neighbour distance^2
+ * for the given particle indices. */
+int  b200_ngb_treefind(const int *idx, int n, int desngb, float *h2_out);
+
+/* ---- parity / debug accessors (used by tests through the same ABI) ------------------ */
+/* force_treeevaluate_direct(), forcetree.c:1896: direct summation for the targets. */
+int  b200_direct(const int *targets, int n, double *acc_out /*[n][3]*/);
+/* tree walk without the G / OldAcc epilogue: raw double accelerations + per-target
+ * (particle, node) interaction counts, as gravtree.c:189-190 leaves GravDataResult. */
+int  b200_walk_raw(const int *targets, int n, double *acc_out /*[n][3]*/, int *cost_out /*[n][2]*/);
+/* Tree dump in this library's node order (depth-first pre-order).  Any pointer may be
+ * NULL.  center/len define the geometry the reference builds at forcetree.c:241-345. */
+int  b200_get_tree(int *num_nodes, float *center /*[m][3]*/, float *len, float *mass,
+                   float *s /*[m][3]*/, float *Q /*[m][7]: Q11 Q22 Q33 Q12 Q13 Q23 P*/,
+                   float *oc, float *bmax2, int *count, int *level);
+/* ngb_treefind_variable() lists (forcetree.c:2163) for the given particles with their
+ * current HsmlVelDisp, in the scan order selected by ReferenceNgbOrder. */
+int  b200_ngb_lists(const int *idx, int n, int cap, int *count_out, int *list_out /*[n][cap]*/);
+/* per-slot cumulative probabilities of the last b200_sidm() call: P_max, total Prob over
+ * the neighbour list, chosen partner (-1 none) -- sidm.c:338-383. */
+int  b200_sidm_debug(int nslot, int *slot_particle, double *pmax, double *prob_total, int *partner);
+int  b200_get_scatlog(b200_scatlog *out, int cap, int *n);
+int  b200_get_counters(b200_counters *c);
+/* device pointer + element count of an internal buffer, for NCCL plumbing from the host
+ * language (names: "posm", "velh", "accel", "dvel", ...).  Returns B200_ERR_ARG if unknown. */
+int  b200_device_buffer(const char *name, void **dptr, long long *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

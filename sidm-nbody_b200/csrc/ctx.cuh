@@ -1,0 +1,121 @@
+// ctx.cuh - library-private state of libsidm_b200.so (one CUDA device per process).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/sidm_b200.h"
+#include "tree_logic.h"
+
+namespace b200 {
+
+struct Ctx {
+  bool ready = false;
+  b200_params par{};
+  int n = 0;                 // particles currently held
+  int maxpart = 0, maxnodes = 0;
+  int last_cuda = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // host binding (the reference's &P[1])
+  char *h_base = nullptr; b200_layout lay{}; bool pinned = false; bool have_aos = false;
+  char *d_aos = nullptr; size_t aos_cap = 0;
+
+  // ---- particle state, original index order (struct particle_data fields, allvars.h:422-460)
+  float4 *posm = nullptr;    // PosPred.xyz, Mass
+  float4 *velh = nullptr;    // Vel.xyz, HsmlVelDisp
+  float  *pos0 = nullptr;    // Pos [n][3]
+  float  *velpred = nullptr; // VelPred [n][3]
+  float  *accel = nullptr;   // Accel [n][3]
+  float  *dvel = nullptr;    // dVel [n][3]
+  float  *curtime = nullptr, *oldacc = nullptr, *gravcost = nullptr, *left = nullptr, *right = nullptr;
+  int    *ngb = nullptr, *pid = nullptr, *ptype = nullptr;
+
+  // ---- tree (rebuilt by b200_tree_build)
+  bool tree_valid = false;
+  double *d_bbox = nullptr;        // [6] min xyz, max xyz (double), written by the bbox kernels
+  RootBox *d_root = nullptr;       // root cell
+  float *d_domain = nullptr;       // DomainMin[3], DomainMax[3]  (forcetree.c:192-198)
+  uint64_t *key_hi = nullptr, *key_lo = nullptr;   // original order
+  uint64_t *skey_hi = nullptr, *skey_lo = nullptr; // sorted
+  uint64_t *key_tmp = nullptr;
+  int *sidx = nullptr, *sidx_tmp = nullptr;        // sorted position -> original index
+  int *krank = nullptr;                            // original index -> sorted position
+  int *iota = nullptr;
+  signed char *clev = nullptr;     // common levels with the next sorted particle
+  int *nodestart = nullptr;        // [n+1] exclusive scan of nodes starting at each sorted particle
+  void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  int *d_flags = nullptr;          // [16] device-side status words (error flags, node count, ...)
+  int *h_flags = nullptr;          // pinned mirror
+  // per node (pre-order id)
+  NodeRec *nodes = nullptr;
+  float4 *geom = nullptr;          // centre xyz, len
+  int *nstart = nullptr, *nend = nullptr, *nparent = nullptr, *npstart = nullptr;   // npstart [m+1]
+  unsigned char *nlevel = nullptr, *nnp = nullptr, *nnchild = nullptr;
+  int *ndp = nullptr;              // [m][8] sorted indices of a node's direct particles
+  int *narrive = nullptr;
+  int *nminidx = nullptr;          // min original index below the node (next[] order, forcetree.c:274-279)
+  int *nlstart = nullptr;          // first position of the node's particles in next[] order
+  Moments *nmom = nullptr;
+  // leaf order (particles sorted by (parent node, octant)): every subtree is a contiguous range
+  float4 *leaf_posm = nullptr;
+  int *leaf_orig = nullptr, *orig_leaf = nullptr;
+  int *lrank = nullptr;            // original index -> rank in the reference's next[] chain
+  int num_nodes = 0, max_level = 0;
+
+  // ---- work buffers for the hot calls
+  int *d_active = nullptr, *d_tsorted = nullptr, *d_tkeys = nullptr, *d_tkeys2 = nullptr, *d_tvals2 = nullptr;
+  double *d_acc = nullptr;         // [n][3] raw accelerations per target slot
+  int *d_cost = nullptr;           // [n][2]
+  unsigned long long *d_ctr = nullptr;   // [8] device counters
+  unsigned long long *h_ctr = nullptr;
+
+  // ---- sidm work buffers
+  int *s_slot_part = nullptr;      // [n] buffer slot -> particle
+  int *s_flag = nullptr, *s_pos = nullptr;
+  int *s_ngb = nullptr, *s_partner = nullptr, *s_pass = nullptr, *s_passlist = nullptr;
+  double *s_rand = nullptr, *s_dir = nullptr, *s_pmax = nullptr, *s_prob = nullptr;
+  float *s_dv = nullptr;           // [n][3]
+  int *s_winner = nullptr;         // per particle: last buffer slot that chose it as partner
+  int *s_cand = nullptr; unsigned long long *s_candkey = nullptr; size_t s_cand_cap = 0;
+  int *s_repair = nullptr;
+  b200_scatlog *d_scatlog = nullptr; int scatlog_cap = 0; int scatlog_n = 0;
+  int last_nslot = 0;
+  unsigned long long sidm_calls = 0;
+
+  b200_counters cnt{};
+};
+
+extern Ctx g;
+
+#define CUDA_TRY(x)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess) {                                                             \
+      g.last_cuda = (int)e_;                                                             \
+      fprintf(stderr, "libsidm_b200: %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return B200_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+#define B200_TRY(x) do { int r_ = (x); if (r_ != B200_OK) return r_; } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+inline void count_launch(int k = 1) { g.cnt.kernel_launches += k; }
+
+// device status words (d_flags)
+enum { FL_ERR_COINCIDENT = 0, FL_NUM_NODES = 1, FL_MAX_LEVEL = 2, FL_ERR_NGB = 3, FL_NPASS = 4,
+       FL_NREPAIR = 5, FL_NSCATLOG = 6, FL_NEXPORT = 7, FL_MULTITYPE = 8, FL_COUNT = 16 };
+// device counters (d_ctr)
+enum { CT_PART = 0, CT_NODE = 1, CT_LIST_NODES = 2, CT_LIST_PARTS = 3, CT_CAND = 4, CT_PASS1 = 5,
+       CT_SCATTERED = 6, CT_REJECTED = 7, CT_COUNT = 8 };
+
+// implemented across the .cu files
+int tree_build_impl();
+int walk_impl(const int *d_targets_sorted, int nt, bool raw_only);
+int gravity_impl(const int *active, int nactive, double time);
+int direct_impl(const int *targets, int n, double *acc_out);
+int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only);
+int prepare_targets(const int *active_host, int nactive, int **d_sorted_out);
+
+}  // namespace b200

@@ -1,0 +1,436 @@
+// state.cu - life cycle, particle state (AoS <-> device SoA), prediction, counters.
+// Reference roles: allocate.c:14-185 (buffers), predict.c:106-150 (predict_collisionless_only),
+// sidm.c:970-990 (getvmax).
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+#include "ctx.cuh"
+
+namespace b200 {
+Ctx g;
+
+template <class T>
+static int dalloc(T **p, size_t count) {
+  if (*p) return B200_OK;
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 256);
+  if (e != cudaSuccess) { g.last_cuda = (int)e; return B200_ERR_ALLOC; }
+  return B200_OK;
+}
+template <class T>
+static void dfree(T **p) { if (*p) cudaFree(*p); *p = nullptr; }
+
+static int alloc_all() {
+  const size_t n = (size_t)g.maxpart, m = (size_t)g.maxnodes;
+  B200_TRY(dalloc(&g.posm, n)); B200_TRY(dalloc(&g.velh, n));
+  B200_TRY(dalloc(&g.pos0, 3 * n)); B200_TRY(dalloc(&g.velpred, 3 * n));
+  B200_TRY(dalloc(&g.accel, 3 * n)); B200_TRY(dalloc(&g.dvel, 3 * n));
+  B200_TRY(dalloc(&g.curtime, n)); B200_TRY(dalloc(&g.oldacc, n)); B200_TRY(dalloc(&g.gravcost, n));
+  B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n));
+  B200_TRY(dalloc(&g.ngb, n)); B200_TRY(dalloc(&g.pid, n)); B200_TRY(dalloc(&g.ptype, n));
+  B200_TRY(dalloc(&g.d_bbox, 8)); B200_TRY(dalloc(&g.d_root, 1)); B200_TRY(dalloc(&g.d_domain, 8));
+  B200_TRY(dalloc(&g.key_hi, n)); B200_TRY(dalloc(&g.key_lo, n));
+  B200_TRY(dalloc(&g.skey_hi, n)); B200_TRY(dalloc(&g.skey_lo, n)); B200_TRY(dalloc(&g.key_tmp, n));
+  B200_TRY(dalloc(&g.sidx, n)); B200_TRY(dalloc(&g.sidx_tmp, n)); B200_TRY(dalloc(&g.krank, n));
+  B200_TRY(dalloc(&g.iota, n));
+  B200_TRY(dalloc(&g.clev, n + 1)); B200_TRY(dalloc(&g.nodestart, n + 2));
+  B200_TRY(dalloc(&g.d_flags, (size_t)FL_COUNT)); B200_TRY(dalloc(&g.d_ctr, (size_t)CT_COUNT));
+  B200_TRY(dalloc(&g.nodes, m + 1)); B200_TRY(dalloc(&g.geom, m + 1));
+  B200_TRY(dalloc(&g.nstart, m + 1)); B200_TRY(dalloc(&g.nend, m + 1)); B200_TRY(dalloc(&g.nparent, m + 1));
+  B200_TRY(dalloc(&g.npstart, m + 2));
+  B200_TRY(dalloc(&g.nlevel, m + 1)); B200_TRY(dalloc(&g.nnp, m + 1)); B200_TRY(dalloc(&g.nnchild, m + 1));
+  B200_TRY(dalloc(&g.ndp, 8 * (m + 1))); B200_TRY(dalloc(&g.narrive, m + 1));
+  B200_TRY(dalloc(&g.nminidx, m + 1)); B200_TRY(dalloc(&g.nlstart, m + 1));
+  B200_TRY(dalloc(&g.nmom, m + 1));
+  B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n));
+  B200_TRY(dalloc(&g.lrank, n));
+  B200_TRY(dalloc(&g.d_active, n)); B200_TRY(dalloc(&g.d_tsorted, n)); B200_TRY(dalloc(&g.d_tkeys, n));
+  B200_TRY(dalloc(&g.d_tkeys2, n)); B200_TRY(dalloc(&g.d_tvals2, n));
+  B200_TRY(dalloc(&g.d_acc, 3 * n)); B200_TRY(dalloc(&g.d_cost, 2 * n));
+  B200_TRY(dalloc(&g.s_slot_part, n)); B200_TRY(dalloc(&g.s_flag, n + 1)); B200_TRY(dalloc(&g.s_pos, n + 1));
+  B200_TRY(dalloc(&g.s_ngb, n)); B200_TRY(dalloc(&g.s_partner, n)); B200_TRY(dalloc(&g.s_pass, n + 1));
+  B200_TRY(dalloc(&g.s_passlist, n));
+  B200_TRY(dalloc(&g.s_rand, n)); B200_TRY(dalloc(&g.s_dir, 3 * n)); B200_TRY(dalloc(&g.s_pmax, n));
+  B200_TRY(dalloc(&g.s_prob, n)); B200_TRY(dalloc(&g.s_dv, 3 * n)); B200_TRY(dalloc(&g.s_winner, n));
+  B200_TRY(dalloc(&g.s_repair, n));
+  g.scatlog_cap = 1 << 20;
+  B200_TRY(dalloc(&g.d_scatlog, (size_t)g.scatlog_cap));
+  return B200_OK;
+}
+
+}  // namespace b200
+using namespace b200;
+
+extern "C" const char *b200_version(void) { return "sidm_b200 0.1 (sm_100a)"; }
+extern "C" int b200_last_cuda_error(void) { return g.last_cuda; }
+extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cuda_stream; return B200_OK; }
+
+extern "C" int b200_set_params(const b200_params *p) {
+  if (!p) return B200_ERR_ARG;
+  const int dev = g.par.device, mp = g.par.MaxPart; const double taf = g.par.TreeAllocFactor;
+  const bool was = g.ready;
+  g.par = *p;
+  if (was) { g.par.device = dev; g.par.MaxPart = mp; g.par.TreeAllocFactor = taf; }
+  if (g.par.CrossSectionType < 0 || g.par.CrossSectionType > 3) return B200_ERR_ARG;
+  return B200_OK;
+}
+
+extern "C" int b200_init(const b200_params *p) {
+  if (!p || p->MaxPart <= 0) return B200_ERR_ARG;
+  if (g.ready) return B200_ERR_STATE;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g.last_cuda = (int)e;
+    fprintf(stderr, "libsidm_b200: no CUDA device (%s); this library has no CPU path\n", cudaGetErrorString(e));
+    return B200_ERR_NODEVICE;
+  }
+  if (p->device < 0 || p->device >= ndev) return B200_ERR_ARG;
+  CUDA_TRY(cudaSetDevice(p->device));
+  B200_TRY(b200_set_params(p));
+  g.maxpart = p->MaxPart;
+  double taf = p->TreeAllocFactor > 0 ? p->TreeAllocFactor : 0.8;
+  g.maxnodes = (int)(taf * (double)g.maxpart) + 64;
+  g.stream = nullptr;   // legacy default stream: what torch's current stream is unless the host changes it
+  CUDA_TRY(cudaEventCreate(&g.ev0)); CUDA_TRY(cudaEventCreate(&g.ev1));
+  int rc = alloc_all();
+  if (rc != B200_OK) { b200_finalize(); return rc; }
+  CUDA_TRY(cudaMallocHost((void **)&g.h_flags, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMallocHost((void **)&g.h_ctr, CT_COUNT * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, CT_COUNT * sizeof(unsigned long long), g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  memset(&g.cnt, 0, sizeof(g.cnt));
+  g.n = 0; g.tree_valid = false; g.sidm_calls = 0;
+  g.ready = true;
+  return B200_OK;
+}
+
+extern "C" void b200_finalize(void) {
+  if (g.ready) cudaStreamSynchronize(g.stream);
+  if (g.pinned && g.h_base) cudaHostUnregister(g.h_base);
+  g.pinned = false; g.h_base = nullptr; g.have_aos = false;
+  dfree(&g.d_aos); g.aos_cap = 0;
+  dfree(&g.posm); dfree(&g.velh); dfree(&g.pos0); dfree(&g.velpred); dfree(&g.accel); dfree(&g.dvel);
+  dfree(&g.curtime); dfree(&g.oldacc); dfree(&g.gravcost); dfree(&g.left); dfree(&g.right);
+  dfree(&g.ngb); dfree(&g.pid); dfree(&g.ptype);
+  dfree(&g.d_bbox); dfree(&g.d_root); dfree(&g.d_domain);
+  dfree(&g.key_hi); dfree(&g.key_lo); dfree(&g.skey_hi); dfree(&g.skey_lo); dfree(&g.key_tmp);
+  dfree(&g.sidx); dfree(&g.sidx_tmp); dfree(&g.krank); dfree(&g.iota); dfree(&g.clev); dfree(&g.nodestart);
+  dfree(&g.cub_tmp); g.cub_tmp_bytes = 0;
+  dfree(&g.d_flags); dfree(&g.d_ctr);
+  dfree(&g.nodes); dfree(&g.geom); dfree(&g.nstart); dfree(&g.nend); dfree(&g.nparent); dfree(&g.npstart);
+  dfree(&g.nlevel); dfree(&g.nnp); dfree(&g.nnchild); dfree(&g.ndp); dfree(&g.narrive);
+  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom);
+  dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.lrank);
+  dfree(&g.d_active); dfree(&g.d_tsorted); dfree(&g.d_tkeys); dfree(&g.d_tkeys2); dfree(&g.d_tvals2);
+  dfree(&g.d_acc); dfree(&g.d_cost);
+  dfree(&g.s_slot_part); dfree(&g.s_flag); dfree(&g.s_pos); dfree(&g.s_ngb); dfree(&g.s_partner);
+  dfree(&g.s_pass); dfree(&g.s_passlist); dfree(&g.s_rand); dfree(&g.s_dir); dfree(&g.s_pmax);
+  dfree(&g.s_prob); dfree(&g.s_dv); dfree(&g.s_winner); dfree(&g.s_repair);
+  dfree(&g.s_cand); dfree(&g.s_candkey); g.s_cand_cap = 0;
+  dfree(&g.d_scatlog);
+  if (g.h_flags) cudaFreeHost(g.h_flags); g.h_flags = nullptr;
+  if (g.h_ctr) cudaFreeHost(g.h_ctr); g.h_ctr = nullptr;
+  if (g.ev0) cudaEventDestroy(g.ev0); g.ev0 = nullptr;
+  if (g.ev1) cudaEventDestroy(g.ev1); g.ev1 = nullptr;
+  g.stream = nullptr;
+  g.ready = false; g.n = 0; g.tree_valid = false;
+}
+
+// ----------------------------------------------------------------------------- SoA I/O
+
+static int h2d(void *dst, const void *src, size_t bytes) {
+  if (!src || !bytes) return B200_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+  return B200_OK;
+}
+static int d2h(void *dst, const void *src, size_t bytes) {
+  if (!dst || !bytes) return B200_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
+  return B200_OK;
+}
+
+__global__ void k_pack_soa(int n, const float *pos, const float *vel, const float *mass, const float *hsml,
+                           float4 *posm, float4 *velh, float *pos0, float *velpred, int has_pos, int has_vel) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = posm[i], b = velh[i];
+  if (has_pos) { a.x = pos[3 * i]; a.y = pos[3 * i + 1]; a.z = pos[3 * i + 2]; pos0[3 * i] = a.x; pos0[3 * i + 1] = a.y; pos0[3 * i + 2] = a.z; }
+  if (mass) a.w = mass[i];
+  if (has_vel) { b.x = vel[3 * i]; b.y = vel[3 * i + 1]; b.z = vel[3 * i + 2]; velpred[3 * i] = b.x; velpred[3 * i + 1] = b.y; velpred[3 * i + 2] = b.z; }
+  if (hsml) b.w = hsml[i];
+  posm[i] = a; velh[i] = b;
+}
+
+__global__ void k_fill_i(int n, int *a, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v; }
+__global__ void k_fill_f(int n, float *a, float v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v; }
+
+extern "C" int b200_set_soa(int n, const float *pos, const float *vel, const float *mass, const int *id,
+                            const float *curtime, const float *accel, const float *oldacc,
+                            const float *hsml, const float *dvel) {
+  if (!g.ready) return B200_ERR_STATE;
+  if (n <= 0 || n > g.maxpart) return B200_ERR_ARG;
+  const bool fresh = (n != g.n);
+  g.n = n; g.tree_valid = false;
+  const int B = 256, G = cdiv(n, B);
+  if (fresh) {   // start-up state of init.c:76-100
+    CUDA_TRY(cudaMemsetAsync(g.posm, 0, n * sizeof(float4), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.velh, 0, n * sizeof(float4), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.accel, 0, 3 * n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.dvel, 0, 3 * n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.curtime, 0, n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.oldacc, 0, n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.left, 0, n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.right, 0, n * sizeof(float), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.ngb, 0, n * sizeof(int), g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.pid, 0, n * sizeof(int), g.stream));
+    k_fill_i<<<G, B, 0, g.stream>>>(n, g.ptype, 1);
+    k_fill_f<<<G, B, 0, g.stream>>>(n, g.gravcost, 1.0f);
+    count_launch(2);
+  }
+  // stage through scratch (d_acc is large enough for [n][3] floats twice over)
+  float *st_pos = (float *)g.d_acc, *st_vel = st_pos + 3 * (size_t)n;
+  float *st_mass = (float *)g.d_cost, *st_h = st_mass + n;
+  B200_TRY(h2d(st_pos, pos, 3 * n * sizeof(float)));
+  B200_TRY(h2d(st_vel, vel, 3 * n * sizeof(float)));
+  B200_TRY(h2d(st_mass, mass, n * sizeof(float)));
+  B200_TRY(h2d(st_h, hsml, n * sizeof(float)));
+  k_pack_soa<<<G, B, 0, g.stream>>>(n, st_pos, st_vel, mass ? st_mass : nullptr, hsml ? st_h : nullptr,
+                                    g.posm, g.velh, g.pos0, g.velpred, pos != nullptr, vel != nullptr);
+  count_launch();
+  B200_TRY(h2d(g.pid, id, n * sizeof(int)));
+  B200_TRY(h2d(g.curtime, curtime, n * sizeof(float)));
+  B200_TRY(h2d(g.accel, accel, 3 * n * sizeof(float)));
+  B200_TRY(h2d(g.oldacc, oldacc, n * sizeof(float)));
+  B200_TRY(h2d(g.dvel, dvel, 3 * n * sizeof(float)));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+__global__ void k_unpack_soa(int n, const float4 *posm, const float4 *velh, float *pospred, float *hsml) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (pospred) { float4 a = posm[i]; pospred[3 * i] = a.x; pospred[3 * i + 1] = a.y; pospred[3 * i + 2] = a.z; }
+  if (hsml) hsml[i] = velh[i].w;
+}
+
+extern "C" int b200_get_soa(float *pospred, float *velpred, float *accel, float *oldacc, float *gravcost,
+                            float *hsml, int *ngb, float *dvel, float *left, float *right) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  const int n = g.n;
+  float *st_pos = (float *)g.d_acc; float *st_h = (float *)g.d_cost;
+  if (pospred || hsml) {
+    k_unpack_soa<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.posm, g.velh, pospred ? st_pos : nullptr, hsml ? st_h : nullptr);
+    count_launch();
+  }
+  B200_TRY(d2h(pospred, st_pos, 3 * n * sizeof(float)));
+  B200_TRY(d2h(hsml, st_h, n * sizeof(float)));
+  B200_TRY(d2h(velpred, g.velpred, 3 * n * sizeof(float)));
+  B200_TRY(d2h(accel, g.accel, 3 * n * sizeof(float)));
+  B200_TRY(d2h(oldacc, g.oldacc, n * sizeof(float)));
+  B200_TRY(d2h(gravcost, g.gravcost, n * sizeof(float)));
+  B200_TRY(d2h(ngb, g.ngb, n * sizeof(int)));
+  B200_TRY(d2h(dvel, g.dvel, 3 * n * sizeof(float)));
+  B200_TRY(d2h(left, g.left, n * sizeof(float)));
+  B200_TRY(d2h(right, g.right, n * sizeof(float)));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- AoS I/O
+
+extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *lay, int pin) {
+  if (!g.ready) return B200_ERR_STATE;
+  if (!base || !lay || num_part <= 0 || num_part > g.maxpart || lay->stride <= 0 || (lay->stride & 3)) return B200_ERR_ARG;
+  if (g.pinned && g.h_base && g.h_base != (char *)base) { cudaHostUnregister(g.h_base); g.pinned = false; }
+  g.h_base = (char *)base; g.lay = *lay; g.n = num_part; g.tree_valid = false;
+  const size_t bytes = (size_t)g.maxpart * lay->stride;
+  if (g.aos_cap < bytes) {
+    dfree(&g.d_aos);
+    if (cudaMalloc((void **)&g.d_aos, bytes) != cudaSuccess) return B200_ERR_ALLOC;
+    g.aos_cap = bytes;
+  }
+  if (pin && !g.pinned) {
+    // page-lock the caller's array once (the reference allocates P once, allocate.c:127-160)
+    cudaError_t e = cudaHostRegister(base, (size_t)num_part * lay->stride, cudaHostRegisterDefault);
+    if (e == cudaSuccess) g.pinned = true; else (void)cudaGetLastError();
+  }
+  g.have_aos = true;
+  return B200_OK;
+}
+
+struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc, Left, Right, Ngb, Hsml, dVel; };
+
+__device__ __forceinline__ float ldf(const char *p, int off) { return *(const float *)(p + off); }
+__device__ __forceinline__ int ldi(const char *p, int off) { return *(const int *)(p + off); }
+
+__global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4 *velh, float *pos0, float *velpred,
+                             float *accel, float *dvel, float *curtime, float *oldacc, float *gravcost,
+                             float *left, float *right, int *ngb, int *pid, int *ptype) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const char *p = aos + (size_t)i * L.stride;
+  float4 a, b;
+  a.x = ldf(p, L.PosPred); a.y = ldf(p, L.PosPred + 4); a.z = ldf(p, L.PosPred + 8); a.w = ldf(p, L.Mass);
+  b.x = ldf(p, L.Vel); b.y = ldf(p, L.Vel + 4); b.z = ldf(p, L.Vel + 8); b.w = ldf(p, L.Hsml);
+  posm[i] = a; velh[i] = b;
+  for (int k = 0; k < 3; k++) {
+    pos0[3 * i + k] = ldf(p, L.Pos + 4 * k);
+    velpred[3 * i + k] = ldf(p, L.VelPred + 4 * k);
+    accel[3 * i + k] = ldf(p, L.Accel + 4 * k);
+    dvel[3 * i + k] = ldf(p, L.dVel + 4 * k);
+  }
+  curtime[i] = ldf(p, L.CurrentTime); oldacc[i] = ldf(p, L.OldAcc); gravcost[i] = ldf(p, L.GravCost);
+  left[i] = ldf(p, L.Left); right[i] = ldf(p, L.Right);
+  ngb[i] = ldi(p, L.Ngb); pid[i] = ldi(p, L.ID); ptype[i] = ldi(p, L.Type);
+}
+
+__global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
+                           const float *accel, const float *dvel, const float *oldacc, const float *gravcost,
+                           const float *left, const float *right, const int *ngb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  char *p = aos + (size_t)i * L.stride;
+  float4 a = posm[i];
+  *(float *)(p + L.PosPred) = a.x; *(float *)(p + L.PosPred + 4) = a.y; *(float *)(p + L.PosPred + 8) = a.z;
+  for (int k = 0; k < 3; k++) {
+    *(float *)(p + L.VelPred + 4 * k) = velpred[3 * i + k];
+    *(float *)(p + L.Accel + 4 * k) = accel[3 * i + k];
+    *(float *)(p + L.dVel + 4 * k) = dvel[3 * i + k];
+  }
+  *(float *)(p + L.OldAcc) = oldacc[i]; *(float *)(p + L.GravCost) = gravcost[i];
+  *(float *)(p + L.Left) = left[i]; *(float *)(p + L.Right) = right[i];
+  *(int *)(p + L.Ngb) = ngb[i]; *(float *)(p + L.Hsml) = velh[i].w;
+}
+
+static Lay to_lay(const b200_layout &l) {
+  Lay L{l.stride, l.Pos, l.Vel, l.Mass, l.ID, l.Type, l.CurrentTime, l.PosPred, l.VelPred, l.Accel,
+        l.GravCost, l.OldAcc, l.Left, l.Right, l.NgbVelDisp, l.HsmlVelDisp, l.dVel};
+  return L;
+}
+
+extern "C" int b200_upload(void) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  const int n = g.n;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.d_aos, g.h_base, (size_t)n * g.lay.stride, cudaMemcpyHostToDevice, g.stream));
+  k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype);
+  count_launch();
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
+  g.tree_valid = false;
+  return B200_OK;
+}
+
+extern "C" int b200_download(void) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  const int n = g.n;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb);
+  count_launch();
+  CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_download, g.ev0, g.ev1);
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- predict
+
+// predict_collisionless_only(), predict.c:106-150: PosPred = Pos + Vel*dt_h0 and
+// VelPred = Vel + Accel*dt, float operands, double arithmetic, stored as float.
+__global__ void k_predict(int n, double time, double s_a_inverse, const float *pos0, const float *curtime,
+                          const float *accel, float4 *posm, const float4 *velh, float *velpred) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dt = time - (double)curtime[i];
+  const double dth = dt * s_a_inverse;
+  float4 a = posm[i]; const float4 v = velh[i];
+  a.x = (float)((double)pos0[3 * i] + (double)v.x * dth);
+  a.y = (float)((double)pos0[3 * i + 1] + (double)v.y * dth);
+  a.z = (float)((double)pos0[3 * i + 2] + (double)v.z * dth);
+  posm[i] = a;
+  velpred[3 * i] = (float)((double)v.x + (double)accel[3 * i] * dt);
+  velpred[3 * i + 1] = (float)((double)v.y + (double)accel[3 * i + 1] * dt);
+  velpred[3 * i + 2] = (float)((double)v.z + (double)accel[3 * i + 2] * dt);
+}
+
+namespace b200 {
+double s_a_inverse_at(double time) {   // gravtree.c:42-49
+  if (!g.par.ComovingIntegrationOn) return 1.0;
+  const double O0 = g.par.Omega0, OL = g.par.OmegaLambda;
+  return 1.0 / (g.par.Hubble * sqrt(O0 + time * (1 - O0 - OL) + time * time * time * OL));
+}
+}
+
+extern "C" int b200_predict(double time) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  k_predict<<<cdiv(g.n, 256), 256, 0, g.stream>>>(g.n, time, s_a_inverse_at(time), g.pos0, g.curtime, g.accel, g.posm, g.velh, g.velpred);
+  count_launch();
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_predict, g.ev0, g.ev1);
+  g.tree_valid = false;
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- getvmax
+
+// sidm.c:970-990: max |Vel| over local particles; v2 is formed in float (float products and
+// sums), compared in double.
+__global__ void k_vmax2(int n, const float4 *velh, float *out) {
+  __shared__ float sm[256];
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 v = velh[i];
+    const float v2 = fadd(fadd(fmul(v.x, v.x), fmul(v.y, v.y)), fmul(v.z, v.z));
+    m = fmaxf(m, v2);
+  }
+  sm[threadIdx.x] = m; __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+extern "C" int b200_getvmax(double *vmax) {
+  if (!g.ready || g.n <= 0 || !vmax) return B200_ERR_STATE;
+  const int G = 296;
+  float *part = (float *)g.d_cost;
+  k_vmax2<<<G, 256, 0, g.stream>>>(g.n, g.velh, part);
+  count_launch();
+  float h[296];
+  CUDA_TRY(cudaMemcpyAsync(h, part, G * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  float m = 0; for (int i = 0; i < G; i++) m = fmaxf(m, h[i]);
+  *vmax = sqrt((double)m);
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- counters / buffers
+
+extern "C" int b200_get_counters(b200_counters *c) {
+  if (!c) return B200_ERR_ARG;
+  g.cnt.num_nodes = g.num_nodes; g.cnt.max_level = g.max_level;
+  *c = g.cnt;
+  return B200_OK;
+}
+
+extern "C" int b200_device_buffer(const char *name, void **dptr, long long *nbytes) {
+  if (!g.ready || !name || !dptr || !nbytes) return B200_ERR_ARG;
+  const long long n = g.n;
+  struct { const char *nm; void *p; long long b; } tab[] = {
+      {"posm", g.posm, n * 16}, {"velh", g.velh, n * 16}, {"accel", g.accel, n * 12}, {"dvel", g.dvel, n * 12},
+      {"oldacc", g.oldacc, n * 4}, {"ngb", g.ngb, n * 4}, {"acc_raw", g.d_acc, n * 24}, {"cost", g.d_cost, n * 8},
+      {"velpred", g.velpred, n * 12}, {"pos0", g.pos0, n * 12}, {"curtime", g.curtime, n * 4},
+      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}};
+  for (auto &t : tab) if (!strcmp(t.nm, name)) { *dptr = t.p; *nbytes = t.b; return B200_OK; }
+  return B200_ERR_ARG;
+}

@@ -1,0 +1,274 @@
+// tree_build.cu - force_treebuild() on the GPU (reference: forcetree.c:90-422, 433-571).
+//
+// The reference inserts particles one at a time into a pointer octree and then loops over
+// all particles below every node for its moments.  Here every step is data-parallel:
+//   bbox reduce -> root cell -> per-particle 42-level octant keys (float-exact geometry,
+//   tree_logic.h) -> radix sort (CUB) -> shared-prefix lengths -> scan -> nodes in
+//   depth-first pre-order -> per-node ranges/children by binary search -> leaf-ordered
+//   particle copy -> bottom-up moments by level.
+// HBM traffic per particle (SURVEY.md section 8d "build bytes"): 16 B read + 16 B key write,
+// 8 radix passes over (8 B key + 4 B index), 16 B gather into leaf order; per node 64 B
+// record + 80 B double moments scratch.
+#include <cub/cub.cuh>
+#include "ctx.cuh"
+#include "build_logic.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ bounding box
+__global__ void k_bbox_partial(int n, const float4 *posm, const int *ptype, float *part, int *flags) {
+  __shared__ float sm[6][256];
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  const int t0 = ptype[0];
+  bool multi = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = posm[i];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    multi |= (ptype[i] != t0);
+  }
+  if (multi) flags[FL_MULTITYPE] = 1;
+  for (int k = 0; k < 3; k++) { sm[k][threadIdx.x] = mn[k]; sm[3 + k][threadIdx.x] = mx[k]; }
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; k++) {
+        sm[k][threadIdx.x] = fminf(sm[k][threadIdx.x], sm[k][threadIdx.x + s]);
+        sm[3 + k][threadIdx.x] = fmaxf(sm[3 + k][threadIdx.x], sm[3 + k][threadIdx.x + s]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) part[6 * blockIdx.x + threadIdx.x] = sm[threadIdx.x][0];
+}
+
+__global__ void k_bbox_final(int nblk, const float *part, double *bbox, RootBox *root, float *domain) {
+  // single warp; forcetree.c:179-212: extent in double from float coordinates
+  const int k = threadIdx.x;
+  if (k < 6) {
+    float v = part[k];
+    for (int b = 1; b < nblk; b++) v = (k < 3) ? fminf(v, part[6 * b + k]) : fmaxf(v, part[6 * b + k]);
+    bbox[k] = (double)v;
+    domain[k] = v;           // DomainMin/DomainMax of this type (forcetree.c:192-198)
+  }
+  __syncwarp();
+  if (k == 0) {
+    double mn[3] = {bbox[0], bbox[1], bbox[2]}, mx[3] = {bbox[3], bbox[4], bbox[5]};
+    *root = make_root(mn, mx);
+  }
+}
+
+// ------------------------------------------------------------------ keys
+__global__ void k_keys(int n, const float4 *posm, const RootBox *root, uint64_t *hi, uint64_t *lo, int *iota) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RootBox rb = *root;
+  const float4 p = posm[i];
+  uint64_t h, l;
+  make_key(p.x, p.y, p.z, rb, h, l);
+  hi[i] = h; lo[i] = l; iota[i] = i;
+}
+
+__global__ void k_gather_lo(int n, const int *sidx, const uint64_t *lo, uint64_t *slo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) slo[j] = lo[sidx[j]];
+}
+
+// particles whose first 21 octants agree are ordered by the next 21 (rare: a few pairs in a
+// 1e7-particle cusp); one thread per run of equal high words, insertion sort on the low word
+__global__ void k_fix_ties(int n, const uint64_t *shi, uint64_t *slo, int *sidx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n - 1) return;
+  const uint64_t h = shi[j];
+  if ((j > 0 && shi[j - 1] == h) || shi[j + 1] != h) return;   // not the start of a run
+  int e = j + 1;
+  while (e + 1 < n && shi[e + 1] == h) e++;
+  for (int a = j + 1; a <= e; a++) {
+    const uint64_t l = slo[a]; const int s = sidx[a];
+    int b = a - 1;
+    while (b >= j && (slo[b] > l || (slo[b] == l && sidx[b] > s))) { slo[b + 1] = slo[b]; sidx[b + 1] = sidx[b]; b--; }
+    slo[b + 1] = l; sidx[b + 1] = s;
+  }
+}
+
+// ------------------------------------------------------------------ construction kernels
+__global__ void k_b1(BuildView v, int *cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  int c = b1_common(v, i);
+  if (c >= kMaxLevels) { v.flags[FL_ERR_COINCIDENT] = 1; c = kMaxLevels - 1; }
+  int cp = (i > 0) ? b1_common(v, i - 1) : -1;
+  if (cp >= kMaxLevels) cp = kMaxLevels - 1;
+  v.clev[i] = (signed char)c;
+  cnt[i] = b1_count_from(cp, c, i, v.n);
+}
+__global__ void k_b2(BuildView v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  b2_body(v, i);
+  if (i == 0) v.flags[FL_NUM_NODES] = v.nodestart[v.n];
+  const int c = v.clev[i];
+  if (c >= 0) atomicMax(&v.flags[FL_MAX_LEVEL], c);
+}
+__global__ void k_b3(BuildView v) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id < m) b3_body(v, id);
+}
+__global__ void k_np(BuildView v, int *np32) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id <= m) np32[id] = id < m ? (int)v.nnp[id] : 0;
+}
+__global__ void k_b4(BuildView v) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id < m) b4_body(v, id);
+}
+__global__ void k_b5(BuildView v, int level) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id < m && v.nlevel[id] == level) b5_body(v, id);
+}
+__global__ void k_b6(BuildView v, int level) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id < m && v.nlevel[id] == level) b6_body(v, id);
+}
+
+static int ensure_cub(size_t bytes) {
+  if (bytes <= g.cub_tmp_bytes) return B200_OK;
+  if (g.cub_tmp) cudaFree(g.cub_tmp);
+  g.cub_tmp = nullptr; g.cub_tmp_bytes = 0;
+  bytes = bytes + bytes / 4 + 4096;
+  if (cudaMalloc(&g.cub_tmp, bytes) != cudaSuccess) return B200_ERR_ALLOC;
+  g.cub_tmp_bytes = bytes;
+  return B200_OK;
+}
+
+BuildView make_view() {
+  BuildView v;
+  v.n = g.n; v.maxnodes = g.maxnodes; v.posm = g.posm; v.shi = g.skey_hi; v.slo = g.skey_lo; v.sidx = g.sidx;
+  v.clev = g.clev; v.nodestart = g.nodestart; v.root = g.d_root;
+  v.nodes = g.nodes; v.geom = g.geom; v.nstart = g.nstart; v.nend = g.nend; v.nparent = g.nparent; v.npstart = g.npstart;
+  v.nlevel = g.nlevel; v.nnp = g.nnp; v.nnchild = g.nnchild; v.ndp = g.ndp; v.narrive = g.narrive;
+  v.nminidx = g.nminidx; v.nlstart = g.nlstart; v.nmom = g.nmom;
+  v.leaf_posm = g.leaf_posm; v.leaf_orig = g.leaf_orig; v.orig_leaf = g.orig_leaf; v.krank = g.krank; v.lrank = g.lrank;
+  v.flags = g.d_flags;
+  return v;
+}
+
+int tree_build_impl() {
+  const int n = g.n;
+  const int B = 256, G = cdiv(n, B);
+  cudaStream_t st = g.stream;
+  CUDA_TRY(cudaEventRecord(g.ev0, st));
+  CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), st));
+
+  // 1. bounding box -> root cell (forcetree.c:179-212)
+  const int GB = 296;
+  float *part = (float *)g.d_cost;
+  k_bbox_partial<<<GB, 256, 0, st>>>(n, g.posm, g.ptype, part, g.d_flags);
+  k_bbox_final<<<1, 32, 0, st>>>(GB, part, g.d_bbox, g.d_root, g.d_domain);
+  // 2. keys + sort
+  k_keys<<<G, B, 0, st>>>(n, g.posm, g.d_root, g.key_hi, g.key_lo, g.iota);
+  count_launch(3);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, g.key_hi, g.skey_hi, g.iota, g.sidx, n, 0, 63, st);
+  B200_TRY(ensure_cub(tb));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb, g.key_hi, g.skey_hi, g.iota, g.sidx, n, 0, 63, st));
+  k_gather_lo<<<G, B, 0, st>>>(n, g.sidx, g.key_lo, g.skey_lo);
+  k_fix_ties<<<G, B, 0, st>>>(n, g.skey_hi, g.skey_lo, g.sidx);
+  count_launch(2 + 9);
+  // 3. prefix lengths, node counts, scan
+  BuildView v = make_view();
+  int *cnt = g.sidx_tmp;
+  k_b1<<<G, B, 0, st>>>(v, cnt);
+  size_t tb2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt, g.nodestart, n + 1, st);
+  B200_TRY(ensure_cub(tb2));
+  CUDA_TRY(cudaMemsetAsync(cnt + n, 0, sizeof(int), st));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb2, cnt, g.nodestart, n + 1, st));
+  k_b2<<<G, B, 0, st>>>(v);
+  count_launch(4);
+  // node count / depth / error flags back to the host (the only sync of the build)
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (g.h_flags[FL_MULTITYPE]) return B200_ERR_TYPES;
+  if (g.h_flags[FL_ERR_COINCIDENT]) return B200_ERR_COINCIDENT;
+  const int m = g.h_flags[FL_NUM_NODES];
+  if (m >= g.maxnodes) {   // forcetree.c:233-239
+    fprintf(stderr, "libsidm_b200: maximum number %d of tree-nodes reached (need %d)\n", g.maxnodes, m);
+    return B200_ERR_NODES;
+  }
+  g.num_nodes = m; g.max_level = g.h_flags[FL_MAX_LEVEL];
+  const int GM = cdiv(m + 1, B);
+  // 4. ranges, geometry, children
+  k_b3<<<GM, B, 0, st>>>(v);
+  int *np32 = g.narrive;   // reuse as 32-bit copy of nnp for the scan (narrive is reset below)
+  k_np<<<GM, B, 0, st>>>(v, np32);
+  size_t tb3 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, np32, g.npstart, m + 1, st);
+  B200_TRY(ensure_cub(tb3));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb3, np32, g.npstart, m + 1, st));
+  k_b4<<<GM, B, 0, st>>>(v);
+  count_launch(5);
+  // 5. moments, deepest level first (children before parents)
+  for (int lev = g.max_level; lev >= 0; lev--) k_b5<<<GM, B, 0, st>>>(v, lev);
+  count_launch(g.max_level + 1);
+  // 6. the reference's next[] chain order (only needed to scan neighbours in its order)
+  if (g.par.ReferenceNgbOrder) {
+    for (int lev = 0; lev <= g.max_level; lev++) k_b6<<<GM, B, 0, st>>>(v, lev);
+    count_launch(g.max_level + 1);
+  }
+  CUDA_TRY(cudaEventRecord(g.ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_build, g.ev0, g.ev1);
+  g.tree_valid = true;
+  return B200_OK;
+}
+
+}  // namespace b200
+using namespace b200;
+
+extern "C" int b200_tree_build(void) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  return tree_build_impl();
+}
+
+__global__ void k_tree_dump(int m, const NodeRec *nodes, const float4 *geom, const int *nstart, const int *nend,
+                            const unsigned char *nlevel, float *center, float *len, float *mass, float *s, float *Q,
+                            float *oc, float *bmax2, int *count, int *level) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= m) return;
+  const NodeRec r = nodes[id]; const float4 gm = geom[id];
+  center[3 * id] = gm.x; center[3 * id + 1] = gm.y; center[3 * id + 2] = gm.z; len[id] = gm.w;
+  mass[id] = r.mass; s[3 * id] = r.sx; s[3 * id + 1] = r.sy; s[3 * id + 2] = r.sz;
+  float *q = Q + 7 * id;
+  q[0] = r.q11; q[1] = r.q22; q[2] = r.q33; q[3] = r.q12; q[4] = r.q13; q[5] = r.q23; q[6] = r.p;
+  oc[id] = r.oc; bmax2[id] = r.bmax2; count[id] = nend[id] - nstart[id] + 1; level[id] = nlevel[id];
+}
+
+extern "C" int b200_get_tree(int *num_nodes, float *center, float *len, float *mass, float *s, float *Q,
+                             float *oc, float *bmax2, int *count, int *level) {
+  if (!g.ready || !g.tree_valid) return B200_ERR_STATE;
+  const int m = g.num_nodes;
+  if (num_nodes) *num_nodes = m;
+  if (!center && !len && !mass && !s && !Q && !oc && !bmax2 && !count && !level) return B200_OK;
+  // dump into one scratch allocation, then copy out what was asked for
+  float *d = nullptr;
+  const size_t per = 3 + 1 + 1 + 3 + 7 + 1 + 1 + 1 + 1;
+  if (cudaMalloc((void **)&d, (size_t)m * per * 4) != cudaSuccess) return B200_ERR_ALLOC;
+  float *dc = d, *dl = dc + 3 * (size_t)m, *dm = dl + m, *ds = dm + m, *dq = ds + 3 * (size_t)m, *doc = dq + 7 * (size_t)m,
+        *db = doc + m; int *dcnt = (int *)(db + m), *dlev = dcnt + m;
+  k_tree_dump<<<cdiv(m, 256), 256, 0, g.stream>>>(m, g.nodes, g.geom, g.nstart, g.nend, g.nlevel, dc, dl, dm, ds, dq, doc, db, dcnt, dlev);
+  count_launch();
+  auto out = [&](void *h, const void *dv, size_t b) { if (h) cudaMemcpyAsync(h, dv, b, cudaMemcpyDeviceToHost, g.stream); };
+  out(center, dc, 12 * (size_t)m); out(len, dl, 4 * (size_t)m); out(mass, dm, 4 * (size_t)m); out(s, ds, 12 * (size_t)m);
+  out(Q, dq, 28 * (size_t)m); out(oc, doc, 4 * (size_t)m); out(bmax2, db, 4 * (size_t)m); out(count, dcnt, 4 * (size_t)m);
+  out(level, dlev, 4 * (size_t)m);
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { g.last_cuda = (int)e; return B200_ERR_CUDA; }
+  return B200_OK;
+}

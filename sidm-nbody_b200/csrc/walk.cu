@@ -1,0 +1,288 @@
+// walk.cu - force_treeevaluate() for many targets (reference: forcetree.c:786-1377,
+// gravtree.c:127-324) and force_treeevaluate_direct() (forcetree.c:1896-1975).
+//
+// Walk design ("warp-lockstep pre-order stream"):
+//   * nodes live in depth-first pre-order, so for every target the reference's walk
+//     (open -> nextnode, accept -> sibling) is a strictly increasing sequence of node ids:
+//     open = id+1, accept = skip[id].
+//   * a warp owns 32 targets that are adjacent along the octant-key order.  The warp visits
+//     node `cur` = the smallest id any lane still needs; lanes whose own walk is at `cur`
+//     take their OWN open/accept decision with their own OldAcc (so every target gets exactly
+//     the interaction set the reference gives it), the others idle until the stream reaches
+//     the id they skipped to.  All 32 lanes therefore load the same 64-byte node record
+//     (one broadcast transaction instead of 32 gathers) and the same <=8 leaf particles.
+//   * interaction arithmetic in float, accumulated in float over a few interactions and
+//     flushed into double accumulators (north_star: "float forces accumulated in double").
+// Algorithmic HBM bytes: per warp 64 B per node record streamed + 16 B per
+// leaf particle streamed; per target 16 B read + 32 B written.
+#include <cub/cub.cuh>
+#include "ctx.cuh"
+
+namespace b200 {
+
+double s_a_inverse_at(double time);
+
+struct WalkParams {
+  int nt, num_nodes;
+  const int *tsorted;      // sorted target list: slot ids (or particle ids when slot_part==null)
+  const int *slot_part;    // slot -> particle (null: slot == particle)
+  const float4 *posm; const float *oldacc;
+  const NodeRec *nodes; const float4 *leaf_posm;
+  double *acc; int *cost;
+  float theta2, alpha, h_inv; int criterion;
+  unsigned long long *ctr;
+};
+
+constexpr int kFlushEvery = 8;
+
+__global__ void __launch_bounds__(256) k_walk(WalkParams P) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < P.nt;
+  int slot = 0, part = 0;
+  if (valid) { slot = P.tsorted[t]; part = P.slot_part ? P.slot_part[slot] : slot; }
+  float4 tp = make_float4(0, 0, 0, 0); float oa = 0;
+  if (valid) { tp = P.posm[part]; oa = P.oldacc[part]; }
+  const bool bh = (P.criterion == 0) || (oa == 0.0f);          // forcetree.c:801
+  const float oac = oa * P.alpha;                               // forcetree.c:1129
+  const float h_inv = P.h_inv, theta2 = P.theta2;
+  const int M = P.num_nodes;
+  const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
+
+  int no = valid ? 0 : 0x7fffffff;
+  int cur = 0;
+  double ax = 0, ay = 0, az = 0;
+  float fx = 0, fy = 0, fz = 0;
+  int npart = 0, nnode = 0, it = 0;
+  unsigned wnodes = 0, wparts = 0;
+
+  while (cur < M) {
+    const float4 A = __ldg(nodes4 + 4 * (size_t)cur);
+    const float4 Bv = __ldg(nodes4 + 4 * (size_t)cur + 1);
+    const float4 Cv = __ldg(nodes4 + 4 * (size_t)cur + 2);
+    const float4 Dv = __ldg(nodes4 + 4 * (size_t)cur + 3);
+    const bool act = (no == cur);
+    const float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const bool open = act && (bh ? open_bh(Dv.w, r2, theta2) : open_rel(Bv.x, Bv.y, r2, oac));
+    if (act && !open) {
+      NodeRec n;
+      n.mass = A.w; n.q11 = Cv.x; n.q22 = Cv.y; n.q33 = Cv.z; n.q12 = Cv.w; n.q13 = Dv.x; n.q23 = Dv.y; n.p = Dv.z;
+      pn_force(dx, dy, dz, r2, n, h_inv, fx, fy, fz);
+      nnode++;
+      no = __float_as_int(Bv.w);          // skip
+    }
+    if (open) no = cur + 1;
+    const unsigned om = __ballot_sync(0xffffffffu, open);
+    wnodes++;
+    if (om) {
+      const int pinfo = __float_as_int(Bv.z);
+      const int np = pinfo & 15, ps = pinfo >> 4;
+      wparts += np;
+      for (int k = 0; k < np; k++) {
+        const float4 q = __ldg(P.leaf_posm + ps + k);
+        if (open) { pp_force(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, fx, fy, fz); npart++; }
+      }
+    }
+    if (++it == kFlushEvery) { ax += (double)fx; ay += (double)fy; az += (double)fz; fx = fy = fz = 0; it = 0; }
+    cur = __reduce_min_sync(0xffffffffu, no);
+  }
+  ax += (double)fx; ay += (double)fy; az += (double)fz;
+  if (valid) {
+    P.acc[3 * (size_t)slot] = ax; P.acc[3 * (size_t)slot + 1] = ay; P.acc[3 * (size_t)slot + 2] = az;
+    P.cost[2 * (size_t)slot] = npart; P.cost[2 * (size_t)slot + 1] = nnode;
+  }
+  // DIAG counters (forcetree.c:65-66) and the per-warp list lengths of SURVEY.md 8d
+  unsigned long long sp = npart, sn = nnode;
+  for (int o = 16; o > 0; o >>= 1) { sp += __shfl_down_sync(0xffffffffu, sp, o); sn += __shfl_down_sync(0xffffffffu, sn, o); }
+  if (lane == 0) {
+    atomicAdd(&P.ctr[CT_PART], sp); atomicAdd(&P.ctr[CT_NODE], sn);
+    atomicAdd(&P.ctr[CT_LIST_NODES], (unsigned long long)wnodes); atomicAdd(&P.ctr[CT_LIST_PARTS], (unsigned long long)wparts);
+  }
+}
+
+// sorted target list for an explicit active list: order the slots along the key order so a
+// warp's 32 targets are spatial neighbours
+__global__ void k_target_keys(int nt, const int *active, const int *krank, int *keys, int *vals) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) { keys[t] = krank[active[t]]; vals[t] = t; }
+}
+
+int prepare_targets(const int *active_host, int nactive, int **d_sorted_out) {
+  if (!active_host) { *d_sorted_out = g.sidx; return B200_OK; }   // all particles, key order, slot == particle
+  CUDA_TRY(cudaMemcpyAsync(g.d_active, active_host, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  k_target_keys<<<cdiv(nactive, 256), 256, 0, g.stream>>>(nactive, g.d_active, g.krank, g.d_tkeys, g.d_tvals2);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, g.d_tkeys, g.d_tkeys2, g.d_tvals2, g.d_tsorted, nactive, 0, 32, g.stream);
+  if (tb > g.cub_tmp_bytes) {
+    if (g.cub_tmp) cudaFree(g.cub_tmp);
+    g.cub_tmp = nullptr; g.cub_tmp_bytes = 0;
+    if (cudaMalloc(&g.cub_tmp, tb + 4096) != cudaSuccess) return B200_ERR_ALLOC;
+    g.cub_tmp_bytes = tb + 4096;
+  }
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb, g.d_tkeys, g.d_tkeys2, g.d_tvals2, g.d_tsorted, nactive, 0, 32, g.stream));
+  count_launch(5);
+  *d_sorted_out = g.d_tsorted;
+  return B200_OK;
+}
+
+static float h_inv_of_type1() {
+  // epsilon = max(eps_tree, eps_target) (forcetree.c:800); one collisionless type => its own eps
+  double eps = 0;
+  for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
+  return (float)(1.0 / (2.8 * eps));
+}
+
+// walk for nt targets; d_sorted = sorted slot list; with_slots: slot->particle through d_active
+int walk_impl(const int *d_sorted, int nt, bool with_slots) {
+  WalkParams P;
+  P.nt = nt; P.num_nodes = g.num_nodes; P.tsorted = d_sorted; P.slot_part = with_slots ? g.d_active : nullptr;
+  P.posm = g.posm; P.oldacc = g.oldacc; P.nodes = g.nodes; P.leaf_posm = g.leaf_posm;
+  P.acc = g.d_acc; P.cost = g.d_cost;
+  P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
+  P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
+  CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, 4 * sizeof(unsigned long long), g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  k_walk<<<cdiv(nt, 256), 256, 0, g.stream>>>(P);
+  count_launch();
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_walk, g.ev0, g.ev1);
+  g.cnt.part_interactions = (long long)g.h_ctr[CT_PART]; g.cnt.node_interactions = (long long)g.h_ctr[CT_NODE];
+  g.cnt.list_nodes = (long long)g.h_ctr[CT_LIST_NODES]; g.cnt.list_parts = (long long)g.h_ctr[CT_LIST_PARTS];
+  g.cnt.num_targets = nt;
+  return B200_OK;
+}
+
+// gravtree.c:230-324: Accel <- (float)Acc; OldAcc = |Accel| before G (relative criterion);
+// Accel <- G*Accel + OmegaLambda*H^2*PosPred, or the comoving combination.
+struct EpiParams {
+  int nt; const int *slot_part; const double *acc; const int *cost;
+  const float4 *posm; const float *velpred; float *accel, *oldacc, *gravcost;
+  int criterion, comoving, periodic; double G, H, O0, OL, time;
+};
+__global__ void k_grav_epilogue(EpiParams E) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= E.nt) return;
+  const int p = E.slot_part ? E.slot_part[s] : s;
+  float a[3];
+  for (int k = 0; k < 3; k++) a[k] = (float)E.acc[3 * (size_t)s + k];
+  const float4 pp = E.posm[p];
+  const float pos[3] = {pp.x, pp.y, pp.z};
+  if (!E.comoving) {
+    if (E.criterion == 1)
+      E.oldacc[p] = (float)sqrt((double)fadd(fadd(fmul(a[0], a[0]), fmul(a[1], a[1])), fmul(a[2], a[2])));
+    const double fac1 = E.OL * E.H * E.H;
+    for (int k = 0; k < 3; k++) E.accel[3 * (size_t)p + k] = (float)(E.G * (double)a[k] + fac1 * (double)pos[k]);
+  } else {
+    if (E.criterion == 1) {
+      const double fac3 = 0.5 * E.H * E.H * E.O0 / E.G;
+      double a2 = 0;
+      for (int k = 0; k < 3; k++) { const double x = E.periodic ? (double)a[k] : (double)a[k] + fac3 * (double)pos[k]; a2 += x * x; }
+      E.oldacc[p] = (float)sqrt(a2);
+    }
+    const double t = E.time;
+    const double s_a = sqrt(E.O0 + t * (1 - E.O0 - E.OL) + t * t * t * E.OL);
+    const double fac1 = E.G / (E.H * t * t * s_a), fac2 = -1.5 / t, fac3 = 0.5 * E.H * E.O0 / (t * t * s_a);
+    for (int k = 0; k < 3; k++) {
+      double v = fac1 * (double)a[k] + fac2 * (double)E.velpred[3 * (size_t)p + k];
+      if (!E.periodic) v += fac3 * (double)pos[k];
+      E.accel[3 * (size_t)p + k] = (float)v;
+    }
+  }
+  E.gravcost[p] = (float)(E.cost[2 * (size_t)s] + E.cost[2 * (size_t)s + 1]);
+}
+
+int gravity_impl(const int *active, int nactive, double time) {
+  if (!g.tree_valid) return B200_ERR_STATE;
+  const int nt = active ? nactive : g.n;
+  if (nt <= 0) return B200_OK;
+  int *d_sorted = nullptr;
+  B200_TRY(prepare_targets(active, nt, &d_sorted));
+  B200_TRY(walk_impl(d_sorted, nt, active != nullptr));
+  EpiParams E;
+  E.nt = nt; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
+  E.posm = g.posm; E.velpred = g.velpred; E.accel = g.accel; E.oldacc = g.oldacc; E.gravcost = g.gravcost;
+  E.criterion = g.par.TypeOfOpeningCriterion; E.comoving = g.par.ComovingIntegrationOn;
+  E.periodic = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+  E.G = g.par.G; E.H = g.par.Hubble; E.O0 = g.par.Omega0; E.OL = g.par.OmegaLambda; E.time = time;
+  k_grav_epilogue<<<cdiv(nt, 256), 256, 0, g.stream>>>(E);
+  count_launch();
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ direct summation
+// forcetree.c:1896-1975 in double, spline evaluated analytically; one thread per target,
+// sources tiled through shared memory.
+__device__ __forceinline__ double soft_force_d(double u) {
+  if (u <= 0.5) return 32.0 * (1.0 / 3 - 6.0 / 5 * u * u + u * u * u);
+  return 64.0 * (1.0 / 3 - 3.0 / 4 * u + 3.0 / 5 * u * u - u * u * u / 6) - 1.0 / 15 / (u * u * u);
+}
+__global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int n, const float4 *posm, double h_inv, double *acc) {
+  __shared__ float4 tile[128];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 tp = make_float4(0, 0, 0, 0);
+  if (t < nt) tp = posm[targets[t]];
+  double ax = 0, ay = 0, az = 0;
+  for (int base = 0; base < n; base += 128) {
+    const int j = base + threadIdx.x;
+    tile[threadIdx.x] = j < n ? posm[j] : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    const int lim = min(128, n - base);
+    for (int k = 0; k < lim; k++) {
+      const float4 q = tile[k];
+      const double dx = (double)q.x - (double)tp.x, dy = (double)q.y - (double)tp.y, dz = (double)q.z - (double)tp.z;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double r = sqrt(r2), u = r * h_inv;
+      double fac = 0;
+      if (u >= 1) fac = (double)q.w / (r2 * r);
+      else if (u > 1.0e-4) fac = (double)q.w * h_inv * h_inv * h_inv * soft_force_d(u);
+      ax += dx * fac; ay += dy * fac; az += dz * fac;
+    }
+    __syncthreads();
+  }
+  if (t < nt) { acc[3 * (size_t)t] = ax; acc[3 * (size_t)t + 1] = ay; acc[3 * (size_t)t + 2] = az; }
+}
+
+int direct_impl(const int *targets, int nt, double *acc_out) {
+  if (nt <= 0) return B200_OK;
+  if (nt > g.maxpart) return B200_ERR_ARG;
+  CUDA_TRY(cudaMemcpyAsync(g.d_active, targets, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  k_direct<<<cdiv(nt, 128), 128, 0, g.stream>>>(nt, g.d_active, g.n, g.posm, (double)h_inv_of_type1(), g.d_acc);
+  count_launch();
+  CUDA_TRY(cudaMemcpyAsync(acc_out, g.d_acc, (size_t)nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200
+using namespace b200;
+
+extern "C" int b200_gravity(const int *active, int nactive, double time) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  if (active && (nactive < 0 || nactive > g.n)) return B200_ERR_ARG;
+  return gravity_impl(active, nactive, time);
+}
+
+extern "C" int b200_direct(const int *targets, int n, double *acc_out) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  if (!targets || !acc_out) return B200_ERR_ARG;
+  return direct_impl(targets, n, acc_out);
+}
+
+extern "C" int b200_walk_raw(const int *targets, int n, double *acc_out, int *cost_out) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  if (!targets || n <= 0 || n > g.n) return B200_ERR_ARG;
+  int *d_sorted = nullptr;
+  B200_TRY(prepare_targets(targets, n, &d_sorted));
+  B200_TRY(walk_impl(d_sorted, n, true));
+  if (acc_out) CUDA_TRY(cudaMemcpyAsync(acc_out, g.d_acc, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (cost_out) CUDA_TRY(cudaMemcpyAsync(cost_out, g.d_cost, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return B200_OK;
+}

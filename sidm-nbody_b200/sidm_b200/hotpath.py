@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's hot-path entry points, over the C ABI.
+
+Method names and argument meaning follow the reference (accel.c:27 compute_accelerations,
+gravtree.c:18 gravity_tree, forcetree.c:90 force_treebuild, sidm.c:57 sidm, sidm.c:814
+sidm_ensure_neighbours, init.c:431 setup_smoothinglengths_sidm, sidm.c:970 getvmax,
+forcetree.c:2311 ngb_treefind), so the parity tests read like calls into the reference.
+Particle indices are 0-based (the reference's P[i+1]).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import B200Error, Counters, Params, Replay, check, ptr
+
+DEFAULT_PARAMS = dict(TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolForceAcc=0.005, TypeOfOpeningCriterion=1,
+                      ComovingIntegrationOn=0, G=43007.1, SofteningHalo=0.3, BoxSize=0.0, PeriodicBoundariesOn=0,
+                      Omega0=1.0, OmegaLambda=0.0, Hubble=0.1, DesNumNgb=30, MaxNumNgbDeviation=2,
+                      CrossSectionInternal=2.089, CrossSectionType=0, YukawaVelocity=0.0, CrossSectionPowLaw=0.0,
+                      CrossSectionVelScale=1.0, Seed=55, BunchSizeSidm=0, ReferenceNgbOrder=0)
+
+
+def make_params(max_part, device=0, **kw):
+    cfg = dict(DEFAULT_PARAMS)
+    cfg.update(kw)
+    soft = cfg.pop("SofteningHalo")
+    table = cfg.pop("SofteningTable", None)
+    p = Params(device=device, MaxPart=int(max_part), **cfg)
+    for t in range(6):
+        p.SofteningTable[t] = 0.0
+    p.SofteningTable[1] = soft
+    if table is not None:
+        for t in range(6):
+            p.SofteningTable[t] = table[t]
+    return p
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, np.float32)
+    if shape is not None:
+        assert a.shape == shape, (a.shape, shape)
+    return a
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, np.int32)
+
+
+class HotPath:
+    """One device context (one process = one GPU, like one MPI rank of the reference)."""
+
+    def __init__(self, max_part, device=0, **params):
+        self.lib = capi.load()
+        self.params = make_params(max_part, device, **params)
+        check(self.lib.b200_init(C.byref(self.params)), "b200_init")
+        self.n = 0
+        self.time = 0.0
+        self._aos = None
+
+    def close(self):
+        if self.lib is not None:
+            self.lib.b200_finalize()
+            self.lib = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if k == "SofteningHalo":
+                self.params.SofteningTable[1] = v
+            else:
+                setattr(self.params, k, v)
+        check(self.lib.b200_set_params(C.byref(self.params)), "b200_set_params")
+
+    # ---- particle state ---------------------------------------------------------------
+    def set_particles(self, pos=None, vel=None, mass=None, ids=None, curtime=None, accel=None, oldacc=None,
+                      hsml=None, dvel=None, n=None):
+        n = n if n is not None else (len(mass) if mass is not None else self.n)
+        pos, vel, accel, dvel = _f32(pos), _f32(vel), _f32(accel), _f32(dvel)
+        mass, curtime, oldacc, hsml, ids = _f32(mass), _f32(curtime), _f32(oldacc), _f32(hsml), _i32(ids)
+        check(self.lib.b200_set_soa(n, ptr(pos), ptr(vel), ptr(mass), ptr(ids), ptr(curtime), ptr(accel),
+                                    ptr(oldacc), ptr(hsml), ptr(dvel)), "b200_set_soa")
+        self.n = n
+
+    def get(self, *names):
+        """names from: PosPred VelPred Accel OldAcc GravCost HsmlVelDisp NgbVelDisp dVel Left Right"""
+        n = self.n
+        spec = dict(PosPred=((n, 3), np.float32), VelPred=((n, 3), np.float32), Accel=((n, 3), np.float32),
+                    OldAcc=((n,), np.float32), GravCost=((n,), np.float32), HsmlVelDisp=((n,), np.float32),
+                    NgbVelDisp=((n,), np.int32), dVel=((n, 3), np.float32), Left=((n,), np.float32),
+                    Right=((n,), np.float32))
+        order = ["PosPred", "VelPred", "Accel", "OldAcc", "GravCost", "HsmlVelDisp", "NgbVelDisp", "dVel", "Left", "Right"]
+        out = {k: np.empty(*spec[k]) for k in names}
+        check(self.lib.b200_get_soa(*[ptr(out.get(k)) for k in order]), "b200_get_soa")
+        return out[names[0]] if len(names) == 1 else tuple(out[k] for k in names)
+
+    def bind_particles(self, aos, pin=True):
+        """aos: numpy structured array with capi.PARTICLE_DTYPE (= the reference's &P[1])."""
+        assert aos.flags["C_CONTIGUOUS"]
+        self._aos = aos
+        lay = capi.layout_of(aos.dtype)
+        check(self.lib.b200_bind_particles(aos.ctypes.data_as(C.c_void_p), len(aos), C.byref(lay), int(pin)),
+              "b200_bind_particles")
+        self.n = len(aos)
+
+    def upload(self):
+        check(self.lib.b200_upload(), "b200_upload")
+
+    def download(self):
+        check(self.lib.b200_download(), "b200_download")
+
+    # ---- the hot path -----------------------------------------------------------------
+    def predict_collisionless_only(self, time):
+        self.time = float(time)
+        check(self.lib.b200_predict(float(time)), "b200_predict")
+
+    def force_treebuild(self):
+        check(self.lib.b200_tree_build(), "b200_tree_build")
+        return self.counters().num_nodes
+
+    def gravity_tree(self, active=None, time=None):
+        """walk + epilogue for the active list (None = every particle); the tree must be current."""
+        t = self.time if time is None else float(time)
+        a = _i32(active)
+        check(self.lib.b200_gravity(ptr(a), 0 if a is None else len(a), t), "b200_gravity")
+
+    def sidm(self, active=None, time=None, vmax=0.0, replay_rand=None, replay_dir=None):
+        t = self.time if time is None else float(time)
+        a = _i32(active)
+        rp = None
+        if replay_rand is not None:
+            self._rr = np.ascontiguousarray(replay_rand, np.float64)
+            self._rd = np.ascontiguousarray(replay_dir, np.float64)
+            rp = Replay(rand=self._rr.ctypes.data, dir=self._rd.ctypes.data)
+        check(self.lib.b200_sidm(ptr(a), 0 if a is None else len(a), t, float(vmax),
+                                 C.byref(rp) if rp is not None else None), "b200_sidm")
+
+    def setup_nbr_sidm(self, active=None):
+        a = _i32(active)
+        check(self.lib.b200_setup_nbr_sidm(ptr(a), 0 if a is None else len(a)), "b200_setup_nbr_sidm")
+
+    def sidm_ensure_neighbours(self, mode=0, time=None, vmax=0.0):
+        t = self.time if time is None else float(time)
+        check(self.lib.b200_sidm_ensure_neighbours(int(mode), t, float(vmax), None), "b200_sidm_ensure_neighbours")
+
+    def setup_smoothinglengths_sidm(self, desired_ngb=30):
+        check(self.lib.b200_setup_smoothinglengths_sidm(int(desired_ngb)), "b200_setup_smoothinglengths_sidm")
+
+    def compute_accelerations(self, mode=0, active=None, time=None, vmax=0.0):
+        t = self.time if time is None else float(time)
+        self.time = t
+        a = _i32(active)
+        check(self.lib.b200_compute_accelerations(int(mode), ptr(a), 0 if a is None else len(a), t, float(vmax)),
+              "b200_compute_accelerations")
+
+    def getvmax(self):
+        v = C.c_double(0)
+        check(self.lib.b200_getvmax(C.byref(v)), "b200_getvmax")
+        return v.value
+
+    def ngb_treefind(self, idx, desngb=30):
+        idx = _i32(idx)
+        out = np.empty(len(idx), np.float32)
+        check(self.lib.b200_ngb_treefind(ptr(idx), len(idx), int(desngb), ptr(out)), "b200_ngb_treefind")
+        return out
+
+    # ---- parity / debug ---------------------------------------------------------------
+    def force_treeevaluate_direct(self, targets):
+        t = _i32(targets)
+        acc = np.empty((len(t), 3), np.float64)
+        check(self.lib.b200_direct(ptr(t), len(t), ptr(acc)), "b200_direct")
+        return acc
+
+    def force_treeevaluate(self, targets):
+        """raw double accelerations (pre-G) and (particle, node) interaction counts per target"""
+        t = _i32(targets)
+        acc = np.empty((len(t), 3), np.float64)
+        cost = np.empty((len(t), 2), np.int32)
+        check(self.lib.b200_walk_raw(ptr(t), len(t), ptr(acc), ptr(cost)), "b200_walk_raw")
+        return acc, cost
+
+    def get_tree(self):
+        m = C.c_int(0)
+        check(self.lib.b200_get_tree(C.byref(m), *([None] * 9)), "b200_get_tree")
+        m = m.value
+        d = dict(center=np.empty((m, 3), np.float32), len=np.empty(m, np.float32), mass=np.empty(m, np.float32),
+                 s=np.empty((m, 3), np.float32), Q=np.empty((m, 7), np.float32), oc=np.empty(m, np.float32),
+                 bmax2=np.empty(m, np.float32), count=np.empty(m, np.int32), level=np.empty(m, np.int32))
+        mm = C.c_int(0)
+        check(self.lib.b200_get_tree(C.byref(mm), ptr(d["center"]), ptr(d["len"]), ptr(d["mass"]), ptr(d["s"]),
+                                     ptr(d["Q"]), ptr(d["oc"]), ptr(d["bmax2"]), ptr(d["count"]), ptr(d["level"])),
+              "b200_get_tree")
+        return d
+
+    def ngb_lists(self, idx, cap=512):
+        idx = _i32(idx)
+        cnt = np.empty(len(idx), np.int32)
+        lst = np.full((len(idx), cap), -1, np.int32)
+        check(self.lib.b200_ngb_lists(ptr(idx), len(idx), cap, ptr(cnt), ptr(lst)), "b200_ngb_lists")
+        return cnt, lst
+
+    def sidm_debug(self, nslot):
+        sp = np.empty(nslot, np.int32)
+        pmax = np.empty(nslot, np.float64)
+        prob = np.empty(nslot, np.float64)
+        partner = np.empty(nslot, np.int32)
+        check(self.lib.b200_sidm_debug(nslot, ptr(sp), ptr(pmax), ptr(prob), ptr(partner)), "b200_sidm_debug")
+        return sp, pmax, prob, partner
+
+    def scatlog(self, cap=1 << 20):
+        out = np.zeros(cap, capi.SCATLOG_DTYPE)
+        n = C.c_int(0)
+        check(self.lib.b200_get_scatlog(ptr(out), cap, C.byref(n)), "b200_get_scatlog")
+        return out[:n.value].copy()
+
+    def counters(self):
+        c = Counters()
+        check(self.lib.b200_get_counters(C.byref(c)), "b200_get_counters")
+        return c
+
+    def device_buffer(self, name):
+        p = C.c_void_p(0)
+        nb = C.c_longlong(0)
+        check(self.lib.b200_device_buffer(name.encode(), C.byref(p), C.byref(nb)), "b200_device_buffer")
+        return p.value, nb.value

@@ -1,0 +1,133 @@
+// hostcheck.cu - TEST FIXTURE.  Runs the per-index bodies of the CUDA tree build
+// (csrc/build_logic.h, csrc/tree_logic.h) and the per-lane walk arithmetic in plain
+// sequential host loops, so that `pytest -m "not gpu"` can check the construction logic
+// against the unmodified reference on a machine without a GPU.  It is compiled only by
+// tests/hostcheck/build.py, lives under tests/, and is never loaded by the product package.
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#include <cuda_runtime.h>
+#include "../../sidm-nbody_b200/csrc/build_logic.h"
+
+using namespace b200;
+
+namespace {
+struct Host {
+  int n = 0, m = 0, maxlev = 0;
+  std::vector<float4> posm, geom, leaf_posm;
+  std::vector<uint64_t> hi, lo, shi, slo;
+  std::vector<int> sidx, nodestart, nstart, nend, nparent, npstart, ndp, narrive, nminidx, nlstart, leaf_orig, orig_leaf, krank, lrank;
+  std::vector<signed char> clev;
+  std::vector<unsigned char> nlevel, nnp, nnchild;
+  std::vector<NodeRec> nodes;
+  std::vector<Moments> nmom;
+  RootBox root;
+  int flags[16];
+} H;
+}
+
+extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lorder) {
+  H.n = n;
+  H.posm.resize(n);
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++) {
+    H.posm[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]);
+    for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], (double)pos[3 * i + k]); mx[k] = std::max(mx[k], (double)pos[3 * i + k]); }
+  }
+  H.root = make_root(mn, mx);
+  H.hi.resize(n); H.lo.resize(n);
+  for (int i = 0; i < n; i++) make_key(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], H.root, H.hi[i], H.lo[i]);
+  H.sidx.resize(n); std::iota(H.sidx.begin(), H.sidx.end(), 0);
+  std::stable_sort(H.sidx.begin(), H.sidx.end(), [&](int a, int b) { return key_less(H.hi[a], H.lo[a], H.hi[b], H.lo[b]); });
+  H.shi.resize(n); H.slo.resize(n);
+  for (int j = 0; j < n; j++) { H.shi[j] = H.hi[H.sidx[j]]; H.slo[j] = H.lo[H.sidx[j]]; }
+  const int cap = 4 * n + 64;
+  H.clev.assign(n + 1, 0); H.nodestart.assign(n + 2, 0);
+  H.nodes.assign(cap, NodeRec()); H.geom.resize(cap); H.nstart.assign(cap, 0); H.nend.assign(cap, 0); H.nparent.assign(cap, -1);
+  H.npstart.assign(cap + 1, 0); H.nlevel.assign(cap, 0); H.nnp.assign(cap, 0); H.nnchild.assign(cap, 0); H.ndp.assign(8 * (size_t)cap, -1);
+  H.narrive.assign(cap, 0); H.nminidx.assign(cap, 0); H.nlstart.assign(cap, 0); H.nmom.resize(cap);
+  H.leaf_posm.resize(n); H.leaf_orig.assign(n, 0); H.orig_leaf.assign(n, 0); H.krank.assign(n, 0); H.lrank.assign(n, 0);
+  for (int k = 0; k < 16; k++) H.flags[k] = 0;
+  BuildView v;
+  v.n = n; v.maxnodes = cap; v.posm = H.posm.data(); v.shi = H.shi.data(); v.slo = H.slo.data(); v.sidx = H.sidx.data();
+  v.clev = H.clev.data(); v.nodestart = H.nodestart.data(); v.root = &H.root;
+  v.nodes = H.nodes.data(); v.geom = H.geom.data(); v.nstart = H.nstart.data(); v.nend = H.nend.data(); v.nparent = H.nparent.data();
+  v.npstart = H.npstart.data(); v.nlevel = H.nlevel.data(); v.nnp = H.nnp.data(); v.nnchild = H.nnchild.data(); v.ndp = H.ndp.data();
+  v.narrive = H.narrive.data(); v.nminidx = H.nminidx.data(); v.nlstart = H.nlstart.data(); v.nmom = H.nmom.data();
+  v.leaf_posm = H.leaf_posm.data(); v.leaf_orig = H.leaf_orig.data(); v.orig_leaf = H.orig_leaf.data(); v.krank = H.krank.data();
+  v.lrank = H.lrank.data(); v.flags = H.flags;
+  // B1 + scan
+  std::vector<int> cnt(n + 1, 0);
+  int maxlev = 0;
+  for (int i = 0; i < n; i++) {
+    int c = b1_common(v, i);
+    if (c >= kMaxLevels) return 9005;
+    int cp = i > 0 ? b1_common(v, i - 1) : -1;
+    H.clev[i] = (signed char)c; cnt[i] = b1_count_from(cp, c, i, n);
+    if (c > maxlev) maxlev = c;
+  }
+  int acc = 0;
+  for (int i = 0; i <= n; i++) { H.nodestart[i] = acc; acc += cnt[i]; }
+  H.m = H.nodestart[n]; H.maxlev = maxlev;
+  if (H.m >= cap) return 1;
+  for (int i = 0; i < n; i++) b2_body(v, i);
+  for (int id = 0; id < H.m; id++) b3_body(v, id);
+  int ps = 0;
+  for (int id = 0; id <= H.m; id++) { H.npstart[id] = ps; if (id < H.m) ps += H.nnp[id]; }
+  for (int id = 0; id < H.m; id++) b4_body(v, id);
+  for (int lev = maxlev; lev >= 0; lev--)
+    for (int id = 0; id < H.m; id++) if (H.nlevel[id] == lev) b5_body(v, id);
+  if (want_lorder)
+    for (int lev = 0; lev <= maxlev; lev++)
+      for (int id = 0; id < H.m; id++) if (H.nlevel[id] == lev) b6_body(v, id);
+  return 0;
+}
+
+extern "C" int hc_num_nodes() { return H.m; }
+extern "C" int hc_max_level() { return H.maxlev; }
+extern "C" void hc_get_root(float *out) { out[0] = H.root.cx; out[1] = H.root.cy; out[2] = H.root.cz; out[3] = H.root.len; }
+
+extern "C" void hc_get_tree(float *center, float *len, float *mass, float *s, float *Q, float *oc, float *bmax2, int *count,
+                            int *level, int *skip, int *parent, int *minidx) {
+  for (int id = 0; id < H.m; id++) {
+    const NodeRec &r = H.nodes[id]; const float4 gm = H.geom[id];
+    center[3 * id] = gm.x; center[3 * id + 1] = gm.y; center[3 * id + 2] = gm.z; len[id] = gm.w;
+    mass[id] = r.mass; s[3 * id] = r.sx; s[3 * id + 1] = r.sy; s[3 * id + 2] = r.sz;
+    float *q = Q + 7 * id; q[0] = r.q11; q[1] = r.q22; q[2] = r.q33; q[3] = r.q12; q[4] = r.q13; q[5] = r.q23; q[6] = r.p;
+    oc[id] = r.oc; bmax2[id] = r.bmax2; count[id] = H.nend[id] - H.nstart[id] + 1; level[id] = H.nlevel[id];
+    skip[id] = r.skip; parent[id] = H.nparent[id]; minidx[id] = H.nminidx[id];
+  }
+}
+extern "C" void hc_get_orders(int *sidx, int *leaf_orig, int *lrank) {
+  for (int i = 0; i < H.n; i++) { sidx[i] = H.sidx[i]; leaf_orig[i] = H.leaf_orig[i]; lrank[i] = H.lrank[i]; }
+}
+
+// one target's walk with the lane arithmetic of csrc/walk.cu (float interactions, float
+// partial sums flushed into double)
+extern "C" void hc_walk(int nt, const int *targets, const float *oldacc, int criterion, float theta, float alpha, float eps,
+                        double *acc, int *cost) {
+  const float h_inv = (float)(1.0 / (2.8 * (double)eps)), theta2 = theta * theta;
+  for (int t = 0; t < nt; t++) {
+    const float4 tp = H.posm[targets[t]];
+    const float oa = oldacc[targets[t]];
+    const bool bh = criterion == 0 || oa == 0.0f;
+    const float oac = oa * alpha;
+    double ax = 0, ay = 0, az = 0; float fx = 0, fy = 0, fz = 0; int it = 0, npart = 0, nnode = 0;
+    int no = 0;
+    while (no < H.m) {
+      const NodeRec &n = H.nodes[no];
+      const float dx = n.sx - tp.x, dy = n.sy - tp.y, dz = n.sz - tp.z;
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      const bool open = bh ? open_bh(n.len2, r2, theta2) : open_rel(n.oc, n.bmax2, r2, oac);
+      if (!open) { pn_force(dx, dy, dz, r2, n, h_inv, fx, fy, fz); nnode++; no = n.skip; }
+      else {
+        const int np = n.pinfo & 15, ps = n.pinfo >> 4;
+        for (int k = 0; k < np; k++) { const float4 q = H.leaf_posm[ps + k]; pp_force(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, fx, fy, fz); npart++; }
+        no = no + 1;
+      }
+      if (++it == 8) { ax += fx; ay += fy; az += fz; fx = fy = fz = 0; it = 0; }
+    }
+    ax += fx; ay += fy; az += fz;
+    acc[3 * t] = ax; acc[3 * t + 1] = ay; acc[3 * t + 2] = az; cost[2 * t] = npart; cost[2 * t + 1] = nnode;
+  }
+}
