@@ -1,0 +1,194 @@
+"""ctypes wrapper of oracle/liboracle.so - this repo's CPU restatement of the reference's hot
+path (oracle_tree.c, oracle_sidm.c).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg, never by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+
+
+class OParams(C.Structure):
+    _fields_ = [("theta", C.c_double), ("alpha", C.c_double), ("criterion", C.c_int), ("eps", C.c_double),
+                ("G", C.c_double), ("des_ngb", C.c_int), ("max_dev", C.c_int), ("sigma", C.c_double)]
+
+
+class OSidmOut(C.Structure):
+    _fields_ = [("slot_particle", C.POINTER(C.c_int)), ("rand", C.POINTER(C.c_double)), ("dir", C.POINTER(C.c_double)),
+                ("pmax", C.POINTER(C.c_double)), ("prob", C.POINTER(C.c_double)), ("partner", C.POINTER(C.c_int)),
+                ("ngb", C.POINTER(C.c_int)), ("nslot", C.c_int), ("sct", C.c_int * 4), ("nlog", C.c_int),
+                ("log_i", C.POINTER(C.c_int)), ("log_j", C.POINTER(C.c_int)), ("log_dv", C.POINTER(C.c_float))]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = [os.path.join(HERE, f) for f in ("oracle_tree.c", "oracle_sidm.c", "oracle.h")]
+        if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
+            subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+        L = C.CDLL(LIB)
+        L.otree_build.restype = C.c_void_p
+        L.otree_build.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+        L.otree_free.argtypes = [C.c_void_p]
+        L.otree_num_nodes.argtypes = [C.c_void_p]
+        L.otree_random_subnodes.argtypes = [C.c_void_p]
+        L.otree_dump.argtypes = [C.c_void_p] * 9
+        L.otree_chain.argtypes = [C.c_void_p, C.c_void_p]
+        L.otree_domain.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.otree_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.otree_direct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ograv_epilogue.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ongb_variable.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        L.ongb_treefind.restype = C.c_float
+        L.ongb_treefind.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orng_new.restype = C.c_void_p
+        L.orng_new.argtypes = [C.c_ulong, C.c_int]
+        L.orng_free.argtypes = [C.c_void_p]
+        L.orng_uniform.restype = C.c_double
+        L.orng_uniform.argtypes = [C.c_void_p]
+        L.orng_count.restype = C.c_long
+        L.orng_count.argtypes = [C.c_void_p]
+        L.ogetvmax.restype = C.c_double
+        L.ogetvmax.argtypes = [C.c_int, C.c_void_p]
+        L.osidm_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_void_p]
+        L.osidm_out_free.argtypes = [C.c_void_p]
+        L.osidm_ensure.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Holds one particle set; mirrors the reference's call sequence on it."""
+
+    def __init__(self, pos, vel, mass, theta=0.5, alpha=0.005, criterion=1, eps=0.3, G=43007.1, des_ngb=30,
+                 max_dev=2, sigma=2.089):
+        self.L = lib()
+        self.pos = np.ascontiguousarray(pos, np.float32)
+        self.vel = np.ascontiguousarray(vel, np.float32)
+        self.mass = np.ascontiguousarray(mass, np.float32)
+        self.n = len(self.mass)
+        self.par = OParams(theta, alpha, criterion, eps, G, des_ngb, max_dev, sigma)
+        self.tree = None
+        self.hsml = np.zeros(self.n, np.float32)
+        self.dvel = np.zeros((self.n, 3), np.float32)
+        self.ngb = np.zeros(self.n, np.int32)
+        self.left = np.zeros(self.n, np.float32)
+        self.right = np.zeros(self.n, np.float32)
+        self.rng = None
+
+    def __del__(self):
+        try:
+            if self.tree:
+                self.L.otree_free(self.tree)
+            if self.rng:
+                self.L.orng_free(self.rng)
+        except Exception:
+            pass
+
+    # ---- tree
+    def treebuild(self):
+        if self.tree:
+            self.L.otree_free(self.tree)
+        self.tree = self.L.otree_build(self.n, _p(self.pos), _p(self.mass), self.par.eps)
+        return self.L.otree_num_nodes(self.tree)
+
+    def random_subnodes(self):
+        return self.L.otree_random_subnodes(self.tree)
+
+    def dump(self):
+        m = self.L.otree_num_nodes(self.tree)
+        d = dict(center=np.empty((m, 3), np.float32), len=np.empty(m, np.float32), mass=np.empty(m, np.float32),
+                 s=np.empty((m, 3), np.float32), Q=np.empty((m, 7), np.float32), oc=np.empty(m, np.float32),
+                 bmax2=np.empty(m, np.float32), count=np.empty(m, np.int32))
+        self.L.otree_dump(self.tree, *[_p(d[k]) for k in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count")])
+        return d
+
+    def chain(self):
+        o = np.empty(self.n, np.int32)
+        self.L.otree_chain(self.tree, _p(o))
+        return o
+
+    # ---- forces
+    def force_tree(self, idx, oldacc=None):
+        idx = np.ascontiguousarray(idx, np.int32)
+        oa = None if oldacc is None else np.ascontiguousarray(oldacc, np.float32)
+        acc = np.empty((len(idx), 3))
+        cost = np.empty((len(idx), 2), np.int32)
+        self.L.otree_force(self.tree, C.byref(self.par), len(idx), _p(idx), _p(oa), _p(acc), _p(cost))
+        return acc, cost
+
+    def force_direct(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        acc = np.empty((len(idx), 3))
+        self.L.otree_direct(self.tree, C.byref(self.par), len(idx), _p(idx), _p(acc))
+        return acc
+
+    def epilogue(self, acc):
+        acc = np.ascontiguousarray(acc, np.float64)
+        a = np.empty((len(acc), 3), np.float32)
+        oa = np.zeros(len(acc), np.float32)
+        self.L.ograv_epilogue(C.byref(self.par), len(acc), _p(acc), _p(a), _p(oa))
+        return a, oa
+
+    # ---- neighbours
+    def ngb_variable(self, xyz, h, cap=8192):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        lst = np.empty(cap, np.int32)
+        r2 = np.empty(cap, np.float32)
+        n = self.L.ongb_variable(self.tree, _p(xyz), C.c_float(h), _p(lst), _p(r2), cap)
+        return lst[:n].copy(), r2[:n].copy()
+
+    def ngb_treefind(self, xyz, desngb=30):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        return float(self.L.ongb_treefind(self.tree, _p(xyz), int(desngb)))
+
+    # ---- SIDM
+    def init_rand(self, seed):
+        if self.rng:
+            self.L.orng_free(self.rng)
+        self.rng = self.L.orng_new(int(seed), 1)
+
+    def rng_count(self):
+        return self.L.orng_count(self.rng)
+
+    def getvmax(self):
+        return self.L.ogetvmax(self.n, _p(self.vel))
+
+    def sidm(self, active, dt, vmax):
+        """one sidm() call; dt = per-particle 2(t - t_i) (float32 array or scalar)"""
+        active = np.ascontiguousarray(active, np.int32)
+        dta = np.ascontiguousarray(np.broadcast_to(np.float32(dt), (self.n,)), np.float32)
+        out = OSidmOut()
+        self.L.osidm_pass(self.tree, C.byref(self.par), len(active), _p(active), _p(self.vel), _p(self.mass),
+                          _p(self.hsml), _p(dta), _p(self.dvel), _p(self.ngb), float(vmax), self.rng, C.byref(out))
+        ns, nl = out.nslot, out.nlog
+        res = dict(slot_particle=np.ctypeslib.as_array(out.slot_particle, (ns,)).copy(),
+                   rand=np.ctypeslib.as_array(out.rand, (ns,)).copy(),
+                   dir=np.ctypeslib.as_array(out.dir, (ns * 3,)).reshape(ns, 3).copy(),
+                   pmax=np.ctypeslib.as_array(out.pmax, (ns,)).copy(),
+                   prob=np.ctypeslib.as_array(out.prob, (ns,)).copy(),
+                   partner=np.ctypeslib.as_array(out.partner, (ns,)).copy(),
+                   ngb=np.ctypeslib.as_array(out.ngb, (ns,)).copy(), sct=list(out.sct),
+                   log_i=np.ctypeslib.as_array(out.log_i, (max(nl, 1),))[:nl].copy(),
+                   log_j=np.ctypeslib.as_array(out.log_j, (max(nl, 1),))[:nl].copy(),
+                   log_dv=np.ctypeslib.as_array(out.log_dv, (max(nl, 1) * 3,)).reshape(-1, 3)[:nl].copy())
+        self.L.osidm_out_free(C.byref(out))
+        return res
+
+    def sidm_ensure_neighbours(self, dt, vmax):
+        dta = np.ascontiguousarray(np.broadcast_to(np.float32(dt), (self.n,)), np.float32)
+        return self.L.osidm_ensure(self.tree, C.byref(self.par), self.n, _p(self.vel), _p(self.mass), _p(self.hsml),
+                                   _p(dta), _p(self.dvel), _p(self.ngb), _p(self.left), _p(self.right), float(vmax),
+                                   self.rng)

@@ -398,3 +398,5 @@ float ongb_treefind(const otree *t, const float xyz[3], int desngb)   /* forcetr
   free(list); free(r2);
   return h2max;
 }
+
+const float *otree_positions(const otree *t) { return t->pos; }

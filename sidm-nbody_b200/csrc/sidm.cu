@@ -1,12 +1,870 @@
-// sidm.cu - placeholder entry points (implemented next)
+// sidm.cu - the SIDM scatter step on the GPU.
+// Reference: sidm.c:57-627 (sidm), :630-805 (setup_nbr_sidm), :814-968
+// (sidm_ensure_neighbours), init.c:431-512 (setup_smoothinglengths_sidm),
+// forcetree.c:2163-2297 (ngb_treefind_variable / ngb_treesearch), :2311-2414 (ngb_treefind),
+// accel.c:27-132 (compute_accelerations).
+//
+// The reference runs one sequential loop over a communication buffer.  Inside one bunch that
+// loop only READS particle state (P[j].dVel, P[j].Vel); all writes happen afterwards in two
+// ordered sweeps (sidm.c:495-537 then :559-601).  So the loop body is data-parallel once each
+// buffer slot has its own random number, and the two sweeps become "own kick" followed by
+// "partner kick, last slot in buffer order wins" (atomicMax on the slot index).
+//
+// Kernels: slot assignment (exported-first buffer order) -> pass 1: neighbour count, P_max,
+// uniform, early-out (one thread per slot, range search through the gravity octree in
+// pre-order with skip pointers) -> pass 2 (only slots that passed): cumulative pair
+// probability and partner choice, either in tree order on the fly or, for replay parity, in
+// the reference's own list order (tree order + next[] chains + swap-remove filter) ->
+// resolve sweeps.  Random numbers: counter-based Philox4x32-10 keyed by (seed, call, particle)
+// or the reference's own stream fed per slot (b200_replay).
+#include <cub/cub.cuh>
 #include "ctx.cuh"
+
+namespace b200 {
+
+double s_a_inverse_at(double time);
+
+struct __attribute__((aligned(16))) SearchNode { float cx, cy, cz, len; int skip, pstart, np, pend; };
+
+struct SidmState {
+  SearchNode *snode = nullptr;
+  int *last_active = nullptr; int last_nactive = 0; bool last_all = false;
+  int *slot_of_sorted = nullptr;   // processing order of slots (key order)
+  int *passlist = nullptr;
+  int *logpos = nullptr;
+  double *rr = nullptr, *rd = nullptr; size_t replay_cap = 0;   // staged replay arrays
+  float *dt = nullptr;             // per slot: 2*(time - CurrentTime) (sidm.c:196)
+  unsigned char *already = nullptr;
+  double *ptot = nullptr;
+  int cap_nodes = 0, cap_part = 0;
+} S;
+
+constexpr int kCandCap = 1024;      // per-slot candidate capacity in reference-order mode
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ double u01(uint32_t x) { return (double)x / 4294967296.0; }   // same lattice as gsl_rng_uniform
+
+// ------------------------------------------------------------------ range search
+struct SearchCtx {
+  int M; const SearchNode *snode; const float4 *leaf_posm; const int *leaf_orig;
+};
+
+__device__ __forceinline__ float dist2_ref(float px, float py, float pz, float x, float y, float z) {
+  // forcetree.c:2195-2204: float differences, float products, summed left to right, no FMA
+  const float dx = fadd(px, -x), dy = fadd(py, -y), dz = fadd(pz, -z);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+
+// calls f(leaf_slot, r2, bulk, node) for every candidate the reference's ngb_treesearch() would
+// append (forcetree.c:2224-2297); node tests in double on float operands like the reference
+template <class F>
+__device__ __forceinline__ void range_search(const SearchCtx &C, float x, float y, float z, float h, F &&f) {
+  const float lox = fadd(x, -h), loy = fadd(y, -h), loz = fadd(z, -h);
+  const float hix = fadd(x, h), hiy = fadd(y, h), hiz = fadd(z, h);
+  int no = 0;
+  while (no < C.M) {
+    const SearchNode nd = C.snode[no];
+    const double half = 0.5 * (double)nd.len;
+    const double ax = (double)nd.cx + half, bx = (double)nd.cx - half;
+    const double ay = (double)nd.cy + half, by = (double)nd.cy - half;
+    const double az = (double)nd.cz + half, bz = (double)nd.cz - half;
+    if (ax < (double)lox || bx > (double)hix || ay < (double)loy || by > (double)hiy || az < (double)loz || bz > (double)hiz) { no = nd.skip; continue; }
+    const bool inside = !(ax > (double)hix) && !(bx < (double)lox) && !(ay > (double)hiy) && !(by < (double)loy) && !(az > (double)hiz) && !(bz < (double)loz);
+    if (inside) {
+      for (int L = nd.pstart; L < nd.pend; L++) { const float4 p = C.leaf_posm[L]; f(L, p, dist2_ref(p.x, p.y, p.z, x, y, z), true, no); }
+      no = nd.skip;
+    } else {
+      for (int k = 0; k < nd.np; k++) {
+        const int L = nd.pstart + k;
+        const float4 p = C.leaf_posm[L];
+        if (p.x < lox || p.x > hix || p.y < loy || p.y > hiy || p.z < loz || p.z > hiz) continue;
+        f(L, p, dist2_ref(p.x, p.y, p.z, x, y, z), false, no);
+      }
+      no = no + 1;
+    }
+  }
+}
+
+__global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, const int *npstart, const unsigned char *nnp, SearchNode *out) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= m) return;
+  const float4 gm = geom[id]; const int skip = nodes[id].skip;
+  SearchNode s; s.cx = gm.x; s.cy = gm.y; s.cz = gm.z; s.len = gm.w; s.skip = skip; s.pstart = npstart[id]; s.np = nnp[id]; s.pend = npstart[skip];
+  out[id] = s;
+}
+
+// ------------------------------------------------------------------ slots
+// sidm.c:141-161: particles within h of the domain box are flagged for export and placed first
+__global__ void k_export_flag(int na, const int *active, const float4 *posm, const float4 *velh, const float *domain, int *flag) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int i = active ? active[a] : a;
+  const float4 p = posm[i]; const float h = velh[i].w;
+  const float pp[3] = {p.x, p.y, p.z};
+  int j;
+  for (j = 0; j < 3; j++) {
+    if (pp[j] < fadd(domain[j], h)) break;
+    if (pp[j] > fadd(domain[3 + j], -h)) break;
+  }
+  flag[a] = (j != 3);
+}
+__global__ void k_assign_slots(int na, const int *active, const int *flag, const int *scan, int *slot_part, int *slot_of_active,
+                               const float *curtime, const float *dvel, double time, float *dt, unsigned char *already,
+                               const int *krank, int *keys, int *vals, int *flags_out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int nexport = scan[na];
+  const int i = active ? active[a] : a;
+  const int place = flag[a] ? scan[a] : nexport + (a - scan[a]);
+  slot_part[place] = i;
+  slot_of_active[a] = place;
+  dt[place] = (float)(2 * (time - (double)curtime[i]));             // sidm.c:196
+  already[place] = dvel[3 * (size_t)i] != 0.0f;                    // sidm.c:189-192 (ID = 0)
+  keys[a] = krank[i]; vals[a] = place;
+  if (a == 0) flags_out[FL_NEXPORT] = nexport;
+}
+
+// ------------------------------------------------------------------ pass 1
+struct Pass1 {
+  int ns; const int *order; const int *slot_part; SearchCtx C;
+  const float4 *posm, *velh; const float *dt; const unsigned char *already;
+  const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
+  int *ngb; double *pmax, *rnd; int *pass; int count_only; unsigned long long *ctr;
+};
+__global__ void __launch_bounds__(128) k_pass1(Pass1 P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.ns) return;
+  const int s = P.order[t];
+  const int i = P.slot_part[s];
+  const float4 p = P.posm[i]; const float h = P.velh[i].w;
+  const float sr2 = fmul(h, h);
+  int cnt = 0, cand = 0;
+  range_search(P.C, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  P.ngb[s] = cnt;
+  atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand);
+  if (P.count_only) return;
+  const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
+  const double hh = 1.0 * (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
+  const double pm = P.C_Pmax * (double)p.w * hinv3 * dt_h0;          // sidm.c:338
+  double r;
+  if (P.replay_rand) r = P.replay_rand[s];
+  else r = u01(philox((uint32_t)i, 0u, 0u, 0u, P.k0, P.k1).x);
+  P.pmax[s] = pm; P.rnd[s] = r;
+  const int pass = !(pm < r) && !P.already[s];                        // sidm.c:343-346
+  P.pass[t] = pass;
+}
+
+// ------------------------------------------------------------------ pass 2
+struct Pass2 {
+  int np; const int *passlist; const int *slot_part; SearchCtx C;
+  const float4 *posm, *velh; const float *dvel; const float *dt; const double *rnd;
+  const double *replay_dir; double sigma, s_a_inverse; uint32_t k0, k1; int xs_type; double vc, pl_n, pl_v0;
+  const double *kernel;            // begrun.c:968-992 table, 1002 doubles
+  int *partner; float *dv; double *prob, *ptot;
+  // reference-order mode
+  int ref_order; int *cand; unsigned long long *candkey; int cand_stride; const int *krank, *lrank, *nstart; int *flags;
+};
+
+__device__ __forceinline__ double kernel_w(const double *K, double u, double hinv3) {
+  const int ii = (int)(u * 1000);
+  return hinv3 * (K[ii] + (K[ii + 1] - K[ii]) * (u - ((double)ii) / 1000) * 1000);   // sidm.c:359-363
+}
+
+// probability increment of one pair, sidm.c:366-382
+__device__ __forceinline__ double pair_prob(const Pass2 &P, double mj, double wk, double rv, double dt_h0) {
+  switch (P.xs_type) {
+    case 1: return 0.5 * mj * wk * P.sigma * dt_h0;
+    case 2: { const double beta = rv / P.vc, vd = 1.0 / (1.0 + beta * beta); return 0.5 * mj * wk * rv * vd * vd * P.sigma * dt_h0; }
+    case 3: return 0.5 * mj * wk * rv * pow(rv / P.pl_v0, P.pl_n) * P.sigma * dt_h0;
+    default: return 0.5 * mj * wk * rv * P.sigma * dt_h0;
+  }
+}
+
+__device__ __forceinline__ void unit_vector(const Pass2 &P, int s, int i, double n[3]) {
+  if (P.replay_dir) { n[0] = P.replay_dir[3 * (size_t)s]; n[1] = P.replay_dir[3 * (size_t)s + 1]; n[2] = P.replay_dir[3 * (size_t)s + 2]; return; }
+  // sidm_rand.h:24-37 (Marsaglia), draws from the particle's own Philox stream
+  double y1, y2, r2; uint32_t c = 1;
+  do {
+    const uint4 q = philox((uint32_t)i, c++, 0u, 0u, P.k0, P.k1);
+    y1 = 1.0 - 2.0 * u01(q.x); y2 = 1.0 - 2.0 * u01(q.y); r2 = y1 * y1 + y2 * y2;
+    if (r2 > 1.0) { y1 = 1.0 - 2.0 * u01(q.z); y2 = 1.0 - 2.0 * u01(q.w); r2 = y1 * y1 + y2 * y2; }
+  } while (r2 > 1.0);
+  const double sq = sqrt(1.0 - r2);
+  n[0] = 2.0 * y1 * sq; n[1] = 2.0 * y2 * sq; n[2] = 1.0 - 2.0 * r2;
+}
+
+__global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.np) return;
+  const int s = P.passlist[t];
+  const int i = P.slot_part[s];
+  const float4 p = P.posm[i]; const float4 vi = P.velh[i]; const float h = vi.w;
+  const float sr2 = fmul(h, h);
+  const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
+  const double hh = (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
+  const double rnd = P.rnd[s];
+  double prob = 0, wk = 0, ptot = 0; int partner = -1; double prv[4] = {0, 0, 0, 0}; float pmass = 0;
+
+  auto visit = [&](int j, float r2) {       // one neighbour in list order, sidm.c:352-385
+    if (P.dvel[3 * (size_t)j] != 0.0f) return;
+    const double r = sqrt((double)r2);
+    if (r < hh) wk = kernel_w(P.kernel, r * hinv, hinv3);
+    const float4 vj = P.velh[j];
+    const double rvx = (double)fadd(vi.x, -vj.x), rvy = (double)fadd(vi.y, -vj.y), rvz = (double)fadd(vi.z, -vj.z);
+    const double rv = sqrt(rvx * rvx + rvy * rvy + rvz * rvz);
+    const float mj = P.posm[j].w;
+    const double dp = pair_prob(P, (double)mj, wk, rv, dt_h0);
+    ptot += dp;
+    if (partner >= 0) return;
+    prob += dp;
+    if (prob < rnd) return;
+    partner = j; prv[0] = rvx; prv[1] = rvy; prv[2] = rvz; prv[3] = rv; pmass = mj;
+  };
+
+  if (!P.ref_order) {
+    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) visit(P.C.leaf_orig[L], r2); });
+  } else {
+    // gather every candidate the reference's tree search appends, with a key that reproduces
+    // its order: position along the octant-ordered tree; inside fully-contained cells the
+    // next[] chain rank (forcetree.c:274-279, 2270-2276)
+    int nc = 0; bool over = false;
+    int *cl = P.cand + t; unsigned long long *ck = P.candkey + t; const int st = P.cand_stride;
+    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
+      if (nc >= kCandCap) { over = true; return; }
+      const int o = P.C.leaf_orig[L];
+      const unsigned long long key = bulk ? (((unsigned long long)P.nstart[node] << 32) | (unsigned)P.lrank[o])
+                                          : ((unsigned long long)P.krank[o] << 32);
+      // insertion into the sorted candidate list (short lists: ~60 entries)
+      int k = nc - 1;
+      while (k >= 0 && ck[(size_t)k * st] > key) { ck[(size_t)(k + 1) * st] = ck[(size_t)k * st]; cl[(size_t)(k + 1) * st] = cl[(size_t)k * st]; k--; }
+      ck[(size_t)(k + 1) * st] = key; cl[(size_t)(k + 1) * st] = o;
+      nc++;
+    });
+    if (over) P.flags[FL_ERR_NGB] = 1;
+    // swap-remove sphere filter, forcetree.c:2191-2212
+    int n = nc;
+    for (int a = 0; a < n; a++) {
+      const int j = cl[(size_t)a * st];
+      const float4 q = P.posm[j];
+      const float r2 = dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z);
+      if (r2 >= sr2) { cl[(size_t)a * st] = cl[(size_t)(n - 1) * st]; n--; a--; }
+    }
+    for (int a = 0; a < n; a++) {
+      const int j = cl[(size_t)a * st];
+      const float4 q = P.posm[j];
+      visit(j, dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z));
+    }
+  }
+  P.prob[s] = prob; P.ptot[s] = ptot; P.partner[s] = partner;
+  float dvx = 0, dvy = 0, dvz = 0;
+  if (partner >= 0) {
+    const double rmass = (double)(pmass / (p.w + pmass));            // float division, sidm.c:387
+    double n[3];
+    unit_vector(P, s, i, n);
+    dvx = (float)(rmass * (-prv[0] + prv[3] * n[0]));                 // sidm.c:446-451
+    dvy = (float)(rmass * (-prv[1] + prv[3] * n[1]));
+    dvz = (float)(rmass * (-prv[2] + prv[3] * n[2]));
+  }
+  P.dv[3 * (size_t)s] = dvx; P.dv[3 * (size_t)s + 1] = dvy; P.dv[3 * (size_t)s + 2] = dvz;
+}
+
+// ------------------------------------------------------------------ resolve sweeps
+__global__ void k_clear_slots(int ns, int *partner, float *dv, double *prob, double *ptot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  partner[s] = -1; dv[3 * (size_t)s] = dv[3 * (size_t)s + 1] = dv[3 * (size_t)s + 2] = 0; prob[s] = 0; ptot[s] = 0;
+}
+// sidm.c:495-537: own result -> particle, in/out of range decides confirmation
+__global__ void k_resolve_own(int ns, const int *slot_part, const int *sngb, const float *dv, int lo, int hi, int count_only,
+                              int *ngb, float *dvel, int *confirm, int *winner, const int *partner, unsigned long long *ctr) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  const int i = slot_part[s];
+  const int nb = sngb[s];
+  ngb[i] = nb;
+  if (count_only) return;
+  const float d0 = dv[3 * (size_t)s];
+  int conf = 0;
+  if (nb < lo || nb > hi) { if (d0 != 0.0f) atomicAdd(&ctr[CT_REJECTED], 1ull); }
+  else if (d0 != 0.0f) {
+    dvel[3 * (size_t)i] = d0; dvel[3 * (size_t)i + 1] = dv[3 * (size_t)s + 1]; dvel[3 * (size_t)i + 2] = dv[3 * (size_t)s + 2];
+    atomicAdd(&ctr[CT_SCATTERED], 1ull);
+    conf = 1;
+  }
+  confirm[s] = conf;
+  if (conf) atomicMax(&winner[partner[s]], s);
+}
+// sidm.c:559-601: partner gets -dv; several slots naming one partner: the last in buffer order wins
+__global__ void k_resolve_partner(int ns, const int *confirm, const int *partner, const float *dv, const int *winner, float *dvel,
+                                  const int *logpos, b200_scatlog *log, int logcap, int logbase, const int *slot_part,
+                                  const float4 *posm, const float4 *velh, const int *pid, float time) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns || !confirm[s]) return;
+  const int j = partner[s];
+  if (winner[j] == s) {
+    dvel[3 * (size_t)j] = -dv[3 * (size_t)s]; dvel[3 * (size_t)j + 1] = -dv[3 * (size_t)s + 1]; dvel[3 * (size_t)j + 2] = -dv[3 * (size_t)s + 2];
+  }
+  const int lp = logbase + logpos[s];
+  if (lp < logcap) {
+    const int i = slot_part[s];
+    b200_scatlog e;
+    e.time = time; e.id1 = pid[i]; e.id2 = pid[j]; e.Hsml1 = velh[i].w; e.Hsml2 = velh[j].w;
+    const float4 pi = posm[i], pj = posm[j], vi = velh[i], vj = velh[j];
+    e.x1[0] = pi.x; e.x1[1] = pi.y; e.x1[2] = pi.z; e.x2[0] = pj.x; e.x2[1] = pj.y; e.x2[2] = pj.z;
+    e.v1[0] = vi.x; e.v1[1] = vi.y; e.v1[2] = vi.z; e.v2[0] = vj.x; e.v2[1] = vj.y; e.v2[2] = vj.z;
+    e.dv[0] = dv[3 * (size_t)s]; e.dv[1] = dv[3 * (size_t)s + 1]; e.dv[2] = dv[3 * (size_t)s + 2];
+    log[lp] = e;
+  }
+}
+__global__ void k_reset_winner(int ns, const int *partner, int *winner) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < ns && partner[s] >= 0) winner[partner[s]] = -1;
+}
+
+// ------------------------------------------------------------------ host side
+static double *d_kernel_table = nullptr;
+
+static int ensure_sidm_buffers() {
+  const size_t n = (size_t)g.maxpart, m = (size_t)g.maxnodes;
+  auto al = [](void **p, size_t bytes) { if (*p) return B200_OK; return cudaMalloc(p, bytes + 256) == cudaSuccess ? B200_OK : B200_ERR_ALLOC; };
+  B200_TRY(al((void **)&S.snode, (m + 1) * sizeof(SearchNode)));
+  B200_TRY(al((void **)&S.last_active, n * sizeof(int)));
+  B200_TRY(al((void **)&S.slot_of_sorted, n * sizeof(int)));
+  B200_TRY(al((void **)&S.passlist, n * sizeof(int)));
+  B200_TRY(al((void **)&S.logpos, (n + 1) * sizeof(int)));
+  B200_TRY(al((void **)&S.dt, n * sizeof(float)));
+  B200_TRY(al((void **)&S.already, n));
+  B200_TRY(al((void **)&S.ptot, n * sizeof(double)));
+  if (!d_kernel_table) {
+    double K[1002];
+    const double PI = 3.14159265358979323846;
+    K[1001] = 0;
+    for (int i = 0; i <= 1000; i++) {          // begrun.c:968-992
+      const double r = ((double)i) / 1000;
+      K[i] = r <= 0.5 ? 8 / PI * (1 - 6 * r * r * (1 - r)) : 8 / PI * 2 * (1 - r) * (1 - r) * (1 - r);
+    }
+    if (cudaMalloc((void **)&d_kernel_table, sizeof(K)) != cudaSuccess) return B200_ERR_ALLOC;
+    CUDA_TRY(cudaMemcpy(d_kernel_table, K, sizeof(K), cudaMemcpyHostToDevice));
+  }
+  return B200_OK;
+}
+
+static int cub_scratch(size_t tb) {
+  if (tb <= g.cub_tmp_bytes) return B200_OK;
+  if (g.cub_tmp) cudaFree(g.cub_tmp);
+  g.cub_tmp = nullptr; g.cub_tmp_bytes = 0;
+  if (cudaMalloc(&g.cub_tmp, tb + 4096) != cudaSuccess) return B200_ERR_ALLOC;
+  g.cub_tmp_bytes = tb + 4096;
+  return B200_OK;
+}
+
+static SearchCtx search_ctx() {
+  SearchCtx C; C.M = g.num_nodes; C.snode = S.snode; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
+  return C;
+}
+
+static bool search_nodes_current = false;
+int refresh_search_nodes() {
+  B200_TRY(ensure_sidm_buffers());
+  k_search_nodes<<<cdiv(g.num_nodes, 256), 256, 0, g.stream>>>(g.num_nodes, g.nodes, g.geom, g.npstart, g.nnp, S.snode);
+  count_launch();
+  search_nodes_current = true;
+  return B200_OK;
+}
+
+// one sidm() call for a device-resident active list (d_active == nullptr: every particle in
+// index order).  replay arrays are host pointers indexed by buffer slot.
+int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only) {
+  if (!g.tree_valid) return B200_ERR_STATE;
+  B200_TRY(ensure_sidm_buffers());
+  B200_TRY(refresh_search_nodes());
+  cudaStream_t st = g.stream;
+  const int na = nactive;
+  if (na <= 0) return B200_OK;
+  const int B = 256;
+  const double sainv = s_a_inverse_at(time);
+  // C_Pmax, sidm.c:226-316 (types 0..3)
+  const int T = g.par.CrossSectionType;
+  double sigma = g.par.CrossSectionInternal, vc = g.par.YukawaVelocity;
+  if (g.par.ComovingIntegrationOn) { sigma = sigma / pow(time, T == 1 ? 2.5 : 2.0); vc = vc / sqrt(time); }
+  const double ball = (3. / 4. / 3.14159265358979323846) * (g.par.DesNumNgb + g.par.MaxNumNgbDeviation);
+  double C_Pmax;
+  if (T == 0) C_Pmax = 1.0 * ball * 2 * vmax * sigma;
+  else if (T == 1) C_Pmax = 1.0 * ball * sigma;
+  else if (T == 2) {
+    if (2.0 * vmax < vc / sqrt(3.0)) { const double beta = 2.0 * vmax / vc, vd = 1.0 / (1.0 + beta * beta); C_Pmax = 1.0 * ball * 2.0 * vmax * vd * vd * sigma; }
+    else C_Pmax = 1.0 * ball * (3.0 * sqrt(3.0) / 16.0) * vc * sigma;
+  } else C_Pmax = 1.0 * ball * 2 * g.par.CrossSectionVelScale * sigma;
+
+  g.sidm_calls++;
+  const uint32_t k0 = (uint32_t)(g.par.Seed & 0xffffffffu) ^ (uint32_t)(g.sidm_calls * 0x9E3779B9u);
+  const uint32_t k1 = (uint32_t)(g.par.Seed >> 32) ^ (uint32_t)(g.sidm_calls >> 32) ^ 0x5851F42Du;
+
+  CUDA_TRY(cudaMemsetAsync(g.d_ctr + CT_CAND, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_ERR_NGB, 0, sizeof(int), st));
+
+  int bunch = g.par.BunchSizeSidm > 0 ? g.par.BunchSizeSidm : na;
+  int logbase = g.scatlog_n, tot_pass1 = 0;
+  size_t replay_off = 0;
+  for (int b0 = 0; b0 < na; b0 += bunch) {
+    const int nb = (na - b0 < bunch) ? na - b0 : bunch;
+    const int *act = d_active ? d_active + b0 : nullptr;
+    if (!d_active && b0 > 0) return B200_ERR_ARG;     // bunches need an explicit list
+    const int G = cdiv(nb, B);
+    // slots: exported-first buffer order
+    k_export_flag<<<G, B, 0, st>>>(nb, act, g.posm, g.velh, g.d_domain, g.s_flag);
+    CUDA_TRY(cudaMemsetAsync(g.s_flag + nb, 0, sizeof(int), st));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, g.s_flag, g.s_pos, nb + 1, st);
+    B200_TRY(cub_scratch(tb));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb, g.s_flag, g.s_pos, nb + 1, st));
+    int *slot_of_active = g.s_repair;     // scratch
+    k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
+                                    g.krank, g.d_tkeys, g.d_tvals2, g.d_flags);
+    // processing order: slots sorted along the tree key order (spatial coherence inside a warp)
+    size_t tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st);
+    B200_TRY(cub_scratch(tb2));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st));
+    count_launch(2 + 2 + 4);
+    // replay arrays
+    const double *d_rr = nullptr, *d_rd = nullptr;
+    if (replay && replay->rand && !count_only) {
+      const size_t need = (size_t)nb * 4;
+      if (S.replay_cap < need) {
+        if (S.rr) cudaFree(S.rr);
+        if (cudaMalloc((void **)&S.rr, need * sizeof(double)) != cudaSuccess) return B200_ERR_ALLOC;
+        S.replay_cap = need; S.rd = S.rr + nb;
+      }
+      S.rd = S.rr + nb;
+      CUDA_TRY(cudaMemcpyAsync(S.rr, replay->rand + replay_off, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, st));
+      d_rr = S.rr;
+      if (replay->dir) { CUDA_TRY(cudaMemcpyAsync(S.rd, replay->dir + 3 * replay_off, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice, st)); d_rd = S.rd; }
+      replay_off += nb;
+    }
+    // pass 1
+    Pass1 P1;
+    P1.ns = nb; P1.order = S.slot_of_sorted; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
+    P1.posm = g.posm; P1.velh = g.velh; P1.dt = S.dt; P1.already = S.already; P1.replay_rand = d_rr;
+    P1.C_Pmax = C_Pmax; P1.s_a_inverse = sainv; P1.k0 = k0; P1.k1 = k1;
+    P1.ngb = g.s_ngb; P1.pmax = g.s_pmax; P1.rnd = g.s_rand; P1.pass = g.s_pass; P1.count_only = count_only; P1.ctr = g.d_ctr;
+    k_pass1<<<cdiv(nb, 128), 128, 0, st>>>(P1);
+    k_clear_slots<<<G, B, 0, st>>>(nb, g.s_partner, g.s_dv, g.s_prob, S.ptot);
+    count_launch(2);
+    int npass = 0;
+    if (!count_only) {
+      // compact the slots that passed the first approximation, keeping the processing order
+      size_t tb3 = 0;
+      cub::DeviceSelect::Flagged(nullptr, tb3, S.slot_of_sorted, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nb, st);
+      B200_TRY(cub_scratch(tb3));
+      CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb3, S.slot_of_sorted, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nb, st));
+      CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      npass = g.h_flags[FL_NPASS];
+      count_launch(3);
+      tot_pass1 += npass;
+      const bool ref_order = g.par.ReferenceNgbOrder != 0;
+      const int chunk = ref_order ? 131072 : npass;
+      if (ref_order && npass > 0) {
+        const size_t need = (size_t)(npass < chunk ? npass : chunk) * kCandCap;
+        if (g.s_cand_cap < need) {
+          if (g.s_cand) cudaFree(g.s_cand); if (g.s_candkey) cudaFree(g.s_candkey);
+          g.s_cand = nullptr; g.s_candkey = nullptr; g.s_cand_cap = 0;
+          if (cudaMalloc((void **)&g.s_cand, need * sizeof(int)) != cudaSuccess) return B200_ERR_ALLOC;
+          if (cudaMalloc((void **)&g.s_candkey, need * sizeof(unsigned long long)) != cudaSuccess) return B200_ERR_ALLOC;
+          g.s_cand_cap = need;
+        }
+      }
+      for (int c0 = 0; c0 < npass; c0 += chunk) {
+        const int nc = (npass - c0 < chunk) ? npass - c0 : chunk;
+        Pass2 P2;
+        P2.np = nc; P2.passlist = S.passlist + c0; P2.slot_part = g.s_slot_part; P2.C = search_ctx();
+        P2.posm = g.posm; P2.velh = g.velh; P2.dvel = g.dvel; P2.dt = S.dt; P2.rnd = g.s_rand; P2.replay_dir = d_rd;
+        P2.sigma = sigma; P2.s_a_inverse = sainv; P2.k0 = k0; P2.k1 = k1; P2.xs_type = T; P2.vc = vc;
+        P2.pl_n = g.par.CrossSectionPowLaw; P2.pl_v0 = g.par.CrossSectionVelScale; P2.kernel = d_kernel_table;
+        P2.partner = g.s_partner; P2.dv = g.s_dv; P2.prob = g.s_prob; P2.ptot = S.ptot;
+        P2.ref_order = ref_order; P2.cand = g.s_cand; P2.candkey = g.s_candkey; P2.cand_stride = nc;
+        P2.krank = g.krank; P2.lrank = g.lrank; P2.nstart = g.nstart; P2.flags = g.d_flags;
+        k_pass2<<<cdiv(nc, 128), 128, 0, st>>>(P2);
+        count_launch();
+      }
+    }
+    // resolve
+    int *confirm = g.s_pass;   // reuse (pass flags are consumed)
+    CUDA_TRY(cudaMemsetAsync(g.s_winner, 0xff, (size_t)g.n * sizeof(int), st));
+    k_resolve_own<<<G, B, 0, st>>>(nb, g.s_slot_part, g.s_ngb, g.s_dv, g.par.DesNumNgb - g.par.MaxNumNgbDeviation,
+                                   g.par.DesNumNgb + g.par.MaxNumNgbDeviation, count_only, g.ngb, g.dvel, confirm, g.s_winner, g.s_partner, g.d_ctr);
+    count_launch();
+    if (!count_only) {
+      CUDA_TRY(cudaMemsetAsync(confirm + nb, 0, sizeof(int), st));
+      size_t tb4 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb4, confirm, S.logpos, nb + 1, st);
+      B200_TRY(cub_scratch(tb4));
+      CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
+      k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
+                                         g.s_slot_part, g.posm, g.velh, g.pid, (float)time);
+      int nlog = 0;
+      CUDA_TRY(cudaMemcpyAsync(&nlog, S.logpos + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      logbase += nlog;
+      count_launch(3);
+    }
+    g.last_nslot = nb;
+  }
+  g.scatlog_n = logbase < g.scatlog_cap ? logbase : g.scatlog_cap;
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
+  g.cnt.sct_ntot = na; g.cnt.sct_pass1 = tot_pass1;
+  g.cnt.sct_scattered = (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected = (int)g.h_ctr[CT_REJECTED];
+  g.cnt.ngb_candidates = (long long)g.h_ctr[CT_CAND];
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ k nearest (ngb_treefind)
+struct KnnParams { int nq; const int *idx; SearchCtx C; const float4 *posm; int k; float *h2; const SearchNode *snode; const uint64_t *shi, *slo;
+                   const int *nstart; const unsigned char *nlevel; const int *nend; };
+constexpr int kKnnMax = 64;
+
+__global__ void __launch_bounds__(128) k_knn(KnnParams P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nq) return;
+  const int i = P.idx[t];
+  const float4 p = P.posm[i];
+  // starting radius from the local density: descend while the cell holds > 200 particles
+  // (forcetree.c:2327-2347)
+  int th = 0;
+  for (;;) {
+    const SearchNode nd = P.snode[th];
+    const int cnt = P.nend[th] - P.nstart[th] + 1;
+    if (cnt <= 200) break;
+    const int oct = (p.x > nd.cx ? 1 : 0) | (p.y > nd.cy ? 2 : 0) | (p.z > nd.cz ? 4 : 0);
+    int next = -1;
+    const int lev = P.nlevel[th];
+    for (int c = th + 1; c < nd.skip; c = P.snode[c].skip)
+      if (digit_at(P.shi[P.nstart[c]], P.slo[P.nstart[c]], lev) == oct) { next = c; break; }
+    if (next < 0 || P.nend[next] - P.nstart[next] + 1 <= 200) break;
+    th = next;
+  }
+  const int cnt_th = P.nend[th] - P.nstart[th] + 1;
+  float sr = (float)((double)P.snode[th].len * pow((3.0 / (4 * 3.14159265358979323846) * 1.2) * P.k / ((double)(float)cnt_th), 1.0 / 3));
+  float best[kKnnMax];
+  const int K = P.k;
+  float h2max = 0;
+  for (int rep = 0; rep < 200; rep++) {
+    int found = 0;
+    for (int a = 0; a < K; a++) best[a] = 3.4e38f;
+    range_search(P.C, p.x, p.y, p.z, sr, [&](int, const float4 &, float r2, bool, int) {
+      found++;
+      if (r2 < best[K - 1]) {              // keep the K smallest squared distances, sorted
+        int a = K - 2;
+        while (a >= 0 && best[a] > r2) { best[a + 1] = best[a]; a--; }
+        best[a + 1] = r2;
+      }
+    });
+    if (found < K) { if (found > 5) sr = (float)((double)sr * pow((2.1 * (double)(float)K) / found, 1.0 / 3)); else sr *= 2.0f; continue; }
+    h2max = best[K - 1];
+    if (h2max <= fmul(sr, sr)) break;
+    sr = (float)((double)sr * 1.26);
+  }
+  P.h2[t] = h2max;
+}
+
+static int knn_device(const int *d_idx, int nq, int k, float *d_h2) {
+  if (k < 1 || k > kKnnMax) return B200_ERR_ARG;
+  B200_TRY(refresh_search_nodes());
+  KnnParams P; P.nq = nq; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode;
+  P.shi = g.skey_hi; P.slo = g.skey_lo; P.nstart = g.nstart; P.nlevel = g.nlevel; P.nend = g.nend;
+  k_knn<<<cdiv(nq, 128), 128, 0, g.stream>>>(P);
+  count_launch();
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ ensure_neighbours
+// sidm.c:862-888 (ensure==1) or init.c:456-478 (ensure==0): flag particles whose neighbour
+// count is out of range and not yet converged, update the bisection bracket
+__global__ void k_flag_repair(int n, int lo, int hi, int ensure_variant, const int *ngb, const float4 *velh, float *left, float *right, int *flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = 0;
+  const int nb = ngb[i];
+  if (nb < lo || nb > hi) {
+    float L = left[i], R = right[i];
+    const float h = velh[i].w;
+    if (!(L > 0 && R > 0 && (double)fadd(R, -L) < 1.0e-3 * (double)L)) {
+      f = 1;
+      if (ensure_variant) {
+        if (nb < lo) L = (float)fmax((double)h, (double)L);
+        else { if (R != 0) { if (h < R) R = h; } else R = h; }
+      } else {
+        if (nb < lo) L = h;
+        if (nb > hi) R = h;
+      }
+      left[i] = L; right[i] = R;
+    }
+  }
+  flag[i] = f;
+}
+// sidm.c:917-929: new smoothing length for the flagged particles (h from k-NN where asked)
+__global__ void k_new_hsml(int nr, const int *redo, const int *ngb, const float *left, const float *right, float4 *velh, int des,
+                           int ensure_variant, int ntype, int *want_knn) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nr) return;
+  const int i = redo[a];
+  float4 v = velh[i];
+  const float L = left[i], R = right[i];
+  int knn = 0;
+  if (L == 0 || R == 0) {
+    if (ensure_variant && R == 0 && ngb[i] < 15 && ntype > des) knn = 1;
+    else v.w = (float)((double)v.w * (0.5 + 0.5 * pow(ngb[i] / ((double)des), -1.0 / 3)));
+  } else v.w = (float)(0.5 * ((double)L + (double)R));
+  velh[i] = v;
+  want_knn[a] = knn;
+}
+__global__ void k_apply_knn(int nr, const int *redo, const int *want, const float *h2, float4 *velh) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nr || !want[a]) return;
+  velh[redo[a]].w = (float)sqrt((double)h2[a]);
+}
+__global__ void k_zero_lr(int na, const int *active, float *left, float *right) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int i = active ? active[a] : a;
+  left[i] = 0; right[i] = 0;
+}
+__global__ void k_count_out_of_range(int na, const int *active, const int *ngb, int lo, int hi, int *out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int i = active ? active[a] : a;
+  if (ngb[i] < lo || ngb[i] > hi) atomicAdd(out, 1);
+}
+__global__ void k_iota(int n, int *a) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_set_hsml_from_h2(int n, const float *h2, float4 *velh, float *left, float *right) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  velh[i].w = (float)sqrt((double)h2[i]); left[i] = 0; right[i] = 0;
+}
+
+// shared repair loop; ensure_variant 1 = sidm_ensure_neighbours (runs sidm()), 0 = start-up
+// (counts only, setup_nbr_sidm)
+static int repair_loop(int ensure_variant, double time, double vmax, const b200_replay *replay, int maxiter) {
+  cudaStream_t st = g.stream;
+  const int n = g.n, B = 256, G = cdiv(n, B);
+  const int lo = g.par.DesNumNgb - g.par.MaxNumNgbDeviation, hi = g.par.DesNumNgb + g.par.MaxNumNgbDeviation;
+  int iter = 0;
+  size_t roff = 0;
+  int *redo = g.d_active;                 // compacted list (ascending index, like sidm.c:862)
+  int *want = g.d_tsorted; float *h2 = (float *)g.d_tkeys2;
+  for (;;) {
+    k_flag_repair<<<G, B, 0, st>>>(n, lo, hi, ensure_variant, g.ngb, g.velh, g.left, g.right, g.s_flag);
+    size_t tb = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st);
+    B200_TRY(cub_scratch(tb));
+    CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st));
+    CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    count_launch(4);
+    const int nr = g.h_flags[FL_NREPAIR];
+    if (nr == 0) break;
+    k_new_hsml<<<cdiv(nr, B), B, 0, st>>>(nr, redo, g.ngb, g.left, g.right, g.velh, g.par.DesNumNgb, ensure_variant, n, want);
+    count_launch();
+    if (ensure_variant) {
+      B200_TRY(knn_device(redo, nr, g.par.DesNumNgb, h2));      // computed for all flagged, applied where asked (rare)
+      k_apply_knn<<<cdiv(nr, B), B, 0, st>>>(nr, redo, want, h2, g.velh);
+      count_launch();
+    }
+    b200_replay rp; const b200_replay *rpp = nullptr;
+    if (replay && replay->rand) { rp.rand = replay->rand + roff; rp.dir = replay->dir ? replay->dir + 3 * roff : nullptr; rpp = &rp; roff += nr; }
+    B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0));
+    iter++;
+    if (iter > maxiter) { fprintf(stderr, "libsidm_b200: failed to converge in ensure_neighbours\n"); return B200_ERR_HSML; }
+  }
+  g.cnt.ensure_iterations = iter;
+  return B200_OK;
+}
+
+}  // namespace b200
 using namespace b200;
-extern "C" int b200_sidm(const int *, int, double, double, const b200_replay *) { return B200_ERR_STATE; }
-extern "C" int b200_setup_nbr_sidm(const int *, int) { return B200_ERR_STATE; }
-extern "C" int b200_sidm_ensure_neighbours(int, double, double, const b200_replay *) { return B200_ERR_STATE; }
-extern "C" int b200_setup_smoothinglengths_sidm(int) { return B200_ERR_STATE; }
-extern "C" int b200_compute_accelerations(int, const int *, int, double, double) { return B200_ERR_STATE; }
-extern "C" int b200_ngb_treefind(const int *, int, int, float *) { return B200_ERR_STATE; }
-extern "C" int b200_ngb_lists(const int *, int, int, int *, int *) { return B200_ERR_STATE; }
-extern "C" int b200_sidm_debug(int, int *, double *, double *, int *) { return B200_ERR_STATE; }
-extern "C" int b200_get_scatlog(b200_scatlog *, int, int *) { return B200_ERR_STATE; }
+
+static int stage_active(const int *active, int nactive, const int **d_out, int *n_out) {
+  B200_TRY(ensure_sidm_buffers());
+  if (!active) { *d_out = nullptr; *n_out = g.n; S.last_all = true; S.last_nactive = g.n; return B200_OK; }
+  if (nactive < 0 || nactive > g.n) return B200_ERR_ARG;
+  CUDA_TRY(cudaMemcpyAsync(S.last_active, active, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  S.last_all = false; S.last_nactive = nactive;
+  *d_out = S.last_active; *n_out = nactive;
+  return B200_OK;
+}
+
+extern "C" int b200_sidm(const int *active, int nactive, double time, double vmax, const b200_replay *replay) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  const int *d; int na;
+  B200_TRY(stage_active(active, nactive, &d, &na));
+  g.scatlog_n = 0;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  int rc = sidm_impl(d, na, time, vmax, replay, false);
+  cudaEventRecord(g.ev1, g.stream); cudaEventSynchronize(g.ev1);
+  cudaEventElapsedTime(&g.cnt.ms_sidm, g.ev0, g.ev1);
+  return rc;
+}
+
+extern "C" int b200_setup_nbr_sidm(const int *active, int nactive) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  const int *d; int na;
+  B200_TRY(stage_active(active, nactive, &d, &na));
+  return sidm_impl(d, na, 0.0, 0.0, nullptr, true);
+}
+
+extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, const b200_replay *replay) {
+  (void)mode;   // restoring / resetting the time line (sidm.c:943-965) is the host driver's job
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  B200_TRY(ensure_sidm_buffers());
+  cudaStream_t st = g.stream;
+  const int lo = g.par.DesNumNgb - g.par.MaxNumNgbDeviation, hi = g.par.DesNumNgb + g.par.MaxNumNgbDeviation;
+  const int na = S.last_nactive > 0 ? S.last_nactive : g.n;
+  const int *act = (S.last_all || S.last_nactive == 0) ? nullptr : S.last_active;
+  CUDA_TRY(cudaEventRecord(g.ev0, st));
+  // candidates among the active particles, sidm.c:836-846
+  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_NREPAIR, 0, sizeof(int), st));
+  k_count_out_of_range<<<cdiv(na, 256), 256, 0, st>>>(na, act, g.ngb, lo, hi, g.d_flags + FL_NREPAIR);
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  count_launch();
+  g.cnt.ensure_iterations = 0;
+  int rc = B200_OK;
+  if (g.h_flags[FL_NREPAIR] > 0) {
+    k_zero_lr<<<cdiv(na, 256), 256, 0, st>>>(na, act, g.left, g.right);     // sidm.c:857-859
+    k_iota<<<cdiv(g.n, 256), 256, 0, st>>>(g.n, g.iota);
+    count_launch(2);
+    rc = repair_loop(1, time, vmax, replay, 30);
+  }
+  cudaEventRecord(g.ev1, st); cudaEventSynchronize(g.ev1);
+  cudaEventElapsedTime(&g.cnt.ms_ensure, g.ev0, g.ev1);
+  return rc;
+}
+
+extern "C" int b200_setup_smoothinglengths_sidm(int desired_ngb) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  B200_TRY(ensure_sidm_buffers());
+  cudaStream_t st = g.stream;
+  const int n = g.n;
+  k_iota<<<cdiv(n, 256), 256, 0, st>>>(n, g.iota);
+  float *h2 = (float *)g.d_tkeys2;
+  B200_TRY(knn_device(g.iota, n, desired_ngb, h2));                          // init.c:440-444
+  k_set_hsml_from_h2<<<cdiv(n, 256), 256, 0, st>>>(n, h2, g.velh, g.left, g.right);
+  count_launch(2);
+  S.last_all = true; S.last_nactive = n;
+  B200_TRY(sidm_impl(nullptr, n, 0.0, 0.0, nullptr, true));                  // setup_nbr_sidm(), init.c:446
+  return repair_loop(0, 0.0, 0.0, nullptr, 60);                              // init.c:453-509
+}
+
+extern "C" int b200_compute_accelerations(int mode, const int *active, int nactive, double time, double vmax) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  B200_TRY(b200_predict(time));                    // gravtree.c:72 predict_collisionless_only(All.Time)
+  B200_TRY(b200_tree_build());                     // gravtree.c:76 force_treebuild()
+  B200_TRY(b200_gravity(active, nactive, time));   // gravtree.c:127-324
+  if (mode == 0) {                                 // accel.c:60-65
+    B200_TRY(b200_sidm(active, nactive, time, vmax, nullptr));
+    B200_TRY(b200_sidm_ensure_neighbours(mode, time, vmax, nullptr));
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_ngb_treefind(const int *idx, int n, int desngb, float *h2_out) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  if (!idx || n <= 0 || n > g.n || !h2_out) return B200_ERR_ARG;
+  B200_TRY(ensure_sidm_buffers());
+  CUDA_TRY(cudaMemcpyAsync(g.d_active, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  float *h2 = (float *)g.d_tkeys2;
+  B200_TRY(knn_device(g.d_active, n, desngb, h2));
+  CUDA_TRY(cudaMemcpyAsync(h2_out, h2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// neighbour lists for tests: the list pass 2 would scan (ordered per ReferenceNgbOrder)
+struct ListParams { int nq; const int *idx; SearchCtx C; const float4 *posm, *velh; int cap; int *count, *list; int ref_order;
+                    const int *krank, *lrank, *nstart; unsigned long long *keys; };
+__global__ void k_ngb_lists(ListParams P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nq) return;
+  const int i = P.idx[t];
+  const float4 p = P.posm[i]; const float h = P.velh[i].w; const float sr2 = fmul(h, h);
+  int *out = P.list + (size_t)t * P.cap; unsigned long long *ck = P.keys + (size_t)t * P.cap;
+  int nc = 0;
+  if (!P.ref_order) {
+    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) { if (nc < P.cap) out[nc] = P.C.leaf_orig[L]; nc++; } });
+    P.count[t] = nc;
+    return;
+  }
+  range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
+    if (nc >= P.cap) { nc++; return; }
+    const int o = P.C.leaf_orig[L];
+    const unsigned long long key = bulk ? (((unsigned long long)P.nstart[node] << 32) | (unsigned)P.lrank[o]) : ((unsigned long long)P.krank[o] << 32);
+    int k = nc - 1;
+    while (k >= 0 && ck[k] > key) { ck[k + 1] = ck[k]; out[k + 1] = out[k]; k--; }
+    ck[k + 1] = key; out[k + 1] = o; nc++;
+  });
+  if (nc > P.cap) { P.count[t] = nc; return; }
+  int n = nc;
+  for (int a = 0; a < n; a++) {
+    const float4 q = P.posm[out[a]];
+    if (dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z) >= sr2) { out[a] = out[n - 1]; n--; a--; }
+  }
+  P.count[t] = n;
+}
+
+extern "C" int b200_ngb_lists(const int *idx, int n, int cap, int *count_out, int *list_out) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  if (!idx || n <= 0 || cap <= 0 || !count_out || !list_out) return B200_ERR_ARG;
+  B200_TRY(refresh_search_nodes());
+  int *d_idx, *d_cnt, *d_list; unsigned long long *d_keys;
+  if (cudaMalloc((void **)&d_idx, (size_t)n * 4) != cudaSuccess) return B200_ERR_ALLOC;
+  if (cudaMalloc((void **)&d_cnt, (size_t)n * 4) != cudaSuccess) return B200_ERR_ALLOC;
+  if (cudaMalloc((void **)&d_list, (size_t)n * cap * 4) != cudaSuccess) return B200_ERR_ALLOC;
+  if (cudaMalloc((void **)&d_keys, (size_t)n * cap * 8) != cudaSuccess) return B200_ERR_ALLOC;
+  cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream);
+  cudaMemsetAsync(d_list, 0xff, (size_t)n * cap * 4, g.stream);
+  ListParams P; P.nq = n; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.velh = g.velh; P.cap = cap; P.count = d_cnt; P.list = d_list;
+  P.ref_order = g.par.ReferenceNgbOrder; P.krank = g.krank; P.lrank = g.lrank; P.nstart = g.nstart; P.keys = d_keys;
+  k_ngb_lists<<<cdiv(n, 64), 64, 0, g.stream>>>(P);
+  count_launch();
+  cudaMemcpyAsync(count_out, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream);
+  cudaMemcpyAsync(list_out, d_list, (size_t)n * cap * 4, cudaMemcpyDeviceToHost, g.stream);
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  cudaFree(d_idx); cudaFree(d_cnt); cudaFree(d_list); cudaFree(d_keys);
+  if (e != cudaSuccess) { g.last_cuda = (int)e; return B200_ERR_CUDA; }
+  return B200_OK;
+}
+
+extern "C" int b200_sidm_debug(int nslot, int *slot_particle, double *pmax, double *prob_total, int *partner) {
+  if (!g.ready || nslot <= 0 || nslot > g.last_nslot) return B200_ERR_ARG;
+  cudaStream_t st = g.stream;
+  if (slot_particle) cudaMemcpyAsync(slot_particle, g.s_slot_part, (size_t)nslot * 4, cudaMemcpyDeviceToHost, st);
+  if (pmax) cudaMemcpyAsync(pmax, g.s_pmax, (size_t)nslot * 8, cudaMemcpyDeviceToHost, st);
+  if (prob_total) cudaMemcpyAsync(prob_total, S.ptot, (size_t)nslot * 8, cudaMemcpyDeviceToHost, st);
+  if (partner) cudaMemcpyAsync(partner, g.s_partner, (size_t)nslot * 4, cudaMemcpyDeviceToHost, st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return B200_OK;
+}
+
+extern "C" int b200_get_scatlog(b200_scatlog *out, int cap, int *n) {
+  if (!g.ready || !out || !n) return B200_ERR_ARG;
+  const int m = g.scatlog_n < cap ? g.scatlog_n : cap;
+  if (m > 0) CUDA_TRY(cudaMemcpy(out, g.d_scatlog, (size_t)m * sizeof(b200_scatlog), cudaMemcpyDeviceToHost));
+  *n = m;
+  return B200_OK;
+}

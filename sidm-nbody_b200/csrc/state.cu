@@ -171,7 +171,8 @@ extern "C" int b200_set_soa(int n, const float *pos, const float *vel, const flo
   if (!g.ready) return B200_ERR_STATE;
   if (n <= 0 || n > g.maxpart) return B200_ERR_ARG;
   const bool fresh = (n != g.n);
-  g.n = n; g.tree_valid = false;
+  g.n = n;
+  if (fresh || pos || mass) g.tree_valid = false;   // the tree depends on PosPred and Mass only
   const int B = 256, G = cdiv(n, B);
   if (fresh) {   // start-up state of init.c:76-100
     CUDA_TRY(cudaMemsetAsync(g.posm, 0, n * sizeof(float4), g.stream));

@@ -1,0 +1,71 @@
+"""CPU: the per-index bodies of the CUDA tree build and the per-lane walk arithmetic
+(csrc/build_logic.h, csrc/tree_logic.h), run sequentially on the host by tests/hostcheck,
+against the golden vectors from the unmodified reference.  This checks the construction
+logic the GPU executes (key-prefix octree, pre-order ids, moment shifts, next[] ranks)
+where no GPU is available; the GPU run itself is checked by the -m gpu tests."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "hernquist3k.npz")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    sys.path.insert(0, os.path.join(HERE, "hostcheck"))
+    import build
+    return C.CDLL(build.build())
+
+
+def _sorted_view(center, length):
+    a = np.concatenate([center, length[:, None]], axis=1).astype(np.float32).copy()
+    v = a.view([("a", "<u4"), ("b", "<u4"), ("c", "<u4"), ("d", "<u4")]).ravel()
+    o = np.argsort(v, order=["a", "b", "c", "d"])
+    return v[o], o
+
+
+def test_key_tree_equals_insertion_tree(hc):
+    g = np.load(GOLD)
+    pos, mass = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["mass"])
+    n = len(mass)
+    assert hc.hc_build(n, pos.ctypes, mass.ctypes, 1) == 0
+    m = hc.hc_num_nodes()
+    assert m == len(g["node_len"])
+    d = dict(center=np.empty((m, 3), np.float32), len=np.empty(m, np.float32), mass=np.empty(m, np.float32),
+             s=np.empty((m, 3), np.float32), Q=np.empty((m, 7), np.float32), oc=np.empty(m, np.float32),
+             bmax2=np.empty(m, np.float32), count=np.empty(m, np.int32), level=np.empty(m, np.int32),
+             skip=np.empty(m, np.int32), parent=np.empty(m, np.int32), minidx=np.empty(m, np.int32))
+    hc.hc_get_tree(*[d[k].ctypes for k in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count", "level", "skip",
+                                           "parent", "minidx")])
+    kr, orr = _sorted_view(g["node_center"], g["node_len"])
+    kh, oh = _sorted_view(d["center"], d["len"])
+    assert np.array_equal(kr, kh)
+    for k in ("count", "mass", "oc"):
+        assert np.array_equal(g["node_" + k][orr], d[k][oh]), k
+    np.testing.assert_allclose(d["bmax2"][oh], g["node_bmax2"][orr], rtol=3e-7)
+    scale = (g["node_mass"][orr] * g["node_len"][orr] ** 2)[:, None]
+    assert np.max(np.abs(g["node_Q"][orr] - d["Q"][oh]) / scale) < 1e-6
+    # pre-order invariants the walk relies on
+    ids = np.arange(m)
+    assert np.all(d["skip"] > ids) and d["skip"][0] == m
+    assert np.all(d["parent"][1:] < ids[1:]) and np.all(d["parent"][1:] >= 0)
+    # next[] chain rank
+    sidx, lo, lr = (np.empty(n, np.int32) for _ in range(3))
+    hc.hc_get_orders(sidx.ctypes, lo.ctypes, lr.ctypes)
+    assert np.array_equal(np.argsort(lr), g["chain"])
+    # walk arithmetic: same interaction lists as the reference, float-level agreement
+    idx = np.ascontiguousarray(g["idx"])
+    acc = np.empty((len(idx), 3))
+    cost = np.empty((len(idx), 2), np.int32)
+    zero = np.zeros(n, np.float32)
+    hc.hc_walk(len(idx), idx.ctypes, zero.ctypes, 1, C.c_float(0.5), C.c_float(0.005), C.c_float(0.3), acc.ctypes, cost.ctypes)
+    assert np.array_equal(cost, g["cost_bh"])
+    assert np.sqrt(((acc - g["acc_bh"]) ** 2).sum() / (g["acc_bh"] ** 2).sum()) < 1e-6
+    oa = np.ascontiguousarray(g["oldacc"])
+    hc.hc_walk(len(idx), idx.ctypes, oa.ctypes, 1, C.c_float(0.5), C.c_float(0.005), C.c_float(0.3), acc.ctypes, cost.ctypes)
+    assert (cost == g["cost_rel"]).all(axis=1).mean() > 0.995
+    assert np.sqrt(((acc - g["acc_rel"]) ** 2).sum() / (g["acc_rel"] ** 2).sum()) < 1e-5

@@ -1,0 +1,108 @@
+"""CPU: the oracle restatement (oracle/*.c) against the committed golden vectors that
+tests/golden/make_golden.py produced by running the unmodified reference.  Bit-exact where
+the arithmetic is restated operation for operation (tree, forces, neighbour lists, RNG
+stream, scattered pairs)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "hernquist3k.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(GOLD))
+
+
+@pytest.fixture(scope="module")
+def orc(gold):
+    import oracle
+    O = oracle.Oracle(gold["pos"], gold["vel"], gold["mass"], sigma=float(gold["sigma"]))
+    O.treebuild()
+    return O
+
+
+def test_tree_bit_exact(gold, orc):
+    d = orc.dump()
+    assert orc.random_subnodes() == 0
+    for k in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count"):
+        assert np.array_equal(d[k], gold["node_" + k]), k
+    assert np.array_equal(orc.chain(), gold["chain"])
+
+
+def test_forces_bit_exact(gold, orc):
+    idx = gold["idx"]
+    acc, cost = orc.force_tree(idx)                       # OldAcc = 0 -> BH criterion
+    assert np.array_equal(acc, gold["acc_bh"]) and np.array_equal(cost, gold["cost_bh"])
+    acc, cost = orc.force_tree(idx, gold["oldacc"])       # relative criterion
+    assert np.array_equal(acc, gold["acc_rel"]) and np.array_equal(cost, gold["cost_rel"])
+    assert np.array_equal(orc.force_direct(idx), gold["direct"])
+
+
+def test_gravity_tree_epilogue(gold, orc):
+    n = len(gold["mass"])
+    full = np.arange(n, dtype=np.int32)
+    acc, _ = orc.force_tree(full)
+    a, oa = orc.epilogue(acc)
+    assert np.array_equal(a, gold["g1_acc"]) and np.array_equal(oa, gold["g1_old"])
+    acc2, _ = orc.force_tree(full, oa)
+    a2, oa2 = orc.epilogue(acc2)
+    assert np.array_equal(a2, gold["g2_acc"]) and np.array_equal(oa2, gold["g2_old"])
+
+
+def test_neighbours_bit_exact(gold, orc):
+    idx, pos, h = gold["idx"], gold["pos"], gold["hsml"]
+    knn = np.array([orc.ngb_treefind(pos[i], 30) for i in idx], np.float32)
+    assert np.array_equal(knn, gold["knn"])
+    for k, i in enumerate(idx):
+        lst, _ = orc.ngb_variable(pos[i], h[i])
+        ref = gold["nlist"][k]
+        ref = ref[ref >= 0]
+        assert np.array_equal(lst, ref)
+
+
+def test_mt19937_known_answer():
+    """sidm_rand.c:29-36: after seeding with 55 and 1e6 warm-up draws the reference prints
+    0.565737; the next draw is the first one sidm() uses."""
+    import oracle
+    L = oracle.lib()
+    r = L.orng_new(55, 0)
+    for _ in range(1000000):
+        L.orng_uniform(r)
+    v = L.orng_uniform(r)
+    L.orng_free(r)
+    assert abs(v - 0.5657367655) < 1e-9
+
+
+def test_sidm_pass_reproduces_reference(gold, orc):
+    n = len(gold["mass"])
+    orc.hsml[:] = gold["hsml"]
+    orc.dvel[:] = 0
+    orc.init_rand(55)
+    dt32 = np.float32(2 * (float(gold["t_sidm"]) - 0.0))
+    res = orc.sidm(np.arange(n, dtype=np.int32), dt32, float(gold["vmax"]))
+    assert orc.rng_count() == len(gold["draws"])
+    _check_stream(res, gold["draws"])
+    assert np.array_equal(orc.dvel, gold["dvel1"]) and np.array_equal(orc.ngb, gold["ngb1"])
+    assert np.array_equal(res["log_i"] + 1, gold["log_id1"]) and np.array_equal(res["log_j"] + 1, gold["log_id2"])
+    assert np.array_equal(res["log_dv"], gold["log_dv"])
+
+
+def _check_stream(res, draws):
+    """walk the logged MT19937 stream the way sidm() consumes it: one uniform per buffer slot
+    (sidm.c:341) and, after a hit, Marsaglia pairs until one is accepted (sidm_rand.h:27-31)."""
+    pos = 0
+    for s in range(len(res["rand"])):
+        assert res["rand"][s] == draws[pos]
+        pos += 1
+        if res["partner"][s] >= 0:
+            while True:
+                y1, y2 = 1.0 - 2.0 * draws[pos], 1.0 - 2.0 * draws[pos + 1]
+                pos += 2
+                r2 = y1 * y1 + y2 * y2
+                if r2 <= 1.0:
+                    break
+            sq = np.sqrt(1.0 - r2)
+            assert np.allclose(res["dir"][s], [2 * y1 * sq, 2 * y2 * sq, 1 - 2 * r2], rtol=0, atol=1e-15)
+    assert pos == len(draws)
