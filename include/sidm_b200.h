@@ -111,10 +111,11 @@ typedef struct b200_counters {
   long long list_nodes;            /* node records a 32-target warp streamed (I_n sum) */
   long long list_parts;            /* particle records a warp streamed       (I_p sum) */
   long long num_targets;
-  /* last sidm() call: the SCT line (sidm.c:614-620) */
+  /* since the last b200_sidm(), repair passes included: the step's SCT lines summed (sidm.c:614-620) */
   int       sct_ntot, sct_pass1, sct_scattered, sct_rejected;
   long long ngb_candidates;        /* cube candidates examined (C in SURVEY 8d)       */
   int       ensure_iterations;     /* passes of the last sidm_ensure_neighbours       */
+  int       ensure_repaired;       /* particles re-done, summed over those passes     */
   /* device milliseconds of the last calls (CUDA events) */
   float     ms_upload, ms_predict, ms_build, ms_walk, ms_sidm, ms_ensure, ms_download;
   long long kernel_launches;       /* cumulative launches of this library's kernels   */
@@ -136,6 +137,7 @@ int  b200_upload(void);                        /* host AoS -> device (all fields
 int  b200_download(void);                      /* device -> host AoS (fields the path writes:
                                                   PosPred VelPred Accel GravCost OldAcc Left
                                                   Right NgbVelDisp HsmlVelDisp dVel)      */
+int  b200_download_to(void *dst);              /* same, into another array of the bound layout */
 /* Structure-of-arrays alternative used by the tests / bench (host pointers, float32/int32;
  * any pointer may be NULL = keep current).  pos/vel are [n][3]. */
 int  b200_set_soa(int num_part, const float *pos, const float *vel, const float *mass,
@@ -165,6 +167,9 @@ int  b200_setup_smoothinglengths_sidm(int desired_ngb);
 /* compute_accelerations(mode), accel.c:27-132: predict + build + gravity
  * (+ sidm + ensure_neighbours when mode==0). */
 int  b200_compute_accelerations(int mode, const int *active, int nactive, double time, double vmax);
+/* advance(), predict.c:245-345 ("next" row f1 of SURVEY.md section 8): kick-drift of the active
+ * particles with Accel*dt + dVel, dVel cleared; *num_scattered (may be NULL) = n_scat_particles. */
+int  b200_advance(const int *active, int nactive, double time, int *num_scattered);
 /* getvmax(), sidm.c:970-990. */
 int  b200_getvmax(double *vmax);
 /* ngb_treefind(xyz, desngb, 0, type), forcetree.c:2311: exact k-th neighbour distance^2

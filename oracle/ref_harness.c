@@ -17,7 +17,20 @@
  * `All` fields begrun()/init() would (begrun.c:16-60, init.c:20-180) from a plain
  * struct, ref_set_particles() fills P[1..N] the way init.c:76-100 does.
  */
+#ifndef B200_SHIM
 #include "forcetree.c"          /* the reference's own file, unmodified */
+#else
+/* drop-in build: the reference driver linked against sidm-nbody_b200/shim/b200_shim.c instead of
+ * gravtree.c / forcetree.c / sidm.c (GPU box only; proves the boundary on the reference's own
+ * accel.c:compute_accelerations) */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <mpi.h>
+#include "allvars.h"
+#include "proto.h"
+#endif
 #include "sidm_rand.h"
 #include <gsl/gsl_rng.h>
 
@@ -48,7 +61,9 @@ typedef struct ref_cfg {
 static int ref_ready = 0;
 
 int ref_sizeof_particle(void) { return (int)sizeof(struct particle_data); }
+#ifndef B200_SHIM
 int ref_sizeof_node(void)     { return (int)sizeof(struct NODE); }
+#endif
 
 int ref_setup(const ref_cfg *c)
 {
@@ -224,6 +239,7 @@ void ref_all_active(double tcur, double tnext)
   find_next_time();
 }
 
+#ifndef B200_SHIM
 /* ------------------------------------------------------- tree dump */
 
 int ref_treebuild(void) { return force_treebuild(); }   /* uses P[].PosPred, forcetree.c:90 */
@@ -304,6 +320,8 @@ float ref_ngb_treefind(const float *xyz, int desngb, float hguess)
   int *nl; float *rl; float x[3] = { xyz[0], xyz[1], xyz[2] };
   return ngb_treefind(x, desngb, hguess, 1, &nl, &rl);
 }
+
+#endif /* !B200_SHIM */
 
 /* ------------------------------------------------------- hot-path entry points */
 

@@ -46,7 +46,8 @@ DEFAULTS = dict(BufferSizeMB=100, TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolFo
 
 
 def lib_path(kind="diag"):
-    name = {"diag": "libsidmref.so", "fast": "libsidmref_fast.so", "periodic": "libsidmref_per.so"}[kind]
+    name = {"diag": "libsidmref.so", "fast": "libsidmref_fast.so", "periodic": "libsidmref_per.so",
+            "b200": "libsidmref_b200.so"}[kind]
     return os.path.join(HERE, "_ref", name)
 
 

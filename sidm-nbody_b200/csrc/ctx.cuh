@@ -33,6 +33,7 @@ struct Ctx {
 
   // ---- tree (rebuilt by b200_tree_build)
   bool tree_valid = false;
+  unsigned long long tree_epoch = 0, search_epoch = ~0ull;   // bumped by every tree build
   double *d_bbox = nullptr;        // [6] min xyz, max xyz (double), written by the bbox kernels
   RootBox *d_root = nullptr;       // root cell
   float *d_domain = nullptr;       // DomainMin[3], DomainMax[3]  (forcetree.c:192-198)

@@ -373,12 +373,12 @@ static SearchCtx search_ctx() {
   return C;
 }
 
-static bool search_nodes_current = false;
 int refresh_search_nodes() {
   B200_TRY(ensure_sidm_buffers());
+  if (g.search_epoch == g.tree_epoch) return B200_OK;
+  g.search_epoch = g.tree_epoch;
   k_search_nodes<<<cdiv(g.num_nodes, 256), 256, 0, g.stream>>>(g.num_nodes, g.nodes, g.geom, g.npstart, g.nnp, S.snode);
   count_launch();
-  search_nodes_current = true;
   return B200_OK;
 }
 
@@ -527,9 +527,10 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
-  g.cnt.sct_ntot = na; g.cnt.sct_pass1 = tot_pass1;
-  g.cnt.sct_scattered = (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected = (int)g.h_ctr[CT_REJECTED];
-  g.cnt.ngb_candidates = (long long)g.h_ctr[CT_CAND];
+  // totals since the last b200_sidm(): the sum of the reference's SCT lines for this step
+  g.cnt.sct_ntot += na; g.cnt.sct_pass1 += tot_pass1;
+  g.cnt.sct_scattered += (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected += (int)g.h_ctr[CT_REJECTED];
+  g.cnt.ngb_candidates += (long long)g.h_ctr[CT_CAND];
   return B200_OK;
 }
 
@@ -633,10 +634,10 @@ __global__ void k_new_hsml(int nr, const int *redo, const int *ngb, const float 
   velh[i] = v;
   want_knn[a] = knn;
 }
-__global__ void k_apply_knn(int nr, const int *redo, const int *want, const float *h2, float4 *velh) {
+__global__ void k_apply_knn(int nw, const int *wlist, const float *h2, float4 *velh) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= nr || !want[a]) return;
-  velh[redo[a]].w = (float)sqrt((double)h2[a]);
+  if (a >= nw) return;
+  velh[wlist[a]].w = (float)sqrt((double)h2[a]);
 }
 __global__ void k_zero_lr(int na, const int *active, float *left, float *right) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,14 +682,27 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     k_new_hsml<<<cdiv(nr, B), B, 0, st>>>(nr, redo, g.ngb, g.left, g.right, g.velh, g.par.DesNumNgb, ensure_variant, n, want);
     count_launch();
     if (ensure_variant) {
-      B200_TRY(knn_device(redo, nr, g.par.DesNumNgb, h2));      // computed for all flagged, applied where asked (rare)
-      k_apply_knn<<<cdiv(nr, B), B, 0, st>>>(nr, redo, want, h2, g.velh);
-      count_launch();
+      // exact k-th neighbour distance where sidm.c:918-922 asks for it (rare: Ngb < 15 with no upper bracket)
+      int *wlist = g.d_tkeys;
+      size_t tbw = 0;
+      cub::DeviceSelect::Flagged(nullptr, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st);
+      B200_TRY(cub_scratch(tbw));
+      CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st));
+      CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      count_launch(2);
+      const int nw = g.h_flags[FL_NPASS];
+      if (nw > 0) {
+        B200_TRY(knn_device(wlist, nw, g.par.DesNumNgb, h2));
+        k_apply_knn<<<cdiv(nw, B), B, 0, st>>>(nw, wlist, h2, g.velh);
+        count_launch();
+      }
     }
     b200_replay rp; const b200_replay *rpp = nullptr;
     if (replay && replay->rand) { rp.rand = replay->rand + roff; rp.dir = replay->dir ? replay->dir + 3 * roff : nullptr; rpp = &rp; roff += nr; }
     B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0));
     iter++;
+    g.cnt.ensure_repaired += nr;
     if (iter > maxiter) { fprintf(stderr, "libsidm_b200: failed to converge in ensure_neighbours\n"); return B200_ERR_HSML; }
   }
   g.cnt.ensure_iterations = iter;
@@ -713,6 +727,8 @@ extern "C" int b200_sidm(const int *active, int nactive, double time, double vma
   const int *d; int na;
   B200_TRY(stage_active(active, nactive, &d, &na));
   g.scatlog_n = 0;
+  g.cnt.sct_ntot = g.cnt.sct_pass1 = g.cnt.sct_scattered = g.cnt.sct_rejected = 0; g.cnt.ngb_candidates = 0;
+  g.cnt.ensure_iterations = 0; g.cnt.ensure_repaired = 0;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   int rc = sidm_impl(d, na, time, vmax, replay, false);
   cudaEventRecord(g.ev1, g.stream); cudaEventSynchronize(g.ev1);
@@ -742,7 +758,6 @@ extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, c
   CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   count_launch();
-  g.cnt.ensure_iterations = 0;
   int rc = B200_OK;
   if (g.h_flags[FL_NREPAIR] > 0) {
     k_zero_lr<<<cdiv(na, 256), 256, 0, st>>>(na, act, g.left, g.right);     // sidm.c:857-859

@@ -8,6 +8,7 @@
 
 namespace b200 {
 Ctx g;
+double s_a_inverse_at(double time);
 
 template <class T>
 static int dalloc(T **p, size_t count) {
@@ -328,6 +329,15 @@ extern "C" int b200_upload(void) {
   return B200_OK;
 }
 
+extern "C" int b200_download_to(void *dst) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  char *keep = g.h_base;
+  if (dst) g.h_base = (char *)dst;
+  const int rc = b200_download();
+  g.h_base = keep;
+  return rc;
+}
+
 extern "C" int b200_download(void) {
   if (!g.ready || !g.have_aos) return B200_ERR_STATE;
   const int n = g.n;
@@ -380,6 +390,58 @@ extern "C" int b200_predict(double time) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_predict, g.ev0, g.ev1);
+  g.tree_valid = false;
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- advance
+// advance(), predict.c:245-345: leap-frog update of the active particles,
+//   dt = 2*(time - CurrentTime); Pos += Vel*dt/2; Vel += Accel*dt + dVel; dVel = 0;
+//   Pos += Vel*dt/2; CurrentTime = time + dt/2  (dt_h0 = dt/S(a) for the drifts when comoving)
+__global__ void k_advance(int na, const int *active, double time, double s_a_inverse, float *pos0, float4 *velh, float *velpred,
+                          const float *accel, float *dvel, float *curtime, int *nscat) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int i = active ? active[a] : a;
+  const double dt = 2 * (time - (double)curtime[i]);
+  const double dth = dt * s_a_inverse;
+  if (dvel[3 * (size_t)i] != 0.0f) atomicAdd(nscat, 1);
+  float4 v = velh[i];
+  float vv[3] = {v.x, v.y, v.z};
+  for (int j = 0; j < 3; j++) {
+    float x = pos0[3 * (size_t)i + j];
+    x = (float)((double)x + 0.5 * (double)vv[j] * dth);
+    vv[j] = (float)((double)vv[j] + (double)accel[3 * (size_t)i + j] * dt + (double)dvel[3 * (size_t)i + j]);
+    velpred[3 * (size_t)i + j] = vv[j];
+    dvel[3 * (size_t)i + j] = 0;
+    x = (float)((double)x + 0.5 * (double)vv[j] * dth);
+    pos0[3 * (size_t)i + j] = x;
+  }
+  v.x = vv[0]; v.y = vv[1]; v.z = vv[2];
+  velh[i] = v;
+  curtime[i] = (float)(time + 0.5 * dt);
+}
+
+extern "C" int b200_advance(const int *active, int nactive, double time, int *num_scattered) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  const int na = active ? nactive : g.n;
+  if (na < 0 || na > g.n) return B200_ERR_ARG;
+  if (na == 0) return B200_OK;
+  const int *d_act = nullptr;
+  if (active) {
+    CUDA_TRY(cudaMemcpyAsync(g.d_active, active, (size_t)na * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    d_act = g.d_active;
+  }
+  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_NSCATLOG, 0, sizeof(int), g.stream));
+  k_advance<<<cdiv(na, 256), 256, 0, g.stream>>>(na, d_act, time, s_a_inverse_at(time), g.pos0, g.velh, g.velpred, g.accel, g.dvel,
+                                                 g.curtime, g.d_flags + FL_NSCATLOG);
+  count_launch();
+  if (num_scattered) {
+    CUDA_TRY(cudaMemcpyAsync(g.h_flags + FL_NSCATLOG, g.d_flags + FL_NSCATLOG, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    *num_scattered = g.h_flags[FL_NSCATLOG];
+  }
+  CUDA_TRY(cudaGetLastError());
   g.tree_valid = false;
   return B200_OK;
 }

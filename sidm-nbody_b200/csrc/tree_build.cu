@@ -224,7 +224,7 @@ int tree_build_impl() {
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_build, g.ev0, g.ev1);
-  g.tree_valid = true;
+  g.tree_valid = true; g.tree_epoch++;
   return B200_OK;
 }
 

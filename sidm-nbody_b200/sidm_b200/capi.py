@@ -53,7 +53,7 @@ class Counters(C.Structure):
                 ("node_interactions", C.c_longlong), ("list_nodes", C.c_longlong), ("list_parts", C.c_longlong),
                 ("num_targets", C.c_longlong), ("sct_ntot", C.c_int), ("sct_pass1", C.c_int),
                 ("sct_scattered", C.c_int), ("sct_rejected", C.c_int), ("ngb_candidates", C.c_longlong),
-                ("ensure_iterations", C.c_int), ("ms_upload", C.c_float), ("ms_predict", C.c_float),
+                ("ensure_iterations", C.c_int), ("ensure_repaired", C.c_int), ("ms_upload", C.c_float), ("ms_predict", C.c_float),
                 ("ms_build", C.c_float), ("ms_walk", C.c_float), ("ms_sidm", C.c_float), ("ms_ensure", C.c_float),
                 ("ms_download", C.c_float), ("kernel_launches", C.c_longlong)]
 
@@ -77,7 +77,7 @@ def layout_of(dtype=PARTICLE_DTYPE):
 
 
 EXPORTS = ["b200_init", "b200_set_params", "b200_finalize", "b200_last_cuda_error", "b200_set_stream", "b200_version",
-           "b200_bind_particles", "b200_upload", "b200_download", "b200_set_soa", "b200_get_soa", "b200_predict",
+           "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_advance", "b200_set_soa", "b200_get_soa", "b200_predict",
            "b200_tree_build", "b200_gravity", "b200_sidm", "b200_setup_nbr_sidm", "b200_sidm_ensure_neighbours",
            "b200_setup_smoothinglengths_sidm", "b200_compute_accelerations", "b200_getvmax", "b200_ngb_treefind",
            "b200_direct", "b200_walk_raw", "b200_get_tree", "b200_ngb_lists", "b200_sidm_debug", "b200_get_scatlog",
@@ -113,6 +113,8 @@ def load():
         _lib.b200_setup_nbr_sidm.argtypes = [C.c_void_p, C.c_int]
         _lib.b200_device_buffer.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
         _lib.b200_getvmax.argtypes = [C.c_void_p]
+        _lib.b200_advance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        _lib.b200_download_to.argtypes = [C.c_void_p]
     return _lib
 
 

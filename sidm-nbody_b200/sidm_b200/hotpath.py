@@ -114,8 +114,20 @@ class HotPath:
     def upload(self):
         check(self.lib.b200_upload(), "b200_upload")
 
-    def download(self):
-        check(self.lib.b200_download(), "b200_download")
+    def download(self, into=None):
+        if into is None:
+            check(self.lib.b200_download(), "b200_download")
+        else:
+            assert into.dtype == self._aos.dtype and len(into) >= self.n and into.flags["C_CONTIGUOUS"]
+            check(self.lib.b200_download_to(into.ctypes.data_as(C.c_void_p)), "b200_download_to")
+
+    def advance(self, active=None, time=None, count=False):
+        """advance(), predict.c:245: leap-frog kick+drift of the active particles, clears dVel"""
+        t = self.time if time is None else float(time)
+        a = _i32(active)
+        ns = C.c_int(0)
+        check(self.lib.b200_advance(ptr(a), 0 if a is None else len(a), t, C.byref(ns) if count else None), "b200_advance")
+        return ns.value
 
     # ---- the hot path -----------------------------------------------------------------
     def predict_collisionless_only(self, time):
@@ -225,6 +237,18 @@ class HotPath:
         c = Counters()
         check(self.lib.b200_get_counters(C.byref(c)), "b200_get_counters")
         return c
+
+    def peek(self, name, dtype, shape):
+        """copy an internal device buffer (b200_device_buffer name) to the host - debugging / bench set-up"""
+        addr, nb = self.device_buffer(name)
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= nb, (out.nbytes, nb)
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        rc = rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(addr), out.nbytes, 2)
+        if rc != 0:
+            raise B200Error(9001, f"cudaMemcpy({name}) -> {rc}")
+        return out
 
     def device_buffer(self, name):
         p = C.c_void_p(0)

@@ -1,0 +1,42 @@
+"""helper for tests/test_gpu_dropin.py: runs the reference DRIVER (accel.c compute_accelerations,
+init.c setup_smoothinglengths_sidm, timeline.c ...) either with its own CPU hot path
+(kind=diag) or linked against the product's shim + libsidm_b200.so (kind=b200), on the same
+seeded input, and writes the particle fields the path owns."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "sidm-nbody_b200"))
+
+
+def main(kind, out, n):
+    import refdrv
+    from sidm_b200 import ic
+    pos, vel, mass, ids = ic.hernquist(n, seed=9)
+    os.chdir(tempfile.mkdtemp())
+    R = refdrv.Reference(kind)
+    R.setup(n, CrossSectionInternal=0.0)
+    R.init_rand(55)
+    R.set_particles(pos, vel, mass, ids)
+    R.treebuild()
+    R.setup_smoothinglengths_sidm(30)                  # init.c:431 (reference code; its k-NN + count calls hit the path)
+    h0, ngb0 = R.get("HSML"), R.get("NGB")
+    R.all_active(0.0, 0.0)
+    R.getvmax()
+    R.compute_accelerations(1)                         # accel.c:27, start-up forces (BH, OldAcc = 0)
+    acc1, old1 = R.get("ACCEL"), R.get("OLDACC")
+    rng = np.random.default_rng(4)
+    R.set("HSML", (h0 * rng.choice(np.array([1, 1, 1, 0.8, 1.3], np.float32), n)).astype(np.float32))
+    R.all_active(0.0, 0.01)
+    R.compute_accelerations(0)                         # gravity (relative criterion) + sidm + ensure_neighbours
+    np.savez(out, h0=h0, ngb0=ngb0, acc1=acc1, old1=old1, acc2=R.get("ACCEL"), old2=R.get("OLDACC"),
+             h2=R.get("HSML"), ngb2=R.get("NGB"), dvel=R.get("DVEL"), pospred=R.get("POSPRED"),
+             nactive=len(R.active()))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]))
