@@ -146,6 +146,19 @@ int  b200_set_soa(int num_part, const float *pos, const float *vel, const float 
 int  b200_get_soa(float *pospred, float *velpred, float *accel, float *oldacc, float *gravcost,
                   float *hsml, int *ngb, float *dvel, float *left, float *right);
 
+/* ---- sharding over the GPUs of one box (replaces domain.c + the hypercube
+ * exchanges of gravtree.c:171-222 and sidm.c:204-553) -------------------------------------
+ * Every rank holds all particles and builds the same tree; rank r evaluates the 32-entry
+ * blocks b (b % world == r) of each work list sorted along the tree order, then the ranks
+ * all-gather the per-target results.  The library packs into `send`, calls
+ * fn(bytes_per_rank, user) - which must all-gather send[0..bytes) of every rank into
+ * recv[rank*bytes ..] on the library's stream (ncclAllGather / torch.distributed) - and unpacks
+ * `recv`.  send/recv are device pointers owned by the caller; cap_bytes = size of `send`
+ * (recv holds world*cap_bytes).  world == 1 switches sharding off. */
+typedef int (*b200_allgather_fn)(long long bytes_per_rank, void *user);
+int  b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes,
+                    b200_allgather_fn fn, void *user);
+
 /* ---- the hot path ---------------------------------------------------------------- */
 /* predict_collisionless_only(time), predict.c:106: PosPred, VelPred for all particles. */
 int  b200_predict(double time);

@@ -242,7 +242,6 @@ void ref_all_active(double tcur, double tnext)
 #ifndef B200_SHIM
 /* ------------------------------------------------------- tree dump */
 
-int ref_treebuild(void) { return force_treebuild(); }   /* uses P[].PosPred, forcetree.c:90 */
 int ref_tree_first(void) { return trees[1] - All.MaxPart; }
 int ref_tree_numnodes(void) { return numnodestree[1]; }
 
@@ -324,6 +323,8 @@ float ref_ngb_treefind(const float *xyz, int desngb, float hguess)
 #endif /* !B200_SHIM */
 
 /* ------------------------------------------------------- hot-path entry points */
+
+int ref_treebuild(void) { return force_treebuild(); }   /* uses P[].PosPred, forcetree.c:90 */
 
 void ref_gravity_tree(void) { gravity_tree(); }
 void ref_determine_interior(void) { determine_interior(); }

@@ -66,9 +66,10 @@ class Reference:
         L.ref_get_time.restype = C.c_double
         L.ref_getvmax.restype = C.c_double
         L.ref_get_vmax_global.restype = C.c_double
-        L.ref_ngb_treefind.restype = C.c_float
-        L.ref_ngb_treefind.argtypes = [C.c_void_p, C.c_int, C.c_float]
-        L.ref_ngb_variable.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        if kind != "b200":   # tree / search accessors need the reference's own forcetree.c statics
+            L.ref_ngb_treefind.restype = C.c_float
+            L.ref_ngb_treefind.argtypes = [C.c_void_p, C.c_int, C.c_float]
+            L.ref_ngb_variable.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_set_time.argtypes = [C.c_double]
         L.ref_set_vmax.argtypes = [C.c_double]
         L.ref_all_active.argtypes = [C.c_double, C.c_double]

@@ -25,7 +25,7 @@ struct BuildView {
   NodeRec *nodes; float4 *geom; int *nstart, *nend, *nparent, *npstart;
   unsigned char *nlevel, *nnp, *nnchild; int *ndp; int *narrive; int *nminidx; int *nlstart; Moments *nmom;
   // leaf order
-  float4 *leaf_posm; int *leaf_orig, *orig_leaf; int *krank; int *lrank;
+  float4 *leaf_posm; int *leaf_orig, *orig_leaf; int *krank; int *lrank; int *leaf_parent;
   int *flags;                 // device status words
 };
 
@@ -119,6 +119,7 @@ B200_HD void b4_body(const BuildView &v, int id) {
     v.leaf_posm[ps + k] = v.posm[o];
     v.leaf_orig[ps + k] = o;
     v.orig_leaf[o] = ps + k;
+    v.leaf_parent[ps + k] = id;
     if (o < mn) mn = o;
   }
   v.nminidx[id] = mn;        // completed bottom-up in b5

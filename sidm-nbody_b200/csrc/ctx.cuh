@@ -60,11 +60,12 @@ struct Ctx {
   Moments *nmom = nullptr;
   // leaf order (particles sorted by (parent node, octant)): every subtree is a contiguous range
   float4 *leaf_posm = nullptr;
-  int *leaf_orig = nullptr, *orig_leaf = nullptr;
+  int *leaf_orig = nullptr, *orig_leaf = nullptr, *leaf_parent = nullptr;
   int *lrank = nullptr;            // original index -> rank in the reference's next[] chain
   int num_nodes = 0, max_level = 0;
 
   // ---- work buffers for the hot calls
+  int *d_shard_list = nullptr;
   int *d_active = nullptr, *d_tsorted = nullptr, *d_tkeys = nullptr, *d_tkeys2 = nullptr, *d_tvals2 = nullptr;
   double *d_acc = nullptr;         // [n][3] raw accelerations per target slot
   int *d_cost = nullptr;           // [n][2]
@@ -84,8 +85,25 @@ struct Ctx {
   int last_nslot = 0;
   unsigned long long sidm_calls = 0;
 
+  // ---- sharding across the GPUs of one box (b200_set_shard): this rank works on the 32-entry
+  // blocks b of every sorted work list with b % world == rank; results are all-gathered
+  int shard_rank = 0, shard_world = 1;
+  void *shard_send = nullptr, *shard_recv = nullptr; long long shard_cap = 0;
+  b200_allgather_fn shard_fn = nullptr; void *shard_user = nullptr;
+
   b200_counters cnt{};
 };
+
+// number of entries of a sorted list of length nt that rank r of `world` owns
+inline int shard_count(int nt, int world, int r) {
+  const int nblk = (nt + 31) / 32;
+  long long c = 0;
+  for (int q = r; q < nblk; q += world) { const int lo = q * 32; c += (nt - lo < 32) ? nt - lo : 32; }
+  return (int)c;
+}
+inline int shard_max_blocks(int nt, int world) { const int nblk = (nt + 31) / 32; return (nblk + world - 1) / world; }
+int shard_select(const int *d_in, int nt, int *d_out, int *n_own);
+int shard_exchange(long long bytes_per_rank);
 
 extern Ctx g;
 

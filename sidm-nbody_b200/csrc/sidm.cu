@@ -24,7 +24,8 @@ namespace b200 {
 
 double s_a_inverse_at(double time);
 
-struct __attribute__((aligned(16))) SearchNode { float cx, cy, cz, len; int skip, pstart, np, pend; };
+// search record: the cell bounds c -/+ 0.5*len formed in double exactly as forcetree.c:2252-2276 forms them per test
+struct __attribute__((aligned(16))) SearchNode { double lo[3], hi[3]; int skip, pstart, np, pend; };
 
 struct SidmState {
   SearchNode *snode = nullptr;
@@ -57,6 +58,7 @@ __device__ __forceinline__ double u01(uint32_t x) { return (double)x / 429496729
 // ------------------------------------------------------------------ range search
 struct SearchCtx {
   int M; const SearchNode *snode; const float4 *leaf_posm; const int *leaf_orig;
+  const int *nparent, *leaf_parent, *orig_leaf;
 };
 
 __device__ __forceinline__ float dist2_ref(float px, float py, float pz, float x, float y, float z) {
@@ -65,28 +67,51 @@ __device__ __forceinline__ float dist2_ref(float px, float py, float pz, float x
   return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
 }
 
-// calls f(leaf_slot, r2, bulk, node) for every candidate the reference's ngb_treesearch() would
-// append (forcetree.c:2224-2297); node tests in double on float operands like the reference
+// Smallest ancestor cell of particle `i` that contains the search cube with a safety margin.
+// The reference starts every search at the root; all it does above this ancestor is open
+// the cells on the path and discard their other children (they cannot reach into the cube:
+// the margin covers the <= 42 float roundings of the centre recursion), so starting here
+// yields the same candidates in the same order while skipping ~15 levels of the descent.
+__device__ __forceinline__ int search_start(const SearchCtx &C, int i, float x, float y, float z, float h) {
+  const double lox = (double)fadd(x, -h), loy = (double)fadd(y, -h), loz = (double)fadd(z, -h);
+  const double hix = (double)fadd(x, h), hiy = (double)fadd(y, h), hiz = (double)fadd(z, h);
+  const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h);
+  int no = C.leaf_parent[C.orig_leaf[i]];
+  while (no > 0) {
+    const SearchNode &nd = C.snode[no];
+    if (nd.lo[0] + m <= lox && nd.lo[1] + m <= loy && nd.lo[2] + m <= loz && nd.hi[0] - m >= hix && nd.hi[1] - m >= hiy && nd.hi[2] - m >= hiz) break;
+    no = C.nparent[no];
+  }
+  return no;
+}
+
+// calls f(leaf_slot, pos, r2, bulk, node) for every candidate the reference's ngb_treesearch()
+// would append (forcetree.c:2224-2297), in its order, visiting the subtree of `start` in
+// pre-order with skip pointers; cell tests in double on float operands like the reference.
+// One query per thread (a warp-lockstep variant like the gravity walk was measured slower: the
+// 32 cubes of a warp are small compared with the cells between them, so the union of their
+// paths is ~10x one path).  `valid` lets padding lanes fall through.
 template <class F>
-__device__ __forceinline__ void range_search(const SearchCtx &C, float x, float y, float z, float h, F &&f) {
+__device__ __forceinline__ void range_search(const SearchCtx &C, bool valid, int start, float x, float y, float z, float h, F &&f) {
+  if (!valid) return;
   const float lox = fadd(x, -h), loy = fadd(y, -h), loz = fadd(z, -h);
   const float hix = fadd(x, h), hiy = fadd(y, h), hiz = fadd(z, h);
-  int no = 0;
-  while (no < C.M) {
-    const SearchNode nd = C.snode[no];
-    const double half = 0.5 * (double)nd.len;
-    const double ax = (double)nd.cx + half, bx = (double)nd.cx - half;
-    const double ay = (double)nd.cy + half, by = (double)nd.cy - half;
-    const double az = (double)nd.cz + half, bz = (double)nd.cz - half;
-    if (ax < (double)lox || bx > (double)hix || ay < (double)loy || by > (double)hiy || az < (double)loz || bz > (double)hiz) { no = nd.skip; continue; }
-    const bool inside = !(ax > (double)hix) && !(bx < (double)lox) && !(ay > (double)hiy) && !(by < (double)loy) && !(az > (double)hiz) && !(bz < (double)loz);
+  const double dlx = lox, dly = loy, dlz = loz, dhx = hix, dhy = hiy, dhz = hiz;
+  int no = start;
+  const int stop = C.snode[start].skip;
+  while (no < stop) {
+    const double2 *q = reinterpret_cast<const double2 *>(C.snode + no);
+    const double2 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);      // lo.xy | lo.z hi.x | hi.yz
+    const int4 info = __ldg(reinterpret_cast<const int4 *>(q + 3));         // skip, pstart, np, pend
+    if (a1.y < dlx || a0.x > dhx || a2.x < dly || a0.y > dhy || a2.y < dlz || a1.x > dhz) { no = info.x; continue; }
+    const bool inside = !(a1.y > dhx) && !(a0.x < dlx) && !(a2.x > dhy) && !(a0.y < dly) && !(a2.y > dhz) && !(a1.x < dlz);
     if (inside) {
-      for (int L = nd.pstart; L < nd.pend; L++) { const float4 p = C.leaf_posm[L]; f(L, p, dist2_ref(p.x, p.y, p.z, x, y, z), true, no); }
-      no = nd.skip;
+      for (int L = info.y; L < info.w; L++) { const float4 p = __ldg(C.leaf_posm + L); f(L, p, dist2_ref(p.x, p.y, p.z, x, y, z), true, no); }
+      no = info.x;
     } else {
-      for (int k = 0; k < nd.np; k++) {
-        const int L = nd.pstart + k;
-        const float4 p = C.leaf_posm[L];
+      for (int k = 0; k < info.z; k++) {
+        const int L = info.y + k;
+        const float4 p = __ldg(C.leaf_posm + L);
         if (p.x < lox || p.x > hix || p.y < loy || p.y > hiy || p.z < loz || p.z > hiz) continue;
         f(L, p, dist2_ref(p.x, p.y, p.z, x, y, z), false, no);
       }
@@ -99,7 +124,11 @@ __global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, 
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= m) return;
   const float4 gm = geom[id]; const int skip = nodes[id].skip;
-  SearchNode s; s.cx = gm.x; s.cy = gm.y; s.cz = gm.z; s.len = gm.w; s.skip = skip; s.pstart = npstart[id]; s.np = nnp[id]; s.pend = npstart[skip];
+  const double half = 0.5 * (double)gm.w;
+  SearchNode s;
+  s.lo[0] = (double)gm.x - half; s.lo[1] = (double)gm.y - half; s.lo[2] = (double)gm.z - half;
+  s.hi[0] = (double)gm.x + half; s.hi[1] = (double)gm.y + half; s.hi[2] = (double)gm.z + half;
+  s.skip = skip; s.pstart = npstart[id]; s.np = nnp[id]; s.pend = npstart[skip];
   out[id] = s;
 }
 
@@ -143,15 +172,20 @@ struct Pass1 {
 };
 __global__ void __launch_bounds__(128) k_pass1(Pass1 P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.ns) return;
-  const int s = P.order[t];
-  const int i = P.slot_part[s];
-  const float4 p = P.posm[i]; const float h = P.velh[i].w;
+  const bool valid = t < P.ns;
+  const int s = valid ? P.order[t] : 0;
+  const int i = valid ? P.slot_part[s] : 0;
+  const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
+  const float h = valid ? P.velh[i].w : 0.0f;
   const float sr2 = fmul(h, h);
   int cnt = 0, cand = 0;
-  range_search(P.C, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
+  range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  unsigned long long wc = cand;
+  for (int o = 16; o > 0; o >>= 1) wc += __shfl_down_sync(0xffffffffu, wc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&P.ctr[CT_CAND], wc);
+  if (!valid) return;
   P.ngb[s] = cnt;
-  atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand);
   if (P.count_only) return;
   const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
   const double hh = 1.0 * (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
@@ -205,14 +239,17 @@ __device__ __forceinline__ void unit_vector(const Pass2 &P, int s, int i, double
 
 __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.np) return;
-  const int s = P.passlist[t];
-  const int i = P.slot_part[s];
-  const float4 p = P.posm[i]; const float4 vi = P.velh[i]; const float h = vi.w;
+  const bool valid = t < P.np;
+  const int s = valid ? P.passlist[t] : 0;
+  const int i = valid ? P.slot_part[s] : 0;
+  const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
+  const float4 vi = valid ? P.velh[i] : make_float4(0, 0, 0, 0);
+  const float h = vi.w;
   const float sr2 = fmul(h, h);
-  const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
+  const double dt_h0 = valid ? (double)P.dt[s] * P.s_a_inverse : 0.0;
+  const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
   const double hh = (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
-  const double rnd = P.rnd[s];
+  const double rnd = valid ? P.rnd[s] : 2.0;
   double prob = 0, wk = 0, ptot = 0; int partner = -1; double prv[4] = {0, 0, 0, 0}; float pmass = 0;
 
   auto visit = [&](int j, float r2) {       // one neighbour in list order, sidm.c:352-385
@@ -232,14 +269,14 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
   };
 
   if (!P.ref_order) {
-    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) visit(P.C.leaf_orig[L], r2); });
+    range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) visit(P.C.leaf_orig[L], r2); });
   } else {
     // gather every candidate the reference's tree search appends, with a key that reproduces
     // its order: position along the octant-ordered tree; inside fully-contained cells the
     // next[] chain rank (forcetree.c:274-279, 2270-2276)
     int nc = 0; bool over = false;
     int *cl = P.cand + t; unsigned long long *ck = P.candkey + t; const int st = P.cand_stride;
-    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
+    range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
       if (nc >= kCandCap) { over = true; return; }
       const int o = P.C.leaf_orig[L];
       const unsigned long long key = bulk ? (((unsigned long long)P.nstart[node] << 32) | (unsigned)P.lrank[o])
@@ -265,6 +302,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
       visit(j, dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z));
     }
   }
+  if (!valid) return;
   P.prob[s] = prob; P.ptot[s] = ptot; P.partner[s] = partner;
   float dvx = 0, dvy = 0, dvz = 0;
   if (partner >= 0) {
@@ -331,6 +369,28 @@ __global__ void k_reset_winner(int ns, const int *partner, int *winner) {
   if (s < ns && partner[s] >= 0) winner[partner[s]] = -1;
 }
 
+// multi-GPU: per-slot results of this rank's share of the buffer -> all ranks
+struct __attribute__((aligned(16))) SlotRec { int ngb, partner; float dv[3]; int pass, pad0, pad1; };
+__global__ void k_slot_pack(int nown, const int *order, const int *sngb, const int *partner, const float *dv, const int *pass, int count_only, SlotRec *send) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nown) return;
+  const int s = order[k];
+  SlotRec r; r.ngb = sngb[s]; r.partner = partner[s]; r.dv[0] = dv[3 * (size_t)s]; r.dv[1] = dv[3 * (size_t)s + 1]; r.dv[2] = dv[3 * (size_t)s + 2];
+  r.pass = count_only ? 0 : pass[k]; r.pad0 = r.pad1 = 0;
+  send[k] = r;
+}
+__global__ void k_slot_unpack(int ns, int world, int per_rank, const int *sorted_slots, const SlotRec *recv, int *sngb, int *partner, float *dv, unsigned long long *ctr) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)world * per_rank) return;
+  const int q = (int)(g / per_rank), k = (int)(g % per_rank);
+  const long long j = ((long long)(k >> 5) * world + q) * 32 + (k & 31);
+  if (j >= ns) return;
+  const int s = sorted_slots[j];
+  const SlotRec r = recv[g];
+  sngb[s] = r.ngb; partner[s] = r.partner; dv[3 * (size_t)s] = r.dv[0]; dv[3 * (size_t)s + 1] = r.dv[1]; dv[3 * (size_t)s + 2] = r.dv[2];
+  if (r.pass) atomicAdd(&ctr[CT_PASS1], 1ull);
+}
+
 // ------------------------------------------------------------------ host side
 static double *d_kernel_table = nullptr;
 
@@ -370,6 +430,7 @@ static int cub_scratch(size_t tb) {
 
 static SearchCtx search_ctx() {
   SearchCtx C; C.M = g.num_nodes; C.snode = S.snode; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
+  C.nparent = g.nparent; C.leaf_parent = g.leaf_parent; C.orig_leaf = g.orig_leaf;
   return C;
 }
 
@@ -452,22 +513,28 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       if (replay->dir) { CUDA_TRY(cudaMemcpyAsync(S.rd, replay->dir + 3 * replay_off, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice, st)); d_rd = S.rd; }
       replay_off += nb;
     }
+    // this rank's share of the buffer (all of it on one GPU)
+    const int *order = S.slot_of_sorted; int nord = nb;
+    if (g.shard_world > 1) { B200_TRY(shard_select(S.slot_of_sorted, nb, g.d_shard_list, &nord)); order = g.d_shard_list; }
     // pass 1
     Pass1 P1;
-    P1.ns = nb; P1.order = S.slot_of_sorted; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
+    P1.ns = nord; P1.order = order; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
     P1.posm = g.posm; P1.velh = g.velh; P1.dt = S.dt; P1.already = S.already; P1.replay_rand = d_rr;
     P1.C_Pmax = C_Pmax; P1.s_a_inverse = sainv; P1.k0 = k0; P1.k1 = k1;
     P1.ngb = g.s_ngb; P1.pmax = g.s_pmax; P1.rnd = g.s_rand; P1.pass = g.s_pass; P1.count_only = count_only; P1.ctr = g.d_ctr;
-    k_pass1<<<cdiv(nb, 128), 128, 0, st>>>(P1);
     k_clear_slots<<<G, B, 0, st>>>(nb, g.s_partner, g.s_dv, g.s_prob, S.ptot);
+    if (nord > 0) k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     count_launch(2);
     int npass = 0;
     if (!count_only) {
       // compact the slots that passed the first approximation, keeping the processing order
       size_t tb3 = 0;
-      cub::DeviceSelect::Flagged(nullptr, tb3, S.slot_of_sorted, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nb, st);
-      B200_TRY(cub_scratch(tb3));
-      CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb3, S.slot_of_sorted, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nb, st));
+      CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_NPASS, 0, sizeof(int), st));
+      if (nord > 0) {
+        cub::DeviceSelect::Flagged(nullptr, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st);
+        B200_TRY(cub_scratch(tb3));
+        CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st));
+      }
       CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       npass = g.h_flags[FL_NPASS];
@@ -499,6 +566,16 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         count_launch();
       }
     }
+    if (g.shard_world > 1) {
+      // exchange {Ngb, partner, dv} of every slot (replaces the result + confirm hypercube
+      // passes of sidm.c:463-553); the two write sweeps below then run identically on all ranks
+      const int per_rank = shard_max_blocks(nb, g.shard_world) * 32;
+      if (nord > 0) { k_slot_pack<<<cdiv(nord, B), B, 0, st>>>(nord, order, g.s_ngb, g.s_partner, g.s_dv, g.s_pass, count_only, (SlotRec *)g.shard_send); count_launch(); }
+      B200_TRY(shard_exchange((long long)per_rank * sizeof(SlotRec)));
+      const long long tot = (long long)g.shard_world * per_rank;
+      k_slot_unpack<<<cdiv(tot, B), B, 0, st>>>(nb, g.shard_world, per_rank, S.slot_of_sorted, (const SlotRec *)g.shard_recv, g.s_ngb, g.s_partner, g.s_dv, g.d_ctr);
+      count_launch();
+    }
     // resolve
     int *confirm = g.s_pass;   // reuse (pass flags are consumed)
     CUDA_TRY(cudaMemsetAsync(g.s_winner, 0xff, (size_t)g.n * sizeof(int), st));
@@ -528,6 +605,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   CUDA_TRY(cudaGetLastError());
   if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
   // totals since the last b200_sidm(): the sum of the reference's SCT lines for this step
+  if (g.shard_world > 1) tot_pass1 = (int)g.h_ctr[CT_PASS1];
   g.cnt.sct_ntot += na; g.cnt.sct_pass1 += tot_pass1;
   g.cnt.sct_scattered += (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected += (int)g.h_ctr[CT_REJECTED];
   g.cnt.ngb_candidates += (long long)g.h_ctr[CT_CAND];
@@ -535,39 +613,45 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
 }
 
 // ------------------------------------------------------------------ k nearest (ngb_treefind)
-struct KnnParams { int nq; const int *idx; SearchCtx C; const float4 *posm; int k; float *h2; const SearchNode *snode; const uint64_t *shi, *slo;
+struct KnnParams { int nq; const int *idx; SearchCtx C; const float4 *posm; int k; float *h2; const SearchNode *snode; const float4 *geom; const uint64_t *shi, *slo;
                    const int *nstart; const unsigned char *nlevel; const int *nend; };
 constexpr int kKnnMax = 64;
 
 __global__ void __launch_bounds__(128) k_knn(KnnParams P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.nq) return;
-  const int i = P.idx[t];
-  const float4 p = P.posm[i];
-  // starting radius from the local density: descend while the cell holds > 200 particles
-  // (forcetree.c:2327-2347)
-  int th = 0;
-  for (;;) {
-    const SearchNode nd = P.snode[th];
-    const int cnt = P.nend[th] - P.nstart[th] + 1;
-    if (cnt <= 200) break;
-    const int oct = (p.x > nd.cx ? 1 : 0) | (p.y > nd.cy ? 2 : 0) | (p.z > nd.cz ? 4 : 0);
-    int next = -1;
-    const int lev = P.nlevel[th];
-    for (int c = th + 1; c < nd.skip; c = P.snode[c].skip)
-      if (digit_at(P.shi[P.nstart[c]], P.slo[P.nstart[c]], lev) == oct) { next = c; break; }
-    if (next < 0 || P.nend[next] - P.nstart[next] + 1 <= 200) break;
-    th = next;
-  }
-  const int cnt_th = P.nend[th] - P.nstart[th] + 1;
-  float sr = (float)((double)P.snode[th].len * pow((3.0 / (4 * 3.14159265358979323846) * 1.2) * P.k / ((double)(float)cnt_th), 1.0 / 3));
-  float best[kKnnMax];
+  const bool valid = t < P.nq;
+  const int i = valid ? P.idx[t] : 0;
+  const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
   const int K = P.k;
+  float sr = 1.0f;
+  if (valid) {
+    // starting radius from the local density: descend while the cell holds > 200 particles
+    // (forcetree.c:2327-2347)
+    int th = 0;
+    for (;;) {
+      const int skip = P.snode[th].skip;
+      const float4 gc = P.geom[th];
+      const int cnt = P.nend[th] - P.nstart[th] + 1;
+      if (cnt <= 200) break;
+      const int oct = (p.x > gc.x ? 1 : 0) | (p.y > gc.y ? 2 : 0) | (p.z > gc.z ? 4 : 0);
+      int next = -1;
+      const int lev = P.nlevel[th];
+      for (int c = th + 1; c < skip; c = P.snode[c].skip)
+        if (digit_at(P.shi[P.nstart[c]], P.slo[P.nstart[c]], lev) == oct) { next = c; break; }
+      if (next < 0 || P.nend[next] - P.nstart[next] + 1 <= 200) break;
+      th = next;
+    }
+    const int cnt_th = P.nend[th] - P.nstart[th] + 1;
+    sr = (float)((double)P.geom[th].w * pow((3.0 / (4 * 3.14159265358979323846) * 1.2) * K / ((double)(float)cnt_th), 1.0 / 3));
+  }
+  float best[kKnnMax];
   float h2max = 0;
-  for (int rep = 0; rep < 200; rep++) {
+  bool done = !valid;
+  for (int rep = 0; rep < 200 && !done; rep++) {
     int found = 0;
     for (int a = 0; a < K; a++) best[a] = 3.4e38f;
-    range_search(P.C, p.x, p.y, p.z, sr, [&](int, const float4 &, float r2, bool, int) {
+    const int start = done ? 0 : search_start(P.C, i, p.x, p.y, p.z, sr);
+    range_search(P.C, !done, start, p.x, p.y, p.z, sr, [&](int, const float4 &, float r2, bool, int) {
       found++;
       if (r2 < best[K - 1]) {              // keep the K smallest squared distances, sorted
         int a = K - 2;
@@ -575,18 +659,19 @@ __global__ void __launch_bounds__(128) k_knn(KnnParams P) {
         best[a + 1] = r2;
       }
     });
+    if (done) continue;
     if (found < K) { if (found > 5) sr = (float)((double)sr * pow((2.1 * (double)(float)K) / found, 1.0 / 3)); else sr *= 2.0f; continue; }
     h2max = best[K - 1];
-    if (h2max <= fmul(sr, sr)) break;
+    if (h2max <= fmul(sr, sr)) { done = true; continue; }
     sr = (float)((double)sr * 1.26);
   }
-  P.h2[t] = h2max;
+  if (valid) P.h2[t] = h2max;
 }
 
 static int knn_device(const int *d_idx, int nq, int k, float *d_h2) {
   if (k < 1 || k > kKnnMax) return B200_ERR_ARG;
   B200_TRY(refresh_search_nodes());
-  KnnParams P; P.nq = nq; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode;
+  KnnParams P; P.nq = nq; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode; P.geom = g.geom;
   P.shi = g.skey_hi; P.slo = g.skey_lo; P.nstart = g.nstart; P.nlevel = g.nlevel; P.nend = g.nend;
   k_knn<<<cdiv(nq, 128), 128, 0, g.stream>>>(P);
   count_launch();
@@ -815,17 +900,19 @@ struct ListParams { int nq; const int *idx; SearchCtx C; const float4 *posm, *ve
                     const int *krank, *lrank, *nstart; unsigned long long *keys; };
 __global__ void k_ngb_lists(ListParams P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.nq) return;
-  const int i = P.idx[t];
-  const float4 p = P.posm[i]; const float h = P.velh[i].w; const float sr2 = fmul(h, h);
-  int *out = P.list + (size_t)t * P.cap; unsigned long long *ck = P.keys + (size_t)t * P.cap;
+  const bool valid = t < P.nq;
+  const int i = valid ? P.idx[t] : 0;
+  const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
+  const float h = valid ? P.velh[i].w : 0.0f; const float sr2 = fmul(h, h);
+  int *out = P.list + (size_t)(valid ? t : 0) * P.cap; unsigned long long *ck = P.keys + (size_t)(valid ? t : 0) * P.cap;
   int nc = 0;
+  const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
   if (!P.ref_order) {
-    range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) { if (nc < P.cap) out[nc] = P.C.leaf_orig[L]; nc++; } });
-    P.count[t] = nc;
+    range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int L, const float4 &, float r2, bool, int) { if (r2 < sr2) { if (nc < P.cap) out[nc] = P.C.leaf_orig[L]; nc++; } });
+    if (valid) P.count[t] = nc;
     return;
   }
-  range_search(P.C, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
+  range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
     if (nc >= P.cap) { nc++; return; }
     const int o = P.C.leaf_orig[L];
     const unsigned long long key = bulk ? (((unsigned long long)P.nstart[node] << 32) | (unsigned)P.lrank[o]) : ((unsigned long long)P.krank[o] << 32);
@@ -833,6 +920,7 @@ __global__ void k_ngb_lists(ListParams P) {
     while (k >= 0 && ck[k] > key) { ck[k + 1] = ck[k]; out[k + 1] = out[k]; k--; }
     ck[k + 1] = key; out[k + 1] = o; nc++;
   });
+  if (!valid) return;
   if (nc > P.cap) { P.count[t] = nc; return; }
   int n = nc;
   for (int a = 0; a < n; a++) {

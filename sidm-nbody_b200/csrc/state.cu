@@ -42,8 +42,9 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.ndp, 8 * (m + 1))); B200_TRY(dalloc(&g.narrive, m + 1));
   B200_TRY(dalloc(&g.nminidx, m + 1)); B200_TRY(dalloc(&g.nlstart, m + 1));
   B200_TRY(dalloc(&g.nmom, m + 1));
-  B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n));
+  B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n)); B200_TRY(dalloc(&g.leaf_parent, n));
   B200_TRY(dalloc(&g.lrank, n));
+  B200_TRY(dalloc(&g.d_shard_list, n + 64));
   B200_TRY(dalloc(&g.d_active, n)); B200_TRY(dalloc(&g.d_tsorted, n)); B200_TRY(dalloc(&g.d_tkeys, n));
   B200_TRY(dalloc(&g.d_tkeys2, n)); B200_TRY(dalloc(&g.d_tvals2, n));
   B200_TRY(dalloc(&g.d_acc, 3 * n)); B200_TRY(dalloc(&g.d_cost, 2 * n));
@@ -64,6 +65,38 @@ using namespace b200;
 extern "C" const char *b200_version(void) { return "sidm_b200 0.1 (sm_100a)"; }
 extern "C" int b200_last_cuda_error(void) { return g.last_cuda; }
 extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cuda_stream; return B200_OK; }
+
+extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes, b200_allgather_fn fn, void *user) {
+  if (world < 1 || rank < 0 || rank >= world) return B200_ERR_ARG;
+  if (world > 1 && (!send || !recv || !fn || cap_bytes <= 0)) return B200_ERR_ARG;
+  g.shard_rank = rank; g.shard_world = world; g.shard_send = send; g.shard_recv = recv; g.shard_cap = cap_bytes;
+  g.shard_fn = fn; g.shard_user = user;
+  return B200_OK;
+}
+
+// own[k] = in[(k/32*world + rank)*32 + k%32] : this rank's blocks of a sorted work list
+__global__ void k_shard_select(int nt, int world, int rank, const int *in, int *out, int nown_max) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nown_max) return;
+  const long long j = ((long long)(k >> 5) * world + rank) * 32 + (k & 31);
+  if (j < nt) out[k] = in[j];
+}
+namespace b200 {
+int shard_select(const int *d_in, int nt, int *d_out, int *n_own) {
+  const int nown = shard_count(nt, g.shard_world, g.shard_rank);
+  *n_own = nown;
+  if (nown > 0) {
+    k_shard_select<<<cdiv(nown, 256), 256, 0, g.stream>>>(nt, g.shard_world, g.shard_rank, d_in, d_out, nown);
+    count_launch();
+  }
+  return B200_OK;
+}
+int shard_exchange(long long bytes_per_rank) {
+  if (bytes_per_rank > g.shard_cap) return B200_ERR_ARG;
+  const int rc = g.shard_fn(bytes_per_rank, g.shard_user);
+  return rc == 0 ? B200_OK : B200_ERR_STATE;
+}
+}
 
 extern "C" int b200_set_params(const b200_params *p) {
   if (!p) return B200_ERR_ARG;
@@ -122,7 +155,8 @@ extern "C" void b200_finalize(void) {
   dfree(&g.nodes); dfree(&g.geom); dfree(&g.nstart); dfree(&g.nend); dfree(&g.nparent); dfree(&g.npstart);
   dfree(&g.nlevel); dfree(&g.nnp); dfree(&g.nnchild); dfree(&g.ndp); dfree(&g.narrive);
   dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom);
-  dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.lrank);
+  dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.leaf_parent); dfree(&g.lrank);
+  dfree(&g.d_shard_list);
   dfree(&g.d_active); dfree(&g.d_tsorted); dfree(&g.d_tkeys); dfree(&g.d_tkeys2); dfree(&g.d_tvals2);
   dfree(&g.d_acc); dfree(&g.d_cost);
   dfree(&g.s_slot_part); dfree(&g.s_flag); dfree(&g.s_pos); dfree(&g.s_ngb); dfree(&g.s_partner);

@@ -152,7 +152,7 @@ BuildView make_view() {
   v.nodes = g.nodes; v.geom = g.geom; v.nstart = g.nstart; v.nend = g.nend; v.nparent = g.nparent; v.npstart = g.npstart;
   v.nlevel = g.nlevel; v.nnp = g.nnp; v.nnchild = g.nnchild; v.ndp = g.ndp; v.narrive = g.narrive;
   v.nminidx = g.nminidx; v.nlstart = g.nlstart; v.nmom = g.nmom;
-  v.leaf_posm = g.leaf_posm; v.leaf_orig = g.leaf_orig; v.orig_leaf = g.orig_leaf; v.krank = g.krank; v.lrank = g.lrank;
+  v.leaf_posm = g.leaf_posm; v.leaf_orig = g.leaf_orig; v.orig_leaf = g.orig_leaf; v.krank = g.krank; v.lrank = g.lrank; v.leaf_parent = g.leaf_parent;
   v.flags = g.d_flags;
   return v;
 }

@@ -121,11 +121,11 @@ B200_HD bool key_less(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo) {
 // in depth-first pre-order so that "open" is always id+1 and "accept" jumps to `skip`.
 struct __attribute__((aligned(16))) NodeRec {
   float sx, sy, sz, mass;          // centre of mass, mass                  (NODE.s, .mass)
-  float oc, bmax2;                 // relative criterion: mass*len^4, bmax2 (NODE.oc, .bmax2)
+  float len2, bmax2;               // len*len (BH test; oc = mass*len2*len2 is recomputed), bmax2 (NODE.bmax2)
   int   pinfo;                     // (first leaf slot << 4) | number of direct particles
   int   skip;                      // next node in pre-order outside this subtree
   float q11, q22, q33, q12;        // raw second moments about the c.o.m.   (NODE.Q11..)
-  float q13, q23, p, len2;         // ... trace P, len*len for the BH test
+  float q13, q23, p, oc;           // ... trace P; oc = mass*len^4 as the reference stores it (NODE.oc)
 };
 
 // raw moments of a node about its geometric centre, in double (forcetree.c:433-571)
@@ -241,6 +241,53 @@ B200_HD void pn_force(float dx, float dy, float dz, float r2, const NodeRec &n, 
   ax += dx * fac + ff * (q11dx + q12dy + q13dz);
   ay += dy * fac + ff * (q12dx + q22dy + q23dz);
   az += dz * fac + ff * (q13dx + q23dy + q33dz);
+}
+
+// fast forms used by the GPU walk: one MUFU.RSQ instead of an IEEE sqrt + division (2 ulp, far
+// inside the 1e-4 tolerance); the softened branch (r < h) is rare and keeps the spline.
+B200_HD float rsqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+B200_HD void pp_force_fast(float dx, float dy, float dz, float mass, float h_inv, float h2, float &ax, float &ay, float &az) {
+  const float r2 = dx * dx + dy * dy + dz * dz;
+  float fac;
+  if (r2 >= h2) {
+    const float ri = rsqrt_fast(r2);
+    fac = mass * ri * ri * ri;
+  } else {
+    const float u = sqrtf(r2) * h_inv;
+    if (!(u > 1.0e-4f)) return;
+    fac = mass * h_inv * h_inv * h_inv * soft_force(u);
+  }
+  ax += dx * fac; ay += dy * fac; az += dz * fac;
+}
+B200_HD void pn_force_fast(float dx, float dy, float dz, float r2, float mass, float q11, float q22, float q33, float q12, float q13,
+                           float q23, float pp, float h_inv, float h2, float &ax, float &ay, float &az) {
+  const float qx = q11 * dx + q12 * dy + q13 * dz;
+  const float qy = q12 * dx + q22 * dy + q23 * dz;
+  const float qz = q13 * dx + q23 * dy + q33 * dz;
+  const float potq = 0.5f * (dx * qx + dy * qy + dz * qz);          // 1/2 y^T Q y
+  float fac, ff;
+  if (r2 >= h2) {
+    const float ri = rsqrt_fast(r2), r2i = ri * ri, r3i = r2i * ri, r5i = r2i * r3i;
+    fac = mass * r3i + (15 * potq * r2i - 1.5f * pp) * r5i;
+    ff = -3 * r5i;
+  } else {
+    const float r = sqrtf(r2), u = r * h_inv;
+    if (!(u > 1.0e-4f)) return;
+    float w2, w3, w4;
+    soft_w234(u, w2, w3, w4);
+    const float wf = soft_force(u);
+    const float ri = 1.0f / r;
+    const float h2i = h_inv * h_inv, h3i = h2i * h_inv, h4i = h2i * h2i, h5i = h2i * h3i, h6i = h3i * h3i;
+    fac = mass * h3i * wf + potq * h6i * w3 * ri + 0.5f * pp * w4 * h4i * ri;
+    ff = w2 * h5i;
+  }
+  ax += dx * fac + ff * qx; ay += dy * fac + ff * qy; az += dz * fac + ff * qz;
 }
 
 // opening tests.  true = open the cell.

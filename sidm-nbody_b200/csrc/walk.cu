@@ -33,7 +33,7 @@ struct WalkParams {
   unsigned long long *ctr;
 };
 
-constexpr int kFlushEvery = 8;
+constexpr int kFlushEvery = 32;
 
 __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31;
@@ -46,42 +46,45 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   const bool bh = (P.criterion == 0) || (oa == 0.0f);          // forcetree.c:801
   const float oac = oa * P.alpha;                               // forcetree.c:1129
   const float h_inv = P.h_inv, theta2 = P.theta2;
+  const float h2 = 1.0f / (h_inv * h_inv);
   const int M = P.num_nodes;
   const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
 
   int no = valid ? 0 : 0x7fffffff;
-  int cur = 0;
+  int cur = __reduce_min_sync(0xffffffffu, no);
   double ax = 0, ay = 0, az = 0;
   float fx = 0, fy = 0, fz = 0;
   int npart = 0, nnode = 0, it = 0;
   unsigned wnodes = 0, wparts = 0;
 
   while (cur < M) {
-    const float4 A = __ldg(nodes4 + 4 * (size_t)cur);
-    const float4 Bv = __ldg(nodes4 + 4 * (size_t)cur + 1);
-    const float4 Cv = __ldg(nodes4 + 4 * (size_t)cur + 2);
-    const float4 Dv = __ldg(nodes4 + 4 * (size_t)cur + 3);
+    const float4 *nd = nodes4 + 4 * (size_t)cur;
+    const float4 A = __ldg(nd);              // s.xyz, mass
+    const float4 Bv = __ldg(nd + 1);         // len2, bmax2, pinfo, skip
     const bool act = (no == cur);
     const float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
     const float r2 = dx * dx + dy * dy + dz * dz;
-    const bool open = act && (bh ? open_bh(Dv.w, r2, theta2) : open_rel(Bv.x, Bv.y, r2, oac));
+    // forcetree.c:967 / :1253-1257; oc = mass*len^4 formed exactly as the build stores it
+    const bool open_b = Bv.x > r2 * theta2;
+    const bool open_r = (fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y);
+    const bool open = act && (bh ? open_b : open_r);
     if (act && !open) {
-      NodeRec n;
-      n.mass = A.w; n.q11 = Cv.x; n.q22 = Cv.y; n.q33 = Cv.z; n.q12 = Cv.w; n.q13 = Dv.x; n.q23 = Dv.y; n.p = Dv.z;
-      pn_force(dx, dy, dz, r2, n, h_inv, fx, fy, fz);
+      const float4 Cv = __ldg(nd + 2);       // Q11 Q22 Q33 Q12
+      const float4 Dv = __ldg(nd + 3);       // Q13 Q23 P oc
+      pn_force_fast(dx, dy, dz, r2, A.w, Cv.x, Cv.y, Cv.z, Cv.w, Dv.x, Dv.y, Dv.z, h_inv, h2, fx, fy, fz);
       nnode++;
-      no = __float_as_int(Bv.w);          // skip
+      no = __float_as_int(Bv.w);             // accept: jump over the subtree
     }
     if (open) no = cur + 1;
-    const unsigned om = __ballot_sync(0xffffffffu, open);
     wnodes++;
-    if (om) {
+    if (__any_sync(0xffffffffu, open)) {
       const int pinfo = __float_as_int(Bv.z);
-      const int np = pinfo & 15, ps = pinfo >> 4;
+      const int np = pinfo & 15;
+      const float4 *lp = P.leaf_posm + (pinfo >> 4);
       wparts += np;
       for (int k = 0; k < np; k++) {
-        const float4 q = __ldg(P.leaf_posm + ps + k);
-        if (open) { pp_force(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, fx, fy, fz); npart++; }
+        const float4 q = __ldg(lp + k);
+        if (open) { pp_force_fast(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, h2, fx, fy, fz); npart++; }
       }
     }
     if (++it == kFlushEvery) { ax += (double)fx; ay += (double)fy; az += (double)fz; fx = fy = fz = 0; it = 0; }
@@ -143,8 +146,7 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, 4 * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  k_walk<<<cdiv(nt, 256), 256, 0, g.stream>>>(P);
-  count_launch();
+  if (nt > 0) { k_walk<<<cdiv(nt, 256), 256, 0, g.stream>>>(P); count_launch(); }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -159,13 +161,14 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
 // gravtree.c:230-324: Accel <- (float)Acc; OldAcc = |Accel| before G (relative criterion);
 // Accel <- G*Accel + OmegaLambda*H^2*PosPred, or the comoving combination.
 struct EpiParams {
-  int nt; const int *slot_part; const double *acc; const int *cost;
+  int nt; const int *list; const int *slot_part; const double *acc; const int *cost;
   const float4 *posm; const float *velpred; float *accel, *oldacc, *gravcost;
   int criterion, comoving, periodic; double G, H, O0, OL, time;
 };
 __global__ void k_grav_epilogue(EpiParams E) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= E.nt) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= E.nt) return;
+  const int s = E.list ? E.list[k] : k;
   const int p = E.slot_part ? E.slot_part[s] : s;
   float a[3];
   for (int k = 0; k < 3; k++) a[k] = (float)E.acc[3 * (size_t)s + k];
@@ -195,21 +198,50 @@ __global__ void k_grav_epilogue(EpiParams E) {
   E.gravcost[p] = (float)(E.cost[2 * (size_t)s] + E.cost[2 * (size_t)s + 1]);
 }
 
+// multi-GPU: {Accel, OldAcc} of this rank's targets -> send buffer, and back from all ranks
+__global__ void k_grav_pack(int nw, const int *work, const int *slot_part, const float *accel, const float *oldacc, float4 *send) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nw) return;
+  const int s = work[k]; const int p = slot_part ? slot_part[s] : s;
+  send[k] = make_float4(accel[3 * (size_t)p], accel[3 * (size_t)p + 1], accel[3 * (size_t)p + 2], oldacc[p]);
+}
+__global__ void k_grav_unpack(int nt, int world, int per_rank, const int *sorted, const int *slot_part, const float4 *recv, float *accel, float *oldacc) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)world * per_rank) return;
+  const int q = (int)(g / per_rank), k = (int)(g % per_rank);
+  const long long j = ((long long)(k >> 5) * world + q) * 32 + (k & 31);
+  if (j >= nt) return;
+  const int s = sorted[j]; const int p = slot_part ? slot_part[s] : s;
+  const float4 v = recv[g];
+  accel[3 * (size_t)p] = v.x; accel[3 * (size_t)p + 1] = v.y; accel[3 * (size_t)p + 2] = v.z; oldacc[p] = v.w;
+}
+
 int gravity_impl(const int *active, int nactive, double time) {
   if (!g.tree_valid) return B200_ERR_STATE;
   const int nt = active ? nactive : g.n;
   if (nt <= 0) return B200_OK;
   int *d_sorted = nullptr;
   B200_TRY(prepare_targets(active, nt, &d_sorted));
-  B200_TRY(walk_impl(d_sorted, nt, active != nullptr));
+  const int *work = d_sorted; int nw = nt;
+  if (g.shard_world > 1) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw)); work = g.d_shard_list; }
+  B200_TRY(walk_impl(work, nw, active != nullptr));
   EpiParams E;
-  E.nt = nt; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
+  E.nt = nw; E.list = work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
   E.posm = g.posm; E.velpred = g.velpred; E.accel = g.accel; E.oldacc = g.oldacc; E.gravcost = g.gravcost;
   E.criterion = g.par.TypeOfOpeningCriterion; E.comoving = g.par.ComovingIntegrationOn;
   E.periodic = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   E.G = g.par.G; E.H = g.par.Hubble; E.O0 = g.par.Omega0; E.OL = g.par.OmegaLambda; E.time = time;
-  k_grav_epilogue<<<cdiv(nt, 256), 256, 0, g.stream>>>(E);
-  count_launch();
+  if (nw > 0) { k_grav_epilogue<<<cdiv(nw, 256), 256, 0, g.stream>>>(E); count_launch(); }
+  if (g.shard_world > 1) {
+    // all-gather of the partial results (the reduce step of gravtree.c:208-222 becomes a gather:
+    // every target is evaluated completely by exactly one rank)
+    const int per_rank = shard_max_blocks(nt, g.shard_world) * 32;
+    if (nw > 0) { k_grav_pack<<<cdiv(nw, 256), 256, 0, g.stream>>>(nw, work, E.slot_part, g.accel, g.oldacc, (float4 *)g.shard_send); count_launch(); }
+    B200_TRY(shard_exchange((long long)per_rank * sizeof(float4)));
+    const long long tot = (long long)g.shard_world * per_rank;
+    k_grav_unpack<<<cdiv(tot, 256), 256, 0, g.stream>>>(nt, g.shard_world, per_rank, d_sorted, E.slot_part, (const float4 *)g.shard_recv, g.accel, g.oldacc);
+    count_launch();
+  }
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;

@@ -2,19 +2,84 @@
 
 Replaces the role of the reference's domain.c + hypercube exchanges: the
 particle state is replicated on every GPU (1e7 particles = a few GB of 180 GB), every rank
-builds the same octree, and the TARGETS are split: rank r walks / scatters the 32-particle
-blocks b of the octant-key order with b % world == r (interleaved blocks balance the dense
-centre across ranks and keep every warp's targets spatial neighbours).  Results are
-exchanged with NCCL all-gathers over NVLink through torch.distributed.
+builds the same octree, and the TARGETS are split: rank r walks / scatters the 32-entry
+blocks b of every work list sorted along the octant-key order with b % world == r
+(interleaved blocks balance the dense centre across ranks and keep each warp's targets
+spatial neighbours).  Per-target results are exchanged with one NCCL all-gather per phase
+over NVLink; the library packs/unpacks and calls back into `torch.distributed` for the
+collective (include/sidm_b200.h: b200_set_shard).  Counter-based per-particle random numbers
+make the N-GPU result identical to the 1-GPU result.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_longlong, C.c_void_p)
+SLOT_REC_BYTES = 32        # struct SlotRec in csrc/sidm.cu; gravity sends 16-byte float4 records
+
+
+def shard_max_blocks(nt, world):
+    return ((nt + 31) // 32 + world - 1) // world
+
+
+def shard_positions(nt, world, rank):
+    """positions j of a sorted work list of length nt that rank owns (mirror of k_shard_select)"""
+    k = np.arange(shard_max_blocks(nt, world) * 32, dtype=np.int64)
+    j = ((k >> 5) * world + rank) * 32 + (k & 31)
+    return j[j < nt]
+
+
+def unpack_positions(nt, world):
+    """for the concatenated all-gather buffer [world][per_rank]: list position of every entry, -1 = padding
+    (mirror of k_grav_unpack / k_slot_unpack)"""
+    per_rank = shard_max_blocks(nt, world) * 32
+    g = np.arange(world * per_rank, dtype=np.int64)
+    q, k = g // per_rank, g % per_rank
+    j = ((k >> 5) * world + q) * 32 + (k & 31)
+    return np.where(j < nt, j, -1), per_rank
+
+
+def buffer_bytes(n, world):
+    return shard_max_blocks(n, world) * 32 * SLOT_REC_BYTES
 
 
 class Sharder:
     def __init__(self, hp, world=1, rank=0):
         self.hp, self.world, self.rank = hp, int(world), int(rank)
+        self._cb = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            cap = buffer_bytes(hp.params.MaxPart, self.world)
+            self.send = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            self.recv = torch.empty(cap * self.world, dtype=torch.uint8, device="cuda")
+            self.exchanges = 0
+            self.bytes = 0
+
+            host_staged = dist.get_backend() == "gloo"      # test harness: several ranks sharing one GPU
+
+            def allgather(nbytes, user):
+                try:
+                    if host_staged:
+                        out = torch.empty(self.world * nbytes, dtype=torch.uint8)
+                        dist.all_gather_into_tensor(out, self.send[:nbytes].cpu())
+                        self.recv[: self.world * nbytes].copy_(out)
+                    else:
+                        dist.all_gather_into_tensor(self.recv[: self.world * nbytes], self.send[:nbytes])
+                    self.exchanges += 1
+                    self.bytes += int(nbytes)
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("all-gather failed:", e, flush=True)
+                    return 1
+
+            self._cb = ALLGATHER_FN(allgather)
+            rc = hp.lib.b200_set_shard(self.rank, self.world, C.c_void_p(self.send.data_ptr()), C.c_void_p(self.recv.data_ptr()),
+                                       C.c_longlong(cap), self._cb, None)
+            if rc != 0:
+                raise RuntimeError(f"b200_set_shard -> {rc}")
 
     def describe(self):
         if self.world == 1:
@@ -23,7 +88,4 @@ class Sharder:
                 "NCCL all-gather of accelerations and scatter proposals")
 
     def compute_accelerations(self, mode, time, vmax, active=None):
-        if self.world == 1:
-            self.hp.compute_accelerations(mode, active, time, vmax)
-            return
-        raise NotImplementedError("multi-GPU path")
+        self.hp.compute_accelerations(mode, active, time, vmax)

@@ -16,7 +16,7 @@ struct Host {
   int n = 0, m = 0, maxlev = 0;
   std::vector<float4> posm, geom, leaf_posm;
   std::vector<uint64_t> hi, lo, shi, slo;
-  std::vector<int> sidx, nodestart, nstart, nend, nparent, npstart, ndp, narrive, nminidx, nlstart, leaf_orig, orig_leaf, krank, lrank;
+  std::vector<int> sidx, nodestart, nstart, nend, nparent, npstart, ndp, narrive, nminidx, nlstart, leaf_orig, orig_leaf, krank, lrank, leaf_parent;
   std::vector<signed char> clev;
   std::vector<unsigned char> nlevel, nnp, nnchild;
   std::vector<NodeRec> nodes;
@@ -46,7 +46,7 @@ extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lor
   H.nodes.assign(cap, NodeRec()); H.geom.resize(cap); H.nstart.assign(cap, 0); H.nend.assign(cap, 0); H.nparent.assign(cap, -1);
   H.npstart.assign(cap + 1, 0); H.nlevel.assign(cap, 0); H.nnp.assign(cap, 0); H.nnchild.assign(cap, 0); H.ndp.assign(8 * (size_t)cap, -1);
   H.narrive.assign(cap, 0); H.nminidx.assign(cap, 0); H.nlstart.assign(cap, 0); H.nmom.resize(cap);
-  H.leaf_posm.resize(n); H.leaf_orig.assign(n, 0); H.orig_leaf.assign(n, 0); H.krank.assign(n, 0); H.lrank.assign(n, 0);
+  H.leaf_posm.resize(n); H.leaf_orig.assign(n, 0); H.orig_leaf.assign(n, 0); H.krank.assign(n, 0); H.lrank.assign(n, 0); H.leaf_parent.assign(n, 0);
   for (int k = 0; k < 16; k++) H.flags[k] = 0;
   BuildView v;
   v.n = n; v.maxnodes = cap; v.posm = H.posm.data(); v.shi = H.shi.data(); v.slo = H.slo.data(); v.sidx = H.sidx.data();
@@ -55,7 +55,7 @@ extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lor
   v.npstart = H.npstart.data(); v.nlevel = H.nlevel.data(); v.nnp = H.nnp.data(); v.nnchild = H.nnchild.data(); v.ndp = H.ndp.data();
   v.narrive = H.narrive.data(); v.nminidx = H.nminidx.data(); v.nlstart = H.nlstart.data(); v.nmom = H.nmom.data();
   v.leaf_posm = H.leaf_posm.data(); v.leaf_orig = H.leaf_orig.data(); v.orig_leaf = H.orig_leaf.data(); v.krank = H.krank.data();
-  v.lrank = H.lrank.data(); v.flags = H.flags;
+  v.lrank = H.lrank.data(); v.leaf_parent = H.leaf_parent.data(); v.flags = H.flags;
   // B1 + scan
   std::vector<int> cnt(n + 1, 0);
   int maxlev = 0;

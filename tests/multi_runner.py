@@ -1,0 +1,54 @@
+"""helper for tests/test_gpu_multi.py: runs two steps of the hot path as rank RANK of WORLD
+(gloo = ranks share cuda:0 and stage the all-gather through the host; nccl = one GPU each)
+and writes the particle fields the path owns."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sidm-nbody_b200"))
+
+
+def main(out, n, backend):
+    import torch
+    import torch.distributed as dist
+    from sidm_b200 import HotPath, ic
+    from sidm_b200.multi import Sharder
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group(backend)
+    pos, vel, mass, ids = ic.hernquist(n, seed=13)
+    hp = HotPath(n, device=dev, CrossSectionInternal=400.0, Seed=7)
+    sh = Sharder(hp, world, rank)
+    hp.set_particles(pos, vel, mass, ids)
+    hp.predict_collisionless_only(0.0)
+    hp.force_treebuild()
+    hp.setup_smoothinglengths_sidm(30)
+    vmax = hp.getvmax()
+    sh.compute_accelerations(1, time=0.0, vmax=vmax)
+    acc1, old1 = hp.get("Accel", "OldAcc")
+    dt = 0.004
+    t = 0.0
+    res = {}
+    for step in range(2):
+        sh.compute_accelerations(0, time=t + dt / 2, vmax=vmax)
+        c = hp.counters()
+        res[f"acc{step}"], res[f"old{step}"], res[f"dvel{step}"], res[f"h{step}"], res[f"ngb{step}"] = hp.get(
+            "Accel", "OldAcc", "dVel", "HsmlVelDisp", "NgbVelDisp")
+        res[f"sct{step}"] = np.array([c.sct_ntot, c.sct_pass1, c.sct_scattered, c.sct_rejected, c.ensure_iterations])
+        hp.advance(time=t + dt / 2)
+        t += dt
+    if rank == 0:
+        np.savez(out, acc_start=acc1, old_start=old1, **res)
+    hp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]), sys.argv[3])
