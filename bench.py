@@ -399,7 +399,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=lambda s: int(float(s)), default=10_000_000)
     ap.add_argument("--ref-procs", type=int, default=0, help="host processes for the reference arm (0 = all that fit)")
-    ap.add_argument("--ref-sample", type=int, default=8000, help="active particles per reference process per step")
+    ap.add_argument("--ref-sample", type=int, default=60000, help="active particles per reference process per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -91,6 +91,8 @@ struct Ctx {
   void *shard_send = nullptr, *shard_recv = nullptr; long long shard_cap = 0;
   b200_allgather_fn shard_fn = nullptr; void *shard_user = nullptr;
 
+  float4 *d_ewald = nullptr; double ewald_box = -1;   // (ED+1)^3 correction table, scaled for ewald_box
+
   b200_counters cnt{};
 };
 

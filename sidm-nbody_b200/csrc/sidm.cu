@@ -59,7 +59,20 @@ __device__ __forceinline__ double u01(uint32_t x) { return (double)x / 429496729
 struct SearchCtx {
   int M; const SearchNode *snode; const float4 *leaf_posm; const int *leaf_orig;
   const int *nparent, *leaf_parent, *orig_leaf;
+  double box;                      // > 0: periodic box (ngb_periodic(), forcetree.c:1999-2006)
 };
+
+// ngb_periodic(): float argument, wrapped with double Box / BoxHalf, rounded back to float
+__device__ __forceinline__ float ngb_periodic(float x, double box) {
+  const double bh = 0.5 * box;
+  while ((double)x > bh) x = (float)((double)x - box);
+  while ((double)x < -bh) x = (float)((double)x + box);
+  return x;
+}
+__device__ __forceinline__ float dist2_per(float px, float py, float pz, float x, float y, float z, double box) {
+  const float dx = ngb_periodic(fadd(px, -x), box), dy = ngb_periodic(fadd(py, -y), box), dz = ngb_periodic(fadd(pz, -z), box);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
 
 __device__ __forceinline__ float dist2_ref(float px, float py, float pz, float x, float y, float z) {
   // forcetree.c:2195-2204: float differences, float products, summed left to right, no FMA
@@ -76,6 +89,7 @@ __device__ __forceinline__ int search_start(const SearchCtx &C, int i, float x, 
   const double lox = (double)fadd(x, -h), loy = (double)fadd(y, -h), loz = (double)fadd(z, -h);
   const double hix = (double)fadd(x, h), hiy = (double)fadd(y, h), hiz = (double)fadd(z, h);
   const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h);
+  if (C.box > 0) return 0;
   int no = C.leaf_parent[C.orig_leaf[i]];
   while (no > 0) {
     const SearchNode &nd = C.snode[no];
@@ -96,6 +110,38 @@ __device__ __forceinline__ void range_search(const SearchCtx &C, bool valid, int
   if (!valid) return;
   const float lox = fadd(x, -h), loy = fadd(y, -h), loz = fadd(z, -h);
   const float hix = fadd(x, h), hiy = fadd(y, h), hiz = fadd(z, h);
+  if (C.box > 0) {
+    // periodic variant of the same walk (forcetree.c:2228-2276 under PERIODIC): everything is
+    // measured relative to the search centre through ngb_periodic(); always from the root
+    const double box = C.box;
+    const double sminx = fadd(lox, -x), sminy = fadd(loy, -y), sminz = fadd(loz, -z);
+    const double smaxx = fadd(hix, -x), smaxy = fadd(hiy, -y), smaxz = fadd(hiz, -z);
+    int no = 0;
+    while (no < C.M) {
+      const double2 *q = reinterpret_cast<const double2 *>(C.snode + no);
+      const double2 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
+      const int4 info = __ldg(reinterpret_cast<const int4 *>(q + 3));
+      const float cx = (float)(0.5 * (a0.x + a1.y)), cy = (float)(0.5 * (a0.y + a2.x)), cz = (float)(0.5 * (a1.x + a2.y));
+      const double half = 0.5 * (a1.y - a0.x);
+      const double px = ngb_periodic(fadd(cx, -x), box), py = ngb_periodic(fadd(cy, -y), box), pz = ngb_periodic(fadd(cz, -z), box);
+      if (px + half < sminx || px - half > smaxx || py + half < sminy || py - half > smaxy || pz + half < sminz || pz - half > smaxz) { no = info.x; continue; }
+      const bool inside = !(px + half > smaxx) && !(px - half < sminx) && !(py + half > smaxy) && !(py - half < sminy) && !(pz + half > smaxz) && !(pz - half < sminz);
+      if (inside) {
+        for (int L = info.y; L < info.w; L++) { const float4 p = __ldg(C.leaf_posm + L); f(L, p, dist2_per(p.x, p.y, p.z, x, y, z, box), true, no); }
+        no = info.x;
+      } else {
+        for (int k = 0; k < info.z; k++) {
+          const int L = info.y + k;
+          const float4 p = __ldg(C.leaf_posm + L);
+          const double ex = ngb_periodic(fadd(p.x, -x), box), ey = ngb_periodic(fadd(p.y, -y), box), ez = ngb_periodic(fadd(p.z, -z), box);
+          if (ex < sminx || ex > smaxx || ey < sminy || ey > smaxy || ez < sminz || ez > smaxz) continue;
+          f(L, p, dist2_per(p.x, p.y, p.z, x, y, z, box), false, no);
+        }
+        no = no + 1;
+      }
+    }
+    return;
+  }
   const double dlx = lox, dly = loy, dlz = loz, dhx = hix, dhy = hiy, dhz = hiz;
   int no = start;
   const int stop = C.snode[start].skip;
@@ -293,13 +339,13 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
     for (int a = 0; a < n; a++) {
       const int j = cl[(size_t)a * st];
       const float4 q = P.posm[j];
-      const float r2 = dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z);
+      const float r2 = P.C.box > 0 ? dist2_per(q.x, q.y, q.z, p.x, p.y, p.z, P.C.box) : dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z);
       if (r2 >= sr2) { cl[(size_t)a * st] = cl[(size_t)(n - 1) * st]; n--; a--; }
     }
     for (int a = 0; a < n; a++) {
       const int j = cl[(size_t)a * st];
       const float4 q = P.posm[j];
-      visit(j, dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z));
+      visit(j, P.C.box > 0 ? dist2_per(q.x, q.y, q.z, p.x, p.y, p.z, P.C.box) : dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z));
     }
   }
   if (!valid) return;
@@ -431,6 +477,7 @@ static int cub_scratch(size_t tb) {
 static SearchCtx search_ctx() {
   SearchCtx C; C.M = g.num_nodes; C.snode = S.snode; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
   C.nparent = g.nparent; C.leaf_parent = g.leaf_parent; C.orig_leaf = g.orig_leaf;
+  C.box = (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? g.par.BoxSize : 0.0;
   return C;
 }
 
@@ -925,7 +972,7 @@ __global__ void k_ngb_lists(ListParams P) {
   int n = nc;
   for (int a = 0; a < n; a++) {
     const float4 q = P.posm[out[a]];
-    if (dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z) >= sr2) { out[a] = out[n - 1]; n--; a--; }
+    if ((P.C.box > 0 ? dist2_per(q.x, q.y, q.z, p.x, p.y, p.z, P.C.box) : dist2_ref(q.x, q.y, q.z, p.x, p.y, p.z)) >= sr2) { out[a] = out[n - 1]; n--; a--; }
   }
   P.count[t] = n;
 }

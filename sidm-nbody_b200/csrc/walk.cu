@@ -21,6 +21,7 @@
 namespace b200 {
 
 double s_a_inverse_at(double time);
+int ewald_tables(const float4 **out);
 
 struct WalkParams {
   int nt, num_nodes;
@@ -31,10 +32,41 @@ struct WalkParams {
   double *acc; int *cost;
   float theta2, alpha, h_inv; int criterion;
   unsigned long long *ctr;
+  // periodic box (forcetree.c:870-877,921-930): nearest image + Ewald correction table
+  float box, boxhalf, ewald_fac; const float4 *ewald;
 };
+
+constexpr int kEwaldN = 64, kEwaldD = 32;        // EN, ED of ewald.c:12-14
+
+// ewald_corr(), ewald.c:171-238: fold into the first octant, trilinear interpolation of the
+// (ED+1)^3 table; the table holds {fx, fy, fz, unused} per grid point, already scaled by 1/L^2
+__device__ __forceinline__ void ewald_corr(const float4 *tab, float fac, float dx, float dy, float dz, float &cx, float &cy, float &cz) {
+  const float sx = dx < 0 ? 1.0f : -1.0f, sy = dy < 0 ? 1.0f : -1.0f, sz = dz < 0 ? 1.0f : -1.0f;
+  float u = fabsf(dx) * fac, v = fabsf(dy) * fac, w = fabsf(dz) * fac;
+  int i = (int)u, j = (int)v, k = (int)w;
+  if (i >= kEwaldD) i = kEwaldD - 1;
+  if (j >= kEwaldD) j = kEwaldD - 1;
+  if (k >= kEwaldD) k = kEwaldD - 1;
+  u -= i; v -= j; w -= k;
+  const int S1 = kEwaldD + 1, S2 = S1 * S1;
+  const float4 *b = tab + (i * S2 + j * S1 + k);
+  const float4 t000 = __ldg(b), t001 = __ldg(b + 1), t010 = __ldg(b + S1), t011 = __ldg(b + S1 + 1);
+  const float4 t100 = __ldg(b + S2), t101 = __ldg(b + S2 + 1), t110 = __ldg(b + S2 + S1), t111 = __ldg(b + S2 + S1 + 1);
+  const float f1 = (1 - u) * (1 - v) * (1 - w), f2 = (1 - u) * (1 - v) * w, f3 = (1 - u) * v * (1 - w), f4 = (1 - u) * v * w;
+  const float f5 = u * (1 - v) * (1 - w), f6 = u * (1 - v) * w, f7 = u * v * (1 - w), f8 = u * v * w;
+  cx = sx * (t000.x * f1 + t001.x * f2 + t010.x * f3 + t011.x * f4 + t100.x * f5 + t101.x * f6 + t110.x * f7 + t111.x * f8);
+  cy = sy * (t000.y * f1 + t001.y * f2 + t010.y * f3 + t011.y * f4 + t100.y * f5 + t101.y * f6 + t110.y * f7 + t111.y * f8);
+  cz = sz * (t000.z * f1 + t001.z * f2 + t010.z * f3 + t011.z * f4 + t100.z * f5 + t101.z * f6 + t110.z * f7 + t111.z * f8);
+}
+__device__ __forceinline__ float wrap_image(float d, float box, float boxhalf) {
+  while (d > boxhalf) d -= box;
+  while (d < -boxhalf) d += box;
+  return d;
+}
 
 constexpr int kFlushEvery = 32;
 
+template <bool PER>
 __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +94,8 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
     const float4 A = __ldg(nd);              // s.xyz, mass
     const float4 Bv = __ldg(nd + 1);         // len2, bmax2, pinfo, skip
     const bool act = (no == cur);
-    const float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+    float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+    if (PER) { dx = wrap_image(dx, P.box, P.boxhalf); dy = wrap_image(dy, P.box, P.boxhalf); dz = wrap_image(dz, P.box, P.boxhalf); }
     const float r2 = dx * dx + dy * dy + dz * dz;
     // forcetree.c:967 / :1253-1257; oc = mass*len^4 formed exactly as the build stores it
     const bool open_b = Bv.x > r2 * theta2;
@@ -72,6 +105,11 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
       const float4 Cv = __ldg(nd + 2);       // Q11 Q22 Q33 Q12
       const float4 Dv = __ldg(nd + 3);       // Q13 Q23 P oc
       pn_force_fast(dx, dy, dz, r2, A.w, Cv.x, Cv.y, Cv.z, Cv.w, Dv.x, Dv.y, Dv.z, h_inv, h2, fx, fy, fz);
+      if (PER) {                             // forcetree.c:1076-1082
+        float ex, ey, ez;
+        ewald_corr(P.ewald, P.ewald_fac, dx, dy, dz, ex, ey, ez);
+        fx += A.w * ex; fy += A.w * ey; fz += A.w * ez;
+      }
       nnode++;
       no = __float_as_int(Bv.w);             // accept: jump over the subtree
     }
@@ -84,7 +122,17 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
       wparts += np;
       for (int k = 0; k < np; k++) {
         const float4 q = __ldg(lp + k);
-        if (open) { pp_force_fast(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, h2, fx, fy, fz); npart++; }
+        if (open) {
+          float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
+          if (PER) { px = wrap_image(px, P.box, P.boxhalf); py = wrap_image(py, P.box, P.boxhalf); pz = wrap_image(pz, P.box, P.boxhalf); }
+          pp_force_fast(px, py, pz, q.w, h_inv, h2, fx, fy, fz);
+          if (PER && (px * px + py * py + pz * pz) * h_inv * h_inv > 1.0e-8f) {     // u > 1e-4, forcetree.c:921-930
+            float ex, ey, ez;
+            ewald_corr(P.ewald, P.ewald_fac, px, py, pz, ex, ey, ez);
+            fx += q.w * ex; fy += q.w * ey; fz += q.w * ez;
+          }
+          npart++;
+        }
       }
     }
     if (++it == kFlushEvery) { ax += (double)fx; ay += (double)fy; az += (double)fz; fx = fy = fz = 0; it = 0; }
@@ -102,6 +150,53 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
     atomicAdd(&P.ctr[CT_PART], sp); atomicAdd(&P.ctr[CT_NODE], sn);
     atomicAdd(&P.ctr[CT_LIST_NODES], (unsigned long long)wnodes); atomicAdd(&P.ctr[CT_LIST_PARTS], (unsigned long long)wparts);
   }
+}
+
+// ------------------------------------------------------------------ Ewald tables
+// ewald_init() / ewald_force(), ewald.c:35-162, 332-381: correction force of the periodic images
+// of a unit point mass in a unit box (alpha = 2, |n|,|h| <= 4 per axis), tabulated on the
+// (ED+1)^3 grid of the first octant, then scaled by 1/L^2 (ewald.c:145-155).  One thread per
+// grid point, double precision, stored as float like the reference's tables.
+__global__ void k_ewald_table(float4 *tab, double inv_box2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int S1 = kEwaldD + 1;
+  if (idx >= S1 * S1 * S1) return;
+  const int i = idx / (S1 * S1), j = (idx / S1) % S1, k = idx % S1;
+  const double PI = 3.14159265358979323846, alpha = 2.0;
+  const double x[3] = {(double)i / kEwaldN, (double)j / kEwaldN, (double)k / kEwaldN};
+  double f[3] = {0, 0, 0};
+  const double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  if (r2 != 0) {
+    for (int a = 0; a < 3; a++) f[a] += x[a] / (r2 * sqrt(r2));
+    for (int n0 = -4; n0 <= 4; n0++) for (int n1 = -4; n1 <= 4; n1++) for (int n2 = -4; n2 <= 4; n2++) {
+      const double d[3] = {x[0] - n0, x[1] - n1, x[2] - n2};
+      const double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      const double val = erfc(alpha * r) + 2 * alpha * r / sqrt(PI) * exp(-alpha * alpha * r * r);
+      for (int a = 0; a < 3; a++) f[a] -= d[a] / (r * r * r) * val;
+    }
+    for (int h0 = -4; h0 <= 4; h0++) for (int h1 = -4; h1 <= 4; h1++) for (int h2_ = -4; h2_ <= 4; h2_++) {
+      const int hh = h0 * h0 + h1 * h1 + h2_ * h2_;
+      if (hh > 0) {
+        const double hdotx = x[0] * h0 + x[1] * h1 + x[2] * h2_;
+        const double val = 2.0 / ((double)hh) * exp(-PI * PI * hh / (alpha * alpha)) * sin(2 * PI * hdotx);
+        f[0] -= h0 * val; f[1] -= h1 * val; f[2] -= h2_ * val;
+      }
+    }
+  }
+  // the reference stores the unit-box value as float, then divides the float by L^2 (a double)
+  tab[idx] = make_float4((float)((double)(float)f[0] * inv_box2), (float)((double)(float)f[1] * inv_box2), (float)((double)(float)f[2] * inv_box2), 0.f);
+}
+
+int ewald_tables(const float4 **out) {
+  const int S1 = kEwaldD + 1, n = S1 * S1 * S1;
+  if (!g.d_ewald && cudaMalloc((void **)&g.d_ewald, (size_t)n * sizeof(float4)) != cudaSuccess) return B200_ERR_ALLOC;
+  if (g.ewald_box != g.par.BoxSize) {
+    k_ewald_table<<<cdiv(n, 128), 128, 0, g.stream>>>(g.d_ewald, 1.0 / (g.par.BoxSize * g.par.BoxSize));
+    count_launch();
+    g.ewald_box = g.par.BoxSize;
+  }
+  *out = g.d_ewald;
+  return B200_OK;
 }
 
 // sorted target list for an explicit active list: order the slots along the key order so a
@@ -146,7 +241,13 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, 4 * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  if (nt > 0) { k_walk<<<cdiv(nt, 256), 256, 0, g.stream>>>(P); count_launch(); }
+  const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+  P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
+  if (per) { B200_TRY(ewald_tables(&P.ewald)); }
+  if (nt > 0) {
+    if (per) k_walk<true><<<cdiv(nt, 256), 256, 0, g.stream>>>(P); else k_walk<false><<<cdiv(nt, 256), 256, 0, g.stream>>>(P);
+    count_launch();
+  }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -254,7 +355,8 @@ __device__ __forceinline__ double soft_force_d(double u) {
   if (u <= 0.5) return 32.0 * (1.0 / 3 - 6.0 / 5 * u * u + u * u * u);
   return 64.0 * (1.0 / 3 - 3.0 / 4 * u + 3.0 / 5 * u * u - u * u * u / 6) - 1.0 / 15 / (u * u * u);
 }
-__global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int n, const float4 *posm, double h_inv, double *acc) {
+__global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int n, const float4 *posm, double h_inv, double *acc,
+                                                double box, const float4 *ewald, float ewald_fac) {
   __shared__ float4 tile[128];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   float4 tp = make_float4(0, 0, 0, 0);
@@ -267,13 +369,23 @@ __global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int 
     const int lim = min(128, n - base);
     for (int k = 0; k < lim; k++) {
       const float4 q = tile[k];
-      const double dx = (double)q.x - (double)tp.x, dy = (double)q.y - (double)tp.y, dz = (double)q.z - (double)tp.z;
+      double dx = (double)q.x - (double)tp.x, dy = (double)q.y - (double)tp.y, dz = (double)q.z - (double)tp.z;
+      if (box > 0) {                     // forcetree.c:1931-1938
+        const double bh = 0.5 * box;
+        while (dx > bh) dx -= box; while (dy > bh) dy -= box; while (dz > bh) dz -= box;
+        while (dx < -bh) dx += box; while (dy < -bh) dy += box; while (dz < -bh) dz += box;
+      }
       const double r2 = dx * dx + dy * dy + dz * dz;
       const double r = sqrt(r2), u = r * h_inv;
       double fac = 0;
       if (u >= 1) fac = (double)q.w / (r2 * r);
       else if (u > 1.0e-4) fac = (double)q.w * h_inv * h_inv * h_inv * soft_force_d(u);
       ax += dx * fac; ay += dy * fac; az += dz * fac;
+      if (box > 0 && u > 1.0e-4) {       // forcetree.c:1963-1971
+        float ex, ey, ez;
+        ewald_corr(ewald, ewald_fac, (float)dx, (float)dy, (float)dz, ex, ey, ez);
+        ax += (double)q.w * ex; ay += (double)q.w * ey; az += (double)q.w * ez;
+      }
     }
     __syncthreads();
   }
@@ -284,7 +396,11 @@ int direct_impl(const int *targets, int nt, double *acc_out) {
   if (nt <= 0) return B200_OK;
   if (nt > g.maxpart) return B200_ERR_ARG;
   CUDA_TRY(cudaMemcpyAsync(g.d_active, targets, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, g.stream));
-  k_direct<<<cdiv(nt, 128), 128, 0, g.stream>>>(nt, g.d_active, g.n, g.posm, (double)h_inv_of_type1(), g.d_acc);
+  const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+  const float4 *ew = nullptr;
+  if (per) { B200_TRY(ewald_tables(&ew)); }
+  k_direct<<<cdiv(nt, 128), 128, 0, g.stream>>>(nt, g.d_active, g.n, g.posm, (double)h_inv_of_type1(), g.d_acc,
+                                                per ? g.par.BoxSize : 0.0, ew, per ? (float)(kEwaldN / g.par.BoxSize) : 0.f);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(acc_out, g.d_acc, (size_t)nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));

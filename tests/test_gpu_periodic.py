@@ -1,0 +1,127 @@
+"""GPU: periodic box (BASELINE config C4 ingredients): nearest-image tree walk with the Ewald
+correction (ewald.c) and the periodic neighbour search, against the unmodified reference
+built with -DPERIODIC (oracle/_ref/libsidmref_per.so)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+BOX = 100.0
+EPS = 0.5
+
+
+def rel_rms(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+@pytest.fixture(scope="module")
+def world(refdrv_mod):
+    if not refdrv_mod.available("periodic"):
+        pytest.skip("oracle/_ref/libsidmref_per.so not built")
+    from sidm_b200 import HotPath, ic
+    pos, vel, mass, ids = ic.periodic_box(24, seed=4, box=BOX, vel_sigma=50.0)
+    n = len(mass)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    R = refdrv_mod.Reference("periodic")
+    R.setup(n, BoxSize=BOX, SofteningHalo=EPS)          # runs the reference's ewald_init()
+    R.set_particles(pos, vel, mass, ids)
+    R.treebuild()
+    table = np.fromfile("ewald_table_64.dat", np.float32).reshape(4, 33, 33, 33)
+    hp = HotPath(n, BoxSize=BOX, PeriodicBoundariesOn=1, SofteningHalo=EPS, ReferenceNgbOrder=1)
+    hp.set_particles(pos, vel, mass, ids)
+    hp.force_treebuild()
+    yield dict(R=R, hp=hp, pos=pos, n=n, table=table)
+    hp.close()
+    os.chdir(cwd)
+
+
+def test_ewald_table(world):
+    """k_ewald_table vs the table the reference writes (ewald.c:35-162), both scaled by 1/L^2"""
+    hp, tab = world["hp"], world["table"]
+    idx = np.arange(0, world["n"], 97, dtype=np.int32)
+    hp.force_treeevaluate(idx)                           # first periodic walk builds the table
+    mine = hp.peek("ewald", np.float32, (33, 33, 33, 4))
+    ref = np.stack([tab[0], tab[1], tab[2]], axis=-1) / np.float32(BOX * BOX)
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(mine[..., :3] - ref)) < 2e-6 * scale
+
+
+def test_periodic_forces(world):
+    R, hp, n = world["R"], world["hp"], world["n"]
+    idx = np.arange(0, n, 13, dtype=np.int32)
+    R.set("OLDACC", np.zeros(n, np.float32))
+    acc_r, cost_r = R.force_tree(idx)                    # BH
+    hp.set_particles(oldacc=np.zeros(n, np.float32))
+    acc, cost = hp.force_treeevaluate(idx)
+    assert rel_rms(acc, acc_r) < 1e-4
+    assert (cost == cost_r).all(axis=1).mean() > 0.995
+    d, d_r = hp.force_treeevaluate_direct(idx), R.force_direct(idx)
+    assert rel_rms(d, d_r) < 1e-4
+    # relative criterion with OldAcc from the BH forces
+    full = np.arange(n, dtype=np.int32)
+    af, _ = R.force_tree(full, want_cost=False)
+    a32 = af.astype(np.float32)
+    oa = np.sqrt((a32[:, 0] * a32[:, 0] + a32[:, 1] * a32[:, 1] + a32[:, 2] * a32[:, 2]).astype(np.float64)).astype(np.float32)
+    R.set("OLDACC", oa)
+    hp.set_particles(oldacc=oa)
+    acc_r, cost_r = R.force_tree(idx)
+    acc, cost = hp.force_treeevaluate(idx)
+    assert rel_rms(acc, acc_r) < 1e-4
+    assert (cost == cost_r).all(axis=1).mean() > 0.995
+
+
+def test_periodic_neighbours(world):
+    R, hp, pos, n = world["R"], world["hp"], world["pos"], world["n"]
+    idx = np.concatenate([np.arange(0, n, 61), np.argsort(pos[:, 0])[:40], np.argsort(-pos[:, 2])[:40]]).astype(np.int32)
+    h2 = hp.ngb_treefind(idx, 30)
+    ref = np.array([R.ngb_treefind(pos[i], 30) for i in idx], np.float32)
+    assert np.array_equal(h2, ref)                      # k-NN distances across the box faces
+    h = np.zeros(n, np.float32)
+    h[idx] = np.sqrt(h2.astype(np.float64)).astype(np.float32) * np.float32(1.1)
+    hp.set_particles(hsml=h)
+    cnt, lst = hp.ngb_lists(idx, cap=512)
+    for k, i in enumerate(idx):
+        rl, _ = R.ngb_variable(pos[i], h[i])
+        assert cnt[k] == len(rl)
+        assert np.array_equal(lst[k, :cnt[k]], rl), f"periodic neighbour list of particle {i} differs"
+
+
+def test_comoving_periodic_gravity_tree(refdrv_mod):
+    """gravity_tree() with ComovingIntegrationOn + periodic box: prediction with dt/S(a), the
+    OldAcc and fac1/fac2 combination of gravtree.c:252-298 (run in a fresh process: one reference
+    library instance holds one configuration)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, tempfile, numpy as np
+sys.path.insert(0, "oracle"); sys.path.insert(0, "sidm-nbody_b200")
+import refdrv
+from sidm_b200 import HotPath, ic
+BOX, EPS, A = 100.0, 0.5, 0.1
+pos, vel, mass, ids = ic.periodic_box(20, seed=5, box=BOX, vel_sigma=30.0)
+n = len(mass)
+root = os.getcwd(); os.chdir(tempfile.mkdtemp())
+R = refdrv.Reference("periodic")
+R.setup(n, BoxSize=BOX, SofteningHalo=EPS, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1, Time=A)
+R.set_particles(pos, vel, mass, ids)
+R.all_active(A, A * 1.01)
+R.gravity_tree(); R.gravity_tree()
+os.chdir(root)
+hp = HotPath(n, BoxSize=BOX, PeriodicBoundariesOn=1, SofteningHalo=EPS, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1)
+hp.set_particles(pos, vel, mass, ids, curtime=np.full(n, A, np.float32))
+t = R.time
+for rep in range(2):
+    hp.predict_collisionless_only(t); hp.force_treebuild(); hp.gravity_tree(time=t)
+acc, oa, pp, vp = hp.get("Accel", "OldAcc", "PosPred", "VelPred")
+ar, orr = R.get("ACCEL").astype(np.float64), R.get("OLDACC")
+assert np.array_equal(pp, R.get("POSPRED")), "PosPred"
+err = np.sqrt(((acc - ar) ** 2).sum() / (ar ** 2).sum())
+print("comoving rel rms", err, float(np.max(np.abs(oa / orr - 1))))
+assert err < 1e-4 and np.allclose(oa, orr, rtol=1e-3)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
