@@ -25,7 +25,10 @@ typedef struct oparams {
   double eps;              /* Plummer softening of the (single) particle type */
   double G;
   int    des_ngb, max_dev; /* All.DesNumNgb, All.MaxNumNgbDeviation */
-  double sigma;            /* All.CrossSectionInternal (hard sphere, CROSS_SECTION_TYPE 0) */
+  double sigma;            /* All.CrossSectionInternal */
+  int    xs_type;          /* the reference's compile-time CROSS_SECTION_TYPE, 0..3 (sidm.c:226-316, 366-382) */
+  double vc;               /* All.YukawaVelocity        (type 2) */
+  double pl_n, pl_v0;      /* All.CrossSectionPowLaw, All.CrossSectionVelScale (type 3) */
 } oparams;
 
 /* ---- tree (forcetree.c:90-571) ---- */

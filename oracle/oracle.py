@@ -15,7 +15,8 @@ LIB = os.path.join(HERE, "liboracle.so")
 
 class OParams(C.Structure):
     _fields_ = [("theta", C.c_double), ("alpha", C.c_double), ("criterion", C.c_int), ("eps", C.c_double),
-                ("G", C.c_double), ("des_ngb", C.c_int), ("max_dev", C.c_int), ("sigma", C.c_double)]
+                ("G", C.c_double), ("des_ngb", C.c_int), ("max_dev", C.c_int), ("sigma", C.c_double),
+                ("xs_type", C.c_int), ("vc", C.c_double), ("pl_n", C.c_double), ("pl_v0", C.c_double)]
 
 
 class OSidmOut(C.Structure):
@@ -73,13 +74,13 @@ class Oracle:
     """Holds one particle set; mirrors the reference's call sequence on it."""
 
     def __init__(self, pos, vel, mass, theta=0.5, alpha=0.005, criterion=1, eps=0.3, G=43007.1, des_ngb=30,
-                 max_dev=2, sigma=2.089):
+                 max_dev=2, sigma=2.089, xs_type=0, vc=0.0, pl_n=0.0, pl_v0=1.0):
         self.L = lib()
         self.pos = np.ascontiguousarray(pos, np.float32)
         self.vel = np.ascontiguousarray(vel, np.float32)
         self.mass = np.ascontiguousarray(mass, np.float32)
         self.n = len(self.mass)
-        self.par = OParams(theta, alpha, criterion, eps, G, des_ngb, max_dev, sigma)
+        self.par = OParams(theta, alpha, criterion, eps, G, des_ngb, max_dev, sigma, xs_type, vc, pl_n, pl_v0)
         self.tree = None
         self.hsml = np.zeros(self.n, np.float32)
         self.dvel = np.zeros((self.n, 3), np.float32)

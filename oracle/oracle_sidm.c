@@ -122,7 +122,14 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
   }
   free(exp);
 
-  const double C_Pmax = 1.0 * (3. / 4. / 3.14159265358979323846) * (p->des_ngb + p->max_dev) * 2 * vmax * p->sigma;   /* sidm.c:278-280 */
+  const double ball = 1.0 * (3. / 4. / 3.14159265358979323846) * (p->des_ngb + p->max_dev);
+  double C_Pmax;                                            /* sidm.c:276-314, non-comoving branch */
+  if (p->xs_type == 1) C_Pmax = ball * p->sigma;
+  else if (p->xs_type == 2) {
+    if (2.0 * vmax < p->vc / sqrt(3.0)) { double beta = 2.0 * vmax / p->vc, v_dep = 1.0 / (1.0 + beta * beta); C_Pmax = ball * 2.0 * vmax * v_dep * v_dep * p->sigma; }
+    else C_Pmax = ball * (3.0 * sqrt(3.0) / 16.0) * p->vc * p->sigma;
+  } else if (p->xs_type == 3) C_Pmax = ball * 2 * p->pl_v0 * p->sigma;
+  else C_Pmax = ball * 2 * vmax * p->sigma;
   const double sigma = p->sigma;
   int cap = t ? 0 : 0; (void)cap;
   int lcap = 65536; int *list = malloc(sizeof(int) * lcap); float *r2l = malloc(sizeof(float) * lcap);
@@ -153,7 +160,10 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
       }
       double rvx = vel[3 * i] - vel[3 * j], rvy = vel[3 * i + 1] - vel[3 * j + 1], rvz = vel[3 * i + 2] - vel[3 * j + 2];   /* float sub */
       double rv = sqrt(rvx * rvx + rvy * rvy + rvz * rvz);
-      Prob += 0.5 * mass[j] * wk * rv * sigma * dt_h0;
+      if (p->xs_type == 1) Prob += 0.5 * mass[j] * wk * sigma * dt_h0;                       /* sidm.c:374 */
+      else if (p->xs_type == 2) { double beta = rv / p->vc, v_dep = 1.0 / (1.0 + beta * beta); Prob += 0.5 * mass[j] * wk * rv * v_dep * v_dep * sigma * dt_h0; }
+      else if (p->xs_type == 3) Prob += 0.5 * mass[j] * wk * rv * pow(rv / p->pl_v0, p->pl_n) * sigma * dt_h0;
+      else Prob += 0.5 * mass[j] * wk * rv * sigma * dt_h0;                                  /* sidm.c:372 */
       if (Prob < rnd) continue;
       out->partner[s] = j;
       double rmass = mass[j] / (mass[i] + mass[j]);         /* float expr widened */

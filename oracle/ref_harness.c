@@ -56,6 +56,7 @@ typedef struct ref_cfg {
   double BoxSize;
   double Omega0, OmegaLambda, Hubble;
   double Time;
+  double YukawaVelocity, CrossSectionPowLaw, CrossSectionVelScale;
 } ref_cfg;
 
 static int ref_ready = 0;
@@ -96,6 +97,11 @@ int ref_setup(const ref_cfg *c)
   All.CrossSectionInternal = c->CrossSectionInternal;
   All.CrossSection = c->CrossSectionInternal;
   All.ProbabilityTol = c->ProbabilityTol;
+#if (CROSS_SECTION_TYPE == 2 || CROSS_SECTION_TYPE == 4)
+  All.YukawaVelocity = c->YukawaVelocity;
+#elif (CROSS_SECTION_TYPE == 3)
+  All.CrossSectionPowLaw = c->CrossSectionPowLaw; All.CrossSectionVelScale = c->CrossSectionVelScale;
+#endif
   All.Seed1 = c->Seed1; All.Seed2 = c->Seed2;
   All.BoxSize = c->BoxSize; All.BoxHalf = c->BoxSize / 2;
   All.Omega0 = c->Omega0; All.OmegaLambda = c->OmegaLambda; All.Hubble = c->Hubble;

@@ -34,7 +34,8 @@ class RefCfg(C.Structure):
                 ("CrossSectionInternal", C.c_double), ("ProbabilityTol", C.c_double),
                 ("Seed1", C.c_int), ("Seed2", C.c_int), ("BoxSize", C.c_double),
                 ("Omega0", C.c_double), ("OmegaLambda", C.c_double), ("Hubble", C.c_double),
-                ("Time", C.c_double)]
+                ("Time", C.c_double), ("YukawaVelocity", C.c_double), ("CrossSectionPowLaw", C.c_double),
+                ("CrossSectionVelScale", C.c_double)]
 
 
 DEFAULTS = dict(BufferSizeMB=100, TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolForceAcc=0.005,
@@ -42,12 +43,13 @@ DEFAULTS = dict(BufferSizeMB=100, TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolFo
                 TreeUpdateFrequency=0.0, G=43007.1, SofteningHalo=0.3, DesNumNgb=30,
                 MaxNumNgbDeviation=2, CrossSectionInternal=2.089, ProbabilityTol=0.2,
                 Seed1=55, Seed2=497527, BoxSize=0.0, Omega0=1.0, OmegaLambda=0.0, Hubble=0.1,
-                Time=0.0)
+                Time=0.0, YukawaVelocity=0.0, CrossSectionPowLaw=0.0, CrossSectionVelScale=1.0)
 
 
 def lib_path(kind="diag"):
     name = {"diag": "libsidmref.so", "fast": "libsidmref_fast.so", "periodic": "libsidmref_per.so",
-            "b200": "libsidmref_b200.so"}[kind]
+            "b200": "libsidmref_b200.so", "x1": "libsidmref_x1.so", "x2": "libsidmref_x2.so",
+            "x3": "libsidmref_x3.so"}[kind]
     return os.path.join(HERE, "_ref", name)
 
 

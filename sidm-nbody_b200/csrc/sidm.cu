@@ -518,6 +518,14 @@ static int ensure_sidm_buffers() {
   return B200_OK;
 }
 
+// called by b200_finalize(): the buffers above are sized by the MaxPart of one b200_init()
+void sidm_release() {
+  void **ptrs[] = {(void **)&S.snode, (void **)&S.snodef, (void **)&S.last_active, (void **)&S.slot_of_sorted, (void **)&S.passlist,
+                   (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot};
+  for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+  S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false;
+}
+
 static int cub_scratch(size_t tb) {
   if (tb <= g.cub_tmp_bytes) return B200_OK;
   if (g.cub_tmp) cudaFree(g.cub_tmp);

@@ -327,7 +327,8 @@ int gravity_impl(const int *active, int nactive, double time) {
   if (g.shard_world > 1) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw)); work = g.d_shard_list; }
   B200_TRY(walk_impl(work, nw, active != nullptr));
   EpiParams E;
-  E.nt = nw; E.list = work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
+  // all particles on one rank: run the epilogue in particle order (coalesced) instead of key order
+  E.nt = nw; E.list = (!active && g.shard_world == 1) ? nullptr : work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
   E.posm = g.posm; E.velpred = g.velpred; E.accel = g.accel; E.oldacc = g.oldacc; E.gravcost = g.gravcost;
   E.criterion = g.par.TypeOfOpeningCriterion; E.comoving = g.par.ComovingIntegrationOn;
   E.periodic = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
