@@ -247,7 +247,9 @@ B200_HD void pn_force(float dx, float dy, float dz, float r2, const NodeRec &n, 
 // inside the 1e-4 tolerance); the softened branch (r < h) is rare and keeps the spline.
 B200_HD float rsqrt_fast(float x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(x);
+  float y;                                   // one MUFU.RSQ, no denormal fix-up (r2 >= h^2 here)
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 #else
   return 1.0f / sqrtf(x);
 #endif

@@ -66,6 +66,73 @@ __device__ __forceinline__ float wrap_image(float d, float box, float boxhalf) {
 
 constexpr int kFlushEvery = 32;
 
+// MODE: 0 = lanes of this warp use different criteria, 1 = all relative (forcetree.c:1097),
+// 2 = all BH (forcetree.c:817); the choice is warp-uniform, the arithmetic identical.
+template <bool PER, int MODE>
+__device__ __forceinline__ void walk_loop(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no,
+                                          double &ax, double &ay, double &az, int &npart, int &nnode, unsigned &wnodes, unsigned &wparts) {
+  const float h_inv = P.h_inv, theta2 = P.theta2;
+  const float h2 = 1.0f / (h_inv * h_inv);
+  const int M = P.num_nodes;
+  const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
+  int cur = __reduce_min_sync(0xffffffffu, no);
+  while (cur < M) {
+    float fx = 0, fy = 0, fz = 0;
+    // float partial sums over <= kFlushEvery cells, then one flush into the double accumulators
+    for (int it = 0; it < kFlushEvery && cur < M; it++) {
+      const float4 *nd = nodes4 + 4 * (size_t)cur;
+      const float4 A = __ldg(nd);              // s.xyz, mass
+      const float4 Bv = __ldg(nd + 1);         // len2, bmax2, pinfo, skip
+      const bool act = (no == cur);
+      float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+      if (PER) { dx = wrap_image(dx, P.box, P.boxhalf); dy = wrap_image(dy, P.box, P.boxhalf); dz = wrap_image(dz, P.box, P.boxhalf); }
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      // forcetree.c:967 / :1253-1257; oc = mass*len^4 formed exactly as the build stores it
+      bool crit;
+      if (MODE == 2) crit = Bv.x > r2 * theta2;
+      else if (MODE == 1) crit = (fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y);
+      else crit = bh ? (Bv.x > r2 * theta2) : ((fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y));
+      const bool open = act && crit;
+      if (act && !crit) {
+        const float4 Cv = __ldg(nd + 2);       // Q11 Q22 Q33 Q12
+        const float4 Dv = __ldg(nd + 3);       // Q13 Q23 P oc
+        pn_force_fast(dx, dy, dz, r2, A.w, Cv.x, Cv.y, Cv.z, Cv.w, Dv.x, Dv.y, Dv.z, h_inv, h2, fx, fy, fz);
+        if (PER) {                             // forcetree.c:1076-1082
+          float ex, ey, ez;
+          ewald_corr(P.ewald, P.ewald_fac, dx, dy, dz, ex, ey, ez);
+          fx += A.w * ex; fy += A.w * ey; fz += A.w * ez;
+        }
+        nnode++;
+        no = __float_as_int(Bv.w);             // accept: jump over the subtree
+      }
+      if (open) no = cur + 1;
+      wnodes++;
+      if (__any_sync(0xffffffffu, open)) {
+        const int pinfo = __float_as_int(Bv.z);
+        const int np = pinfo & 15;
+        const float4 *lp = P.leaf_posm + (pinfo >> 4);
+        wparts += np;
+        for (int k = 0; k < np; k++) {
+          const float4 q = __ldg(lp + k);
+          if (open) {
+            float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
+            if (PER) { px = wrap_image(px, P.box, P.boxhalf); py = wrap_image(py, P.box, P.boxhalf); pz = wrap_image(pz, P.box, P.boxhalf); }
+            pp_force_fast(px, py, pz, q.w, h_inv, h2, fx, fy, fz);
+            if (PER && (px * px + py * py + pz * pz) * h_inv * h_inv > 1.0e-8f) {     // u > 1e-4, forcetree.c:921-930
+              float ex, ey, ez;
+              ewald_corr(P.ewald, P.ewald_fac, px, py, pz, ex, ey, ez);
+              fx += q.w * ex; fy += q.w * ey; fz += q.w * ez;
+            }
+            npart++;
+          }
+        }
+      }
+      cur = __reduce_min_sync(0xffffffffu, no);
+    }
+    ax += (double)fx; ay += (double)fy; az += (double)fz;
+  }
+}
+
 template <bool PER>
 __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31;
@@ -77,68 +144,14 @@ __global__ void __launch_bounds__(256) k_walk(WalkParams P) {
   if (valid) { tp = P.posm[part]; oa = P.oldacc[part]; }
   const bool bh = (P.criterion == 0) || (oa == 0.0f);          // forcetree.c:801
   const float oac = oa * P.alpha;                               // forcetree.c:1129
-  const float h_inv = P.h_inv, theta2 = P.theta2;
-  const float h2 = 1.0f / (h_inv * h_inv);
-  const int M = P.num_nodes;
-  const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
-
   int no = valid ? 0 : 0x7fffffff;
-  int cur = __reduce_min_sync(0xffffffffu, no);
   double ax = 0, ay = 0, az = 0;
-  float fx = 0, fy = 0, fz = 0;
-  int npart = 0, nnode = 0, it = 0;
+  int npart = 0, nnode = 0;
   unsigned wnodes = 0, wparts = 0;
-
-  while (cur < M) {
-    const float4 *nd = nodes4 + 4 * (size_t)cur;
-    const float4 A = __ldg(nd);              // s.xyz, mass
-    const float4 Bv = __ldg(nd + 1);         // len2, bmax2, pinfo, skip
-    const bool act = (no == cur);
-    float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
-    if (PER) { dx = wrap_image(dx, P.box, P.boxhalf); dy = wrap_image(dy, P.box, P.boxhalf); dz = wrap_image(dz, P.box, P.boxhalf); }
-    const float r2 = dx * dx + dy * dy + dz * dz;
-    // forcetree.c:967 / :1253-1257; oc = mass*len^4 formed exactly as the build stores it
-    const bool open_b = Bv.x > r2 * theta2;
-    const bool open_r = (fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y);
-    const bool open = act && (bh ? open_b : open_r);
-    if (act && !open) {
-      const float4 Cv = __ldg(nd + 2);       // Q11 Q22 Q33 Q12
-      const float4 Dv = __ldg(nd + 3);       // Q13 Q23 P oc
-      pn_force_fast(dx, dy, dz, r2, A.w, Cv.x, Cv.y, Cv.z, Cv.w, Dv.x, Dv.y, Dv.z, h_inv, h2, fx, fy, fz);
-      if (PER) {                             // forcetree.c:1076-1082
-        float ex, ey, ez;
-        ewald_corr(P.ewald, P.ewald_fac, dx, dy, dz, ex, ey, ez);
-        fx += A.w * ex; fy += A.w * ey; fz += A.w * ez;
-      }
-      nnode++;
-      no = __float_as_int(Bv.w);             // accept: jump over the subtree
-    }
-    if (open) no = cur + 1;
-    wnodes++;
-    if (__any_sync(0xffffffffu, open)) {
-      const int pinfo = __float_as_int(Bv.z);
-      const int np = pinfo & 15;
-      const float4 *lp = P.leaf_posm + (pinfo >> 4);
-      wparts += np;
-      for (int k = 0; k < np; k++) {
-        const float4 q = __ldg(lp + k);
-        if (open) {
-          float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
-          if (PER) { px = wrap_image(px, P.box, P.boxhalf); py = wrap_image(py, P.box, P.boxhalf); pz = wrap_image(pz, P.box, P.boxhalf); }
-          pp_force_fast(px, py, pz, q.w, h_inv, h2, fx, fy, fz);
-          if (PER && (px * px + py * py + pz * pz) * h_inv * h_inv > 1.0e-8f) {     // u > 1e-4, forcetree.c:921-930
-            float ex, ey, ez;
-            ewald_corr(P.ewald, P.ewald_fac, px, py, pz, ex, ey, ez);
-            fx += q.w * ex; fy += q.w * ey; fz += q.w * ez;
-          }
-          npart++;
-        }
-      }
-    }
-    if (++it == kFlushEvery) { ax += (double)fx; ay += (double)fy; az += (double)fz; fx = fy = fz = 0; it = 0; }
-    cur = __reduce_min_sync(0xffffffffu, no);
-  }
-  ax += (double)fx; ay += (double)fy; az += (double)fz;
+  const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
+  if (all_rel) walk_loop<PER, 1>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
+  else if (all_bh) walk_loop<PER, 2>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
+  else walk_loop<PER, 0>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
   if (valid) {
     P.acc[3 * (size_t)slot] = ax; P.acc[3 * (size_t)slot + 1] = ay; P.acc[3 * (size_t)slot + 2] = az;
     P.cost[2 * (size_t)slot] = npart; P.cost[2 * (size_t)slot + 1] = nnode;
