@@ -33,7 +33,8 @@ struct __attribute__((aligned(16))) SearchNode { double lo[3], hi[3]; int skip, 
 // wholesale does not change the candidate order (always ascending leaf index) nor the set
 // (every candidate still passes the exact float sphere test).  32 bytes instead of 64 halves
 // the L1 traffic of the divergent per-lane loads that bound this kernel (ncu: l1tex 83 % busy).
-struct __attribute__((aligned(16))) SearchNodeF { float lo[3], hi[3]; int skip; int pinfo; };   // pinfo = pstart<<4 | np
+struct __attribute__((aligned(16))) SearchNodeF { float lo[3], hi[3]; int skip; int pinfo; };   // pinfo = pstart<<5 | bucket<<4 | np
+constexpr int kBucket = 8;   // subtrees with <= kBucket particles are scanned as one leaf range instead of being descended
 
 struct SidmState {
   SearchNode *snode = nullptr;
@@ -201,10 +202,11 @@ __device__ __forceinline__ void range_search_fast(const SearchCtx &C, bool valid
     const float4 *q = reinterpret_cast<const float4 *>(C.snodef + no);
     const float4 a = __ldg(q), b = __ldg(q + 1);                  // lo.xyz hi.x | hi.yz skip pinfo
     const int skip = __float_as_int(b.z), pinfo = __float_as_int(b.w);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(C.snodef + skip));     // the jump target, if this cell is skipped or taken whole
     if (a.w < lox || a.x > hix || b.x < loy || a.y > hiy || b.y < loz || a.z > hiz) { no = skip; continue; }
     bulk = (a.x >= lox) && (a.w <= hix) && (a.y >= loy) && (b.x <= hiy) && (a.z >= loz) && (b.y <= hiz);
-    pnode = no; pk = pinfo >> 4;
-    if (bulk) { pe = C.snodef[skip].pinfo >> 4; no = skip; } else { pe = pk + (pinfo & 15); no = no + 1; }
+    pnode = no; pk = pinfo >> 5;
+    if (bulk) { pe = C.snodef[skip].pinfo >> 5; no = skip; } else { pe = pk + (pinfo & 15); no = (pinfo & 16) ? skip : no + 1; }
   }
 }
 
@@ -225,9 +227,11 @@ __global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, 
     if ((double)h < s.hi[k]) h = nextafterf(h, INFINITY);
     t.lo[k] = l; t.hi[k] = h;
   }
-  t.skip = skip; t.pinfo = (s.pstart << 4) | s.np;
+  const int cnt = s.pend - s.pstart;
+  const int bucket = (cnt <= kBucket && id > 0) ? 1 : 0;
+  t.skip = skip; t.pinfo = (s.pstart << 5) | (bucket << 4) | (bucket ? cnt : s.np);
   outf[id] = t;
-  if (id == m - 1) { SearchNodeF e; for (int k = 0; k < 3; k++) { e.lo[k] = 0; e.hi[k] = 0; } e.skip = m; e.pinfo = npstart[m] << 4; outf[m] = e; }
+  if (id == m - 1) { SearchNodeF e; for (int k = 0; k < 3; k++) { e.lo[k] = 0; e.hi[k] = 0; } e.skip = m; e.pinfo = npstart[m] << 5; outf[m] = e; }
 }
 
 // ------------------------------------------------------------------ slots
@@ -268,7 +272,7 @@ struct Pass1 {
   const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
   int *ngb; double *pmax, *rnd; int *pass; int count_only; unsigned long long *ctr;
 };
-__global__ void __launch_bounds__(128) k_pass1(Pass1 P) {
+__global__ void __launch_bounds__(128, 16) k_pass1(Pass1 P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < P.ns;
   const int s = valid ? P.order[t] : 0;
