@@ -261,7 +261,8 @@ __global__ void k_assign_slots(int na, const int *active, const int *flag, const
   slot_of_active[a] = place;
   dt[place] = (float)(2 * (time - (double)curtime[i]));             // sidm.c:196
   already[place] = dvel[3 * (size_t)i] != 0.0f;                    // sidm.c:189-192 (ID = 0)
-  keys[a] = krank[i]; vals[a] = place;
+  if (active) { keys[a] = krank[i]; vals[a] = place; }
+  else vals[krank[i]] = place;          // every particle active: the key order is the tree build's own order
   if (a == 0) flags_out[FL_NEXPORT] = nexport;
 }
 
@@ -602,14 +603,17 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     B200_TRY(cub_scratch(tb));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb, g.s_flag, g.s_pos, nb + 1, st));
     int *slot_of_active = g.s_repair;     // scratch
-    k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
-                                    g.krank, g.d_tkeys, g.d_tvals2, g.d_flags);
     // processing order: slots sorted along the tree key order (spatial coherence inside a warp)
-    size_t tb2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st);
-    B200_TRY(cub_scratch(tb2));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st));
-    count_launch(2 + 2 + 4);
+    k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
+                                    g.krank, g.d_tkeys, act ? g.d_tvals2 : S.slot_of_sorted, g.d_flags);
+    count_launch(4);
+    if (act) {
+      size_t tb2 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st);
+      B200_TRY(cub_scratch(tb2));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st));
+      count_launch(4);
+    }
     // replay arrays
     const double *d_rr = nullptr, *d_rd = nullptr;
     if (replay && replay->rand && !count_only) {
