@@ -299,8 +299,14 @@ def main_b200(args):
     walk_bytes = a_per_launch * 32 + warps * (48 * i_n + 16 * i_p)
     achieved = walk_bytes / (wms * 1e-3) / 1e9
     flops = (inter_n * 70.0 + inter_p * 20.0) / args.steps
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tj) and world == 1:
+        t = json.load(open(tj))
+        if int(t.get("particles", 0)) == n:
+            traffic = t["traffic_bytes_per_launch"]      # ncu dram read+write bytes of one k_walk launch (profiles/)
     roofline = {"bound": "hbm", "kernel": "k_walk", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": wms,
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": wms,
                 "algorithmic_bytes_per_launch": walk_bytes, "I_n_per_warp": i_n, "I_p_per_warp": i_p,
                 "interactions_per_target": {"node": inter_n / max(1, ntarg), "particle": inter_p / max(1, ntarg)},
                 "fp32_tflops_est": flops / (wms * 1e-3) / 1e12,
