@@ -372,9 +372,9 @@ def run_e2e(hp, sh, n, mass, ids, vmax, tcur, args, world, rank, step_fn):
 
     def one(k):
         hp.bind_particles(snaps[k % nsnap], pin=False)
-        hp.upload()
+        sh.upload()                                  # own rows over PCIe (+ NVLink all-gather when sharded)
         sh.compute_accelerations(0, time=times[k % nsnap], vmax=vmax)
-        hp.download(into=out)
+        sh.download(into=out)
         return int(hp.counters().sct_scattered)
 
     steps = max(2, min(args.steps, 5))
@@ -392,7 +392,9 @@ def run_e2e(hp, sh, n, mass, ids, vmax, tcur, args, world, rank, step_fn):
         dt = float(tt.item())
     for a in snaps + [out]:
         rt.cudaHostUnregister(a.ctypes.data)
-    return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(snaps[0].nbytes), "d2h_bytes_per_step": int(out.nbytes),
+    rows = sh.rows()[1] if world > 1 else n
+    return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(rows * snaps[0].itemsize * world),
+            "d2h_bytes_per_step": int(rows * out.itemsize * world),
             "steps": steps, "ms_per_step": dt / steps * 1e3,
             "api": "b200_bind_particles + b200_upload + b200_compute_accelerations(0) + b200_download_to on pinned 124-byte particle_data arrays (successive states of the run)"}
 

@@ -138,6 +138,13 @@ int  b200_download(void);                      /* device -> host AoS (fields the
                                                   PosPred VelPred Accel GravCost OldAcc Left
                                                   Right NgbVelDisp HsmlVelDisp dVel)      */
 int  b200_download_to(void *dst);              /* same, into another array of the bound layout */
+/* Multi-GPU variants (after b200_set_shard): each rank owns host rows [first, first+count) of the
+ * global particle order (the reference's per-rank P[] after its domain decomposition).  Upload
+ * copies only those rows over PCIe and replicates them to every rank with one all-gather over
+ * NVLink; download returns only the rank's own rows.  `rows_per_rank` >= count is the common slice
+ * length of the all-gather (ceil(N/world)); the shard buffers must hold rows_per_rank*stride bytes. */
+int  b200_upload_shard(int first, int count, int rows_per_rank);
+int  b200_download_shard(void *dst, int first, int count);
 /* Structure-of-arrays alternative used by the tests / bench (host pointers, float32/int32;
  * any pointer may be NULL = keep current).  pos/vel are [n][3]. */
 int  b200_set_soa(int num_part, const float *pos, const float *vel, const float *mass,

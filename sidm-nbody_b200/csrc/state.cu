@@ -390,6 +390,51 @@ extern "C" int b200_download(void) {
   return B200_OK;
 }
 
+extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  if (g.shard_world <= 1) return b200_upload();
+  const int n = g.n; const size_t st = (size_t)g.lay.stride;
+  if (first < 0 || count < 0 || first + count > n || rows_per_rank < count || (long long)rows_per_rank * g.shard_world < n) return B200_ERR_ARG;
+  const long long bytes = (long long)rows_per_rank * (long long)st;
+  if (bytes > g.shard_cap) return B200_ERR_ARG;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync((char *)g.shard_send, g.h_base + (size_t)first * st, (size_t)count * st, cudaMemcpyHostToDevice, g.stream));
+  B200_TRY(shard_exchange(bytes));                       // every rank's rows -> all ranks, over NVLink
+  // rank q's rows start at q*rows_per_rank: compact them into the device image of the whole array
+  for (int q = 0; q < g.shard_world; q++) {
+    const long long f = (long long)q * rows_per_rank;
+    if (f >= n) break;
+    const long long c = (n - f < rows_per_rank) ? n - f : rows_per_rank;
+    CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)c * st, cudaMemcpyDeviceToDevice, g.stream));
+  }
+  k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype);
+  count_launch();
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
+  g.tree_valid = false;
+  return B200_OK;
+}
+
+extern "C" int b200_download_shard(void *dst, int first, int count) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  const int n = g.n; const size_t st = (size_t)g.lay.stride;
+  if (first < 0 || count < 0 || first + count > n) return B200_ERR_ARG;
+  char *out = dst ? (char *)dst : g.h_base;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb);
+  count_launch();
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync(out + (size_t)first * st, g.d_aos + (size_t)first * st, (size_t)count * st, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_download, g.ev0, g.ev1);
+  return B200_OK;
+}
+
 // ----------------------------------------------------------------------------- predict
 
 // predict_collisionless_only(), predict.c:106-150: PosPred = Pos + Vel*dt_h0 and

@@ -41,18 +41,21 @@ def unpack_positions(nt, world):
     return np.where(j < nt, j, -1), per_rank
 
 
-def buffer_bytes(n, world):
-    return shard_max_blocks(n, world) * 32 * SLOT_REC_BYTES
+def buffer_bytes(n, world, stride=0):
+    """size of the send buffer: per-slot records of one rank's share, or - when the host array is
+    sharded too (stride = bytes per particle row) - one rank's rows of the array-of-structs"""
+    rows = -(-n // world)
+    return max(shard_max_blocks(n, world) * 32 * SLOT_REC_BYTES, rows * stride)
 
 
 class Sharder:
-    def __init__(self, hp, world=1, rank=0):
+    def __init__(self, hp, world=1, rank=0, aos_stride=124):
         self.hp, self.world, self.rank = hp, int(world), int(rank)
         self._cb = None
         if self.world > 1:
             import torch
             import torch.distributed as dist
-            cap = buffer_bytes(hp.params.MaxPart, self.world)
+            cap = buffer_bytes(hp.params.MaxPart, self.world, aos_stride)
             self.send = torch.empty(cap, dtype=torch.uint8, device="cuda")
             self.recv = torch.empty(cap * self.world, dtype=torch.uint8, device="cuda")
             self.exchanges = 0
@@ -89,3 +92,29 @@ class Sharder:
 
     def compute_accelerations(self, mode, time, vmax, active=None):
         self.hp.compute_accelerations(mode, active, time, vmax)
+
+    # host array-of-structs sharded over the ranks (the reference's per-rank P[]): rank r owns rows
+    # [r*rows, (r+1)*rows); PCIe carries only the own rows, NVLink replicates them
+    def rows(self):
+        per = -(-self.hp.n // self.world)
+        first = min(self.rank * per, self.hp.n)
+        return first, min(per, self.hp.n - first), per
+
+    def upload(self):
+        if self.world == 1:
+            self.hp.upload()
+            return
+        first, cnt, per = self.rows()
+        rc = self.hp.lib.b200_upload_shard(first, cnt, per)
+        if rc != 0:
+            raise RuntimeError(f"b200_upload_shard -> {rc}")
+
+    def download(self, into=None):
+        if self.world == 1:
+            self.hp.download(into=into)
+            return
+        first, cnt, per = self.rows()
+        dst = None if into is None else into.ctypes.data_as(C.c_void_p)
+        rc = self.hp.lib.b200_download_shard(dst, first, cnt)
+        if rc != 0:
+            raise RuntimeError(f"b200_download_shard -> {rc}")

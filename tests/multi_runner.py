@@ -42,6 +42,26 @@ def main(out, n, backend):
         res[f"sct{step}"] = np.array([c.sct_ntot, c.sct_pass1, c.sct_scattered, c.sct_rejected, c.ensure_iterations])
         hp.advance(time=t + dt / 2)
         t += dt
+    # the host array-of-structs path: own rows over PCIe, replication by all-gather, own rows back
+    from sidm_b200 import capi
+    velh = hp.peek("velh", np.float32, (n, 4))
+    aos = np.zeros(n, capi.PARTICLE_DTYPE)
+    aos["Pos"] = hp.peek("pos0", np.float32, (n, 3)); aos["PosPred"] = aos["Pos"]
+    aos["Vel"] = velh[:, :3]; aos["VelPred"] = aos["Vel"]; aos["HsmlVelDisp"] = velh[:, 3]
+    aos["Mass"] = mass; aos["ID"] = ids; aos["Type"] = 1; aos["Potential"] = 7.0; aos["ForceFlag"] = 3
+    aos["CurrentTime"] = hp.peek("curtime", np.float32, (n,))
+    aos["Accel"], aos["OldAcc"], aos["NgbVelDisp"] = hp.get("Accel", "OldAcc", "NgbVelDisp")
+    back = aos.copy()
+    hp.bind_particles(aos, pin=False)
+    sh.upload()
+    sh.compute_accelerations(0, time=t + dt / 2, vmax=vmax)
+    sh.download(into=back)
+    first, cnt, per = sh.rows() if world > 1 else (0, n, n)
+    lo, hi = 0, min(n, -(-n // 2))                     # rows rank 0 owns when world == 2
+    for f in ("Accel", "OldAcc", "dVel", "HsmlVelDisp", "NgbVelDisp", "PosPred", "Potential", "ForceFlag"):
+        res["aos_" + f] = back[f][lo:hi].copy()
+    if world > 1 and rank == 0:
+        assert np.array_equal(back["Accel"][hi:], aos["Accel"][hi:]), "rows of other ranks must stay untouched"
     if rank == 0:
         np.savez(out, acc_start=acc1, old_start=old1, **res)
     hp.close()

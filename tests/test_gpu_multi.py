@@ -22,7 +22,7 @@ def _launch(world, out, backend):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", runner, out, str(N), backend]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0, (r.stdout[-1500:] + "\n".join(l for l in r.stderr.splitlines() if "Error" in l or "assert" in l or "File" in l)[-3000:])
     return np.load(out)
 
 
