@@ -396,7 +396,8 @@ def run_e2e(hp, sh, n, mass, ids, vmax, tcur, args, world, rank, step_fn):
     return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(rows * snaps[0].itemsize * world),
             "d2h_bytes_per_step": int(rows * out.itemsize * world),
             "steps": steps, "ms_per_step": dt / steps * 1e3,
-            "api": "b200_bind_particles + b200_upload + b200_compute_accelerations(0) + b200_download_to on pinned 124-byte particle_data arrays (successive states of the run)"}
+            "api": ("b200_bind_particles + b200_upload + b200_compute_accelerations(0) + b200_download_to on pinned 124-byte particle_data arrays (successive states of the run)"
+                    if world == 1 else "b200_upload_shard (own rows over PCIe + NVLink all-gather) + b200_compute_accelerations(0) + b200_download_shard, pinned 124-byte particle_data rows per rank")}
 
 
 def main():
