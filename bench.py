@@ -266,7 +266,7 @@ def main_b200(args):
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     walk_ms, build_ms, sidm_ms, ens_ms = [], [], [], []
-    list_nodes = list_parts = ntarg = 0
+    list_nodes = list_parts = ntarg = num_lists = 0
     inter_p = inter_n = 0
     scat = rep_it = rep_n = cand = 0
     ev0.record()
@@ -274,7 +274,7 @@ def main_b200(args):
         step()
         c = hp.counters()
         walk_ms.append(c.ms_walk); build_ms.append(c.ms_build); sidm_ms.append(c.ms_sidm); ens_ms.append(c.ms_ensure)
-        list_nodes += c.list_nodes; list_parts += c.list_parts; ntarg += c.num_targets
+        list_nodes += c.list_nodes; list_parts += c.list_parts; ntarg += c.num_targets; num_lists += c.num_lists
         inter_p += c.part_interactions; inter_n += c.node_interactions
         scat += c.sct_scattered; rep_it += c.ensure_iterations; rep_n += c.ensure_repaired; cand += c.ngb_candidates
     ev1.record()
@@ -293,10 +293,10 @@ def main_b200(args):
     peak, peak_src = peaks()
     wms = float(np.mean(walk_ms))
     a_per_launch = ntarg / args.steps
-    warps = a_per_launch / 32.0
-    i_n = list_nodes / max(1, args.steps) / warps
-    i_p = list_parts / max(1, args.steps) / warps
-    walk_bytes = a_per_launch * 32 + warps * (48 * i_n + 16 * i_p)
+    lists = num_lists / args.steps                       # interaction lists per launch (one per warp of 32 targets)
+    i_n = list_nodes / max(1, args.steps) / lists
+    i_p = list_parts / max(1, args.steps) / lists
+    walk_bytes = a_per_launch * 32 + lists * (48 * i_n + 16 * i_p)
     achieved = walk_bytes / (wms * 1e-3) / 1e9
     flops = (inter_n * 70.0 + inter_p * 20.0) / args.steps
     traffic = None
@@ -307,7 +307,7 @@ def main_b200(args):
             traffic = t["traffic_bytes_per_launch"]      # ncu dram read+write bytes of one k_walk launch (profiles/)
     roofline = {"bound": "hbm", "kernel": "k_walk", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": wms,
-                "algorithmic_bytes_per_launch": walk_bytes, "I_n_per_warp": i_n, "I_p_per_warp": i_p,
+                "algorithmic_bytes_per_launch": walk_bytes, "I_n_per_list": i_n, "I_p_per_list": i_p, "targets_per_list": a_per_launch / lists,
                 "interactions_per_target": {"node": inter_n / max(1, ntarg), "particle": inter_p / max(1, ntarg)},
                 "fp32_tflops_est": flops / (wms * 1e-3) / 1e12,
                 "note": "walk is FP32-issue bound, not HBM bound: see DESIGN.md section 5"}

@@ -111,6 +111,7 @@ typedef struct b200_counters {
   long long list_nodes;            /* node records a 32-target warp streamed (I_n sum) */
   long long list_parts;            /* particle records a warp streamed       (I_p sum) */
   long long num_targets;
+  long long num_lists;             /* interaction lists walked (one per warp of 32 targets)         */
   /* since the last b200_sidm(), repair passes included: the step's SCT lines summed (sidm.c:614-620) */
   int       sct_ntot, sct_pass1, sct_scattered, sct_rejected;
   long long ngb_candidates;        /* cube candidates examined (C in SURVEY 8d)       */

@@ -96,14 +96,17 @@ struct Ctx {
   b200_counters cnt{};
 };
 
+// sharded work lists are dealt out in blocks of kShardBlock consecutive entries of the key order
+// (= the 32 targets one warp of the walk shares an interaction list between)
+constexpr int kShardBlock = 32, kShardShift = 5;
 // number of entries of a sorted list of length nt that rank r of `world` owns
 inline int shard_count(int nt, int world, int r) {
-  const int nblk = (nt + 31) / 32;
+  const int nblk = (nt + kShardBlock - 1) / kShardBlock;
   long long c = 0;
-  for (int q = r; q < nblk; q += world) { const int lo = q * 32; c += (nt - lo < 32) ? nt - lo : 32; }
+  for (int q = r; q < nblk; q += world) { const int lo = q * kShardBlock; c += (nt - lo < kShardBlock) ? nt - lo : kShardBlock; }
   return (int)c;
 }
-inline int shard_max_blocks(int nt, int world) { const int nblk = (nt + 31) / 32; return (nblk + world - 1) / world; }
+inline int shard_max_blocks(int nt, int world) { const int nblk = (nt + kShardBlock - 1) / kShardBlock; return (nblk + world - 1) / world; }
 int shard_select(const int *d_in, int nt, int *d_out, int *n_own);
 int shard_exchange(long long bytes_per_rank);
 

@@ -486,7 +486,7 @@ __global__ void k_slot_unpack(int ns, int world, int per_rank, const int *sorted
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)world * per_rank) return;
   const int q = (int)(g / per_rank), k = (int)(g % per_rank);
-  const long long j = ((long long)(k >> 5) * world + q) * 32 + (k & 31);
+  const long long j = ((long long)(k >> kShardShift) * world + q) * kShardBlock + (k & (kShardBlock - 1));
   if (j >= ns) return;
   const int s = sorted_slots[j];
   const SlotRec r = recv[g];
@@ -685,7 +685,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     if (g.shard_world > 1) {
       // exchange {Ngb, partner, dv} of every slot (replaces the result + confirm hypercube
       // passes of sidm.c:463-553); the two write sweeps below then run identically on all ranks
-      const int per_rank = shard_max_blocks(nb, g.shard_world) * 32;
+      const int per_rank = shard_max_blocks(nb, g.shard_world) * kShardBlock;
       if (nord > 0) { k_slot_pack<<<cdiv(nord, B), B, 0, st>>>(nord, order, g.s_ngb, g.s_partner, g.s_dv, g.s_pass, count_only, (SlotRec *)g.shard_send); count_launch(); }
       B200_TRY(shard_exchange((long long)per_rank * sizeof(SlotRec)));
       const long long tot = (long long)g.shard_world * per_rank;

@@ -78,7 +78,7 @@ extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long 
 __global__ void k_shard_select(int nt, int world, int rank, const int *in, int *out, int nown_max) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nown_max) return;
-  const long long j = ((long long)(k >> 5) * world + rank) * 32 + (k & 31);
+  const long long j = ((long long)(k >> kShardShift) * world + rank) * kShardBlock + (k & (kShardBlock - 1));
   if (j < nt) out[k] = in[j];
 }
 namespace b200 {

@@ -121,12 +121,13 @@ B200_HD bool key_less(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo) {
 // in depth-first pre-order so that "open" is always id+1 and "accept" jumps to `skip`.
 struct __attribute__((aligned(16))) NodeRec {
   float sx, sy, sz, mass;          // centre of mass, mass                  (NODE.s, .mass)
-  float len2, bmax2;               // len*len (BH test; oc = mass*len2*len2 is recomputed), bmax2 (NODE.bmax2)
+  float oc, bmax2;                 // oc = mass*len^4 as the reference stores it (NODE.oc), NODE.bmax2
   int   pinfo;                     // (first leaf slot << 4) | number of direct particles
   int   skip;                      // next node in pre-order outside this subtree
   float q11, q22, q33, q12;        // raw second moments about the c.o.m.   (NODE.Q11..)
-  float q13, q23, p, oc;           // ... trace P; oc = mass*len^4 as the reference stores it (NODE.oc)
+  float q13, q23, p, len2;         // ... trace P; len*len (BH test, forcetree.c:967)
 };
+// the first 32 bytes decide open/accept for the relative criterion (the BH test needs len2)
 
 // raw moments of a node about its geometric centre, in double (forcetree.c:433-571)
 struct Moments { double m, s[3], r[6]; };   // r: xx yy zz xy xz yz

@@ -66,6 +66,24 @@ __device__ __forceinline__ float wrap_image(float d, float box, float boxhalf) {
 
 constexpr int kFlushEvery = 32;
 
+// softened (r < h) node and particle factors, forcetree.c:1026-1074 / :904-915.  Rare (only cells
+// and particles within 2.8 eps of the target), so kept out of line to keep the hot loop short.
+__device__ __forceinline__ float2 pn_soft(float r2, float potq, float mass, float pp, float h_inv) {
+  const float r = sqrtf(r2), u = r * h_inv;
+  if (!(u > 1.0e-4f)) return make_float2(0.f, 0.f);
+  float w2, w3, w4;
+  soft_w234(u, w2, w3, w4);
+  const float wf = soft_force(u);
+  const float ri = 1.0f / r;
+  const float h2i = h_inv * h_inv, h3i = h2i * h_inv, h4i = h2i * h2i, h5i = h2i * h3i, h6i = h3i * h3i;
+  return make_float2(mass * h3i * wf + potq * h6i * w3 * ri + 0.5f * pp * w4 * h4i * ri, w2 * h5i);   // fac, ff
+}
+__device__ __forceinline__ float pp_soft(float r2, float mass, float h_inv) {
+  const float u = sqrtf(r2) * h_inv;
+  if (!(u > 1.0e-4f)) return 0.f;
+  return mass * h_inv * h_inv * h_inv * soft_force(u);
+}
+
 // MODE: 0 = lanes of this warp use different criteria, 1 = all relative (forcetree.c:1097),
 // 2 = all BH (forcetree.c:817); the choice is warp-uniform, the arithmetic identical.
 template <bool PER, int MODE>
@@ -79,34 +97,52 @@ __device__ __forceinline__ void walk_loop(const WalkParams &P, const float4 tp, 
   while (cur < M) {
     float fx = 0, fy = 0, fz = 0;
     // float partial sums over <= kFlushEvery cells, then one flush into the double accumulators
-    for (int it = 0; it < kFlushEvery && cur < M; it++) {
+    int it = 0;
+    for (; it < kFlushEvery && cur < M; it++) {
       const float4 *nd = nodes4 + 4 * (size_t)cur;
       const float4 A = __ldg(nd);              // s.xyz, mass
-      const float4 Bv = __ldg(nd + 1);         // len2, bmax2, pinfo, skip
-      const bool act = (no == cur);
+      const float4 Bv = __ldg(nd + 1);         // oc, bmax2, pinfo, skip
+#ifdef WALK_EARLY_Q
+      // request the second half with the first (volatile asm: the compiler may not sink it into the
+      // accept branch): one dependent cache access per visit instead of two
+      float4 Cv, Dv;                           // Q11 Q22 Q33 Q12 | Q13 Q23 P len2
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Cv.x), "=f"(Cv.y), "=f"(Cv.z), "=f"(Cv.w) : "l"(nd + 2));
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Dv.x), "=f"(Dv.y), "=f"(Dv.z), "=f"(Dv.w) : "l"(nd + 3));
+#else
+      const float4 Cv = __ldg(nd + 2);         // Q11 Q22 Q33 Q12
+      const float4 Dv = __ldg(nd + 3);         // Q13 Q23 P len2
+#endif
       float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
       if (PER) { dx = wrap_image(dx, P.box, P.boxhalf); dy = wrap_image(dy, P.box, P.boxhalf); dz = wrap_image(dz, P.box, P.boxhalf); }
-      const float r2 = dx * dx + dy * dy + dz * dz;
-      // forcetree.c:967 / :1253-1257; oc = mass*len^4 formed exactly as the build stores it
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      // forcetree.c:967 / :1253-1257
       bool crit;
-      if (MODE == 2) crit = Bv.x > r2 * theta2;
-      else if (MODE == 1) crit = (fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y);
-      else crit = bh ? (Bv.x > r2 * theta2) : ((fmul(fmul(A.w, Bv.x), Bv.x) > oac * r2 * r2 * r2) || (r2 < Bv.y));
-      const bool open = act && crit;
-      if (act && !crit) {
-        const float4 Cv = __ldg(nd + 2);       // Q11 Q22 Q33 Q12
-        const float4 Dv = __ldg(nd + 3);       // Q13 Q23 P oc
-        pn_force_fast(dx, dy, dz, r2, A.w, Cv.x, Cv.y, Cv.z, Cv.w, Dv.x, Dv.y, Dv.z, h_inv, h2, fx, fy, fz);
+      if (MODE == 1) crit = (Bv.x > oac * r2 * r2 * r2) || (r2 < Bv.y);
+      else if (MODE == 2) crit = Dv.w > r2 * theta2;
+      else crit = bh ? (Dv.w > r2 * theta2) : ((Bv.x > oac * r2 * r2 * r2) || (r2 < Bv.y));
+      const bool act = (no == cur);
+      const bool acc = act && !crit, open = act && crit;
+      if (acc) {
+        const float qx = fmaf(Dv.x, dz, fmaf(Cv.w, dy, Cv.x * dx));
+        const float qy = fmaf(Dv.y, dz, fmaf(Cv.y, dy, Cv.w * dx));
+        const float qz = fmaf(Cv.z, dz, fmaf(Dv.y, dy, Dv.x * dx));
+        const float t = fmaf(dz, qz, fmaf(dy, qy, dx * qx));               // y^T Q y = 2 potq
+        // fac = m/r^3 + (15 potq/r^2 - 1.5 P)/r^5 ; ff = -3/r^5   (forcetree.c:1262-1301)
+        const float ri = rsqrt_fast(r2), r2i = ri * ri, r3i = r2i * ri, r5i = r3i * r2i;
+        float fac = fmaf(fmaf(t * r2i, 7.5f, -1.5f * Dv.z), r5i, A.w * r3i);
+        float ff = -3.0f * r5i;
+        if (r2 < h2) { const float2 v = pn_soft(r2, 0.5f * t, A.w, Dv.z, h_inv); fac = v.x; ff = v.y; }
+        fx = fmaf(ff, qx, fmaf(dx, fac, fx));
+        fy = fmaf(ff, qy, fmaf(dy, fac, fy));
+        fz = fmaf(ff, qz, fmaf(dz, fac, fz));
         if (PER) {                             // forcetree.c:1076-1082
           float ex, ey, ez;
           ewald_corr(P.ewald, P.ewald_fac, dx, dy, dz, ex, ey, ez);
           fx += A.w * ex; fy += A.w * ey; fz += A.w * ez;
         }
         nnode++;
-        no = __float_as_int(Bv.w);             // accept: jump over the subtree
       }
-      if (open) no = cur + 1;
-      wnodes++;
+      no = acc ? __float_as_int(Bv.w) : (open ? cur + 1 : no);   // accept: jump over the subtree; open: first child
       if (__any_sync(0xffffffffu, open)) {
         const int pinfo = __float_as_int(Bv.z);
         const int np = pinfo & 15;
@@ -117,24 +153,35 @@ __device__ __forceinline__ void walk_loop(const WalkParams &P, const float4 tp, 
           if (open) {
             float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
             if (PER) { px = wrap_image(px, P.box, P.boxhalf); py = wrap_image(py, P.box, P.boxhalf); pz = wrap_image(pz, P.box, P.boxhalf); }
-            pp_force_fast(px, py, pz, q.w, h_inv, h2, fx, fy, fz);
-            if (PER && (px * px + py * py + pz * pz) * h_inv * h_inv > 1.0e-8f) {     // u > 1e-4, forcetree.c:921-930
+            const float pr2 = fmaf(pz, pz, fmaf(py, py, px * px));
+            const float ri = rsqrt_fast(pr2);
+            float fac = q.w * ri * ri * ri;                                  // m/r^3, forcetree.c:1135-1186
+            if (pr2 < h2) fac = pp_soft(pr2, q.w, h_inv);
+            fx = fmaf(px, fac, fx); fy = fmaf(py, fac, fy); fz = fmaf(pz, fac, fz);
+            if (PER && pr2 * h_inv * h_inv > 1.0e-8f) {                      // u > 1e-4, forcetree.c:921-930
               float ex, ey, ez;
               ewald_corr(P.ewald, P.ewald_fac, px, py, pz, ex, ey, ez);
               fx += q.w * ex; fy += q.w * ey; fz += q.w * ez;
             }
-            npart++;
           }
         }
+        if (open) npart += np;
       }
       cur = __reduce_min_sync(0xffffffffu, no);
     }
     ax += (double)fx; ay += (double)fy; az += (double)fz;
+    wnodes += it;                              // node records this warp streamed (I_n)
   }
 }
 
+#ifndef WALK_THREADS
+#define WALK_THREADS 128
+#endif
+#ifndef WALK_MINBLOCKS
+#define WALK_MINBLOCKS 10
+#endif
 template <bool PER>
-__global__ void __launch_bounds__(256) k_walk(WalkParams P) {
+__global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < P.nt;
@@ -258,7 +305,7 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
   P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
   if (per) { B200_TRY(ewald_tables(&P.ewald)); }
   if (nt > 0) {
-    if (per) k_walk<true><<<cdiv(nt, 256), 256, 0, g.stream>>>(P); else k_walk<false><<<cdiv(nt, 256), 256, 0, g.stream>>>(P);
+    if (per) k_walk<true><<<cdiv(nt, WALK_THREADS), WALK_THREADS, 0, g.stream>>>(P); else k_walk<false><<<cdiv(nt, WALK_THREADS), WALK_THREADS, 0, g.stream>>>(P);
     count_launch();
   }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -269,6 +316,7 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
   g.cnt.part_interactions = (long long)g.h_ctr[CT_PART]; g.cnt.node_interactions = (long long)g.h_ctr[CT_NODE];
   g.cnt.list_nodes = (long long)g.h_ctr[CT_LIST_NODES]; g.cnt.list_parts = (long long)g.h_ctr[CT_LIST_PARTS];
   g.cnt.num_targets = nt;
+  g.cnt.num_lists = (nt + 31) / 32;
   return B200_OK;
 }
 
@@ -323,7 +371,7 @@ __global__ void k_grav_unpack(int nt, int world, int per_rank, const int *sorted
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)world * per_rank) return;
   const int q = (int)(g / per_rank), k = (int)(g % per_rank);
-  const long long j = ((long long)(k >> 5) * world + q) * 32 + (k & 31);
+  const long long j = ((long long)(k >> kShardShift) * world + q) * kShardBlock + (k & (kShardBlock - 1));
   if (j >= nt) return;
   const int s = sorted[j]; const int p = slot_part ? slot_part[s] : s;
   const float4 v = recv[g];
@@ -350,7 +398,7 @@ int gravity_impl(const int *active, int nactive, double time) {
   if (g.shard_world > 1) {
     // all-gather of the partial results (the reduce step of gravtree.c:208-222 becomes a gather:
     // every target is evaluated completely by exactly one rank)
-    const int per_rank = shard_max_blocks(nt, g.shard_world) * 32;
+    const int per_rank = shard_max_blocks(nt, g.shard_world) * kShardBlock;
     if (nw > 0) { k_grav_pack<<<cdiv(nw, 256), 256, 0, g.stream>>>(nw, work, E.slot_part, g.accel, g.oldacc, (float4 *)g.shard_send); count_launch(); }
     B200_TRY(shard_exchange((long long)per_rank * sizeof(float4)));
     const long long tot = (long long)g.shard_world * per_rank;

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libsidm_b200.so")
+# B200_LIB: build-variant override for kernel experiments (scripts/); the default is the in-tree library
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(PKG_DIR, "libsidm_b200.so")
 
 ERRORS = {1: "tree nodes exhausted (forcetree.c:233 endrun(1))", 3: "allocation failed (endrun(3))",
           78: "neighbour list overflow (endrun(78))", 1155: "smoothing-length iteration failed (endrun(1155))",
@@ -51,7 +52,7 @@ class Replay(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("num_nodes", C.c_int), ("max_level", C.c_int), ("part_interactions", C.c_longlong),
                 ("node_interactions", C.c_longlong), ("list_nodes", C.c_longlong), ("list_parts", C.c_longlong),
-                ("num_targets", C.c_longlong), ("sct_ntot", C.c_int), ("sct_pass1", C.c_int),
+                ("num_targets", C.c_longlong), ("num_lists", C.c_longlong), ("sct_ntot", C.c_int), ("sct_pass1", C.c_int),
                 ("sct_scattered", C.c_int), ("sct_rejected", C.c_int), ("ngb_candidates", C.c_longlong),
                 ("ensure_iterations", C.c_int), ("ensure_repaired", C.c_int), ("ms_upload", C.c_float), ("ms_predict", C.c_float),
                 ("ms_build", C.c_float), ("ms_walk", C.c_float), ("ms_sidm", C.c_float), ("ms_ensure", C.c_float),

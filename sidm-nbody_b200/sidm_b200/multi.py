@@ -20,24 +20,27 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_longlong, C.c_void_p)
 SLOT_REC_BYTES = 32        # struct SlotRec in csrc/sidm.cu; gravity sends 16-byte float4 records
 
 
+SHARD_BLOCK = 32      # kShardBlock of csrc/ctx.cuh: the 32 targets one warp of the walk handles
+
+
 def shard_max_blocks(nt, world):
-    return ((nt + 31) // 32 + world - 1) // world
+    return ((nt + SHARD_BLOCK - 1) // SHARD_BLOCK + world - 1) // world
 
 
 def shard_positions(nt, world, rank):
     """positions j of a sorted work list of length nt that rank owns (mirror of k_shard_select)"""
-    k = np.arange(shard_max_blocks(nt, world) * 32, dtype=np.int64)
-    j = ((k >> 5) * world + rank) * 32 + (k & 31)
+    k = np.arange(shard_max_blocks(nt, world) * SHARD_BLOCK, dtype=np.int64)
+    j = ((k // SHARD_BLOCK) * world + rank) * SHARD_BLOCK + (k % SHARD_BLOCK)
     return j[j < nt]
 
 
 def unpack_positions(nt, world):
     """for the concatenated all-gather buffer [world][per_rank]: list position of every entry, -1 = padding
     (mirror of k_grav_unpack / k_slot_unpack)"""
-    per_rank = shard_max_blocks(nt, world) * 32
+    per_rank = shard_max_blocks(nt, world) * SHARD_BLOCK
     g = np.arange(world * per_rank, dtype=np.int64)
     q, k = g // per_rank, g % per_rank
-    j = ((k >> 5) * world + q) * 32 + (k & 31)
+    j = ((k // SHARD_BLOCK) * world + q) * SHARD_BLOCK + (k % SHARD_BLOCK)
     return np.where(j < nt, j, -1), per_rank
 
 
@@ -45,7 +48,7 @@ def buffer_bytes(n, world, stride=0):
     """size of the send buffer: per-slot records of one rank's share, or - when the host array is
     sharded too (stride = bytes per particle row) - one rank's rows of the array-of-structs"""
     rows = -(-n // world)
-    return max(shard_max_blocks(n, world) * 32 * SLOT_REC_BYTES, rows * stride)
+    return max(shard_max_blocks(n, world) * SHARD_BLOCK * SLOT_REC_BYTES, rows * stride)
 
 
 class Sharder:

@@ -31,7 +31,7 @@ def _worker(rank, world, port, nt, q):
     work = rng.permutation(nt).astype(np.int64)            # a sorted work list (slot ids)
     truth = (work * 3 + 1).astype(np.float32)              # what the "kernel" computes per entry
     mine = multi.shard_positions(nt, world, rank)
-    per_rank = multi.shard_max_blocks(nt, world) * 32
+    per_rank = multi.shard_max_blocks(nt, world) * multi.SHARD_BLOCK
     send = torch.zeros(per_rank, dtype=torch.float32)
     send[: len(mine)] = torch.from_numpy(truth[mine])      # own results, packed in block order
     recv = torch.empty(world * per_rank, dtype=torch.float32)
@@ -45,7 +45,7 @@ def _worker(rank, world, port, nt, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nt", [1, 31, 32, 33, 1000, 4097])
+@pytest.mark.parametrize("nt", [1, 31, 32, 33, 63, 64, 65, 1000, 4097])
 def test_shard_roundtrip_world2(nt):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -69,5 +69,5 @@ def test_shard_partition_properties():
             allpos = np.concatenate([multi.shard_positions(nt, world, r) for r in range(world)])
             assert sorted(allpos.tolist()) == list(range(nt))          # a partition of the list
             sizes = [len(multi.shard_positions(nt, world, r)) for r in range(world)]
-            assert max(sizes) - min(sizes) <= 32                         # balanced to one block
+            assert max(sizes) - min(sizes) <= multi.SHARD_BLOCK                         # balanced to one block
             assert multi.buffer_bytes(nt, world) >= max(sizes) * multi.SLOT_REC_BYTES
