@@ -130,6 +130,10 @@ int  b200_last_cuda_error(void);
 /* run on the caller's CUDA stream (a cudaStream_t); default is the legacy default stream */
 int  b200_set_stream(void *cuda_stream);
 const char *b200_version(void);
+/* run-time switches.  "overlap" (default 1): b200_compute_accelerations(0) issues the gravity walk and
+ * the SIDM chain on two CUDA streams so the SIDM repair loop's small launches hide behind the walk
+ * (one GPU only); 0 runs the phases one after the other as accel.c:39-65 does. */
+int  b200_set_option(const char *name, int value);
 
 /* ---- particle state -------------------------------------------------------------- */
 /* Bind the host AoS (the reference's &P[1]).  pin!=0 page-locks it for async DMA. */

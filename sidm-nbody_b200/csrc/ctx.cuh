@@ -16,6 +16,14 @@ struct Ctx {
   int last_cuda = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // second, high-priority stream: inside b200_compute_accelerations() the SIDM chain (search,
+  // scatter, repair loop - many small latency-bound launches with host round trips) runs here
+  // while the gravity walk fills the machine on `stream` (both only read the tree)
+  cudaStream_t stream_sidm = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
+  bool opt_overlap = true;         // b200_set_option("overlap", 0|1)
+  bool overlap_now = false;        // true while the SIDM chain is being issued on stream_sidm
+  bool walk_pending = false;       // a deferred walk whose counters / timing are still to be read
 
   // host binding (the reference's &P[1])
   char *h_base = nullptr; b200_layout lay{}; bool pinned = false; bool have_aos = false;
@@ -107,7 +115,7 @@ inline int shard_count(int nt, int world, int r) {
   return (int)c;
 }
 inline int shard_max_blocks(int nt, int world) { const int nblk = (nt + kShardBlock - 1) / kShardBlock; return (nblk + world - 1) / world; }
-int shard_select(const int *d_in, int nt, int *d_out, int *n_own);
+int shard_select(const int *d_in, int nt, int *d_out, int *n_own, cudaStream_t st);
 int shard_exchange(long long bytes_per_rank);
 
 extern Ctx g;
@@ -136,8 +144,10 @@ enum { CT_PART = 0, CT_NODE = 1, CT_LIST_NODES = 2, CT_LIST_PARTS = 3, CT_CAND =
 
 // implemented across the .cu files
 int tree_build_impl();
-int walk_impl(const int *d_targets_sorted, int nt, bool raw_only);
-int gravity_impl(const int *active, int nactive, double time);
+int walk_impl(const int *d_targets_sorted, int nt, bool with_slots, bool defer_sync = false);
+int gravity_impl(const int *active, int nactive, double time, bool defer_sync = false);
+int gravity_finish();
+inline cudaStream_t sidm_stream() { return g.overlap_now ? g.stream_sidm : g.stream; }
 int direct_impl(const int *targets, int n, double *acc_out);
 int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only);
 int prepare_targets(const int *active_host, int nactive, int **d_sorted_out);

@@ -48,6 +48,10 @@ struct SidmState {
   unsigned char *already = nullptr;
   double *ptot = nullptr;
   int cap_nodes = 0, cap_part = 0;
+  // scratch private to the SIDM chain (it may run on its own stream next to the gravity walk,
+  // which owns S.x_redo / g.d_t* / S.cub_tmp)
+  int *x_redo = nullptr, *x_want = nullptr, *x_keys = nullptr, *x_keys2 = nullptr, *x_vals = nullptr, *x_shard = nullptr;
+  void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
 } S;
 
 constexpr int kCandCap = 1024;      // per-slot candidate capacity in reference-order mode
@@ -509,6 +513,9 @@ static int ensure_sidm_buffers() {
   B200_TRY(al((void **)&S.dt, n * sizeof(float)));
   B200_TRY(al((void **)&S.already, n));
   B200_TRY(al((void **)&S.ptot, n * sizeof(double)));
+  B200_TRY(al((void **)&S.x_redo, n * sizeof(int))); B200_TRY(al((void **)&S.x_want, n * sizeof(int)));
+  B200_TRY(al((void **)&S.x_keys, n * sizeof(int))); B200_TRY(al((void **)&S.x_keys2, n * sizeof(int)));
+  B200_TRY(al((void **)&S.x_vals, n * sizeof(int))); B200_TRY(al((void **)&S.x_shard, (n + 64) * sizeof(int)));
   if (!d_kernel_table) {
     double K[1002];
     const double PI = 3.14159265358979323846;
@@ -526,17 +533,19 @@ static int ensure_sidm_buffers() {
 // called by b200_finalize(): the buffers above are sized by the MaxPart of one b200_init()
 void sidm_release() {
   void **ptrs[] = {(void **)&S.snode, (void **)&S.snodef, (void **)&S.last_active, (void **)&S.slot_of_sorted, (void **)&S.passlist,
-                   (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot};
+                   (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot,
+                   (void **)&S.x_redo, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
-  S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false;
+  S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false; S.cub_tmp_bytes = 0;
 }
 
 static int cub_scratch(size_t tb) {
-  if (tb <= g.cub_tmp_bytes) return B200_OK;
-  if (g.cub_tmp) cudaFree(g.cub_tmp);
-  g.cub_tmp = nullptr; g.cub_tmp_bytes = 0;
-  if (cudaMalloc(&g.cub_tmp, tb + 4096) != cudaSuccess) return B200_ERR_ALLOC;
-  g.cub_tmp_bytes = tb + 4096;
+  if (tb <= S.cub_tmp_bytes) return B200_OK;
+  if (S.cub_tmp) { cudaStreamSynchronize(sidm_stream()); cudaFree(S.cub_tmp); }
+  S.cub_tmp = nullptr; S.cub_tmp_bytes = 0;
+  if (tb < ((size_t)64 << 20)) tb = (size_t)64 << 20;      // grow once: cudaMalloc / cudaFree serialise the device
+  if (cudaMalloc(&S.cub_tmp, tb + 4096) != cudaSuccess) return B200_ERR_ALLOC;
+  S.cub_tmp_bytes = tb + 4096;
   return B200_OK;
 }
 
@@ -551,7 +560,7 @@ int refresh_search_nodes() {
   B200_TRY(ensure_sidm_buffers());
   if (g.search_epoch == g.tree_epoch) return B200_OK;
   g.search_epoch = g.tree_epoch;
-  k_search_nodes<<<cdiv(g.num_nodes, 256), 256, 0, g.stream>>>(g.num_nodes, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
+  k_search_nodes<<<cdiv(g.num_nodes, 256), 256, 0, sidm_stream()>>>(g.num_nodes, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
   count_launch();
   return B200_OK;
 }
@@ -562,7 +571,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   if (!g.tree_valid) return B200_ERR_STATE;
   B200_TRY(ensure_sidm_buffers());
   B200_TRY(refresh_search_nodes());
-  cudaStream_t st = g.stream;
+  cudaStream_t st = sidm_stream();
   const int na = nactive;
   if (na <= 0) return B200_OK;
   const int B = 256;
@@ -601,17 +610,17 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, g.s_flag, g.s_pos, nb + 1, st);
     B200_TRY(cub_scratch(tb));
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb, g.s_flag, g.s_pos, nb + 1, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, g.s_flag, g.s_pos, nb + 1, st));
     int *slot_of_active = g.s_repair;     // scratch
     // processing order: slots sorted along the tree key order (spatial coherence inside a warp)
     k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
-                                    g.krank, g.d_tkeys, act ? g.d_tvals2 : S.slot_of_sorted, g.d_flags);
+                                    g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags);
     count_launch(4);
     if (act) {
       size_t tb2 = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st);
+      cub::DeviceRadixSort::SortPairs(nullptr, tb2, S.x_keys, S.x_keys2, S.x_vals, S.slot_of_sorted, nb, 0, 32, st);
       B200_TRY(cub_scratch(tb2));
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb2, g.d_tkeys, g.d_tkeys2, g.d_tvals2, S.slot_of_sorted, nb, 0, 32, st));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb2, S.x_keys, S.x_keys2, S.x_vals, S.slot_of_sorted, nb, 0, 32, st));
       count_launch(4);
     }
     // replay arrays
@@ -631,7 +640,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     }
     // this rank's share of the buffer (all of it on one GPU)
     const int *order = S.slot_of_sorted; int nord = nb;
-    if (g.shard_world > 1) { B200_TRY(shard_select(S.slot_of_sorted, nb, g.d_shard_list, &nord)); order = g.d_shard_list; }
+    if (g.shard_world > 1) { B200_TRY(shard_select(S.slot_of_sorted, nb, S.x_shard, &nord, st)); order = S.x_shard; }
     // pass 1
     Pass1 P1;
     P1.ns = nord; P1.order = order; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
@@ -649,7 +658,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       if (nord > 0) {
         cub::DeviceSelect::Flagged(nullptr, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st);
         B200_TRY(cub_scratch(tb3));
-        CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st));
+        CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st));
       }
       CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
@@ -703,7 +712,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       size_t tb4 = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tb4, confirm, S.logpos, nb + 1, st);
       B200_TRY(cub_scratch(tb4));
-      CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
+      CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
       k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
                                          g.s_slot_part, g.posm, g.velh, g.pid, (float)time);
       int nlog = 0;
@@ -715,7 +724,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     g.last_nslot = nb;
   }
   g.scatlog_n = logbase < g.scatlog_cap ? logbase : g.scatlog_cap;
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctr + CT_CAND, g.d_ctr + CT_CAND, (CT_COUNT - CT_CAND) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
@@ -789,7 +798,7 @@ static int knn_device(const int *d_idx, int nq, int k, float *d_h2) {
   B200_TRY(refresh_search_nodes());
   KnnParams P; P.nq = nq; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode; P.geom = g.geom;
   P.shi = g.skey_hi; P.slo = g.skey_lo; P.nstart = g.nstart; P.nlevel = g.nlevel; P.nend = g.nend;
-  k_knn<<<cdiv(nq, 128), 128, 0, g.stream>>>(P);
+  k_knn<<<cdiv(nq, 128), 128, 0, sidm_stream()>>>(P);
   count_launch();
   return B200_OK;
 }
@@ -862,19 +871,19 @@ __global__ void k_set_hsml_from_h2(int n, const float *h2, float4 *velh, float *
 // shared repair loop; ensure_variant 1 = sidm_ensure_neighbours (runs sidm()), 0 = start-up
 // (counts only, setup_nbr_sidm)
 static int repair_loop(int ensure_variant, double time, double vmax, const b200_replay *replay, int maxiter) {
-  cudaStream_t st = g.stream;
+  cudaStream_t st = sidm_stream();
   const int n = g.n, B = 256, G = cdiv(n, B);
   const int lo = g.par.DesNumNgb - g.par.MaxNumNgbDeviation, hi = g.par.DesNumNgb + g.par.MaxNumNgbDeviation;
   int iter = 0;
   size_t roff = 0;
-  int *redo = g.d_active;                 // compacted list (ascending index, like sidm.c:862)
-  int *want = g.d_tsorted; float *h2 = (float *)g.d_tkeys2;
+  int *redo = S.x_redo;                 // compacted list (ascending index, like sidm.c:862)
+  int *want = S.x_want; float *h2 = (float *)S.x_keys2;
   for (;;) {
     k_flag_repair<<<G, B, 0, st>>>(n, lo, hi, ensure_variant, g.ngb, g.velh, g.left, g.right, g.s_flag);
     size_t tb = 0;
     cub::DeviceSelect::Flagged(nullptr, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st);
     B200_TRY(cub_scratch(tb));
-    CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st));
+    CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st));
     CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     count_launch(4);
@@ -884,11 +893,11 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     count_launch();
     if (ensure_variant) {
       // exact k-th neighbour distance where sidm.c:918-922 asks for it (rare: Ngb < 15 with no upper bracket)
-      int *wlist = g.d_tkeys;
+      int *wlist = S.x_keys;
       size_t tbw = 0;
       cub::DeviceSelect::Flagged(nullptr, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st);
       B200_TRY(cub_scratch(tbw));
-      CUDA_TRY(cub::DeviceSelect::Flagged(g.cub_tmp, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st));
+      CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st));
       CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       count_launch(2);
@@ -917,7 +926,7 @@ static int stage_active(const int *active, int nactive, const int **d_out, int *
   B200_TRY(ensure_sidm_buffers());
   if (!active) { *d_out = nullptr; *n_out = g.n; S.last_all = true; S.last_nactive = g.n; return B200_OK; }
   if (nactive < 0 || nactive > g.n) return B200_ERR_ARG;
-  CUDA_TRY(cudaMemcpyAsync(S.last_active, active, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(S.last_active, active, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, sidm_stream()));
   S.last_all = false; S.last_nactive = nactive;
   *d_out = S.last_active; *n_out = nactive;
   return B200_OK;
@@ -930,10 +939,10 @@ extern "C" int b200_sidm(const int *active, int nactive, double time, double vma
   g.scatlog_n = 0;
   g.cnt.sct_ntot = g.cnt.sct_pass1 = g.cnt.sct_scattered = g.cnt.sct_rejected = 0; g.cnt.ngb_candidates = 0;
   g.cnt.ensure_iterations = 0; g.cnt.ensure_repaired = 0;
-  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev_s0, sidm_stream()));
   int rc = sidm_impl(d, na, time, vmax, replay, false);
-  cudaEventRecord(g.ev1, g.stream); cudaEventSynchronize(g.ev1);
-  cudaEventElapsedTime(&g.cnt.ms_sidm, g.ev0, g.ev1);
+  cudaEventRecord(g.ev_s1, sidm_stream()); cudaEventSynchronize(g.ev_s1);
+  cudaEventElapsedTime(&g.cnt.ms_sidm, g.ev_s0, g.ev_s1);
   return rc;
 }
 
@@ -948,11 +957,11 @@ extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, c
   (void)mode;   // restoring / resetting the time line (sidm.c:943-965) is the host driver's job
   if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
   B200_TRY(ensure_sidm_buffers());
-  cudaStream_t st = g.stream;
+  cudaStream_t st = sidm_stream();
   const int lo = g.par.DesNumNgb - g.par.MaxNumNgbDeviation, hi = g.par.DesNumNgb + g.par.MaxNumNgbDeviation;
   const int na = S.last_nactive > 0 ? S.last_nactive : g.n;
   const int *act = (S.last_all || S.last_nactive == 0) ? nullptr : S.last_active;
-  CUDA_TRY(cudaEventRecord(g.ev0, st));
+  CUDA_TRY(cudaEventRecord(g.ev_s0, st));
   // candidates among the active particles, sidm.c:836-846
   CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_NREPAIR, 0, sizeof(int), st));
   k_count_out_of_range<<<cdiv(na, 256), 256, 0, st>>>(na, act, g.ngb, lo, hi, g.d_flags + FL_NREPAIR);
@@ -966,18 +975,18 @@ extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, c
     count_launch(2);
     rc = repair_loop(1, time, vmax, replay, 30);
   }
-  cudaEventRecord(g.ev1, st); cudaEventSynchronize(g.ev1);
-  cudaEventElapsedTime(&g.cnt.ms_ensure, g.ev0, g.ev1);
+  cudaEventRecord(g.ev_s1, st); cudaEventSynchronize(g.ev_s1);
+  cudaEventElapsedTime(&g.cnt.ms_ensure, g.ev_s0, g.ev_s1);
   return rc;
 }
 
 extern "C" int b200_setup_smoothinglengths_sidm(int desired_ngb) {
   if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
   B200_TRY(ensure_sidm_buffers());
-  cudaStream_t st = g.stream;
+  cudaStream_t st = sidm_stream();
   const int n = g.n;
   k_iota<<<cdiv(n, 256), 256, 0, st>>>(n, g.iota);
-  float *h2 = (float *)g.d_tkeys2;
+  float *h2 = (float *)S.x_keys2;
   B200_TRY(knn_device(g.iota, n, desired_ngb, h2));                          // init.c:440-444
   k_set_hsml_from_h2<<<cdiv(n, 256), 256, 0, st>>>(n, h2, g.velh, g.left, g.right);
   count_launch(2);
@@ -990,23 +999,49 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   if (!g.ready || g.n <= 0) return B200_ERR_STATE;
   B200_TRY(b200_predict(time));                    // gravtree.c:72 predict_collisionless_only(All.Time)
   B200_TRY(b200_tree_build());                     // gravtree.c:76 force_treebuild()
-  B200_TRY(b200_gravity(active, nactive, time));   // gravtree.c:127-324
-  if (mode == 0) {                                 // accel.c:60-65
+  if (mode != 0) return b200_gravity(active, nactive, time);     // accel.c:62: no SIDM in mode 1
+  // gravity_tree() and sidm() + sidm_ensure_neighbours() (accel.c:39-65) are independent once the
+  // tree exists: they read the same particles and tree and write disjoint fields (Accel, OldAcc,
+  // GravCost | dVel, NgbVelDisp, HsmlVelDisp, Left, Right).  One GPU: the walk is issued without a
+  // host sync on the main stream and the SIDM chain - a throughput-bound search followed by a tail
+  // of small launches with host round trips - on a second, high-priority stream, so the tail costs
+  // no wall time.  Sharded over several GPUs the two phases stay in sequence (their collectives are
+  // issued on the host's stream).
+  const bool overlap = g.opt_overlap && g.shard_world == 1;
+  if (active && (nactive < 0 || nactive > g.n)) return B200_ERR_ARG;
+  if (!overlap) {
+    B200_TRY(b200_gravity(active, nactive, time));   // gravtree.c:127-324
     B200_TRY(b200_sidm(active, nactive, time, vmax, nullptr));
-    B200_TRY(b200_sidm_ensure_neighbours(mode, time, vmax, nullptr));
+    return b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);
   }
-  return B200_OK;
+  CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
+  CUDA_TRY(cudaStreamWaitEvent(g.stream_sidm, g.ev_fork, 0));
+  int rc = gravity_impl(active, nactive, time, true);
+  int rs = B200_OK;
+  if (rc == B200_OK) {
+    g.overlap_now = true;
+    rs = b200_sidm(active, nactive, time, vmax, nullptr);
+    if (rs == B200_OK) rs = b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);
+    g.overlap_now = false;
+  }
+  cudaStreamSynchronize(g.stream_sidm);
+  const int rf = gravity_finish();
+  // later work on the main stream is ordered after the SIDM chain
+  cudaEventRecord(g.ev_join, g.stream_sidm); cudaStreamWaitEvent(g.stream, g.ev_join, 0);
+  if (rc != B200_OK) return rc;
+  if (rs != B200_OK) return rs;
+  return rf;
 }
 
 extern "C" int b200_ngb_treefind(const int *idx, int n, int desngb, float *h2_out) {
   if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
   if (!idx || n <= 0 || n > g.n || !h2_out) return B200_ERR_ARG;
   B200_TRY(ensure_sidm_buffers());
-  CUDA_TRY(cudaMemcpyAsync(g.d_active, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, g.stream));
-  float *h2 = (float *)g.d_tkeys2;
-  B200_TRY(knn_device(g.d_active, n, desngb, h2));
-  CUDA_TRY(cudaMemcpyAsync(h2_out, h2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(S.x_redo, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, sidm_stream()));
+  float *h2 = (float *)S.x_keys2;
+  B200_TRY(knn_device(S.x_redo, n, desngb, h2));
+  CUDA_TRY(cudaMemcpyAsync(h2_out, h2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, sidm_stream()));
+  CUDA_TRY(cudaStreamSynchronize(sidm_stream()));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -1055,15 +1090,15 @@ extern "C" int b200_ngb_lists(const int *idx, int n, int cap, int *count_out, in
   if (cudaMalloc((void **)&d_cnt, (size_t)n * 4) != cudaSuccess) return B200_ERR_ALLOC;
   if (cudaMalloc((void **)&d_list, (size_t)n * cap * 4) != cudaSuccess) return B200_ERR_ALLOC;
   if (cudaMalloc((void **)&d_keys, (size_t)n * cap * 8) != cudaSuccess) return B200_ERR_ALLOC;
-  cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream);
-  cudaMemsetAsync(d_list, 0xff, (size_t)n * cap * 4, g.stream);
+  cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, sidm_stream());
+  cudaMemsetAsync(d_list, 0xff, (size_t)n * cap * 4, sidm_stream());
   ListParams P; P.nq = n; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.velh = g.velh; P.cap = cap; P.count = d_cnt; P.list = d_list;
   P.ref_order = g.par.ReferenceNgbOrder; P.krank = g.krank; P.lrank = g.lrank; P.nstart = g.nstart; P.keys = d_keys;
-  k_ngb_lists<<<cdiv(n, 64), 64, 0, g.stream>>>(P);
+  k_ngb_lists<<<cdiv(n, 64), 64, 0, sidm_stream()>>>(P);
   count_launch();
-  cudaMemcpyAsync(count_out, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream);
-  cudaMemcpyAsync(list_out, d_list, (size_t)n * cap * 4, cudaMemcpyDeviceToHost, g.stream);
-  cudaError_t e = cudaStreamSynchronize(g.stream);
+  cudaMemcpyAsync(count_out, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, sidm_stream());
+  cudaMemcpyAsync(list_out, d_list, (size_t)n * cap * 4, cudaMemcpyDeviceToHost, sidm_stream());
+  cudaError_t e = cudaStreamSynchronize(sidm_stream());
   cudaFree(d_idx); cudaFree(d_cnt); cudaFree(d_list); cudaFree(d_keys);
   if (e != cudaSuccess) { g.last_cuda = (int)e; return B200_ERR_CUDA; }
   return B200_OK;
@@ -1071,7 +1106,7 @@ extern "C" int b200_ngb_lists(const int *idx, int n, int cap, int *count_out, in
 
 extern "C" int b200_sidm_debug(int nslot, int *slot_particle, double *pmax, double *prob_total, int *partner) {
   if (!g.ready || nslot <= 0 || nslot > g.last_nslot) return B200_ERR_ARG;
-  cudaStream_t st = g.stream;
+  cudaStream_t st = sidm_stream();
   if (slot_particle) cudaMemcpyAsync(slot_particle, g.s_slot_part, (size_t)nslot * 4, cudaMemcpyDeviceToHost, st);
   if (pmax) cudaMemcpyAsync(pmax, g.s_pmax, (size_t)nslot * 8, cudaMemcpyDeviceToHost, st);
   if (prob_total) cudaMemcpyAsync(prob_total, S.ptot, (size_t)nslot * 8, cudaMemcpyDeviceToHost, st);

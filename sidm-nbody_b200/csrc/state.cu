@@ -65,6 +65,11 @@ using namespace b200;
 extern "C" const char *b200_version(void) { return "sidm_b200 0.1 (sm_100a)"; }
 extern "C" int b200_last_cuda_error(void) { return g.last_cuda; }
 extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cuda_stream; return B200_OK; }
+extern "C" int b200_set_option(const char *name, int value) {
+  if (!name) return B200_ERR_ARG;
+  if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
+  return B200_ERR_ARG;
+}
 
 extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes, b200_allgather_fn fn, void *user) {
   if (world < 1 || rank < 0 || rank >= world) return B200_ERR_ARG;
@@ -82,11 +87,11 @@ __global__ void k_shard_select(int nt, int world, int rank, const int *in, int *
   if (j < nt) out[k] = in[j];
 }
 namespace b200 {
-int shard_select(const int *d_in, int nt, int *d_out, int *n_own) {
+int shard_select(const int *d_in, int nt, int *d_out, int *n_own, cudaStream_t st) {
   const int nown = shard_count(nt, g.shard_world, g.shard_rank);
   *n_own = nown;
   if (nown > 0) {
-    k_shard_select<<<cdiv(nown, 256), 256, 0, g.stream>>>(nt, g.shard_world, g.shard_rank, d_in, d_out, nown);
+    k_shard_select<<<cdiv(nown, 256), 256, 0, st>>>(nt, g.shard_world, g.shard_rank, d_in, d_out, nown);
     count_launch();
   }
   return B200_OK;
@@ -126,6 +131,14 @@ extern "C" int b200_init(const b200_params *p) {
   g.maxnodes = (int)(taf * (double)g.maxpart) + 64;
   g.stream = nullptr;   // legacy default stream: what torch's current stream is unless the host changes it
   CUDA_TRY(cudaEventCreate(&g.ev0)); CUDA_TRY(cudaEventCreate(&g.ev1));
+  CUDA_TRY(cudaEventCreate(&g.ev_s0)); CUDA_TRY(cudaEventCreate(&g.ev_s1));
+  CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+  {
+    int plo = 0, phi = 0;                 // numerically lowest = highest priority
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&g.stream_sidm, cudaStreamNonBlocking, phi));
+  }
+  g.opt_overlap = getenv("B200_NO_OVERLAP") == nullptr; g.overlap_now = false; g.walk_pending = false;
   int rc = alloc_all();
   if (rc != B200_OK) { b200_finalize(); return rc; }
   CUDA_TRY(cudaMallocHost((void **)&g.h_flags, FL_COUNT * sizeof(int)));
@@ -171,6 +184,12 @@ extern "C" void b200_finalize(void) {
   if (g.h_ctr) cudaFreeHost(g.h_ctr); g.h_ctr = nullptr;
   if (g.ev0) cudaEventDestroy(g.ev0); g.ev0 = nullptr;
   if (g.ev1) cudaEventDestroy(g.ev1); g.ev1 = nullptr;
+  if (g.ev_s0) cudaEventDestroy(g.ev_s0); g.ev_s0 = nullptr;
+  if (g.ev_s1) cudaEventDestroy(g.ev_s1); g.ev_s1 = nullptr;
+  if (g.ev_fork) cudaEventDestroy(g.ev_fork); g.ev_fork = nullptr;
+  if (g.ev_join) cudaEventDestroy(g.ev_join); g.ev_join = nullptr;
+  if (g.stream_sidm) cudaStreamDestroy(g.stream_sidm); g.stream_sidm = nullptr;
+  g.overlap_now = false; g.walk_pending = false;
   g.stream = nullptr;
   g.ready = false; g.n = 0; g.tree_valid = false;
 }

@@ -292,7 +292,14 @@ static float h_inv_of_type1() {
 }
 
 // walk for nt targets; d_sorted = sorted slot list; with_slots: slot->particle through d_active
-int walk_impl(const int *d_sorted, int nt, bool with_slots) {
+static int walk_read_counters() {
+  cudaEventElapsedTime(&g.cnt.ms_walk, g.ev0, g.ev1);
+  g.cnt.part_interactions = (long long)g.h_ctr[CT_PART]; g.cnt.node_interactions = (long long)g.h_ctr[CT_NODE];
+  g.cnt.list_nodes = (long long)g.h_ctr[CT_LIST_NODES]; g.cnt.list_parts = (long long)g.h_ctr[CT_LIST_PARTS];
+  return B200_OK;
+}
+
+int walk_impl(const int *d_sorted, int nt, bool with_slots, bool defer_sync) {
   WalkParams P;
   P.nt = nt; P.num_nodes = g.num_nodes; P.tsorted = d_sorted; P.slot_part = with_slots ? g.d_active : nullptr;
   P.posm = g.posm; P.oldacc = g.oldacc; P.nodes = g.nodes; P.leaf_posm = g.leaf_posm;
@@ -310,13 +317,12 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots) {
   }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  CUDA_TRY(cudaGetLastError());
-  cudaEventElapsedTime(&g.cnt.ms_walk, g.ev0, g.ev1);
-  g.cnt.part_interactions = (long long)g.h_ctr[CT_PART]; g.cnt.node_interactions = (long long)g.h_ctr[CT_NODE];
-  g.cnt.list_nodes = (long long)g.h_ctr[CT_LIST_NODES]; g.cnt.list_parts = (long long)g.h_ctr[CT_LIST_PARTS];
   g.cnt.num_targets = nt;
   g.cnt.num_lists = (nt + 31) / 32;
+  if (defer_sync) { g.walk_pending = true; return B200_OK; }      // gravity_finish() reads the counters
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  walk_read_counters();
   return B200_OK;
 }
 
@@ -378,15 +384,22 @@ __global__ void k_grav_unpack(int nt, int world, int per_rank, const int *sorted
   accel[3 * (size_t)p] = v.x; accel[3 * (size_t)p + 1] = v.y; accel[3 * (size_t)p + 2] = v.z; oldacc[p] = v.w;
 }
 
-int gravity_impl(const int *active, int nactive, double time) {
+int gravity_finish() {
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  if (g.walk_pending) { walk_read_counters(); g.walk_pending = false; }
+  return B200_OK;
+}
+
+int gravity_impl(const int *active, int nactive, double time, bool defer_sync) {
   if (!g.tree_valid) return B200_ERR_STATE;
   const int nt = active ? nactive : g.n;
   if (nt <= 0) return B200_OK;
   int *d_sorted = nullptr;
   B200_TRY(prepare_targets(active, nt, &d_sorted));
   const int *work = d_sorted; int nw = nt;
-  if (g.shard_world > 1) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw)); work = g.d_shard_list; }
-  B200_TRY(walk_impl(work, nw, active != nullptr));
+  if (g.shard_world > 1) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw, g.stream)); work = g.d_shard_list; }
+  B200_TRY(walk_impl(work, nw, active != nullptr, defer_sync));
   EpiParams E;
   // all particles on one rank: run the epilogue in particle order (coalesced) instead of key order
   E.nt = nw; E.list = (!active && g.shard_world == 1) ? nullptr : work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
@@ -405,9 +418,8 @@ int gravity_impl(const int *active, int nactive, double time) {
     k_grav_unpack<<<cdiv(tot, 256), 256, 0, g.stream>>>(nt, g.shard_world, per_rank, d_sorted, E.slot_part, (const float4 *)g.shard_recv, g.accel, g.oldacc);
     count_launch();
   }
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+  if (defer_sync) return B200_OK;
+  return gravity_finish();
 }
 
 // ------------------------------------------------------------------ direct summation

@@ -80,6 +80,9 @@ class HotPath:
                 setattr(self.params, k, v)
         check(self.lib.b200_set_params(C.byref(self.params)), "b200_set_params")
 
+    def set_option(self, name, value):
+        check(self.lib.b200_set_option(name.encode(), int(value)), "b200_set_option")
+
     # ---- particle state ---------------------------------------------------------------
     def set_particles(self, pos=None, vel=None, mass=None, ids=None, curtime=None, accel=None, oldacc=None,
                       hsml=None, dvel=None, n=None):
