@@ -22,6 +22,7 @@ struct Ctx {
   cudaStream_t stream_sidm = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   bool opt_overlap = true;         // b200_set_option("overlap", 0|1)
+  bool opt_group_search = true;    // b200_set_option("group_search", 0|1): warp-shared neighbour search for all-active passes
   bool overlap_now = false;        // true while the SIDM chain is being issued on stream_sidm
   bool walk_pending = false;       // a deferred walk whose counters / timing are still to be read
 

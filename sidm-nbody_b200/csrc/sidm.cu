@@ -52,6 +52,8 @@ struct SidmState {
   // which owns S.x_redo / g.d_t* / S.cub_tmp)
   int *x_redo = nullptr, *x_want = nullptr, *x_keys = nullptr, *x_keys2 = nullptr, *x_vals = nullptr, *x_shard = nullptr;
   void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  // query groups of the warp-shared search (k_pass1_group): leaf range + tree node of each group
+  int2 *groups = nullptr; int *gnode = nullptr, *gflag = nullptr, *gpos = nullptr, *order_leaf = nullptr; int ngroups = 0;
 } S;
 
 constexpr int kCandCap = 1024;      // per-slot candidate capacity in reference-order mode
@@ -305,6 +307,220 @@ __global__ void __launch_bounds__(128, 16) k_pass1(Pass1 P) {
   P.pass[t] = pass;
 }
 
+// ------------------------------------------------------------------ pass 1, warp-shared search
+// When every particle is a query (all-active steps, start-up) the queries are grouped by tree
+// node: a group = the particles of a subtree with <= 32 particles whose parent holds more (or the
+// direct particles of a bigger cell), i.e. one compact cell, contiguous in leaf order.  One warp
+// per group: lane = query.  The warp walks the tree ONCE for the union of its search cubes
+// (warp-uniform pre-order walk, broadcast loads) and every lane tests every candidate of the
+// overlapping leaf cells against its own sphere with the reference's float test
+// (forcetree.c:2195-2206).  The neighbour SET of a query does not depend on how the candidates
+// were found, so the counts equal those of the per-query walk (k_pass1) bit for bit; what changes
+// is the cost: ~10x fewer instructions, coalesced candidate loads instead of divergent ones.
+constexpr int kGroupCell = 512;   // query groups are cut from subtrees with at most this many particles
+__device__ __forceinline__ int group_chunks(const SearchNode &nd) {
+  const int cnt = nd.pend - nd.pstart;
+  return cnt <= kGroupCell ? (cnt + 31) / 32 : (nd.np > 0 ? 1 : 0);
+}
+// number of groups each node contributes: a subtree with <= kGroupCell particles whose parent holds
+// more is cut into ceil(cnt/32) equal runs of its leaf range; a bigger cell contributes its direct particles
+__global__ void k_group_flag(int m, const SearchNode *sn, const int *nparent, int *flag) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id > m) return;
+  if (id == m) { flag[m] = 0; return; }
+  const int cnt = sn[id].pend - sn[id].pstart;
+  int f = group_chunks(sn[id]);
+  if (cnt <= kGroupCell && id > 0) { const int par = nparent[id]; if (sn[par].pend - sn[par].pstart <= kGroupCell) f = 0; }
+  flag[id] = f;
+}
+__global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const int *pos, int2 *groups, int *gnode) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= m || !flag[id]) return;
+  const int cnt = sn[id].pend - sn[id].pstart, c = flag[id], g0 = pos[id];
+  if (cnt > kGroupCell) { groups[g0] = make_int2(sn[id].pstart, sn[id].np); gnode[g0] = id; return; }
+  const int base = cnt / c, rem = cnt % c;
+  int at = sn[id].pstart;
+  for (int j = 0; j < c; j++) { const int nj = base + (j < rem); groups[g0 + j] = make_int2(at, nj); gnode[g0 + j] = id; at += nj; }
+}
+
+__device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }   // monotone float -> int
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
+
+struct Pass1G {
+  int ng; const int2 *groups; const int *gnode; SearchCtx C; const float4 *velh; const int *slot_of_part;
+  const float *dt; const unsigned char *already; const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
+  int *ngb; double *pmax, *rnd; int *pass; int *order_leaf; int count_only; unsigned long long *ctr;
+};
+constexpr int kGroupTiny = 4;
+constexpr int kQCap = 320;         // warp-private cell queue of the lane-parallel walk
+
+// packed fp32 pairs (sm_100a add.rn.f32x2 = SASS FADD2): two candidates per instruction
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void up2(f2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+// squares as two scalar __fmul_rn: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// with --fmad=false, which would break the FMA-free neighbour test; scalar .rn products are left alone
+__device__ __forceinline__ f2 sq2(f2 a) { float x, y; up2(a, x, y); return pk2(__fmul_rn(x, x), __fmul_rn(y, y)); }
+
+struct Cube { float lx, ly, lz, hx, hy, hz; };
+// warp-uniform pre-order walk (every lane visits every cell): fallback of the lane-parallel walk
+__device__ __noinline__ void group_walk_uniform(const SearchCtx &C, const Cube &U, int A, int stop, const float4 &p, float sr2, int &cnt, unsigned &cand) {
+  int no = A;
+  while (no < stop) {
+    const float4 *q = reinterpret_cast<const float4 *>(C.snodef + no);
+    const float4 a = __ldg(q), b = __ldg(q + 1);           // lo.xyz hi.x | hi.yz skip pinfo
+    const int skip = __float_as_int(b.z), pinfo = __float_as_int(b.w);
+    if (a.w < U.lx || a.x > U.hx || b.x < U.ly || a.y > U.hy || b.y < U.lz || a.z > U.hz) { no = skip; continue; }
+    const bool whole = (pinfo & 16) || ((a.x >= U.lx) && (a.w <= U.hx) && (a.y >= U.ly) && (b.x <= U.hy) && (a.z >= U.lz) && (b.y <= U.hz));
+    const int pk = pinfo >> 5;
+    int pe;
+    if (whole) { pe = (pinfo & 16) ? pk + (pinfo & 15) : (C.snodef[skip].pinfo >> 5); no = skip; }
+    else { pe = pk + (pinfo & 15); no = no + 1; }
+    cand += (unsigned)(pe - pk);
+    for (int k = pk; k < pe; k++) { const float4 c0 = __ldg(C.leaf_posm + k); cnt += dist2_ref(c0.x, c0.y, c0.z, p.x, p.y, p.z) < sr2; }
+  }
+}
+__device__ __forceinline__ void pass1_finish(const Pass1G &P, int L, int i, const float4 &p, float h, int cnt) {
+  const int s = P.slot_of_part[i];
+  P.ngb[s] = cnt;
+  P.order_leaf[L] = s;
+  if (P.count_only) { P.pass[L] = 0; return; }
+  const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
+  const double hh = 1.0 * (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
+  const double pm = P.C_Pmax * (double)p.w * hinv3 * dt_h0;          // sidm.c:338
+  double r;
+  if (P.replay_rand) r = P.replay_rand[s];
+  else r = u01(philox((uint32_t)i, 0u, 0u, 0u, P.k0, P.k1).x);
+  P.pmax[s] = pm; P.rnd[s] = r;
+  P.pass[L] = !(pm < r) && !P.already[s];                             // sidm.c:343-346
+}
+__global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= P.ng) return;                                   // warp-uniform
+  const int2 gr = P.groups[w];
+  const bool valid = lane < gr.y;
+  const int L = gr.x + (valid ? lane : 0);
+  const float4 p = P.C.leaf_posm[L];
+  const int i = P.C.leaf_orig[L];
+  const float h = valid ? P.velh[i].w : 0.0f;
+  const float sr2 = fmul(h, h);
+  if (gr.y <= kGroupTiny) {
+    // a few stray particles (direct particles of a big cell): per-query tree walks, as k_pass1
+    int cnt = 0, cand = 0;
+    const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
+    range_search_fast(P.C, valid, start, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+    if (valid) { atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand); pass1_finish(P, L, i, p, h, cnt); }
+    return;
+  }
+  // union of the group's search cubes
+  const float big = 3.0e38f;
+  Cube U;
+  U.lx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(valid ? fadd(p.x, -h) : big)));
+  U.ly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(valid ? fadd(p.y, -h) : big)));
+  U.lz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(valid ? fadd(p.z, -h) : big)));
+  U.hx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.x, h) : -big)));
+  U.hy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.y, h) : -big)));
+  U.hz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.z, h) : -big)));
+  // smallest ancestor cell that contains the union with a safety margin (cf. search_start)
+  int A = P.gnode[w];
+  {
+    const double mg = 1.0e-5 * (fmax(fabs((double)U.lx), fabs((double)U.hx)) + fmax(fabs((double)U.ly), fabs((double)U.hy)) +
+                                fmax(fabs((double)U.lz), fabs((double)U.hz)) + ((double)U.hx - (double)U.lx));
+    while (A > 0) {
+      const SearchNode &nd = P.C.snode[A];
+      if (nd.lo[0] + mg <= (double)U.lx && nd.lo[1] + mg <= (double)U.ly && nd.lo[2] + mg <= (double)U.lz &&
+          nd.hi[0] - mg >= (double)U.hx && nd.hi[1] - mg >= (double)U.hy && nd.hi[2] - mg >= (double)U.hz) break;
+      A = P.C.nparent[A];
+    }
+  }
+  const int stopA = P.C.snodef[A].skip;
+
+  // Lane-parallel walk: a warp-private LIFO of (cell, end of its sibling chain).  Each trip every
+  // lane pops one cell, tests it against the union cube, pushes the next sibling and - if the cell
+  // is opened - its first child, and yields the leaf range whose particles have to be tested (the
+  // cell's own particles, or the whole subtree of a cell that lies inside the cube or is a bucket).
+  // The ranges of a trip are flattened over the lanes: 32 candidates are fetched at once (coalesced
+  // within a range), staged in shared memory, and every lane tests all of them against its own
+  // sphere two at a time (packed add.rn.f32x2 for the differences and sums, scalar products: every
+  // operation individually rounded, i.e. exactly the FMA-free float test of forcetree.c:2195-2206).
+  __shared__ int2 s_q[4][kQCap];
+  __shared__ __align__(8) float s_cx[4][32], s_cy[4][32], s_cz[4][32];
+  const int wib = threadIdx.x >> 5;
+  int2 *q = s_q[wib]; float *cx = s_cx[wib], *cy = s_cy[wib], *cz = s_cz[wib];
+  const unsigned lt = (1u << lane) - 1u;
+  const f2 nqx = bc2(-p.x), nqy = bc2(-p.y), nqz = bc2(-p.z);
+  int cnt = 0; unsigned cand = 0;
+  int qn = 1;
+  if (lane == 0) q[0] = make_int2(A, stopA);
+  __syncwarp();
+  bool overflow = false;
+  while (qn > 0) {
+    const int take = qn < 32 ? qn : 32, base = qn - take;
+    const int2 it = lane < take ? q[base + lane] : make_int2(-1, -1);
+    __syncwarp();
+    qn = base;
+    int pk = 0, pe = 0, sib = -1, child = -1, cstop = 0;
+    if (lane < take) {
+      const float4 *rq = reinterpret_cast<const float4 *>(P.C.snodef + it.x);
+      const float4 a = __ldg(rq), b = __ldg(rq + 1);       // lo.xyz hi.x | hi.yz skip pinfo
+      const int skip = __float_as_int(b.z), pinfo = __float_as_int(b.w);
+      if (skip < it.y) sib = skip;
+      if (!(a.w < U.lx || a.x > U.hx || b.x < U.ly || a.y > U.hy || b.y < U.lz || a.z > U.hz)) {
+        const bool whole = (pinfo & 16) || ((a.x >= U.lx) && (a.w <= U.hx) && (a.y >= U.ly) && (b.x <= U.hy) && (a.z >= U.lz) && (b.y <= U.hz));
+        pk = pinfo >> 5;
+        if (whole) pe = (pinfo & 16) ? pk + (pinfo & 15) : (P.C.snodef[skip].pinfo >> 5);
+        else { pe = pk + (pinfo & 15); if (it.x + 1 < skip) { child = it.x + 1; cstop = skip; } }
+      }
+    }
+    const unsigned m1 = __ballot_sync(0xffffffffu, sib >= 0), m2 = __ballot_sync(0xffffffffu, child >= 0);
+    const int n1 = __popc(m1), n2 = __popc(m2);
+    if (qn + n1 + n2 > kQCap) { overflow = true; break; }
+    if (sib >= 0) q[qn + __popc(m1 & lt)] = make_int2(sib, it.y);
+    if (child >= 0) q[qn + n1 + __popc(m2 & lt)] = make_int2(child, cstop);
+    qn += n1 + n2;
+    __syncwarp();
+    // flatten this trip's leaf ranges over the lanes
+    const int len = pe - pk;
+    int inc = len;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int T = __shfl_sync(0xffffffffu, inc, 31), exc = inc - len;
+    cand += (unsigned)T;
+    for (int c0 = 0; c0 < T; c0 += 32) {
+      const int idx = c0 + lane;
+      int r = 0;                                            // the last lane whose range starts at or before idx
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, exc, (r + step) & 31);
+        if (r + step < 32 && v <= idx) r += step;
+      }
+      const int pk_r = __shfl_sync(0xffffffffu, pk, r), exc_r = __shfl_sync(0xffffffffu, exc, r);
+      float4 c = make_float4(big, big, big, 0.f);          // padding fails every sphere test (r2 = inf)
+      if (idx < T) c = __ldg(P.C.leaf_posm + pk_r + (idx - exc_r));
+      cx[lane] = c.x; cy[lane] = c.y; cz[lane] = c.z;
+      __syncwarp();
+      const int nv = (T - c0 < 32) ? T - c0 : 32, npair = (nv + 1) >> 1;
+      const unsigned long long *px = reinterpret_cast<const unsigned long long *>(cx), *py = reinterpret_cast<const unsigned long long *>(cy),
+                               *pz = reinterpret_cast<const unsigned long long *>(cz);
+#pragma unroll 4
+      for (int k = 0; k < npair; k++) {
+        f2 X, Y, Z; X.v = px[k]; Y.v = py[k]; Z.v = pz[k];
+        const f2 dx = add2(X, nqx), dy = add2(Y, nqy), dz = add2(Z, nqz);
+        float ra, rb;
+        up2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), ra, rb);
+        cnt += (ra < sr2) + (rb < sr2);
+      }
+      __syncwarp();
+    }
+  }
+  if (overflow) {                                           // queue full (never seen in practice): plain uniform walk
+    cnt = 0; cand = 0;
+    group_walk_uniform(P.C, U, A, stopA, p, sr2, cnt, cand);
+  }
+  if (lane == 0) atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand * (unsigned)gr.y);
+  if (valid) pass1_finish(P, L, i, p, h, cnt);
+}
+
 // ------------------------------------------------------------------ pass 2
 struct Pass2 {
   int np; const int *passlist; const int *slot_part; SearchCtx C;
@@ -516,6 +732,9 @@ static int ensure_sidm_buffers() {
   B200_TRY(al((void **)&S.x_redo, n * sizeof(int))); B200_TRY(al((void **)&S.x_want, n * sizeof(int)));
   B200_TRY(al((void **)&S.x_keys, n * sizeof(int))); B200_TRY(al((void **)&S.x_keys2, n * sizeof(int)));
   B200_TRY(al((void **)&S.x_vals, n * sizeof(int))); B200_TRY(al((void **)&S.x_shard, (n + 64) * sizeof(int)));
+  B200_TRY(al((void **)&S.groups, (n + m + 1) * sizeof(int2))); B200_TRY(al((void **)&S.gnode, (n + m + 1) * sizeof(int)));
+  B200_TRY(al((void **)&S.gflag, (m + 2) * sizeof(int))); B200_TRY(al((void **)&S.gpos, (m + 2) * sizeof(int)));
+  B200_TRY(al((void **)&S.order_leaf, n * sizeof(int)));
   if (!d_kernel_table) {
     double K[1002];
     const double PI = 3.14159265358979323846;
@@ -534,9 +753,10 @@ static int ensure_sidm_buffers() {
 void sidm_release() {
   void **ptrs[] = {(void **)&S.snode, (void **)&S.snodef, (void **)&S.last_active, (void **)&S.slot_of_sorted, (void **)&S.passlist,
                    (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot,
-                   (void **)&S.x_redo, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp};
+                   (void **)&S.x_redo, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp,
+                   (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
-  S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false; S.cub_tmp_bytes = 0;
+  S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false; S.cub_tmp_bytes = 0; S.ngroups = 0;
 }
 
 static int cub_scratch(size_t tb) {
@@ -560,8 +780,21 @@ int refresh_search_nodes() {
   B200_TRY(ensure_sidm_buffers());
   if (g.search_epoch == g.tree_epoch) return B200_OK;
   g.search_epoch = g.tree_epoch;
-  k_search_nodes<<<cdiv(g.num_nodes, 256), 256, 0, sidm_stream()>>>(g.num_nodes, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
-  count_launch();
+  cudaStream_t st = sidm_stream();
+  const int m = g.num_nodes;
+  k_search_nodes<<<cdiv(m, 256), 256, 0, st>>>(m, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
+  // query groups of the warp-shared search
+  k_group_flag<<<cdiv(m + 1, 256), 256, 0, st>>>(m, S.snode, g.nparent, S.gflag);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, S.gflag, S.gpos, m + 1, st);
+  B200_TRY(cub_scratch(tb));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, S.gflag, S.gpos, m + 1, st));
+  k_group_emit<<<cdiv(m, 256), 256, 0, st>>>(m, S.snode, S.gflag, S.gpos, S.groups, S.gnode);
+  CUDA_TRY(cudaMemcpyAsync(&S.ngroups, S.gpos + m, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  count_launch(5);
+  static const bool dbg = getenv("B200_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "libsidm_b200: %d query groups for %d particles (%.1f per warp)\n", S.ngroups, g.n, (double)g.n / (S.ngroups > 0 ? S.ngroups : 1));
   return B200_OK;
 }
 
@@ -648,7 +881,16 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     P1.C_Pmax = C_Pmax; P1.s_a_inverse = sainv; P1.k0 = k0; P1.k1 = k1;
     P1.ngb = g.s_ngb; P1.pmax = g.s_pmax; P1.rnd = g.s_rand; P1.pass = g.s_pass; P1.count_only = count_only; P1.ctr = g.d_ctr;
     k_clear_slots<<<G, B, 0, st>>>(nb, g.s_partner, g.s_dv, g.s_prob, S.ptot);
-    if (nord > 0) k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
+    // every particle is a query, one GPU, open boundaries: warp-shared search over the query groups
+    const bool grouped = !act && nb == g.n && g.shard_world == 1 && !(P1.C.box > 0) && S.ngroups > 0 && g.opt_group_search;
+    if (grouped) {
+      Pass1G PG;
+      PG.ng = S.ngroups; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
+      PG.dt = S.dt; PG.already = S.already; PG.replay_rand = d_rr; PG.C_Pmax = C_Pmax; PG.s_a_inverse = sainv; PG.k0 = k0; PG.k1 = k1;
+      PG.ngb = g.s_ngb; PG.pmax = g.s_pmax; PG.rnd = g.s_rand; PG.pass = g.s_pass; PG.order_leaf = S.order_leaf; PG.count_only = count_only; PG.ctr = g.d_ctr;
+      k_pass1_group<<<cdiv((long long)S.ngroups * 32, 128), 128, 0, st>>>(PG);
+      order = S.order_leaf;        // the pass flags are indexed by leaf position
+    } else if (nord > 0) k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     count_launch(2);
     int npass = 0;
     if (!count_only) {

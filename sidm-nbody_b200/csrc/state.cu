@@ -68,6 +68,7 @@ extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cud
 extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
   if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
+  if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
   return B200_ERR_ARG;
 }
 

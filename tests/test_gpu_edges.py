@@ -83,3 +83,33 @@ def test_partial_and_empty_active_lists():
         assert np.array_equal(dv != 0, O.dvel != 0)
         assert np.array_equal(ngb[active], O.ngb[active])
         np.testing.assert_allclose(dv, O.dvel, rtol=3e-6, atol=1e-30)
+
+
+def test_group_search_equals_per_query_search():
+    """the warp-shared neighbour search of all-active passes (k_pass1_group) must return the counts
+    of the per-query tree search (k_pass1, the restatement of forcetree.c:2163-2297) bit for bit,
+    and the same scatter decisions for the same per-particle random numbers"""
+    from sidm_b200 import HotPath, ic
+    n = 60000
+    pos, vel, mass, ids = ic.hernquist(n, seed=11)
+    out = {}
+    for mode in (0, 1):
+        with HotPath(n, CrossSectionInternal=208.9, Seed=9) as hp:
+            hp.set_option("group_search", mode)
+            hp.set_particles(pos, vel, mass, ids)
+            hp.predict_collisionless_only(0.0)
+            hp.force_treebuild()
+            hp.setup_smoothinglengths_sidm(30)
+            h0, ngb0 = hp.get("HsmlVelDisp", "NgbVelDisp")
+            vmax = hp.getvmax()
+            hp.set_particles(curtime=np.zeros(n, np.float32))
+            hp.sidm(time=0.01, vmax=vmax)                      # all particles, Philox keyed per particle
+            ngb1, dvel = hp.get("NgbVelDisp", "dVel")
+            c = hp.counters()
+            out[mode] = (h0, ngb0, ngb1, dvel, c.sct_pass1, c.sct_scattered)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][3], out[1][3])
+    assert out[0][4] == out[1][4] and out[0][5] == out[1][5]
+    assert out[0][5] > 0
