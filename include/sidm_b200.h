@@ -132,7 +132,8 @@ int  b200_set_stream(void *cuda_stream);
 const char *b200_version(void);
 /* run-time switches.  "overlap" (default 1): b200_compute_accelerations(0) issues the gravity walk and
  * the SIDM chain on two CUDA streams so the SIDM repair loop's small launches hide behind the walk
- * (one GPU only); 0 runs the phases one after the other as accel.c:39-65 does. */
+ * 0 runs the phases one after the other as accel.c:39-65 does.  "shard_overlap" (default 0): see
+ * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes. */
 int  b200_set_option(const char *name, int value);
 
 /* ---- particle state -------------------------------------------------------------- */
@@ -164,12 +165,16 @@ int  b200_get_soa(float *pospred, float *velpred, float *accel, float *oldacc, f
  * blocks b (b % world == r) of each work list sorted along the tree order, then the ranks
  * all-gather the per-target results.  The library packs into `send`, calls
  * fn(bytes_per_rank, user) - which must all-gather send[0..bytes) of every rank into
- * recv[rank*bytes ..] on the library's stream (ncclAllGather / torch.distributed) - and unpacks
- * `recv`.  send/recv are device pointers owned by the caller; cap_bytes = size of `send`
+ * recv[rank*bytes ..] ordered on the stream b200_current_stream() returns at that moment
+ * (ncclAllGather(..., stream) / torch.distributed under that stream) - and unpacks `recv`.
+ * A host whose callback honours b200_current_stream() sets the option "shard_overlap" to 1: the
+ * SIDM chain then runs on its own stream next to the gravity walk also when sharded (its
+ * collectives are issued first, the gravity exchange last).  send/recv are device pointers owned by the caller; cap_bytes = size of `send`
  * (recv holds world*cap_bytes).  world == 1 switches sharding off. */
 typedef int (*b200_allgather_fn)(long long bytes_per_rank, void *user);
 int  b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes,
                     b200_allgather_fn fn, void *user);
+void *b200_current_stream(void);               /* cudaStream_t of the collective being requested */
 
 /* ---- the hot path ---------------------------------------------------------------- */
 /* predict_collisionless_only(time), predict.c:106: PosPred, VelPred for all particles. */

@@ -48,7 +48,7 @@ DEFAULTS = dict(BufferSizeMB=100, TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolFo
 
 def lib_path(kind="diag"):
     name = {"diag": "libsidmref.so", "fast": "libsidmref_fast.so", "periodic": "libsidmref_per.so",
-            "b200": "libsidmref_b200.so", "x1": "libsidmref_x1.so", "x2": "libsidmref_x2.so",
+            "b200": "libsidmref_b200.so", "b200f": "libsidmref_b200f.so", "x1": "libsidmref_x1.so", "x2": "libsidmref_x2.so",
             "x3": "libsidmref_x3.so"}[kind]
     return os.path.join(HERE, "_ref", name)
 
@@ -68,7 +68,7 @@ class Reference:
         L.ref_get_time.restype = C.c_double
         L.ref_getvmax.restype = C.c_double
         L.ref_get_vmax_global.restype = C.c_double
-        if kind != "b200":   # tree / search accessors need the reference's own forcetree.c statics
+        if kind not in ("b200", "b200f"):   # tree / search accessors need the reference's own forcetree.c statics
             L.ref_ngb_treefind.restype = C.c_float
             L.ref_ngb_treefind.argtypes = [C.c_void_p, C.c_int, C.c_float]
             L.ref_ngb_variable.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]

@@ -7,7 +7,7 @@ import json
 import subprocess
 import sys
 
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r1c"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1h"
 KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
@@ -47,7 +47,7 @@ def to_bytes(v, u):
 def main():
     traffic = None
     for name, note in (('walk', 'k_walk<false>, N=1e7 all-active step (relative criterion)'),
-                       ('pass1', 'k_pass1, full-size launch: 1e7 queries')):
+                       ('pass1', 'k_pass1_group, all-active launch: 1e7 queries in ~346k warp groups')):
         rep = f'gpurun_out/prof_{name}_{TAG}.ncu-rep'
         h, u, v = raw(rep)
         with open(f'profiles/{name}_{TAG}_ncu_summary.txt', 'w') as f:

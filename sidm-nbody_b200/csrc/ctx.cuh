@@ -22,6 +22,9 @@ struct Ctx {
   cudaStream_t stream_sidm = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   bool opt_overlap = true;         // b200_set_option("overlap", 0|1)
+  bool opt_shard_overlap = false;  // b200_set_option("shard_overlap", 1): the host's all-gather callback runs on
+                                   // b200_current_stream(), so the two-stream overlap is also safe when sharded
+  cudaStream_t coll_stream = nullptr;   // stream the pending collective has to be ordered on
   bool opt_group_search = true;    // b200_set_option("group_search", 0|1): warp-shared neighbour search for all-active passes
   bool overlap_now = false;        // true while the SIDM chain is being issued on stream_sidm
   bool walk_pending = false;       // a deferred walk whose counters / timing are still to be read
@@ -117,7 +120,7 @@ inline int shard_count(int nt, int world, int r) {
 }
 inline int shard_max_blocks(int nt, int world) { const int nblk = (nt + kShardBlock - 1) / kShardBlock; return (nblk + world - 1) / world; }
 int shard_select(const int *d_in, int nt, int *d_out, int *n_own, cudaStream_t st);
-int shard_exchange(long long bytes_per_rank);
+int shard_exchange(long long bytes_per_rank, cudaStream_t st);
 
 extern Ctx g;
 

@@ -318,29 +318,38 @@ __global__ void __launch_bounds__(128, 16) k_pass1(Pass1 P) {
 // were found, so the counts equal those of the per-query walk (k_pass1) bit for bit; what changes
 // is the cost: ~10x fewer instructions, coalesced candidate loads instead of divergent ones.
 constexpr int kGroupCell = 512;   // query groups are cut from subtrees with at most this many particles
-__device__ __forceinline__ int group_chunks(const SearchNode &nd) {
+// A group is a run of consecutive leaf slots that lies inside one 32-aligned block of the leaf order
+// and inside one compact cell: a subtree with <= kGroupCell particles whose parent holds more (its
+// leaf range is cut at the multiples of 32), or the direct particles of a bigger cell.  The 32-aligned
+// blocks are also the unit the leaf order is dealt out in when the work is sharded over several GPUs.
+__device__ __forceinline__ int2 group_range(const SearchNode &nd) {      // leaf range the node contributes
   const int cnt = nd.pend - nd.pstart;
-  return cnt <= kGroupCell ? (cnt + 31) / 32 : (nd.np > 0 ? 1 : 0);
+  return cnt <= kGroupCell ? make_int2(nd.pstart, nd.pend) : make_int2(nd.pstart, nd.pstart + nd.np);
 }
-// number of groups each node contributes: a subtree with <= kGroupCell particles whose parent holds
-// more is cut into ceil(cnt/32) equal runs of its leaf range; a bigger cell contributes its direct particles
 __global__ void k_group_flag(int m, const SearchNode *sn, const int *nparent, int *flag) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id > m) return;
   if (id == m) { flag[m] = 0; return; }
   const int cnt = sn[id].pend - sn[id].pstart;
-  int f = group_chunks(sn[id]);
+  const int2 r = group_range(sn[id]);
+  int f = r.y > r.x ? ((r.y - 1) >> 5) - (r.x >> 5) + 1 : 0;            // 32-blocks the range touches
   if (cnt <= kGroupCell && id > 0) { const int par = nparent[id]; if (sn[par].pend - sn[par].pstart <= kGroupCell) f = 0; }
   flag[id] = f;
 }
 __global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const int *pos, int2 *groups, int *gnode) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= m || !flag[id]) return;
-  const int cnt = sn[id].pend - sn[id].pstart, c = flag[id], g0 = pos[id];
-  if (cnt > kGroupCell) { groups[g0] = make_int2(sn[id].pstart, sn[id].np); gnode[g0] = id; return; }
-  const int base = cnt / c, rem = cnt % c;
-  int at = sn[id].pstart;
-  for (int j = 0; j < c; j++) { const int nj = base + (j < rem); groups[g0 + j] = make_int2(at, nj); gnode[g0 + j] = id; at += nj; }
+  const int2 r = group_range(sn[id]);
+  const int c = flag[id], g0 = pos[id], b0 = r.x >> 5;
+  for (int j = 0; j < c; j++) {
+    const int lo = max(r.x, (b0 + j) << 5), hi = min(r.y, (b0 + j + 1) << 5);
+    groups[g0 + j] = make_int2(lo, hi - lo); gnode[g0 + j] = id;
+  }
+}
+// sharded runs: the global processing order of the slots = leaf order
+__global__ void k_order_leaf(int n, const int *leaf_orig, const int *slot_of_part, int *order_leaf) {
+  const int L = blockIdx.x * blockDim.x + threadIdx.x;
+  if (L < n) order_leaf[L] = slot_of_part[leaf_orig[L]];
 }
 
 __device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }   // monotone float -> int
@@ -350,6 +359,7 @@ struct Pass1G {
   int ng; const int2 *groups; const int *gnode; SearchCtx C; const float4 *velh; const int *slot_of_part;
   const float *dt; const unsigned char *already; const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
   int *ngb; double *pmax, *rnd; int *pass; int *order_leaf; int count_only; unsigned long long *ctr;
+  int rank, world;     // sharded: this rank handles the groups of the 32-blocks b with b % world == rank
 };
 constexpr int kGroupTiny = 4;
 constexpr int kQCap = 320;         // warp-private cell queue of the lane-parallel walk
@@ -385,8 +395,10 @@ __device__ __noinline__ void group_walk_uniform(const SearchCtx &C, const Cube &
 __device__ __forceinline__ void pass1_finish(const Pass1G &P, int L, int i, const float4 &p, float h, int cnt) {
   const int s = P.slot_of_part[i];
   P.ngb[s] = cnt;
-  P.order_leaf[L] = s;
-  if (P.count_only) { P.pass[L] = 0; return; }
+  // position of this query in the (rank's) processing order: leaf order, 32-blocks dealt round robin
+  const int k = P.world > 1 ? (((L >> 5) / P.world) << 5) + (L & 31) : L;
+  if (P.world == 1) P.order_leaf[L] = s;
+  if (P.count_only) { P.pass[k] = 0; return; }
   const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
   const double hh = 1.0 * (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
   const double pm = P.C_Pmax * (double)p.w * hinv3 * dt_h0;          // sidm.c:338
@@ -394,12 +406,13 @@ __device__ __forceinline__ void pass1_finish(const Pass1G &P, int L, int i, cons
   if (P.replay_rand) r = P.replay_rand[s];
   else r = u01(philox((uint32_t)i, 0u, 0u, 0u, P.k0, P.k1).x);
   P.pmax[s] = pm; P.rnd[s] = r;
-  P.pass[L] = !(pm < r) && !P.already[s];                             // sidm.c:343-346
+  P.pass[k] = !(pm < r) && !P.already[s];                             // sidm.c:343-346
 }
 __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= P.ng) return;                                   // warp-uniform
   const int2 gr = P.groups[w];
+  if (P.world > 1 && (gr.x >> 5) % P.world != P.rank) return;   // another rank's block
   const bool valid = lane < gr.y;
   const int L = gr.x + (valid ? lane : 0);
   const float4 p = P.C.leaf_posm[L];
@@ -873,7 +886,15 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     }
     // this rank's share of the buffer (all of it on one GPU)
     const int *order = S.slot_of_sorted; int nord = nb;
-    if (g.shard_world > 1) { B200_TRY(shard_select(S.slot_of_sorted, nb, S.x_shard, &nord, st)); order = S.x_shard; }
+    const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+    const bool group_mode = !act && nb == g.n && !periodic_box && S.ngroups > 0 && g.opt_group_search;
+    const int *global_order = S.slot_of_sorted;      // all ranks' slots in processing order
+    if (group_mode && g.shard_world > 1) {           // sharded group search: processing order = leaf order
+      k_order_leaf<<<G, B, 0, st>>>(nb, g.leaf_orig, slot_of_active, S.order_leaf);
+      count_launch();
+      global_order = S.order_leaf;
+    }
+    if (g.shard_world > 1) { B200_TRY(shard_select(global_order, nb, S.x_shard, &nord, st)); order = S.x_shard; }
     // pass 1
     Pass1 P1;
     P1.ns = nord; P1.order = order; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
@@ -881,15 +902,16 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     P1.C_Pmax = C_Pmax; P1.s_a_inverse = sainv; P1.k0 = k0; P1.k1 = k1;
     P1.ngb = g.s_ngb; P1.pmax = g.s_pmax; P1.rnd = g.s_rand; P1.pass = g.s_pass; P1.count_only = count_only; P1.ctr = g.d_ctr;
     k_clear_slots<<<G, B, 0, st>>>(nb, g.s_partner, g.s_dv, g.s_prob, S.ptot);
-    // every particle is a query, one GPU, open boundaries: warp-shared search over the query groups
-    const bool grouped = !act && nb == g.n && g.shard_world == 1 && !(P1.C.box > 0) && S.ngroups > 0 && g.opt_group_search;
+    // every particle is a query, open boundaries: warp-shared search over the query groups
+    const bool grouped = group_mode;
     if (grouped) {
       Pass1G PG;
       PG.ng = S.ngroups; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
       PG.dt = S.dt; PG.already = S.already; PG.replay_rand = d_rr; PG.C_Pmax = C_Pmax; PG.s_a_inverse = sainv; PG.k0 = k0; PG.k1 = k1;
       PG.ngb = g.s_ngb; PG.pmax = g.s_pmax; PG.rnd = g.s_rand; PG.pass = g.s_pass; PG.order_leaf = S.order_leaf; PG.count_only = count_only; PG.ctr = g.d_ctr;
+      PG.rank = g.shard_rank; PG.world = g.shard_world;
       k_pass1_group<<<cdiv((long long)S.ngroups * 32, 128), 128, 0, st>>>(PG);
-      order = S.order_leaf;        // the pass flags are indexed by leaf position
+      if (g.shard_world == 1) order = S.order_leaf;        // the pass flags are indexed by leaf position
     } else if (nord > 0) k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     count_launch(2);
     int npass = 0;
@@ -938,9 +960,9 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       // passes of sidm.c:463-553); the two write sweeps below then run identically on all ranks
       const int per_rank = shard_max_blocks(nb, g.shard_world) * kShardBlock;
       if (nord > 0) { k_slot_pack<<<cdiv(nord, B), B, 0, st>>>(nord, order, g.s_ngb, g.s_partner, g.s_dv, g.s_pass, count_only, (SlotRec *)g.shard_send); count_launch(); }
-      B200_TRY(shard_exchange((long long)per_rank * sizeof(SlotRec)));
+      B200_TRY(shard_exchange((long long)per_rank * sizeof(SlotRec), st));
       const long long tot = (long long)g.shard_world * per_rank;
-      k_slot_unpack<<<cdiv(tot, B), B, 0, st>>>(nb, g.shard_world, per_rank, S.slot_of_sorted, (const SlotRec *)g.shard_recv, g.s_ngb, g.s_partner, g.s_dv, g.d_ctr);
+      k_slot_unpack<<<cdiv(tot, B), B, 0, st>>>(nb, g.shard_world, per_rank, global_order, (const SlotRec *)g.shard_recv, g.s_ngb, g.s_partner, g.s_dv, g.d_ctr);
       count_launch();
     }
     // resolve
@@ -1247,9 +1269,9 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   // GravCost | dVel, NgbVelDisp, HsmlVelDisp, Left, Right).  One GPU: the walk is issued without a
   // host sync on the main stream and the SIDM chain - a throughput-bound search followed by a tail
   // of small launches with host round trips - on a second, high-priority stream, so the tail costs
-  // no wall time.  Sharded over several GPUs the two phases stay in sequence (their collectives are
-  // issued on the host's stream).
-  const bool overlap = g.opt_overlap && g.shard_world == 1;
+  // no wall time.  Sharded over several GPUs this needs a host whose all-gather callback runs on
+  // b200_current_stream() (option "shard_overlap"); the gravity exchange is then issued last.
+  const bool overlap = g.opt_overlap && (g.shard_world == 1 || g.opt_shard_overlap);
   if (active && (nactive < 0 || nactive > g.n)) return B200_ERR_ARG;
   if (!overlap) {
     B200_TRY(b200_gravity(active, nactive, time));   // gravtree.c:127-324

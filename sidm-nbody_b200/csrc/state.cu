@@ -65,10 +65,12 @@ using namespace b200;
 extern "C" const char *b200_version(void) { return "sidm_b200 0.1 (sm_100a)"; }
 extern "C" int b200_last_cuda_error(void) { return g.last_cuda; }
 extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cuda_stream; return B200_OK; }
+extern "C" void *b200_current_stream(void) { return (void *)g.coll_stream; }
 extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
   if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
+  if (!strcmp(name, "shard_overlap")) { g.opt_shard_overlap = value != 0; return B200_OK; }
   return B200_ERR_ARG;
 }
 
@@ -97,8 +99,9 @@ int shard_select(const int *d_in, int nt, int *d_out, int *n_own, cudaStream_t s
   }
   return B200_OK;
 }
-int shard_exchange(long long bytes_per_rank) {
+int shard_exchange(long long bytes_per_rank, cudaStream_t st) {
   if (bytes_per_rank > g.shard_cap) return B200_ERR_ARG;
+  g.coll_stream = st;                    // what b200_current_stream() tells the callback
   const int rc = g.shard_fn(bytes_per_rank, g.shard_user);
   return rc == 0 ? B200_OK : B200_ERR_STATE;
 }
@@ -419,7 +422,7 @@ extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
   if (bytes > g.shard_cap) return B200_ERR_ARG;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   if (count > 0) CUDA_TRY(cudaMemcpyAsync((char *)g.shard_send, g.h_base + (size_t)first * st, (size_t)count * st, cudaMemcpyHostToDevice, g.stream));
-  B200_TRY(shard_exchange(bytes));                       // every rank's rows -> all ranks, over NVLink
+  B200_TRY(shard_exchange(bytes, g.stream));             // every rank's rows -> all ranks, over NVLink
   // rank q's rows start at q*rows_per_rank: compact them into the device image of the whole array
   for (int q = 0; q < g.shard_world; q++) {
     const long long f = (long long)q * rows_per_rank;

@@ -384,7 +384,22 @@ __global__ void k_grav_unpack(int nt, int world, int per_rank, const int *sorted
   accel[3 * (size_t)p] = v.x; accel[3 * (size_t)p + 1] = v.y; accel[3 * (size_t)p + 2] = v.z; oldacc[p] = v.w;
 }
 
+// deferred multi-GPU exchange of {Accel, OldAcc}
+static struct { bool pending = false; int nt = 0, nw = 0; const int *work = nullptr, *sorted = nullptr, *slot_part = nullptr; } GX;
+static int gravity_exchange() {
+  if (!GX.pending) return B200_OK;
+  GX.pending = false;
+  const int per_rank = shard_max_blocks(GX.nt, g.shard_world) * kShardBlock;
+  if (GX.nw > 0) { k_grav_pack<<<cdiv(GX.nw, 256), 256, 0, g.stream>>>(GX.nw, GX.work, GX.slot_part, g.accel, g.oldacc, (float4 *)g.shard_send); count_launch(); }
+  B200_TRY(shard_exchange((long long)per_rank * sizeof(float4), g.stream));
+  const long long tot = (long long)g.shard_world * per_rank;
+  k_grav_unpack<<<cdiv(tot, 256), 256, 0, g.stream>>>(GX.nt, g.shard_world, per_rank, GX.sorted, GX.slot_part, (const float4 *)g.shard_recv, g.accel, g.oldacc);
+  count_launch();
+  return B200_OK;
+}
+
 int gravity_finish() {
+  B200_TRY(gravity_exchange());
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   if (g.walk_pending) { walk_read_counters(); g.walk_pending = false; }
@@ -410,13 +425,11 @@ int gravity_impl(const int *active, int nactive, double time, bool defer_sync) {
   if (nw > 0) { k_grav_epilogue<<<cdiv(nw, 256), 256, 0, g.stream>>>(E); count_launch(); }
   if (g.shard_world > 1) {
     // all-gather of the partial results (the reduce step of gravtree.c:208-222 becomes a gather:
-    // every target is evaluated completely by exactly one rank)
-    const int per_rank = shard_max_blocks(nt, g.shard_world) * kShardBlock;
-    if (nw > 0) { k_grav_pack<<<cdiv(nw, 256), 256, 0, g.stream>>>(nw, work, E.slot_part, g.accel, g.oldacc, (float4 *)g.shard_send); count_launch(); }
-    B200_TRY(shard_exchange((long long)per_rank * sizeof(float4)));
-    const long long tot = (long long)g.shard_world * per_rank;
-    k_grav_unpack<<<cdiv(tot, 256), 256, 0, g.stream>>>(nt, g.shard_world, per_rank, d_sorted, E.slot_part, (const float4 *)g.shard_recv, g.accel, g.oldacc);
-    count_launch();
+    // every target is evaluated completely by exactly one rank).  When the SIDM chain runs next to
+    // the walk the exchange is issued by gravity_finish(), after the SIDM collectives: collectives
+    // of one communicator run in issue order, and this one has to wait for the walk.
+    GX.pending = true; GX.nt = nt; GX.nw = nw; GX.work = work; GX.sorted = d_sorted; GX.slot_part = E.slot_part;
+    if (!defer_sync) B200_TRY(gravity_exchange());
   }
   if (defer_sync) return B200_OK;
   return gravity_finish();

@@ -14,6 +14,10 @@
  *   force_treeallocate/build/free, force_costevaluate/resetcost/getcost_*   forcetree.h:9-27
  *   ngb_treeallocate/build/free, ngb_update_nodes, ngb_treefind             forcetree.h:30-40
  *   set_softenings()          gravtree.c:425    (lives in the replaced file, restated here)
+ *   compute_accelerations()   accel.c:27        only with -DB200_SHIM_ACCEL, linked instead of accel.c:
+ *                                               one upload, ONE library call for gravity + sidm + repair
+ *                                               loop (walk and SIDM chain overlapped on two CUDA streams),
+ *                                               one download - the fast form of the drop-in
  *
  * Error convention: a non-zero return of the C ABI becomes endrun(code) like the CPU code
  * (endrun.c:19-30).  Timers: elapsed device time goes into the same All.CPU_* fields.
@@ -279,4 +283,46 @@ void sidm_ensure_neighbours(int mode)                   /* sidm.c:814-968 */
 }
 
 void update_node_sidm(void) {}                          /* sidm.c:992-997 */
+
+#ifdef B200_SHIM_ACCEL
+/* accel.c:27-132 for collisionless runs, as one coarse call.  Same order of effects as the CPU code:
+ * gravity_tree() bookkeeping (gravtree.c:42-60), forces, determine_interior(), sidm() +
+ * sidm_ensure_neighbours(mode) when mode == 0, timers into All.CPU_Gravity / CPU_EnsureNgb. */
+void compute_accelerations(int mode)
+{
+  b200_counters c;
+  int n, ntot, i;
+  double save;
+  if (ThisTask == 0) { printf("Start force computation...\n"); fflush(stdout); }
+  if (All.TotN_gas > 0) { printf("compute_accelerations: gas particles are not on the GPU path\n"); endrun(9006); }
+  if (All.ComovingIntegrationOn) set_softenings();
+  MPI_Allreduce(&NumForceUpdate, &ntot, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+  All.NumForcesSinceLastDomainDecomp += ntot;
+  All.NumForcesSinceLastTreeConstruction = 0;
+  if (ThisTask == 0) printf("Tree construction.\n");
+  sync_params_and_particles();
+  n = gather_active();
+  b200_check(b200_compute_accelerations(mode, active_list, n, All.Time, vmax), "b200_compute_accelerations");
+  b200_check(b200_download(), "b200_download");
+  b200_get_counters(&c);
+  All.CPU_TreeConstruction += 1e-3 * (c.ms_build + c.ms_predict);
+  All.CPU_TreeWalk += 1e-3 * c.ms_walk;
+  All.CPU_CommSum += 1e-3 * (c.ms_upload + c.ms_download);
+  All.CPU_Gravity += 1e-3 * (c.ms_build + c.ms_predict + c.ms_walk);
+  All.TotNumOfForces += ntot;
+  NoCostFlag = 0;
+  determine_interior();                                 /* accel.c:60 */
+  if (mode == 0) {
+    All.CPU_EnsureNgb += 1e-3 * (c.ms_sidm + c.ms_ensure);
+    print_sct();
+    if (c.ensure_iterations > 0) {                      /* sidm.c:943-955: restore the time line */
+      save = All.TimeStep;
+      find_next_time();
+      All.TimeStep = save;
+    }
+  }
+  (void)i;
+  if (ThisTask == 0) { printf("force computation done.\n"); fflush(stdout); }
+}
+#endif
 #endif

@@ -77,7 +77,7 @@ def layout_of(dtype=PARTICLE_DTYPE):
                                                                  "Left", "Right", "NgbVelDisp", "HsmlVelDisp", "dVel")})
 
 
-EXPORTS = ["b200_init", "b200_set_params", "b200_finalize", "b200_last_cuda_error", "b200_set_stream", "b200_set_option", "b200_set_shard", "b200_version",
+EXPORTS = ["b200_init", "b200_set_params", "b200_finalize", "b200_last_cuda_error", "b200_set_stream", "b200_set_option", "b200_set_shard", "b200_current_stream", "b200_version",
            "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_upload_shard", "b200_download_shard", "b200_advance", "b200_set_soa", "b200_get_soa", "b200_predict",
            "b200_tree_build", "b200_gravity", "b200_sidm", "b200_setup_nbr_sidm", "b200_sidm_ensure_neighbours",
            "b200_setup_smoothinglengths_sidm", "b200_compute_accelerations", "b200_getvmax", "b200_ngb_treefind",
@@ -102,6 +102,7 @@ def load():
         _lib.b200_predict.argtypes = [C.c_double]
         _lib.b200_set_stream.argtypes = [C.c_void_p]
         _lib.b200_set_option.argtypes = [C.c_char_p, C.c_int]
+        _lib.b200_current_stream.restype = C.c_void_p
         _lib.b200_bind_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib.b200_set_soa.argtypes = [C.c_int] + [C.c_void_p] * 9
         _lib.b200_get_soa.argtypes = [C.c_void_p] * 10

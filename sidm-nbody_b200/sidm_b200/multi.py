@@ -68,12 +68,17 @@ class Sharder:
 
             def allgather(nbytes, user):
                 try:
-                    if host_staged:
-                        out = torch.empty(self.world * nbytes, dtype=torch.uint8)
-                        dist.all_gather_into_tensor(out, self.send[:nbytes].cpu())
-                        self.recv[: self.world * nbytes].copy_(out)
-                    else:
-                        dist.all_gather_into_tensor(self.recv[: self.world * nbytes], self.send[:nbytes])
+                    # order the collective on the stream the library is working on (its main stream or
+                    # the SIDM stream): b200_current_stream(), include/sidm_b200.h
+                    sp = hp.lib.b200_current_stream()
+                    stream = torch.cuda.ExternalStream(sp) if sp else torch.cuda.default_stream()
+                    with torch.cuda.stream(stream):
+                        if host_staged:
+                            out = torch.empty(self.world * nbytes, dtype=torch.uint8)
+                            dist.all_gather_into_tensor(out, self.send[:nbytes].cpu())
+                            self.recv[: self.world * nbytes].copy_(out)
+                        else:
+                            dist.all_gather_into_tensor(self.recv[: self.world * nbytes], self.send[:nbytes])
                     self.exchanges += 1
                     self.bytes += int(nbytes)
                     return 0
@@ -86,12 +91,13 @@ class Sharder:
                                        C.c_longlong(cap), self._cb, None)
             if rc != 0:
                 raise RuntimeError(f"b200_set_shard -> {rc}")
+            hp.set_option("shard_overlap", 1)          # the callback above honours b200_current_stream()
 
     def describe(self):
         if self.world == 1:
             return "1 GPU"
-        return (f"{self.world} GPUs: replicated particles + tree, targets split by interleaved 32-particle key-order blocks, "
-                "NCCL all-gather of accelerations and scatter proposals")
+        return (f"{self.world} GPUs: replicated particles + tree, targets split by interleaved 32-particle blocks of the tree order, "
+                "NCCL all-gather of accelerations and scatter proposals, SIDM chain on its own stream next to the walk")
 
     def compute_accelerations(self, mode, time, vmax, active=None):
         self.hp.compute_accelerations(mode, active, time, vmax)

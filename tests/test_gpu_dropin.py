@@ -21,11 +21,14 @@ def _run(kind, out):
     return np.load(out)
 
 
-def test_reference_driver_on_gpu_path(tmp_path, refdrv_mod):
-    if not refdrv_mod.available("b200"):
-        pytest.skip("oracle/_ref/libsidmref_b200.so not built")
+@pytest.mark.parametrize("kind", ["b200", "b200f"])
+def test_reference_driver_on_gpu_path(tmp_path, refdrv_mod, kind):
+    """b200: the reference's accel.c calls the shim's gravity_tree() / sidm() / sidm_ensure_neighbours();
+    b200f: accel.c's compute_accelerations() itself is the shim's (-DB200_SHIM_ACCEL, one coarse call)"""
+    if not refdrv_mod.available(kind):
+        pytest.skip(f"oracle/_ref/libsidmref_{kind}.so not built")
     cpu = _run("diag", str(tmp_path / "cpu.npz"))
-    gpu = _run("b200", str(tmp_path / "gpu.npz"))
+    gpu = _run(kind, str(tmp_path / "gpu.npz"))
     rms = lambda a, b: float(np.sqrt(((a.astype(np.float64) - b) ** 2).sum() / (b.astype(np.float64) ** 2).sum()))
     # start-up: smoothing lengths from the reference's own init.c loop over the GPU k-NN / counts
     assert np.array_equal(cpu["ngb0"], gpu["ngb0"])
