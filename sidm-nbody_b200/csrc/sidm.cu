@@ -318,32 +318,40 @@ __global__ void __launch_bounds__(128, 16) k_pass1(Pass1 P) {
 // were found, so the counts equal those of the per-query walk (k_pass1) bit for bit; what changes
 // is the cost: ~10x fewer instructions, coalesced candidate loads instead of divergent ones.
 constexpr int kGroupCell = 512;   // query groups are cut from subtrees with at most this many particles
-// A group is a run of consecutive leaf slots that lies inside one 32-aligned block of the leaf order
-// and inside one compact cell: a subtree with <= kGroupCell particles whose parent holds more (its
-// leaf range is cut at the multiples of 32), or the direct particles of a bigger cell.  The 32-aligned
-// blocks are also the unit the leaf order is dealt out in when the work is sharded over several GPUs.
+// A group is a run of <= 32 consecutive leaf slots inside one compact cell: a subtree with <=
+// kGroupCell particles whose parent holds more, or the direct particles of a bigger cell.  On one GPU
+// a cell's leaf range is cut into equal runs; sharded over several GPUs it is cut at the multiples of
+// 32 of the leaf order, the blocks the leaf order is dealt out in (b200_set_shard).
 __device__ __forceinline__ int2 group_range(const SearchNode &nd) {      // leaf range the node contributes
   const int cnt = nd.pend - nd.pstart;
   return cnt <= kGroupCell ? make_int2(nd.pstart, nd.pend) : make_int2(nd.pstart, nd.pstart + nd.np);
 }
-__global__ void k_group_flag(int m, const SearchNode *sn, const int *nparent, int *flag) {
+// aligned (sharded runs): cut at the multiples of 32 of the leaf order; else: ceil(len/32) equal runs (better filled warps)
+__global__ void k_group_flag(int m, const SearchNode *sn, const int *nparent, int *flag, int aligned) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id > m) return;
   if (id == m) { flag[m] = 0; return; }
   const int cnt = sn[id].pend - sn[id].pstart;
   const int2 r = group_range(sn[id]);
-  int f = r.y > r.x ? ((r.y - 1) >> 5) - (r.x >> 5) + 1 : 0;            // 32-blocks the range touches
+  int f = 0;
+  if (r.y > r.x) f = aligned ? ((r.y - 1) >> 5) - (r.x >> 5) + 1 : (r.y - r.x + 31) >> 5;
   if (cnt <= kGroupCell && id > 0) { const int par = nparent[id]; if (sn[par].pend - sn[par].pstart <= kGroupCell) f = 0; }
   flag[id] = f;
 }
-__global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const int *pos, int2 *groups, int *gnode) {
+__global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const int *pos, int2 *groups, int *gnode, int aligned) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= m || !flag[id]) return;
   const int2 r = group_range(sn[id]);
   const int c = flag[id], g0 = pos[id], b0 = r.x >> 5;
-  for (int j = 0; j < c; j++) {
-    const int lo = max(r.x, (b0 + j) << 5), hi = min(r.y, (b0 + j + 1) << 5);
-    groups[g0 + j] = make_int2(lo, hi - lo); gnode[g0 + j] = id;
+  if (aligned) {
+    for (int j = 0; j < c; j++) {
+      const int lo = max(r.x, (b0 + j) << 5), hi = min(r.y, (b0 + j + 1) << 5);
+      groups[g0 + j] = make_int2(lo, hi - lo); gnode[g0 + j] = id;
+    }
+  } else {
+    const int len = r.y - r.x, base = len / c, rem = len % c;
+    int at = r.x;
+    for (int j = 0; j < c; j++) { const int nj = base + (j < rem); groups[g0 + j] = make_int2(at, nj); gnode[g0 + j] = id; at += nj; }
   }
 }
 // sharded runs: the global processing order of the slots = leaf order
@@ -362,6 +370,8 @@ struct Pass1G {
   int rank, world;     // sharded: this rank handles the groups of the 32-blocks b with b % world == rank
 };
 constexpr int kGroupTiny = 4;
+constexpr int kWarpQueryMax = 1 << 14;   // up to this many queries a pass is served one warp per query (beyond, the
+                                         // extra work of 32 lanes per query costs more than the shorter tail saves)
 constexpr int kQCap = 320;         // warp-private cell queue of the lane-parallel walk
 
 // packed fp32 pairs (sm_100a add.rn.f32x2 = SASS FADD2): two candidates per instruction
@@ -532,6 +542,92 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   }
   if (lane == 0) atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand * (unsigned)gr.y);
   if (valid) pass1_finish(P, L, i, p, h, cnt);
+}
+
+// ------------------------------------------------------------------ pass 1, one warp per query
+// Small query sets (the repair passes of sidm_ensure_neighbours, individual-time-step active lists):
+// with one thread per query the launch lasts as long as its slowest query - a cube that straddles a
+// high-level cell boundary walks ~1000 cells one after the other (0.6 ms, whether the pass has 10^5
+// queries or one).  Here a warp serves one query with the same lane-parallel cell walk as
+// k_pass1_group and tests 32 candidates per trip, one per lane: the dependent chain shrinks to a few
+// dozen trips.  Same neighbour set, same counts.
+__global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= P.ns) return;                                   // warp-uniform
+  const int s = P.order[w];
+  const int i = P.slot_part[s];
+  const float4 p = P.posm[i];
+  const float h = P.velh[i].w;
+  const float sr2 = fmul(h, h);
+  Cube U;
+  U.lx = fadd(p.x, -h); U.ly = fadd(p.y, -h); U.lz = fadd(p.z, -h);
+  U.hx = fadd(p.x, h); U.hy = fadd(p.y, h); U.hz = fadd(p.z, h);
+  const int A = search_start(P.C, i, p.x, p.y, p.z, h);
+  const int stopA = P.C.snodef[A].skip;
+  __shared__ int2 s_q[4][kQCap];
+  int2 *q = s_q[threadIdx.x >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt = 0; unsigned cand = 0;
+  int qn = 1;
+  if (lane == 0) q[0] = make_int2(A, stopA);
+  __syncwarp();
+  bool overflow = false;
+  while (qn > 0) {
+    const int take = qn < 32 ? qn : 32, base = qn - take;
+    const int2 it = lane < take ? q[base + lane] : make_int2(-1, -1);
+    __syncwarp();
+    qn = base;
+    int pk = 0, pe = 0, sib = -1, child = -1, cstop = 0;
+    if (lane < take) {
+      const float4 *rq = reinterpret_cast<const float4 *>(P.C.snodef + it.x);
+      const float4 a = __ldg(rq), b = __ldg(rq + 1);       // lo.xyz hi.x | hi.yz skip pinfo
+      const int skip = __float_as_int(b.z), pinfo = __float_as_int(b.w);
+      if (skip < it.y) sib = skip;
+      if (!(a.w < U.lx || a.x > U.hx || b.x < U.ly || a.y > U.hy || b.y < U.lz || a.z > U.hz)) {
+        const bool whole = (pinfo & 16) || ((a.x >= U.lx) && (a.w <= U.hx) && (a.y >= U.ly) && (b.x <= U.hy) && (a.z >= U.lz) && (b.y <= U.hz));
+        pk = pinfo >> 5;
+        if (whole) pe = (pinfo & 16) ? pk + (pinfo & 15) : (P.C.snodef[skip].pinfo >> 5);
+        else { pe = pk + (pinfo & 15); if (it.x + 1 < skip) { child = it.x + 1; cstop = skip; } }
+      }
+    }
+    const unsigned m1 = __ballot_sync(0xffffffffu, sib >= 0), m2 = __ballot_sync(0xffffffffu, child >= 0);
+    const int n1 = __popc(m1), n2 = __popc(m2);
+    if (qn + n1 + n2 > kQCap) { overflow = true; break; }
+    if (sib >= 0) q[qn + __popc(m1 & lt)] = make_int2(sib, it.y);
+    if (child >= 0) q[qn + n1 + __popc(m2 & lt)] = make_int2(child, cstop);
+    qn += n1 + n2;
+    __syncwarp();
+    const int len = pe - pk;
+    int inc = len;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int T = __shfl_sync(0xffffffffu, inc, 31), exc = inc - len;
+    cand += (unsigned)T;
+    for (int c0 = 0; c0 < T; c0 += 32) {                   // one candidate per lane
+      const int idx = c0 + lane;
+      int r = 0;
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, exc, (r + step) & 31);
+        if (r + step < 32 && v <= idx) r += step;
+      }
+      const int pk_r = __shfl_sync(0xffffffffu, pk, r), exc_r = __shfl_sync(0xffffffffu, exc, r);
+      bool in = false;
+      if (idx < T) { const float4 c = __ldg(P.C.leaf_posm + pk_r + (idx - exc_r)); in = dist2_ref(c.x, c.y, c.z, p.x, p.y, p.z) < sr2; }
+      cnt += __popc(__ballot_sync(0xffffffffu, in));
+    }
+  }
+  if (overflow) { cnt = 0; cand = 0; group_walk_uniform(P.C, U, A, stopA, p, sr2, cnt, cand); }
+  if (lane != 0) return;
+  atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand);
+  P.ngb[s] = cnt;
+  if (P.count_only) return;
+  const double dt_h0 = (double)P.dt[s] * P.s_a_inverse;
+  const double hh = 1.0 * (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
+  const double pm = P.C_Pmax * (double)p.w * hinv3 * dt_h0;          // sidm.c:338
+  double r;
+  if (P.replay_rand) r = P.replay_rand[s];
+  else r = u01(philox((uint32_t)i, 0u, 0u, 0u, P.k0, P.k1).x);
+  P.pmax[s] = pm; P.rnd[s] = r;
+  P.pass[w] = !(pm < r) && !P.already[s];                             // sidm.c:343-346
 }
 
 // ------------------------------------------------------------------ pass 2
@@ -797,12 +893,13 @@ int refresh_search_nodes() {
   const int m = g.num_nodes;
   k_search_nodes<<<cdiv(m, 256), 256, 0, st>>>(m, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
   // query groups of the warp-shared search
-  k_group_flag<<<cdiv(m + 1, 256), 256, 0, st>>>(m, S.snode, g.nparent, S.gflag);
+  const int aligned = g.shard_world > 1;
+  k_group_flag<<<cdiv(m + 1, 256), 256, 0, st>>>(m, S.snode, g.nparent, S.gflag, aligned);
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, S.gflag, S.gpos, m + 1, st);
   B200_TRY(cub_scratch(tb));
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, S.gflag, S.gpos, m + 1, st));
-  k_group_emit<<<cdiv(m, 256), 256, 0, st>>>(m, S.snode, S.gflag, S.gpos, S.groups, S.gnode);
+  k_group_emit<<<cdiv(m, 256), 256, 0, st>>>(m, S.snode, S.gflag, S.gpos, S.groups, S.gnode, aligned);
   CUDA_TRY(cudaMemcpyAsync(&S.ngroups, S.gpos + m, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   count_launch(5);
@@ -912,7 +1009,11 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       PG.rank = g.shard_rank; PG.world = g.shard_world;
       k_pass1_group<<<cdiv((long long)S.ngroups * 32, 128), 128, 0, st>>>(PG);
       if (g.shard_world == 1) order = S.order_leaf;        // the pass flags are indexed by leaf position
-    } else if (nord > 0) k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
+    } else if (nord > 0) {
+      // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
+      if (nord <= kWarpQueryMax && !periodic_box && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
+      else k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
+    }
     count_launch(2);
     int npass = 0;
     if (!count_only) {

@@ -79,6 +79,7 @@ extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long 
   if (world > 1 && (!send || !recv || !fn || cap_bytes <= 0)) return B200_ERR_ARG;
   g.shard_rank = rank; g.shard_world = world; g.shard_send = send; g.shard_recv = recv; g.shard_cap = cap_bytes;
   g.shard_fn = fn; g.shard_user = user;
+  g.search_epoch = ~0ull;        // the query groups of the SIDM search depend on the sharding (sidm.cu)
   return B200_OK;
 }
 
