@@ -1381,8 +1381,11 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   }
   CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
   CUDA_TRY(cudaStreamWaitEvent(g.stream_sidm, g.ev_fork, 0));
-  int rc = gravity_impl(active, nactive, time, true);
+  // Order of issue: walk first, SIDM chain next to it.  (Measured alternative: SIDM pass alone first,
+  // then walk || repair loop - 35.0 vs 34.4 ms on one GPU, 27.6 vs 26.5 ms on two: the chain's many
+  // small launches cost the walk about as much as they would cost alone.)
   int rs = B200_OK;
+  const int rc = gravity_impl(active, nactive, time, true);
   if (rc == B200_OK) {
     g.overlap_now = true;
     rs = b200_sidm(active, nactive, time, vmax, nullptr);
