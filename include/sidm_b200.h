@@ -70,7 +70,8 @@ typedef struct b200_params {
   int    MaxNumNgbDeviation;
   double CrossSectionInternal;     /* sidm.c:278-280,372                               */
   int    CrossSectionType;         /* compile-time CROSS_SECTION_TYPE of the reference;
-                                      0 (hard sphere) .. 3 supported                    */
+                                      0 hard sphere, 1 ~1/v, 2 Yukawa-like, 3 power law,
+                                      4 Yukawa with angular dependence (sidm.c:391-439)   */
   double YukawaVelocity, CrossSectionPowLaw, CrossSectionVelScale;
   unsigned long long Seed;         /* All.Seed1 + All.Seed2*ThisTask  begrun.c:44      */
   int    BunchSizeSidm;            /* slots per sidm() bunch (allocate.c:64); <=0: one
@@ -94,6 +95,11 @@ typedef struct b200_layout {
 typedef struct b200_replay {
   const double *rand;              /* [nslot]            */
   const double *dir;               /* [nslot][3], used only where a scatter happens */
+  /* CROSS_SECTION_TYPE 4 only (may be NULL): the (rand, cosO-uniform) pairs the reference drew at
+   * sidm.c:393-394 for slot s are extra[2*extra_off[s] .. 2*extra_off[s+1]); honoured by b200_sidm(),
+   * not by the repair passes */
+  const double *extra;
+  const int    *extra_off;         /* [nslot+1]          */
 } b200_replay;
 
 typedef struct b200_scatlog {      /* struct scatlog, sidm.h:1-10 */

@@ -26,8 +26,8 @@ typedef struct oparams {
   double G;
   int    des_ngb, max_dev; /* All.DesNumNgb, All.MaxNumNgbDeviation */
   double sigma;            /* All.CrossSectionInternal */
-  int    xs_type;          /* the reference's compile-time CROSS_SECTION_TYPE, 0..3 (sidm.c:226-316, 366-382) */
-  double vc;               /* All.YukawaVelocity        (type 2) */
+  int    xs_type;          /* the reference's compile-time CROSS_SECTION_TYPE, 0..4 (sidm.c:226-316, 366-439) */
+  double vc;               /* All.YukawaVelocity        (types 2, 4) */
   double pl_n, pl_v0;      /* All.CrossSectionPowLaw, All.CrossSectionVelScale (type 3) */
 } oparams;
 
@@ -72,6 +72,9 @@ typedef struct osidm_out {
   int     sct[4];          /* ntot, pass1, scattered, rejected (sidm.c:614-620) */
   /* scatter log (sidm.c:571-601): id1 id2 per event + dv */
   int     nlog; int *log_i; int *log_j; float *log_dv;
+  /* CROSS_SECTION_TYPE 4 only: the pairs (rand, uniform of cosO) drawn at sidm.c:393-394 for every
+   * crossing of slot s are extra[2*extra_off[s] .. 2*extra_off[s+1]) */
+  double *extra; int *extra_off;
 } osidm_out;
 
 /* one sidm() call for the active list (particle indices, list order).  Reads/writes the

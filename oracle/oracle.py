@@ -23,7 +23,8 @@ class OSidmOut(C.Structure):
     _fields_ = [("slot_particle", C.POINTER(C.c_int)), ("rand", C.POINTER(C.c_double)), ("dir", C.POINTER(C.c_double)),
                 ("pmax", C.POINTER(C.c_double)), ("prob", C.POINTER(C.c_double)), ("partner", C.POINTER(C.c_int)),
                 ("ngb", C.POINTER(C.c_int)), ("nslot", C.c_int), ("sct", C.c_int * 4), ("nlog", C.c_int),
-                ("log_i", C.POINTER(C.c_int)), ("log_j", C.POINTER(C.c_int)), ("log_dv", C.POINTER(C.c_float))]
+                ("log_i", C.POINTER(C.c_int)), ("log_j", C.POINTER(C.c_int)), ("log_dv", C.POINTER(C.c_float)),
+                ("extra", C.POINTER(C.c_double)), ("extra_off", C.POINTER(C.c_int))]
 
 
 _lib = None
@@ -185,6 +186,10 @@ class Oracle:
                    log_i=np.ctypeslib.as_array(out.log_i, (max(nl, 1),))[:nl].copy(),
                    log_j=np.ctypeslib.as_array(out.log_j, (max(nl, 1),))[:nl].copy(),
                    log_dv=np.ctypeslib.as_array(out.log_dv, (max(nl, 1) * 3,)).reshape(-1, 3)[:nl].copy())
+        off = np.ctypeslib.as_array(out.extra_off, (ns + 1,)).copy()
+        nx = int(off[-1])
+        res["extra_off"] = off.astype(np.int32)
+        res["extra"] = np.ctypeslib.as_array(out.extra, (max(nx, 1) * 2,))[:2 * nx].copy()
         self.L.osidm_out_free(C.byref(out))
         return res
 

@@ -2,7 +2,7 @@
  * TEST INFRASTRUCTURE ONLY (see oracle.h).
  *
  * Restates: sidm_rand.c:17-46 + sidm_rand.h:8-37 (MT19937 stream, Marsaglia direction),
- * begrun.c:968-992 (SPH kernel table), sidm.c:57-627 (sidm(), CROSS_SECTION_TYPE 0, one
+ * begrun.c:968-992 (SPH kernel table), sidm.c:57-627 (sidm(), CROSS_SECTION_TYPE 0..4, one
  * bunch), sidm.c:814-968 (sidm_ensure_neighbours, mode 0), sidm.c:970-990 (getvmax).
  * GSL is not vendored by the reference; its gsl_rng_mt19937 is the published MT19937
  * (Matsumoto & Nishimura) with the 2002 seeding, restated here.
@@ -95,6 +95,8 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
   out->dir = calloc(3 * (size_t)(n + 1), sizeof(double)); out->pmax = malloc(sizeof(double) * (n + 1));
   out->prob = calloc(n + 1, sizeof(double)); out->partner = malloc(sizeof(int) * (n + 1)); out->ngb = malloc(sizeof(int) * (n + 1));
   out->log_i = malloc(sizeof(int) * (n + 1)); out->log_j = malloc(sizeof(int) * (n + 1)); out->log_dv = malloc(sizeof(float) * 3 * (size_t)(n + 1));
+  out->extra_off = calloc(n + 2, sizeof(int));
+  int xcap = 1024, xn = 0; out->extra = malloc(sizeof(double) * 2 * xcap);
   float (*dv)[3] = calloc(n + 1, sizeof(float[3]));
   int *already = malloc(sizeof(int) * (n + 1));
   int *confirm = malloc(sizeof(int) * (n + 1));
@@ -137,6 +139,7 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
 
   for (int s = 0; s < n; s++) {                             /* sidm.c:319-460 */
     int i = out->slot_particle[s];
+    out->extra_off[s] = xn; out->extra_off[s + 1] = xn;
     int numngb = ongb_variable(t, pos + 3 * i, hsml[i], list, r2l, lcap);
     out->ngb[s] = numngb;
     double dt_h0 = dt[i];                                   /* s_a_inverse = 1 */
@@ -163,11 +166,34 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
       if (p->xs_type == 1) Prob += 0.5 * mass[j] * wk * sigma * dt_h0;                       /* sidm.c:374 */
       else if (p->xs_type == 2) { double beta = rv / p->vc, v_dep = 1.0 / (1.0 + beta * beta); Prob += 0.5 * mass[j] * wk * rv * v_dep * v_dep * sigma * dt_h0; }
       else if (p->xs_type == 3) Prob += 0.5 * mass[j] * wk * rv * pow(rv / p->pl_v0, p->pl_n) * sigma * dt_h0;
-      else Prob += 0.5 * mass[j] * wk * rv * sigma * dt_h0;                                  /* sidm.c:372 */
+      else Prob += 0.5 * mass[j] * wk * rv * sigma * dt_h0;                                  /* sidm.c:372 (types 0 and 4) */
       if (Prob < rnd) continue;
-      out->partner[s] = j;
+      out->partner[s] = j;                                  /* SidmTarget[i] = j: stays set even if type 4 rejects the angle */
       double rmass = mass[j] / (mass[i] + mass[j]);         /* float expr widened */
       double nx[3];
+      if (p->xs_type == 4) {                                /* sidm.c:391-427: angular dependence by rejection */
+        double beta = rv / p->vc;
+        rnd = orng_uniform(rng);                            /* overwrites the slot's uniform: later neighbours compare with it */
+        double ucos = orng_uniform(rng);
+        if (xn >= xcap) { xcap *= 2; out->extra = realloc(out->extra, sizeof(double) * 2 * xcap); }
+        out->extra[2 * xn] = rnd; out->extra[2 * xn + 1] = ucos; xn++; out->extra_off[s + 1] = xn;
+        double cosO = 2.0 * ucos - 1.0;
+        double sin22 = 0.5 * (1.0 - cosO);
+        double denom = 1.0 + beta * beta * sin22;
+        if (rnd >= 1 / (denom * denom) || rv == 0.0) continue;
+        double rvv[3] = {rvx, rvy, rvz}, np_[3];
+        random_direction(rng, nx);
+        np_[0] = rvv[1] * nx[2] - rvv[2] * nx[1]; np_[1] = rvv[2] * nx[0] - rvv[0] * nx[2]; np_[2] = rvv[0] * nx[1] - rvv[1] * nx[0];   /* perp(), sidm.c:29-52 */
+        double oo = sqrt(np_[0] * np_[0] + np_[1] * np_[1] + np_[2] * np_[2]);
+        np_[0] /= oo; np_[1] /= oo; np_[2] /= oo;
+        double sinO = 1.0 - cosO * cosO > 0.0 ? sqrt(1.0 - cosO * cosO) : 0.0;
+        out->dir[3 * s] = nx[0]; out->dir[3 * s + 1] = nx[1]; out->dir[3 * s + 2] = nx[2];
+        dv[s][0] = rmass * (-rvx + cosO * rvv[0] + sinO * rv * np_[0]);
+        dv[s][1] = rmass * (-rvy + cosO * rvv[1] + sinO * rv * np_[1]);
+        dv[s][2] = rmass * (-rvz + cosO * rvv[2] + sinO * rv * np_[2]);
+        confirm[s] = 0;
+        break;
+      }
       random_direction(rng, nx);
       out->dir[3 * s] = nx[0]; out->dir[3 * s + 1] = nx[1]; out->dir[3 * s + 2] = nx[2];
       dv[s][0] = rmass * (-rvx + rv * nx[0]); dv[s][1] = rmass * (-rvy + rv * nx[1]); dv[s][2] = rmass * (-rvz + rv * nx[2]);
@@ -206,7 +232,7 @@ void osidm_pass(const otree *t, const oparams *p, int nactive, const int *active
 void osidm_out_free(osidm_out *o)
 {
   free(o->slot_particle); free(o->rand); free(o->dir); free(o->pmax); free(o->prob); free(o->partner); free(o->ngb);
-  free(o->log_i); free(o->log_j); free(o->log_dv);
+  free(o->log_i); free(o->log_j); free(o->log_dv); free(o->extra); free(o->extra_off);
   memset(o, 0, sizeof(*o));
 }
 

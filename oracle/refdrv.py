@@ -48,7 +48,7 @@ DEFAULTS = dict(BufferSizeMB=100, TreeAllocFactor=0.8, ErrTolTheta=0.5, ErrTolFo
 
 def lib_path(kind="diag"):
     name = {"diag": "libsidmref.so", "fast": "libsidmref_fast.so", "periodic": "libsidmref_per.so",
-            "b200": "libsidmref_b200.so", "b200f": "libsidmref_b200f.so", "x1": "libsidmref_x1.so", "x2": "libsidmref_x2.so",
+            "b200": "libsidmref_b200.so", "b200f": "libsidmref_b200f.so", "x1": "libsidmref_x1.so", "x2": "libsidmref_x2.so", "x4": "libsidmref_x4.so",
             "x3": "libsidmref_x3.so"}[kind]
     return os.path.join(HERE, "_ref", name)
 

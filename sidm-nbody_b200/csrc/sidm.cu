@@ -44,6 +44,7 @@ struct SidmState {
   int *passlist = nullptr;
   int *logpos = nullptr;
   double *rr = nullptr, *rd = nullptr; size_t replay_cap = 0;   // staged replay arrays
+  double *rx = nullptr; int *ro = nullptr; size_t rx_cap = 0, ro_cap = 0;   // type 4 angle trials
   float *dt = nullptr;             // per slot: 2*(time - CurrentTime) (sidm.c:196)
   unsigned char *already = nullptr;
   double *ptot = nullptr;
@@ -635,6 +636,7 @@ struct Pass2 {
   int np; const int *passlist; const int *slot_part; SearchCtx C;
   const float4 *posm, *velh; const float *dvel; const float *dt; const double *rnd;
   const double *replay_dir; double sigma, s_a_inverse; uint32_t k0, k1; int xs_type; double vc, pl_n, pl_v0;
+  const double *extra; const int *extra_off;   // type 4: replayed (rand, cosO-uniform) pairs per slot
   const double *kernel;            // begrun.c:968-992 table, 1002 doubles
   int *partner; float *dv; double *prob, *ptot;
   // reference-order mode
@@ -652,7 +654,7 @@ __device__ __forceinline__ double pair_prob(const Pass2 &P, double mj, double wk
     case 1: return 0.5 * mj * wk * P.sigma * dt_h0;
     case 2: { const double beta = rv / P.vc, vd = 1.0 / (1.0 + beta * beta); return 0.5 * mj * wk * rv * vd * vd * P.sigma * dt_h0; }
     case 3: return 0.5 * mj * wk * rv * pow(rv / P.pl_v0, P.pl_n) * P.sigma * dt_h0;
-    default: return 0.5 * mj * wk * rv * P.sigma * dt_h0;
+    default: return 0.5 * mj * wk * rv * P.sigma * dt_h0;            // types 0 and 4
   }
 }
 
@@ -681,8 +683,9 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
   const double dt_h0 = valid ? (double)P.dt[s] * P.s_a_inverse : 0.0;
   const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
   const double hh = (double)h, hinv = 1.0 / hh, hinv3 = hinv * hinv * hinv;
-  const double rnd = valid ? P.rnd[s] : 2.0;
+  double rnd = valid ? P.rnd[s] : 2.0;
   double prob = 0, wk = 0, ptot = 0; int partner = -1; double prv[4] = {0, 0, 0, 0}; float pmass = 0;
+  bool done = false; int trial = 0; double cosO = 0;      // type 4: angle trials of this slot (sidm.c:391-398)
 
   auto visit = [&](int j, float r2) {       // one neighbour in list order, sidm.c:352-385
     if (P.dvel[3 * (size_t)j] != 0.0f) return;
@@ -694,10 +697,26 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
     const float mj = P.posm[j].w;
     const double dp = pair_prob(P, (double)mj, wk, rv, dt_h0);
     ptot += dp;
-    if (partner >= 0) return;
+    if (done) return;
     prob += dp;
     if (prob < rnd) return;
-    partner = j; prv[0] = rvx; prv[1] = rvy; prv[2] = rvz; prv[3] = rv; pmass = mj;
+    partner = j;                                         // SidmTarget[i] = j, kept even if the angle is rejected
+    if (P.xs_type == 4) {
+      // sidm.c:391-398: draw a fresh uniform (it REPLACES the slot's uniform for the rest of the scan)
+      // and cos(theta); accept with probability 1/(1 + beta^2 sin^2(theta/2))^2
+      double u1, u2;
+      const int xo = P.extra_off ? P.extra_off[s] + trial : 0;
+      if (P.extra_off && xo < P.extra_off[s + 1]) { u1 = P.extra[2 * (size_t)xo]; u2 = P.extra[2 * (size_t)xo + 1]; }
+      else { const uint4 q = philox((uint32_t)i, (uint32_t)trial, 1u, 0u, P.k0, P.k1); u1 = u01(q.x); u2 = u01(q.y); }
+      trial++;
+      const double beta = rv / P.vc;
+      rnd = u1;
+      cosO = 2.0 * u2 - 1.0;
+      const double sin22 = 0.5 * (1.0 - cosO), denom = 1.0 + beta * beta * sin22;
+      if (rnd >= 1 / (denom * denom) || rv == 0.0) return;
+    }
+    done = true;
+    prv[0] = rvx; prv[1] = rvy; prv[2] = rvz; prv[3] = rv; pmass = mj;
   };
 
   if (!P.ref_order) {
@@ -737,13 +756,23 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
   if (!valid) return;
   P.prob[s] = prob; P.ptot[s] = ptot; P.partner[s] = partner;
   float dvx = 0, dvy = 0, dvz = 0;
-  if (partner >= 0) {
+  if (done) {
     const double rmass = (double)(pmass / (p.w + pmass));            // float division, sidm.c:387
     double n[3];
     unit_vector(P, s, i, n);
-    dvx = (float)(rmass * (-prv[0] + prv[3] * n[0]));                 // sidm.c:446-451
-    dvy = (float)(rmass * (-prv[1] + prv[3] * n[1]));
-    dvz = (float)(rmass * (-prv[2] + prv[3] * n[2]));
+    if (P.xs_type == 4) {                                             // sidm.c:407-423
+      double np_[3] = {prv[1] * n[2] - prv[2] * n[1], prv[2] * n[0] - prv[0] * n[2], prv[0] * n[1] - prv[1] * n[0]};   // perp(), sidm.c:29-52
+      const double oo = sqrt(np_[0] * np_[0] + np_[1] * np_[1] + np_[2] * np_[2]);
+      np_[0] /= oo; np_[1] /= oo; np_[2] /= oo;
+      const double sinO = 1.0 - cosO * cosO > 0.0 ? sqrt(1.0 - cosO * cosO) : 0.0;
+      dvx = (float)(rmass * (-prv[0] + cosO * prv[0] + sinO * prv[3] * np_[0]));
+      dvy = (float)(rmass * (-prv[1] + cosO * prv[1] + sinO * prv[3] * np_[1]));
+      dvz = (float)(rmass * (-prv[2] + cosO * prv[2] + sinO * prv[3] * np_[2]));
+    } else {
+      dvx = (float)(rmass * (-prv[0] + prv[3] * n[0]));               // sidm.c:446-451
+      dvy = (float)(rmass * (-prv[1] + prv[3] * n[1]));
+      dvz = (float)(rmass * (-prv[2] + prv[3] * n[2]));
+    }
   }
   P.dv[3 * (size_t)s] = dvx; P.dv[3 * (size_t)s + 1] = dvy; P.dv[3 * (size_t)s + 2] = dvz;
 }
@@ -865,6 +894,8 @@ void sidm_release() {
                    (void **)&S.x_redo, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp,
                    (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+  if (S.rx) cudaFree(S.rx); if (S.ro) cudaFree(S.ro);
+  S.rx = nullptr; S.ro = nullptr; S.rx_cap = S.ro_cap = 0;
   S.rd = nullptr; S.replay_cap = 0; S.last_nactive = 0; S.last_all = false; S.cub_tmp_bytes = 0; S.ngroups = 0;
 }
 
@@ -925,7 +956,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   if (g.par.ComovingIntegrationOn) { sigma = sigma / pow(time, T == 1 ? 2.5 : 2.0); vc = vc / sqrt(time); }
   const double ball = (3. / 4. / 3.14159265358979323846) * (g.par.DesNumNgb + g.par.MaxNumNgbDeviation);
   double C_Pmax;
-  if (T == 0) C_Pmax = 1.0 * ball * 2 * vmax * sigma;
+  if (T == 0 || T == 4) C_Pmax = 1.0 * ball * 2 * vmax * sigma;          // sidm.c:267-272, 309-313
   else if (T == 1) C_Pmax = 1.0 * ball * sigma;
   else if (T == 2) {
     if (2.0 * vmax < vc / sqrt(3.0)) { const double beta = 2.0 * vmax / vc, vd = 1.0 / (1.0 + beta * beta); C_Pmax = 1.0 * ball * 2.0 * vmax * vd * vd * sigma; }
@@ -980,6 +1011,21 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       d_rr = S.rr;
       if (replay->dir) { CUDA_TRY(cudaMemcpyAsync(S.rd, replay->dir + 3 * replay_off, (size_t)nb * 3 * sizeof(double), cudaMemcpyHostToDevice, st)); d_rd = S.rd; }
       replay_off += nb;
+    }
+    // type 4: the replayed angle trials (one bunch only)
+    const double *d_rx = nullptr; const int *d_ro = nullptr;
+    if (replay && replay->extra_off && replay->extra && !count_only && b0 == 0 && nb == na) {
+      const int nx = replay->extra_off[nb];
+      if (S.rx_cap < (size_t)nx + 1 || S.ro_cap < (size_t)nb + 1) {
+        if (S.rx) cudaFree(S.rx); if (S.ro) cudaFree(S.ro);
+        S.rx = nullptr; S.ro = nullptr;
+        if (cudaMalloc((void **)&S.rx, ((size_t)nx + 1) * 2 * sizeof(double)) != cudaSuccess) return B200_ERR_ALLOC;
+        if (cudaMalloc((void **)&S.ro, ((size_t)nb + 1) * sizeof(int)) != cudaSuccess) return B200_ERR_ALLOC;
+        S.rx_cap = (size_t)nx + 1; S.ro_cap = (size_t)nb + 1;
+      }
+      if (nx > 0) CUDA_TRY(cudaMemcpyAsync(S.rx, replay->extra, (size_t)nx * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(S.ro, replay->extra_off, ((size_t)nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+      d_rx = S.rx; d_ro = S.ro;
     }
     // this rank's share of the buffer (all of it on one GPU)
     const int *order = S.slot_of_sorted; int nord = nb;
@@ -1049,6 +1095,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         P2.posm = g.posm; P2.velh = g.velh; P2.dvel = g.dvel; P2.dt = S.dt; P2.rnd = g.s_rand; P2.replay_dir = d_rd;
         P2.sigma = sigma; P2.s_a_inverse = sainv; P2.k0 = k0; P2.k1 = k1; P2.xs_type = T; P2.vc = vc;
         P2.pl_n = g.par.CrossSectionPowLaw; P2.pl_v0 = g.par.CrossSectionVelScale; P2.kernel = d_kernel_table;
+        P2.extra = d_rx; P2.extra_off = d_ro;
         P2.partner = g.s_partner; P2.dv = g.s_dv; P2.prob = g.s_prob; P2.ptot = S.ptot;
         P2.ref_order = ref_order; P2.cand = g.s_cand; P2.candkey = g.s_candkey; P2.cand_stride = nc;
         P2.krank = g.krank; P2.lrank = g.lrank; P2.nstart = g.nstart; P2.flags = g.d_flags;
@@ -1274,6 +1321,7 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
       }
     }
     b200_replay rp; const b200_replay *rpp = nullptr;
+    rp.extra = nullptr; rp.extra_off = nullptr;
     if (replay && replay->rand) { rp.rand = replay->rand + roff; rp.dir = replay->dir ? replay->dir + 3 * roff : nullptr; rpp = &rp; roff += nr; }
     B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0));
     iter++;

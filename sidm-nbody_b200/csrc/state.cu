@@ -114,7 +114,7 @@ extern "C" int b200_set_params(const b200_params *p) {
   const bool was = g.ready;
   g.par = *p;
   if (was) { g.par.device = dev; g.par.MaxPart = mp; g.par.TreeAllocFactor = taf; }
-  if (g.par.CrossSectionType < 0 || g.par.CrossSectionType > 3) return B200_ERR_ARG;
+  if (g.par.CrossSectionType < 0 || g.par.CrossSectionType > 4) return B200_ERR_ARG;
   return B200_OK;
 }
 

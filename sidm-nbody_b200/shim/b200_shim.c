@@ -70,7 +70,7 @@ static void fill_params(b200_params *p)
 #ifdef SIDM
   p->CrossSectionInternal = All.CrossSectionInternal;
   p->CrossSectionType = CROSS_SECTION_TYPE;
-#if (CROSS_SECTION_TYPE == 2)
+#if (CROSS_SECTION_TYPE == 2) || (CROSS_SECTION_TYPE == 4)
   p->YukawaVelocity = All.YukawaVelocity;
 #elif (CROSS_SECTION_TYPE == 3)
   p->CrossSectionPowLaw = All.CrossSectionPowLaw;

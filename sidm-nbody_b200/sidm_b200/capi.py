@@ -46,7 +46,7 @@ class Layout(C.Structure):
 
 
 class Replay(C.Structure):
-    _fields_ = [("rand", C.c_void_p), ("dir", C.c_void_p)]
+    _fields_ = [("rand", C.c_void_p), ("dir", C.c_void_p), ("extra", C.c_void_p), ("extra_off", C.c_void_p)]
 
 
 class Counters(C.Structure):

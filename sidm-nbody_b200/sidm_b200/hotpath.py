@@ -147,7 +147,7 @@ class HotPath:
         a = _i32(active)
         check(self.lib.b200_gravity(ptr(a), 0 if a is None else len(a), t), "b200_gravity")
 
-    def sidm(self, active=None, time=None, vmax=0.0, replay_rand=None, replay_dir=None):
+    def sidm(self, active=None, time=None, vmax=0.0, replay_rand=None, replay_dir=None, replay_extra=None, replay_extra_off=None):
         t = self.time if time is None else float(time)
         a = _i32(active)
         rp = None
@@ -155,6 +155,10 @@ class HotPath:
             self._rr = np.ascontiguousarray(replay_rand, np.float64)
             self._rd = np.ascontiguousarray(replay_dir, np.float64)
             rp = Replay(rand=self._rr.ctypes.data, dir=self._rd.ctypes.data)
+            if replay_extra_off is not None:
+                self._rx = np.ascontiguousarray(replay_extra if len(replay_extra) else np.zeros(2), np.float64)
+                self._ro = np.ascontiguousarray(replay_extra_off, np.int32)
+                rp.extra, rp.extra_off = self._rx.ctypes.data, self._ro.ctypes.data
         check(self.lib.b200_sidm(ptr(a), 0 if a is None else len(a), t, float(vmax),
                                  C.byref(rp) if rp is not None else None), "b200_sidm")
 

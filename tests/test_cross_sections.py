@@ -1,4 +1,5 @@
-"""Cross-section models 1-3 (reference compile-time CROSS_SECTION_TYPE, sidm.c:226-316,366-382).
+"""Cross-section models 1-4 (reference compile-time CROSS_SECTION_TYPE, sidm.c:226-316,366-439; 4 = Yukawa
+with angular dependence: a rejection step that redraws the slot's uniform, sidm.c:391-427).
 CPU: the oracle against the reference rebuilt with each -DCROSS_SECTION_TYPE (bit-exact kicks);
 GPU: the CUDA pass against the oracle with the reference's random numbers replayed."""
 import os
@@ -8,7 +9,8 @@ import numpy as np
 import pytest
 
 N = 8000
-MODELS = {1: dict(sigma=4000.0), 2: dict(sigma=400.0, vc=60.0), 3: dict(sigma=400.0, pl_n=-1.5, pl_v0=80.0)}
+MODELS = {1: dict(sigma=4000.0), 2: dict(sigma=400.0, vc=60.0), 3: dict(sigma=400.0, pl_n=-1.5, pl_v0=80.0),
+          4: dict(sigma=3000.0, vc=25.0)}
 DT = 0.02
 
 
@@ -29,7 +31,7 @@ def _run_oracle(t, hsml, vmax):
     return O, res
 
 
-@pytest.mark.parametrize("t", [1, 2, 3])
+@pytest.mark.parametrize("t", [1, 2, 3, 4])
 def test_oracle_matches_reference_model(t, refdrv_mod):
     if not refdrv_mod.available(f"x{t}"):
         pytest.skip(f"oracle/_ref/libsidmref_x{t}.so not built")
@@ -59,7 +61,7 @@ def test_oracle_matches_reference_model(t, refdrv_mod):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("t", [1, 2, 3])
+@pytest.mark.parametrize("t", [1, 2, 3, 4])
 def test_gpu_matches_oracle_model(t):
     import oracle
     from sidm_b200 import HotPath
@@ -75,7 +77,8 @@ def test_gpu_matches_oracle_model(t):
                  CrossSectionPowLaw=m.get("pl_n", 0.0), CrossSectionVelScale=m.get("pl_v0", 1.0), ReferenceNgbOrder=1) as hp:
         hp.set_particles(pos, vel, mass, ids, hsml=h)
         hp.force_treebuild()
-        hp.sidm(active=np.arange(N, dtype=np.int32), time=DT / 2, vmax=vmax, replay_rand=res["rand"], replay_dir=res["dir"])
+        hp.sidm(active=np.arange(N, dtype=np.int32), time=DT / 2, vmax=vmax, replay_rand=res["rand"], replay_dir=res["dir"],
+                replay_extra=res["extra"], replay_extra_off=res["extra_off"])
         sp, pmax, ptot, partner = hp.sidm_debug(N)
         np.testing.assert_allclose(pmax, res["pmax"], rtol=1e-12)
         assert np.array_equal(partner, res["partner"])
