@@ -87,6 +87,8 @@ typedef struct b200_layout {
   int stride;
   int Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc;
   int Left, Right, NgbVelDisp, HsmlVelDisp, dVel;
+  int MaxPredTime;                 /* > 0: offset of P[].MaxPredTime (b200_find_timesteps writes it);
+                                      0 = field not bound                                            */
 } b200_layout;
 
 /* Optional replay of the reference's random numbers: the
@@ -206,6 +208,24 @@ int  b200_compute_accelerations(int mode, const int *active, int nactive, double
 /* advance(), predict.c:245-345 ("next" row f1 of SURVEY.md section 8): kick-drift of the active
  * particles with Accel*dt + dVel, dVel cleared; *num_scattered (may be NULL) = n_scat_particles. */
 int  b200_advance(const int *active, int nactive, double time, int *num_scattered);
+/* find_timesteps(mode), timestep.c:17-334 for collisionless particles ("next" row f1): new time step of
+ * every active particle from the acceleration criterion (TypeOfTimestepCriterion 0 or 1), the SIDM
+ * probability limit ProbabilityTol/(C_max m h^-3) and the G*rho limit (timestep.c:247-265), the 1.3*dtold
+ * growth limit (not for mode 2) and the Max/MinSizeTimestep clamps; P[i].MaxPredTime = CurrentTime + dt/2.
+ * The time-line tree itself (timeline.c delete_node / insert_node / construct_timetree) stays with the
+ * host driver, which reads MaxPredTime back (b200_download, or maxpred_out per active entry).
+ * The reference jitters clamped steps with drand48() (timestep.c:283,309); here the uniform comes from
+ * `jitter` (one per active entry, in list order) or, if NULL, from the particle's counter-based stream.
+ * *num_clamped (may be NULL) = number of steps that hit a clamp. */
+typedef struct b200_timestep_params {
+  int    TypeOfTimestepCriterion;          /* 0: sqrt(2 eta eps / |a|), 1: ErrTolVelScale / |a|   */
+  double ErrTolIntAccuracy, ErrTolVelScale, ProbabilityTol, ErrTolDynamicalAccuracy;
+  double MaxSizeTimestep, MinSizeTimestep;
+} b200_timestep_params;
+int  b200_find_timesteps(const int *active, int nactive, int mode, double time, double vmax,
+                         const b200_timestep_params *tp, const double *jitter, float *maxpred_out, int *num_clamped);
+/* host -> device copy into a named internal buffer (see b200_device_buffer), e.g. "maxpred" */
+int  b200_set_field(const char *name, const void *host, long long nbytes);
 /* getvmax(), sidm.c:970-990. */
 int  b200_getvmax(double *vmax);
 /* ngb_treefind(xyz, desngb, 0, type), forcetree.c:2311: exact k-th neighbour distance^2

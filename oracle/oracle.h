@@ -88,4 +88,10 @@ double ogetvmax(int n, const float *vel);          /* sidm.c:970-990 */
  * active neighbour counts are in range; returns passes done or -1155. */
 int    osidm_ensure(const otree *t, const oparams *p, int n, const float *vel, const float *mass, float *hsml,
                     const float *dt, float *dvel, int *ngbcount, float *left, float *right, double vmax, orng *rng);
+/* find_timesteps(mode), timestep.c:17-334, collisionless particles of type 1, no comoving integration,
+ * steps that hit Max/MinSizeTimestep take the uniform jitter[a] (the reference: drand48()).  Writes
+ * maxpred[i] = CurrentTime + dt/2 for the active particles; returns the number of clamped steps. */
+typedef struct otimestep { int crit; double eta, velscale, probtol, dyntol, dtmax, dtmin; } otimestep;
+int    ofind_timesteps(const oparams *p, const otimestep *ts, int nactive, const int *active, int mode, double time, double vmax,
+                       const float *accel, const float *curtime, float *maxpred, const float *hsml, const float *mass, const double *jitter);
 #endif

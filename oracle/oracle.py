@@ -193,6 +193,23 @@ class Oracle:
         self.L.osidm_out_free(C.byref(out))
         return res
 
+    def find_timesteps(self, active, mode, time, vmax, accel, curtime, maxpred, crit=0, eta=0.05, velscale=10.0, probtol=0.2,
+                       dyntol=0.05, dtmax=1e30, dtmin=0.0, jitter=None):
+        """timestep.c:17-334; returns (new MaxPredTime array, number of clamped steps)"""
+        class TS(C.Structure):
+            _fields_ = [("crit", C.c_int), ("eta", C.c_double), ("velscale", C.c_double), ("probtol", C.c_double),
+                        ("dyntol", C.c_double), ("dtmax", C.c_double), ("dtmin", C.c_double)]
+        ts = TS(int(crit), eta, velscale, probtol, dyntol, dtmax, dtmin)
+        active = np.ascontiguousarray(active, np.int32)
+        accel = np.ascontiguousarray(accel, np.float32); curtime = np.ascontiguousarray(curtime, np.float32)
+        mp = np.ascontiguousarray(maxpred, np.float32).copy()
+        jit = np.zeros(len(active)) if jitter is None else np.ascontiguousarray(jitter, np.float64)
+        self.L.ofind_timesteps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 6
+        self.L.ofind_timesteps.restype = C.c_int
+        nc = self.L.ofind_timesteps(C.byref(self.par), C.byref(ts), len(active), _p(active), int(mode), float(time), float(vmax),
+                                    _p(accel), _p(curtime), _p(mp), _p(self.hsml), _p(self.mass), _p(jit))
+        return mp, nc
+
     def sidm_ensure_neighbours(self, dt, vmax):
         dta = np.ascontiguousarray(np.broadcast_to(np.float32(dt), (self.n,)), np.float32)
         return self.L.osidm_ensure(self.tree, C.byref(self.par), self.n, _p(self.vel), _p(self.mass), _p(self.hsml),

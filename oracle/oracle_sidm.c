@@ -275,3 +275,39 @@ int osidm_ensure(const otree *t, const oparams *p, int n, const float *vel, cons
   free(redo);
   return iter;
 }
+
+/* ------------------------------------------------------------------ find_timesteps(), timestep.c:17-334 */
+int ofind_timesteps(const oparams *p, const otimestep *ts, int nactive, const int *active, int mode, double time, double vmax,
+                    const float *accel, const float *curtime, float *maxpred, const float *hsml, const float *mass, const double *jitter)
+{
+  const double PI = 3.14159265358979323846;
+  const double C_Grho = (3. / 4. / PI) * (p->des_ngb + p->max_dev);                     /* :45 */
+  const double s_a = 1;                                                                /* :97 */
+  double C_max;                                                                        /* :100-130 */
+  if (p->xs_type == 1) C_max = 1.0 * (3. / 4. / PI) * (p->des_ngb + p->max_dev) * p->sigma;
+  else if (p->xs_type == 2) {
+    if (2.0 * vmax < p->vc / sqrt(3.0)) { double v_dep = 1.0 / (1.0 + 2.0 * vmax / p->vc); C_max = 1.0 * (3. / 4. / PI) * (p->des_ngb + p->max_dev) * 2.0 * vmax * v_dep * v_dep * p->sigma; }
+    else C_max = 1.0 * (3. / 4. / PI) * (p->des_ngb + p->max_dev) * (3.0 * sqrt(3.0) / 16.0) * p->vc * p->sigma;
+  } else if (p->xs_type == 3) C_max = 1.0 * (3. / 4. / PI) * (p->des_ngb + p->max_dev) * 2 * p->pl_v0 * p->sigma;
+  else C_max = 1.0 * (3. / 4. / PI) * (p->des_ngb + p->max_dev) * 2 * vmax * p->sigma;
+  int clamped = 0;
+  for (int a = 0; a < nactive; a++) {
+    int i = active[a];
+    double ac = sqrt(accel[3 * i] * accel[3 * i] + accel[3 * i + 1] * accel[3 * i + 1] + accel[3 * i + 2] * accel[3 * i + 2]);   /* float expr, :138 */
+    double dtold = 2 * (curtime[i] + maxpred[i] - 2 * time);                            /* float sum first, :142 */
+    double dt;
+    if (ts->crit == 0) dt = sqrt(2 * ts->eta * p->eps / ac * s_a); else dt = ts->velscale / ac;   /* :153-160 */
+    double h = hsml[i], hinv = 1.0 / h, hinv3 = hinv * hinv * hinv;                     /* :247-265 */
+    double dt_sidm = ts->probtol / (C_max * mass[i] * hinv3);
+    if (dt_sidm < dt) dt = dt_sidm;
+    double dt_Grho = ts->dyntol / sqrt(C_Grho * p->G * mass[i] * hinv3);
+    if (dt_Grho < dt) dt = dt_Grho;
+    if (dt > 1.3 * dtold) { if (mode != 2) dt = 1.3 * dtold; }                          /* TIMESTEP_INCREASE_FACTOR, allvars.h:85 */
+    int c = 0;
+    if (dt >= ts->dtmax) { dt = ts->dtmax * (1.00 + 0.02 * jitter[a]); c = 1; }
+    if (dt < ts->dtmin) { dt = ts->dtmin; dt *= 1.0 + 0.02 * jitter[a]; c = 1; }
+    clamped += c;
+    maxpred[i] = curtime[i] + 0.5 * dt;                                                 /* :315 */
+  }
+  return clamped;
+}

@@ -340,6 +340,13 @@ void ref_sidm_ensure_neighbours(int mode) { sidm_ensure_neighbours(mode); }
 void ref_setup_smoothinglengths_sidm(int desngb) { setup_smoothinglengths_sidm(desngb); }
 void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
+/* timestep.c:17 with the accuracy parameters of the parameter file set here; mode 2 = start-up (no growth limit) */
+void ref_find_timesteps(int mode, int crit, double eta, double velscale, double probtol, double dyntol, double dtmax, double dtmin)
+{
+  All.TypeOfTimestepCriterion = crit; All.ErrTolIntAccuracy = eta; All.ErrTolVelScale = velscale;
+  All.ProbabilityTol = probtol; All.ErrTolDynamicalAccuracy = dyntol; All.MaxSizeTimestep = dtmax; All.MinSizeTimestep = dtmin;
+  find_timesteps(mode);
+}
 void ref_force_rebuild_next(void)
 { All.NumForcesSinceLastTreeConstruction = 1 << 30; }
 void ref_set_snapcount(int c) { All.SnapshotFileCount = c; }

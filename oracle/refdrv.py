@@ -229,6 +229,10 @@ class Reference:
     def compute_accelerations(self, mode=0):
         self.lib.ref_compute_accelerations(int(mode))
 
+    def find_timesteps(self, mode, crit=0, eta=0.05, velscale=10.0, probtol=0.2, dyntol=0.05, dtmax=1e30, dtmin=0.0):
+        self.lib.ref_find_timesteps.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6
+        self.lib.ref_find_timesteps(int(mode), int(crit), eta, velscale, probtol, dyntol, dtmax, dtmin)
+
     def advance(self):
         self.lib.ref_advance()
 

@@ -40,6 +40,7 @@ struct Ctx {
   float  *velpred = nullptr; // VelPred [n][3]
   float  *accel = nullptr;   // Accel [n][3]
   float  *dvel = nullptr;    // dVel [n][3]
+  float  *maxpred = nullptr;  // MaxPredTime (written by b200_find_timesteps)
   float  *curtime = nullptr, *oldacc = nullptr, *gravcost = nullptr, *left = nullptr, *right = nullptr;
   int    *ngb = nullptr, *pid = nullptr, *ptype = nullptr;
 

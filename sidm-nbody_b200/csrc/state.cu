@@ -26,7 +26,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.pos0, 3 * n)); B200_TRY(dalloc(&g.velpred, 3 * n));
   B200_TRY(dalloc(&g.accel, 3 * n)); B200_TRY(dalloc(&g.dvel, 3 * n));
   B200_TRY(dalloc(&g.curtime, n)); B200_TRY(dalloc(&g.oldacc, n)); B200_TRY(dalloc(&g.gravcost, n));
-  B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n));
+  B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n)); B200_TRY(dalloc(&g.maxpred, n));
   B200_TRY(dalloc(&g.ngb, n)); B200_TRY(dalloc(&g.pid, n)); B200_TRY(dalloc(&g.ptype, n));
   B200_TRY(dalloc(&g.d_bbox, 8)); B200_TRY(dalloc(&g.d_root, 1)); B200_TRY(dalloc(&g.d_domain, 8));
   B200_TRY(dalloc(&g.key_hi, n)); B200_TRY(dalloc(&g.key_lo, n));
@@ -163,6 +163,7 @@ extern "C" void b200_finalize(void) {
   g.pinned = false; g.h_base = nullptr; g.have_aos = false;
   dfree(&g.d_aos); g.aos_cap = 0;
   dfree(&g.posm); dfree(&g.velh); dfree(&g.pos0); dfree(&g.velpred); dfree(&g.accel); dfree(&g.dvel);
+  dfree(&g.maxpred);
   dfree(&g.curtime); dfree(&g.oldacc); dfree(&g.gravcost); dfree(&g.left); dfree(&g.right);
   dfree(&g.ngb); dfree(&g.pid); dfree(&g.ptype);
   dfree(&g.d_bbox); dfree(&g.d_root); dfree(&g.d_domain);
@@ -324,17 +325,18 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
   return B200_OK;
 }
 
-struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc, Left, Right, Ngb, Hsml, dVel; };
+struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc, Left, Right, Ngb, Hsml, dVel, MaxPred; };
 
 __device__ __forceinline__ float ldf(const char *p, int off) { return *(const float *)(p + off); }
 __device__ __forceinline__ int ldi(const char *p, int off) { return *(const int *)(p + off); }
 
 __global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4 *velh, float *pos0, float *velpred,
                              float *accel, float *dvel, float *curtime, float *oldacc, float *gravcost,
-                             float *left, float *right, int *ngb, int *pid, int *ptype) {
+                             float *left, float *right, int *ngb, int *pid, int *ptype, float *maxpred) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const char *p = aos + (size_t)i * L.stride;
+  if (L.MaxPred > 0) maxpred[i] = ldf(p, L.MaxPred);
   float4 a, b;
   a.x = ldf(p, L.PosPred); a.y = ldf(p, L.PosPred + 4); a.z = ldf(p, L.PosPred + 8); a.w = ldf(p, L.Mass);
   b.x = ldf(p, L.Vel); b.y = ldf(p, L.Vel + 4); b.z = ldf(p, L.Vel + 8); b.w = ldf(p, L.Hsml);
@@ -352,10 +354,11 @@ __global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4
 
 __global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
                            const float *accel, const float *dvel, const float *oldacc, const float *gravcost,
-                           const float *left, const float *right, const int *ngb) {
+                           const float *left, const float *right, const int *ngb, const float *maxpred) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   char *p = aos + (size_t)i * L.stride;
+  if (L.MaxPred > 0) *(float *)(p + L.MaxPred) = maxpred[i];
   float4 a = posm[i];
   *(float *)(p + L.PosPred) = a.x; *(float *)(p + L.PosPred + 4) = a.y; *(float *)(p + L.PosPred + 8) = a.z;
   for (int k = 0; k < 3; k++) {
@@ -370,7 +373,7 @@ __global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const fl
 
 static Lay to_lay(const b200_layout &l) {
   Lay L{l.stride, l.Pos, l.Vel, l.Mass, l.ID, l.Type, l.CurrentTime, l.PosPred, l.VelPred, l.Accel,
-        l.GravCost, l.OldAcc, l.Left, l.Right, l.NgbVelDisp, l.HsmlVelDisp, l.dVel};
+        l.GravCost, l.OldAcc, l.Left, l.Right, l.NgbVelDisp, l.HsmlVelDisp, l.dVel, l.MaxPredTime};
   return L;
 }
 
@@ -380,7 +383,7 @@ extern "C" int b200_upload(void) {
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.d_aos, g.h_base, (size_t)n * g.lay.stride, cudaMemcpyHostToDevice, g.stream));
   k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
-                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype);
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -404,7 +407,7 @@ extern "C" int b200_download(void) {
   const int n = g.n;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
-                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb);
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -432,7 +435,7 @@ extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
     CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)c * st, cudaMemcpyDeviceToDevice, g.stream));
   }
   k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
-                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype);
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -449,7 +452,7 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   char *out = dst ? (char *)dst : g.h_base;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
-                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb);
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred);
   count_launch();
   if (count > 0) CUDA_TRY(cudaMemcpyAsync(out + (size_t)first * st, g.d_aos + (size_t)first * st, (size_t)count * st, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -552,6 +555,114 @@ extern "C" int b200_advance(const int *active, int nactive, double time, int *nu
   return B200_OK;
 }
 
+extern "C" int b200_set_field(const char *name, const void *host, long long nbytes) {
+  void *d = nullptr; long long nb = 0;
+  B200_TRY(b200_device_buffer(name, &d, &nb));
+  if (!host || nbytes <= 0 || nbytes > nb || !d) return B200_ERR_ARG;
+  CUDA_TRY(cudaMemcpyAsync(d, host, (size_t)nbytes, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- find_timesteps
+// timestep.c:17-334 for collisionless particles.  Types as in the C code: Accel, CurrentTime,
+// MaxPredTime, HsmlVelDisp, Mass are floats, |a|^2 and CurrentTime + MaxPredTime are formed in float,
+// everything else in double.  One thread per active particle.
+struct TsParams {
+  int na; const int *active; int mode, crit, comoving; double time, s_a, hubble_a, a3inv, C_max, C_Grho, G;
+  double eta, velscale, probtol, dyntol, dtmax, dtmin; double soft[6];
+  const float *accel, *curtime; float *maxpred; const float4 *velh, *posm; const int *ptype;
+  const double *jitter; uint32_t k0, k1; float *out; int *nclamped;
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+__global__ void k_find_timesteps(TsParams T) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= T.na) return;
+  const int i = T.active ? T.active[a] : a;
+  const float a0 = T.accel[3 * (size_t)i], a1 = T.accel[3 * (size_t)i + 1], a2 = T.accel[3 * (size_t)i + 2];
+  const double ac = sqrt((double)fadd(fadd(fmul(a0, a0), fmul(a1, a1)), fmul(a2, a2)));      // timestep.c:138-140
+  const float ct = T.curtime[i], mp = T.maxpred[i];
+  const double dtold = 2 * ((double)fadd(ct, mp) - 2 * T.time);                                // :142
+  double dt;
+  if (T.crit == 0) dt = sqrt(2 * T.eta * T.soft[T.ptype[i] & 7] / ac * T.s_a);                // :156
+  else dt = T.velscale / ac;                                                                  // :159
+  {                                                                                           // :247-265 (SIDM)
+    const double h = (double)T.velh[i].w, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv;
+    const double m = (double)T.posm[i].w;
+    const double dt_sidm = T.probtol / (T.C_max * m * hinv3);
+    if (dt_sidm < dt) dt = dt_sidm;
+    double dt_Grho;
+    if (T.comoving) dt_Grho = T.dyntol * T.hubble_a * T.time / sqrt(T.C_Grho * T.G * m * hinv3 * T.a3inv);
+    else dt_Grho = T.dyntol / sqrt(T.C_Grho * T.G * m * hinv3);
+    if (dt_Grho < dt) dt = dt_Grho;
+  }
+  if (dt > 1.3 * dtold && T.mode != 2) dt = 1.3 * dtold;                                      // TIMESTEP_INCREASE_FACTOR, :268-272
+  bool clamped = false;
+  double u = 0;
+  if (dt >= T.dtmax || dt < T.dtmin) {
+    clamped = true;
+    u = T.jitter ? T.jitter[a] : (double)mix32((uint32_t)i * 0x9E3779B9u ^ T.k0 ^ mix32(T.k1)) / 4294967296.0;
+  }
+  if (dt >= T.dtmax) dt = T.dtmax * (1.00 + 0.02 * u);                                        // :274-283
+  if (dt < T.dtmin) { dt = T.dtmin; dt *= 1.0 + 0.02 * u; }                                   // :285-310
+  const float np = (float)((double)ct + 0.5 * dt);                                            // :315
+  T.maxpred[i] = np;
+  if (T.out) T.out[a] = np;
+  if (clamped) atomicAdd(T.nclamped, 1);
+}
+
+extern "C" int b200_find_timesteps(const int *active, int nactive, int mode, double time, double vmax,
+                                   const b200_timestep_params *tp, const double *jitter, float *maxpred_out, int *num_clamped) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  if (!tp || (tp->TypeOfTimestepCriterion != 0 && tp->TypeOfTimestepCriterion != 1)) return B200_ERR_ARG;
+  const int na = active ? nactive : g.n;
+  if (na < 0 || na > g.n) return B200_ERR_ARG;
+  if (na == 0) { if (num_clamped) *num_clamped = 0; return B200_OK; }
+  TsParams T;
+  T.na = na; T.active = nullptr; T.mode = mode; T.crit = tp->TypeOfTimestepCriterion; T.comoving = g.par.ComovingIntegrationOn;
+  T.time = time; T.G = g.par.G;
+  if (active) { CUDA_TRY(cudaMemcpyAsync(g.d_active, active, (size_t)na * sizeof(int), cudaMemcpyHostToDevice, g.stream)); T.active = g.d_active; }
+  // constants of timestep.c:45-131
+  const double ball = (3. / 4. / 3.14159265358979323846) * (g.par.DesNumNgb + g.par.MaxNumNgbDeviation);
+  const int X = g.par.CrossSectionType;
+  double sig = g.par.CrossSectionInternal, vc = g.par.YukawaVelocity, s_a = 1, a3inv = 1, hubble_a = 0, tail = 1;
+  if (T.comoving) {
+    hubble_a = g.par.Hubble * sqrt(g.par.Omega0 / pow(time, 3) + (1 - g.par.Omega0 - g.par.OmegaLambda) / pow(time, 2) + g.par.OmegaLambda);
+    s_a = g.par.Hubble * sqrt(g.par.Omega0 + time * (1 - g.par.Omega0 - g.par.OmegaLambda) + pow(time, 3) * g.par.OmegaLambda);
+    a3inv = 1 / (time * time * time);
+    sig = sig / pow(time, X == 1 ? 2.5 : 2.0); vc = vc / sqrt(time); tail = 1 / s_a;
+  }
+  double C_max;
+  if (X == 1) C_max = 1.0 * ball * sig * tail;
+  else if (X == 2) {
+    if (2.0 * vmax < vc / sqrt(3.0)) {
+      // NB the non-comoving branch of the reference uses v_dep = 1/(1 + 2 vmax/vc) here, not 1/(1+beta^2) (timestep.c:108)
+      const double beta = 2.0 * vmax / vc, v_dep = T.comoving ? 1.0 / (1.0 + beta * beta) : 1.0 / (1.0 + 2.0 * vmax / vc);
+      C_max = 1.0 * ball * 2.0 * vmax * v_dep * v_dep * sig * tail;
+    } else C_max = 1.0 * ball * (3.0 * sqrt(3.0) / 16.0) * vc * sig * tail;
+  } else if (X == 3) C_max = T.comoving ? 1.0 * ball * sig * 2 * g.par.CrossSectionVelScale * tail : 1.0 * ball * 2 * g.par.CrossSectionVelScale * sig;
+  else C_max = 1.0 * ball * 2 * vmax * sig * tail;
+  T.C_max = C_max; T.C_Grho = ball; T.s_a = s_a; T.hubble_a = hubble_a; T.a3inv = a3inv;
+  T.eta = tp->ErrTolIntAccuracy; T.velscale = tp->ErrTolVelScale; T.probtol = tp->ProbabilityTol; T.dyntol = tp->ErrTolDynamicalAccuracy;
+  T.dtmax = tp->MaxSizeTimestep; T.dtmin = tp->MinSizeTimestep;
+  for (int t = 0; t < 6; t++) T.soft[t] = g.par.SofteningTable[t];
+  T.accel = g.accel; T.curtime = g.curtime; T.maxpred = g.maxpred; T.velh = g.velh; T.posm = g.posm; T.ptype = g.ptype;
+  static unsigned long long calls = 0; calls++;
+  T.k0 = (uint32_t)(g.par.Seed ^ (calls * 0x9E3779B97F4A7C15ull)); T.k1 = (uint32_t)(calls >> 7) ^ 0x51ED270Bu;
+  T.jitter = nullptr; T.out = nullptr; T.nclamped = g.d_flags + FL_NSCATLOG;
+  if (jitter) { CUDA_TRY(cudaMemcpyAsync(g.d_acc, jitter, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, g.stream)); T.jitter = g.d_acc; }
+  if (maxpred_out) T.out = (float *)g.d_cost;
+  CUDA_TRY(cudaMemsetAsync(T.nclamped, 0, sizeof(int), g.stream));
+  k_find_timesteps<<<cdiv(na, 256), 256, 0, g.stream>>>(T);
+  count_launch();
+  if (maxpred_out) CUDA_TRY(cudaMemcpyAsync(maxpred_out, g.d_cost, (size_t)na * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags + FL_NSCATLOG, g.d_flags + FL_NSCATLOG, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  if (num_clamped) *num_clamped = g.h_flags[FL_NSCATLOG];
+  return B200_OK;
+}
+
 // ----------------------------------------------------------------------------- getvmax
 
 // sidm.c:970-990: max |Vel| over local particles; v2 is formed in float (float products and
@@ -599,7 +710,7 @@ extern "C" int b200_device_buffer(const char *name, void **dptr, long long *nbyt
       {"posm", g.posm, n * 16}, {"velh", g.velh, n * 16}, {"accel", g.accel, n * 12}, {"dvel", g.dvel, n * 12},
       {"oldacc", g.oldacc, n * 4}, {"ngb", g.ngb, n * 4}, {"acc_raw", g.d_acc, n * 24}, {"cost", g.d_cost, n * 8},
       {"velpred", g.velpred, n * 12}, {"pos0", g.pos0, n * 12}, {"curtime", g.curtime, n * 4},
-      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4},
+      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4},
       {"ewald", g.d_ewald, g.d_ewald ? 33LL * 33 * 33 * 16 : 0}};
   for (auto &t : tab) if (!strcmp(t.nm, name)) { *dptr = t.p; *nbytes = t.b; return B200_OK; }
   return B200_ERR_ARG;

@@ -100,6 +100,7 @@ static void fill_layout(b200_layout *l)
   l->NgbVelDisp = (int)offsetof(struct particle_data, NgbVelDisp);
   l->HsmlVelDisp = (int)offsetof(struct particle_data, HsmlVelDisp);
   l->dVel = (int)offsetof(struct particle_data, dVel);
+  l->MaxPredTime = (int)offsetof(struct particle_data, MaxPredTime);
 }
 
 /* walk the ForceFlag-linked active list (timeline.c:20-80) into a 0-based index array */

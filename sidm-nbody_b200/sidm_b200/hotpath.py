@@ -132,6 +132,24 @@ class HotPath:
         check(self.lib.b200_advance(ptr(a), 0 if a is None else len(a), t, C.byref(ns) if count else None), "b200_advance")
         return ns.value
 
+    def set_field(self, name, arr):
+        arr = np.ascontiguousarray(arr)
+        check(self.lib.b200_set_field(name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes), "b200_set_field")
+
+    def find_timesteps(self, mode=0, active=None, time=None, vmax=0.0, crit=0, eta=0.05, velscale=10.0, probtol=0.2, dyntol=0.05,
+                       dtmax=1e30, dtmin=0.0, jitter=None):
+        """find_timesteps(mode), timestep.c:17: new MaxPredTime of the active particles; returns (MaxPredTime per active entry, clamped)"""
+        t = self.time if time is None else float(time)
+        a = _i32(active)
+        na = self.n if a is None else len(a)
+        tp = capi.TimestepParams(int(crit), eta, velscale, probtol, dyntol, dtmax, dtmin)
+        out = np.empty(na, np.float32)
+        nc = C.c_int(0)
+        jit = None if jitter is None else np.ascontiguousarray(jitter, np.float64)
+        check(self.lib.b200_find_timesteps(ptr(a), 0 if a is None else len(a), int(mode), t, float(vmax), C.byref(tp), ptr(jit),
+                                           ptr(out), C.byref(nc)), "b200_find_timesteps")
+        return out, nc.value
+
     # ---- the hot path -----------------------------------------------------------------
     def predict_collisionless_only(self, time):
         self.time = float(time)
