@@ -89,6 +89,7 @@ typedef struct b200_layout {
   int Left, Right, NgbVelDisp, HsmlVelDisp, dVel;
   int MaxPredTime;                 /* > 0: offset of P[].MaxPredTime (b200_find_timesteps writes it);
                                       0 = field not bound                                            */
+  int Potential;                   /* > 0: offset of P[].Potential (b200_compute_potential writes it) */
 } b200_layout;
 
 /* Optional replay of the reference's random numbers: the
@@ -224,6 +225,14 @@ typedef struct b200_timestep_params {
 } b200_timestep_params;
 int  b200_find_timesteps(const int *active, int nactive, int mode, double time, double vmax,
                          const b200_timestep_params *tp, const double *jitter, float *maxpred_out, int *num_clamped);
+/* compute_potential(), potential.c:18-180 ("next" row f2): rebuilds the tree over the predicted positions,
+ * walks it for ALL particles with force_treeevaluate_potential() (forcetree.c:1389-1755, same opening
+ * decisions as the force walk), adds the self energy back and applies G and the Lambda / comoving terms.
+ * P[].Potential on the device (downloaded when the layout binds it) and, if not NULL, pot_out[n].
+ * Open boundaries only (the periodic ewald_pot_corr() table is not built: B200_ERR_ARG). */
+int  b200_compute_potential(float *pot_out);
+/* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
+int  b200_potential_raw(const int *targets, int n, double *pot_out);
 /* host -> device copy into a named internal buffer (see b200_device_buffer), e.g. "maxpred" */
 int  b200_set_field(const char *name, const void *host, long long nbytes);
 /* getvmax(), sidm.c:970-990. */

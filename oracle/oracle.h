@@ -88,6 +88,9 @@ double ogetvmax(int n, const float *vel);          /* sidm.c:970-990 */
  * active neighbour counts are in range; returns passes done or -1155. */
 int    osidm_ensure(const otree *t, const oparams *p, int n, const float *vel, const float *mass, float *hsml,
                     const float *dt, float *dvel, int *ngbcount, float *left, float *right, double vmax, orng *rng);
+/* force_treeevaluate_potential(), forcetree.c:1389-1755 and the epilogue of compute_potential(), potential.c:131-168 */
+void   otree_potential(const otree *t, const oparams *p, int nt, const int *targets, const float *oldacc, double *pot);
+void   opot_epilogue(const oparams *p, int nt, const double *pot, const float *mass, float *out);
 /* find_timesteps(mode), timestep.c:17-334, collisionless particles of type 1, no comoving integration,
  * steps that hit Max/MinSizeTimestep take the uniform jitter[a] (the reference: drand48()).  Writes
  * maxpred[i] = CurrentTime + dt/2 for the active particles; returns the number of clamped steps. */

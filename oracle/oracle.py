@@ -131,6 +131,19 @@ class Oracle:
         self.L.otree_force(self.tree, C.byref(self.par), len(idx), _p(idx), _p(oa), _p(acc), _p(cost))
         return acc, cost
 
+    def potential(self, idx, oldacc=None):
+        """raw tree potentials (forcetree.c:1389) and the float P[].Potential of compute_potential() (potential.c:131-168)"""
+        idx = np.ascontiguousarray(idx, np.int32)
+        oa = None if oldacc is None else np.ascontiguousarray(oldacc, np.float32)
+        pot = np.empty(len(idx))
+        self.L.otree_potential.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.otree_potential(self.tree, C.byref(self.par), len(idx), _p(idx), _p(oa), _p(pot))
+        out = np.empty(len(idx), np.float32)
+        m = np.ascontiguousarray(self.mass[idx])
+        self.L.opot_epilogue.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.opot_epilogue(C.byref(self.par), len(idx), _p(pot), _p(m), _p(out))
+        return pot, out
+
     def force_direct(self, idx):
         idx = np.ascontiguousarray(idx, np.int32)
         acc = np.empty((len(idx), 3))

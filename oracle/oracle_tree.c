@@ -28,7 +28,7 @@ struct otree {
   int *thread;                  /* nextnode[] over the combined index space: particle i -> i, node k -> n+k */
   int randoms;
   float dmin[3], dmax[3];
-  double kf[KLEN + 1], kw2[KLEN + 1], kw3[KLEN + 1], kw4[KLEN + 1];
+  double kf[KLEN + 1], kw2[KLEN + 1], kw3[KLEN + 1], kw4[KLEN + 1], kp[KLEN + 1];
 };
 
 #define ISNODE(c) ((c) <= -2)
@@ -58,9 +58,11 @@ static void fill_tables(otree *t)
     double u = ((double)i) / KLEN;
     if (u <= 0.5) {
       t->kf[i] = 32 * (1.0 / 3 - 6.0 / 5 * pow(u, 2) + pow(u, 3));
+      t->kp[i] = 16.0 / 3 * pow(u, 2) - 48.0 / 5 * pow(u, 4) + 32.0 / 5 * pow(u, 5) - 14.0 / 5;            /* knlpot, forcetree.c:1778 */
       t->kw2[i] = -384.0 / 5 + 96.0 * u; t->kw3[i] = 96.0; t->kw4[i] = 96.0 / 5 * u * (5 * u - 4);
     } else {
       t->kf[i] = 64 * (1.0 / 3 - 3.0 / 4 * u + 3.0 / 5 * pow(u, 2) - pow(u, 3) / 6) - 1.0 / 15 / pow(u, 3);
+      t->kp[i] = 1.0 / 15 / u + 32.0 / 3 * pow(u, 2) - 16.0 * pow(u, 3) + 48.0 / 5 * pow(u, 4) - 32.0 / 15 * pow(u, 5) - 16.0 / 5;   /* :1787 */
       t->kw2[i] = 384.0 / 5 + 1 / (5.0 * pow(u, 5)) - 48.0 / u - 32 * u;
       t->kw3[i] = -32 - 1 / pow(u, 6) + 48 / pow(u, 2);
       t->kw4[i] = -48 + 1 / (5 * pow(u, 4)) + 384.0 / 5 * u - 32 * pow(u, 2);
@@ -288,6 +290,66 @@ void otree_force(const otree *t, const oparams *p, int nt, const int *targets, c
     int c[2];
     walk_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f, acc + 3 * i, c);
     if (cost) { cost[2 * i] = c[0]; cost[2 * i + 1] = c[1]; }
+  }
+}
+
+/* potential of one target: forcetree.c:1417-1577 (BH) and :1585-1755 (relative criterion) */
+static double pot_one(const otree *t, const oparams *p, const float *tp, float oldacc)
+{
+  const int bh = (p->criterion == 0 || oldacc == 0);        /* forcetree.c:1404 */
+  const double h = 2.8 * p->eps, h_inv = 1 / h;
+  const double h2_inv = h_inv * h_inv, h3_inv = h2_inv * h_inv, h5_inv = h2_inv * h3_inv;
+  const double oac = oldacc * p->alpha;
+  double pot = 0;
+  int item = t->n;
+  while (item >= 0) {
+    if (item < t->n) {
+      int j = item;
+      double dx = t->pos[3 * j] - tp[0], dy = t->pos[3 * j + 1] - tp[1], dz = t->pos[3 * j + 2] - tp[2];
+      double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2), u = r * h_inv;
+      if (u >= 1) pot -= t->mass[j] / r;
+      else { int ii; double ff; double wp = lerp_tab(t->kp, u, &ii, &ff); pot += t->mass[j] * h_inv * wp; }
+      item = t->thread[item];
+      continue;
+    }
+    int k = item - t->n;
+    double dx = t->com[k][0] - tp[0], dy = t->com[k][1] - tp[1], dz = t->com[k][2] - tp[2];   /* float - float: no node drift here (forcetree.c:1477,1645) */
+    double r2 = dx * dx + dy * dy + dz * dz;
+    int open = bh ? (t->len[k] * t->len[k] > r2 * p->theta * p->theta)
+                  : (t->oc[k] > oac * r2 * r2 * r2 || r2 < t->bmax2[k]);
+    if (open) { item = t->thread[item]; continue; }
+    const float *Q = t->q[k];
+    double r = sqrt(r2), u = r * h_inv;
+    double q11dx = Q[0] * dx, q12dx = Q[3] * dx, q22dy = Q[1] * dy, q13dx = Q[4] * dx, q23dy = Q[5] * dy, q33dz = Q[2] * dz;
+    double potq = 0.5 * (q11dx * dx + q22dy * dy + q33dz * dz) + q12dx * dy + q13dx * dz + q23dy * dz;
+    if (u >= 1) {
+      double ri = 1 / r, r2i = ri * ri, r3i = r2i * ri;
+      pot += -t->nmass[k] * ri + r3i * (-3 * potq * r2i + 0.5 * Q[6]);
+    } else {
+      int ii; double f2;
+      double wf = lerp_tab(t->kf, u, &ii, &f2);
+      double wp = t->kp[ii] + (t->kp[ii + 1] - t->kp[ii]) * f2, w2 = t->kw2[ii] + (t->kw2[ii + 1] - t->kw2[ii]) * f2;
+      pot += t->nmass[k] * h_inv * wp + potq * w2 * h5_inv + 0.5 * Q[6] * wf * h2_inv * h_inv;
+    }
+    item = t->sib[k];
+  }
+  (void)h3_inv;
+  return pot;
+}
+
+/* raw potentials as force_treeevaluate_potential() leaves them in GravDataPotential (forcetree.c:1389) */
+void otree_potential(const otree *t, const oparams *p, int nt, const int *targets, const float *oldacc, double *pot)
+{
+  for (int i = 0; i < nt; i++) pot[i] = pot_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f);
+}
+/* potential.c:131-168 without comoving integration and Lambda: float Potential = raw; += m/eps (self energy); *= G */
+void opot_epilogue(const oparams *p, int nt, const double *pot, const float *mass, float *out)
+{
+  for (int i = 0; i < nt; i++) {
+    float v = pot[i];
+    v += mass[i] / p->eps;
+    v *= p->G;
+    out[i] = v;
   }
 }
 

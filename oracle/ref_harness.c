@@ -299,6 +299,17 @@ void ref_force_tree(int n, const int *idx, double *acc, int *cost)
     if (cost) { cost[2 * t] = treecost[1] - c0; cost[2 * t + 1] = treecost_quadru[1] - c1; }
   }
 }
+void ref_potential(int n, const int *idx, double *pot)     /* forcetree.c:1389, tree already built */
+{
+  for (int t = 0; t < n; t++) {
+    struct particle_data *p = &P[idx[t] + 1];
+    for (int k = 0; k < 3; k++) GravDataIn[0].Pos[k] = p->PosPred[k];
+    GravDataIn[0].Type = p->Type;
+    GravDataIn[0].OldAcc = p->OldAcc;
+    force_treeevaluate_potential(0);
+    pot[t] = GravDataPotential[0];
+  }
+}
 void ref_force_direct(int n, const int *idx, double *acc)
 {
   for (int t = 0; t < n; t++) {
@@ -340,6 +351,7 @@ void ref_sidm_ensure_neighbours(int mode) { sidm_ensure_neighbours(mode); }
 void ref_setup_smoothinglengths_sidm(int desngb) { setup_smoothinglengths_sidm(desngb); }
 void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
+void ref_compute_potential(void) { compute_potential(); }   /* potential.c:18: rebuilds the tree, all particles */
 /* timestep.c:17 with the accuracy parameters of the parameter file set here; mode 2 = start-up (no growth limit) */
 void ref_find_timesteps(int mode, int crit, double eta, double velscale, double probtol, double dyntol, double dtmax, double dtmin)
 {

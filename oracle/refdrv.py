@@ -188,6 +188,15 @@ class Reference:
         self.lib.ref_force_tree(len(idx), idx.ctypes, acc.ctypes, cost.ctypes if want_cost else None)
         return acc, cost
 
+    def potential(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        pot = np.empty(len(idx), np.float64)
+        self.lib.ref_potential(len(idx), idx.ctypes, pot.ctypes)
+        return pot
+
+    def compute_potential(self):
+        self.lib.ref_compute_potential()
+
     def force_direct(self, idx):
         idx = np.ascontiguousarray(idx, np.int32)
         acc = np.empty((len(idx), 3), np.float64)

@@ -41,6 +41,7 @@ struct Ctx {
   float  *accel = nullptr;   // Accel [n][3]
   float  *dvel = nullptr;    // dVel [n][3]
   float  *maxpred = nullptr;  // MaxPredTime (written by b200_find_timesteps)
+  float  *potential = nullptr; // Potential (written by b200_compute_potential)
   float  *curtime = nullptr, *oldacc = nullptr, *gravcost = nullptr, *left = nullptr, *right = nullptr;
   int    *ngb = nullptr, *pid = nullptr, *ptype = nullptr;
 

@@ -26,7 +26,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.pos0, 3 * n)); B200_TRY(dalloc(&g.velpred, 3 * n));
   B200_TRY(dalloc(&g.accel, 3 * n)); B200_TRY(dalloc(&g.dvel, 3 * n));
   B200_TRY(dalloc(&g.curtime, n)); B200_TRY(dalloc(&g.oldacc, n)); B200_TRY(dalloc(&g.gravcost, n));
-  B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n)); B200_TRY(dalloc(&g.maxpred, n));
+  B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n)); B200_TRY(dalloc(&g.maxpred, n)); B200_TRY(dalloc(&g.potential, n));
   B200_TRY(dalloc(&g.ngb, n)); B200_TRY(dalloc(&g.pid, n)); B200_TRY(dalloc(&g.ptype, n));
   B200_TRY(dalloc(&g.d_bbox, 8)); B200_TRY(dalloc(&g.d_root, 1)); B200_TRY(dalloc(&g.d_domain, 8));
   B200_TRY(dalloc(&g.key_hi, n)); B200_TRY(dalloc(&g.key_lo, n));
@@ -163,7 +163,7 @@ extern "C" void b200_finalize(void) {
   g.pinned = false; g.h_base = nullptr; g.have_aos = false;
   dfree(&g.d_aos); g.aos_cap = 0;
   dfree(&g.posm); dfree(&g.velh); dfree(&g.pos0); dfree(&g.velpred); dfree(&g.accel); dfree(&g.dvel);
-  dfree(&g.maxpred);
+  dfree(&g.maxpred); dfree(&g.potential);
   dfree(&g.curtime); dfree(&g.oldacc); dfree(&g.gravcost); dfree(&g.left); dfree(&g.right);
   dfree(&g.ngb); dfree(&g.pid); dfree(&g.ptype);
   dfree(&g.d_bbox); dfree(&g.d_root); dfree(&g.d_domain);
@@ -325,17 +325,18 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
   return B200_OK;
 }
 
-struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc, Left, Right, Ngb, Hsml, dVel, MaxPred; };
+struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred, Accel, GravCost, OldAcc, Left, Right, Ngb, Hsml, dVel, MaxPred, Pot; };
 
 __device__ __forceinline__ float ldf(const char *p, int off) { return *(const float *)(p + off); }
 __device__ __forceinline__ int ldi(const char *p, int off) { return *(const int *)(p + off); }
 
 __global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4 *velh, float *pos0, float *velpred,
                              float *accel, float *dvel, float *curtime, float *oldacc, float *gravcost,
-                             float *left, float *right, int *ngb, int *pid, int *ptype, float *maxpred) {
+                             float *left, float *right, int *ngb, int *pid, int *ptype, float *maxpred, float *potential) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const char *p = aos + (size_t)i * L.stride;
+  if (L.Pot > 0) potential[i] = ldf(p, L.Pot);
   if (L.MaxPred > 0) maxpred[i] = ldf(p, L.MaxPred);
   float4 a, b;
   a.x = ldf(p, L.PosPred); a.y = ldf(p, L.PosPred + 4); a.z = ldf(p, L.PosPred + 8); a.w = ldf(p, L.Mass);
@@ -354,10 +355,11 @@ __global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4
 
 __global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
                            const float *accel, const float *dvel, const float *oldacc, const float *gravcost,
-                           const float *left, const float *right, const int *ngb, const float *maxpred) {
+                           const float *left, const float *right, const int *ngb, const float *maxpred, const float *potential) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   char *p = aos + (size_t)i * L.stride;
+  if (L.Pot > 0) *(float *)(p + L.Pot) = potential[i];
   if (L.MaxPred > 0) *(float *)(p + L.MaxPred) = maxpred[i];
   float4 a = posm[i];
   *(float *)(p + L.PosPred) = a.x; *(float *)(p + L.PosPred + 4) = a.y; *(float *)(p + L.PosPred + 8) = a.z;
@@ -373,7 +375,7 @@ __global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const fl
 
 static Lay to_lay(const b200_layout &l) {
   Lay L{l.stride, l.Pos, l.Vel, l.Mass, l.ID, l.Type, l.CurrentTime, l.PosPred, l.VelPred, l.Accel,
-        l.GravCost, l.OldAcc, l.Left, l.Right, l.NgbVelDisp, l.HsmlVelDisp, l.dVel, l.MaxPredTime};
+        l.GravCost, l.OldAcc, l.Left, l.Right, l.NgbVelDisp, l.HsmlVelDisp, l.dVel, l.MaxPredTime, l.Potential};
   return L;
 }
 
@@ -383,7 +385,7 @@ extern "C" int b200_upload(void) {
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.d_aos, g.h_base, (size_t)n * g.lay.stride, cudaMemcpyHostToDevice, g.stream));
   k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
-                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred);
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -407,7 +409,7 @@ extern "C" int b200_download(void) {
   const int n = g.n;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
-                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred);
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -435,7 +437,7 @@ extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
     CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)c * st, cudaMemcpyDeviceToDevice, g.stream));
   }
   k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
-                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred);
+                                                   g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -452,7 +454,7 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   char *out = dst ? (char *)dst : g.h_base;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
-                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred);
+                                                 g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   if (count > 0) CUDA_TRY(cudaMemcpyAsync(out + (size_t)first * st, g.d_aos + (size_t)first * st, (size_t)count * st, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -710,7 +712,7 @@ extern "C" int b200_device_buffer(const char *name, void **dptr, long long *nbyt
       {"posm", g.posm, n * 16}, {"velh", g.velh, n * 16}, {"accel", g.accel, n * 12}, {"dvel", g.dvel, n * 12},
       {"oldacc", g.oldacc, n * 4}, {"ngb", g.ngb, n * 4}, {"acc_raw", g.d_acc, n * 24}, {"cost", g.d_cost, n * 8},
       {"velpred", g.velpred, n * 12}, {"pos0", g.pos0, n * 12}, {"curtime", g.curtime, n * 4},
-      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4},
+      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4}, {"potential", g.potential, n * 4},
       {"ewald", g.d_ewald, g.d_ewald ? 33LL * 33 * 33 * 16 : 0}};
   for (auto &t : tab) if (!strcmp(t.nm, name)) { *dptr = t.p; *nbytes = t.b; return B200_OK; }
   return B200_ERR_ARG;

@@ -189,6 +189,11 @@ B200_HD float soft_force(float u) {            // knlforce
   if (u <= 0.5f) return 32.0f * (1.0f / 3 - 1.2f * u * u + u * u * u);
   return 64.0f * (1.0f / 3 - 0.75f * u + 0.6f * u * u - u * u * u / 6) - 1.0f / (15 * u * u * u);
 }
+B200_HD float soft_pot(float u) {              // knlpot, forcetree.c:1778,1787
+  const float u2 = u * u;
+  if (u <= 0.5f) return u2 * (16.0f / 3 + u2 * (-9.6f + 6.4f * u)) - 2.8f;
+  return 1.0f / (15 * u) + u2 * (32.0f / 3 + u * (-16.0f + u * (9.6f - 32.0f / 15 * u))) - 3.2f;
+}
 B200_HD void soft_w234(float u, float &w2, float &w3, float &w4) {   // knlW2, knlW3, knlW4
   if (u <= 0.5f) {
     w2 = -76.8f + 96.0f * u; w3 = 96.0f; w4 = 19.2f * u * (5 * u - 4);

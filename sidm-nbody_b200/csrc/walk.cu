@@ -212,6 +212,122 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParam
   }
 }
 
+static float h_inv_of_type1();
+
+// ------------------------------------------------------------------ potential walk
+// force_treeevaluate_potential(), forcetree.c:1389-1755: the same lock-step walk and the same open/accept
+// decisions as the force walk, scalar accumulator.  Leaf: -m/r, or m/h * knlpot(r/h) inside the softening
+// radius (no u > 1e-4 guard here: the target's own particle contributes -m/eps, which compute_potential()
+// adds back, potential.c:135).  Cell: -M/r + (-3 potq/r^2 + P/2)/r^3, softened form below h.  Open boundaries.
+template <int MODE>
+__device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no, double &pot) {
+  const float h_inv = P.h_inv, theta2 = P.theta2;
+  const float h2 = 1.0f / (h_inv * h_inv);
+  const float h3i = h_inv * h_inv * h_inv, h5i = h3i * h_inv * h_inv;
+  const int M = P.num_nodes;
+  const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
+  int cur = __reduce_min_sync(0xffffffffu, no);
+  while (cur < M) {
+    float f = 0;
+    for (int it = 0; it < kFlushEvery && cur < M; it++) {
+      const float4 *nd = nodes4 + 4 * (size_t)cur;
+      const float4 A = __ldg(nd), Bv = __ldg(nd + 1), Cv = __ldg(nd + 2), Dv = __ldg(nd + 3);
+      const float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      bool crit;
+      if (MODE == 1) crit = (Bv.x > oac * r2 * r2 * r2) || (r2 < Bv.y);
+      else if (MODE == 2) crit = Dv.w > r2 * theta2;
+      else crit = bh ? (Dv.w > r2 * theta2) : ((Bv.x > oac * r2 * r2 * r2) || (r2 < Bv.y));
+      const bool act = (no == cur);
+      const bool acc = act && !crit, open = act && crit;
+      if (acc) {
+        const float qx = fmaf(Dv.x, dz, fmaf(Cv.w, dy, Cv.x * dx));
+        const float qy = fmaf(Dv.y, dz, fmaf(Cv.y, dy, Cv.w * dx));
+        const float qz = fmaf(Cv.z, dz, fmaf(Dv.y, dy, Dv.x * dx));
+        const float potq = 0.5f * fmaf(dz, qz, fmaf(dy, qy, dx * qx));     // 1/2 y^T Q y
+        if (r2 >= h2) {
+          const float ri = rsqrt_fast(r2), r2i = ri * ri, r3i = r2i * ri;
+          f += fmaf(r3i, fmaf(-3.0f * potq, r2i, 0.5f * Dv.z), -A.w * ri);   // forcetree.c:1694-1695
+        } else {
+          const float u = sqrtf(r2) * h_inv;
+          float w2, w3, w4;
+          soft_w234(u, w2, w3, w4);
+          f += A.w * h_inv * soft_pot(u) + potq * w2 * h5i + 0.5f * Dv.z * soft_force(u) * h3i;   // :1722-1723
+        }
+      }
+      no = acc ? __float_as_int(Bv.w) : (open ? cur + 1 : no);
+      if (__any_sync(0xffffffffu, open)) {
+        const int pinfo = __float_as_int(Bv.z);
+        const int np = pinfo & 15;
+        const float4 *lp = P.leaf_posm + (pinfo >> 4);
+        for (int k = 0; k < np; k++) {
+          const float4 q = __ldg(lp + k);
+          if (open) {
+            const float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
+            const float pr2 = fmaf(pz, pz, fmaf(py, py, px * px));
+            if (pr2 >= h2) f -= q.w * rsqrt_fast(pr2);                       // forcetree.c:1625
+            else f += q.w * h_inv * soft_pot(sqrtf(pr2) * h_inv);            // :1629-1631
+          }
+        }
+      }
+      cur = __reduce_min_sync(0xffffffffu, no);
+    }
+    pot += (double)f;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_walk_pot(WalkParams P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < P.nt;
+  int slot = 0, part = 0;
+  if (valid) { slot = P.tsorted[t]; part = P.slot_part ? P.slot_part[slot] : slot; }
+  float4 tp = make_float4(0, 0, 0, 0); float oa = 0;
+  if (valid) { tp = P.posm[part]; oa = P.oldacc[part]; }
+  const bool bh = (P.criterion == 0) || (oa == 0.0f);           // forcetree.c:1404
+  const float oac = oa * P.alpha;
+  int no = valid ? 0 : 0x7fffffff;
+  double pot = 0;
+  const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
+  if (all_rel) walk_loop_pot<1>(P, tp, bh, oac, no, pot);
+  else if (all_bh) walk_loop_pot<2>(P, tp, bh, oac, no, pot);
+  else walk_loop_pot<0>(P, tp, bh, oac, no, pot);
+  if (valid) P.acc[slot] = pot;                                  // raw potential per target slot (GravDataPotential)
+}
+
+// compute_potential(), potential.c:131-168: float Potential <- raw; += m/eps (self energy); *G; Lambda / comoving terms
+__global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, float *potential, double eps, double G,
+                               int comoving, double H, double O0, double OL) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = posm[i];
+  float v = (float)raw[i];
+  v = (float)((double)v + (double)p.w / eps);
+  double r2 = 0;
+  r2 += (double)fmul(p.x, p.x); r2 += (double)fmul(p.y, p.y); r2 += (double)fmul(p.z, p.z);
+  if (comoving) {
+    const double fac = 0.5 * O0 * H * H;
+    v = (float)(G * (double)v - fac * r2);
+  } else {
+    const double fac = -0.5 * OL * H * H;
+    v = (float)((double)v * G);
+    if (fac != 0) v = (float)((double)v + fac * r2);
+  }
+  potential[i] = v;
+}
+
+static int potential_walk(const int *d_sorted, int nt, bool with_slots) {
+  if (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) return B200_ERR_ARG;    // ewald_pot_corr(): not built
+  WalkParams P;
+  P.nt = nt; P.num_nodes = g.num_nodes; P.tsorted = d_sorted; P.slot_part = with_slots ? g.d_active : nullptr;
+  P.posm = g.posm; P.oldacc = g.oldacc; P.nodes = g.nodes; P.leaf_posm = g.leaf_posm;
+  P.acc = g.d_acc; P.cost = g.d_cost;
+  P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
+  P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
+  P.box = 0; P.boxhalf = 0; P.ewald_fac = 0; P.ewald = nullptr;
+  if (nt > 0) { k_walk_pot<<<cdiv(nt, 128), 128, 0, g.stream>>>(P); count_launch(); }
+  return B200_OK;
+}
+
 // ------------------------------------------------------------------ Ewald tables
 // ewald_init() / ewald_force(), ewald.c:35-162, 332-381: correction force of the periodic images
 // of a unit point mass in a unit box (alpha = 2, |n|,|h| <= 4 per axis), tabulated on the
@@ -519,5 +635,32 @@ extern "C" int b200_walk_raw(const int *targets, int n, double *acc_out, int *co
   if (acc_out) CUDA_TRY(cudaMemcpyAsync(acc_out, g.d_acc, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   if (cost_out) CUDA_TRY(cudaMemcpyAsync(cost_out, g.d_cost, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return B200_OK;
+}
+
+extern "C" int b200_potential_raw(const int *targets, int n, double *pot_out) {
+  if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
+  if (!targets || n <= 0 || n > g.n || !pot_out) return B200_ERR_ARG;
+  int *d_sorted = nullptr;
+  B200_TRY(prepare_targets(targets, n, &d_sorted));
+  B200_TRY(potential_walk(d_sorted, n, true));
+  CUDA_TRY(cudaMemcpyAsync(pot_out, g.d_acc, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_compute_potential(float *pot_out) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  B200_TRY(b200_tree_build());                                   // potential.c:47 force_treebuild()
+  B200_TRY(potential_walk(g.sidx, g.n, false));
+  double eps = 0;
+  for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
+  k_pot_epilogue<<<cdiv(g.n, 256), 256, 0, g.stream>>>(g.n, g.d_acc, g.posm, g.potential, eps, g.par.G, g.par.ComovingIntegrationOn,
+                                                     g.par.Hubble, g.par.Omega0, g.par.OmegaLambda);
+  count_launch();
+  if (pot_out) CUDA_TRY(cudaMemcpyAsync(pot_out, g.potential, (size_t)g.n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

@@ -14,6 +14,7 @@
  *   force_treeallocate/build/free, force_costevaluate/resetcost/getcost_*   forcetree.h:9-27
  *   ngb_treeallocate/build/free, ngb_update_nodes, ngb_treefind             forcetree.h:30-40
  *   set_softenings()          gravtree.c:425    (lives in the replaced file, restated here)
+ *   compute_potential()       potential.c:18    only with -DB200_SHIM_ACCEL, linked instead of potential.c
  *   compute_accelerations()   accel.c:27        only with -DB200_SHIM_ACCEL, linked instead of accel.c:
  *                                               one upload, ONE library call for gravity + sidm + repair
  *                                               loop (walk and SIDM chain overlapped on two CUDA streams),
@@ -101,6 +102,7 @@ static void fill_layout(b200_layout *l)
   l->HsmlVelDisp = (int)offsetof(struct particle_data, HsmlVelDisp);
   l->dVel = (int)offsetof(struct particle_data, dVel);
   l->MaxPredTime = (int)offsetof(struct particle_data, MaxPredTime);
+  l->Potential = (int)offsetof(struct particle_data, Potential);
 }
 
 /* walk the ForceFlag-linked active list (timeline.c:20-80) into a 0-based index array */
@@ -286,6 +288,23 @@ void sidm_ensure_neighbours(int mode)                   /* sidm.c:814-968 */
 void update_node_sidm(void) {}                          /* sidm.c:992-997 */
 
 #ifdef B200_SHIM_ACCEL
+/* compute_potential(), potential.c:18-180 (linked instead of potential.c): potential of all particles for
+ * the energy statistics (run.c:51-60 -> global.c) */
+void compute_potential(void)
+{
+  double t0 = second(), t1;
+  if (All.ComovingIntegrationOn) set_softenings();
+  if (ThisTask == 0) { printf("Start computation of potential for all particles...\n"); fflush(stdout); }
+  sync_params_and_particles();
+  b200_check(b200_compute_potential(0), "b200_compute_potential");
+  b200_check(b200_download(), "b200_download");
+  All.NumForcesSinceLastTreeConstruction = All.TreeUpdateFrequency * All.TotNumPart;   /* potential.c:49 */
+  NoCostFlag = 1;
+  if (ThisTask == 0) { printf("potential done.\n"); fflush(stdout); }
+  t1 = second();
+  All.CPU_Potential += timediff(t0, t1);
+}
+
 /* accel.c:27-132 for collisionless runs, as one coarse call.  Same order of effects as the CPU code:
  * gravity_tree() bookkeeping (gravtree.c:42-60), forces, determine_interior(), sidm() +
  * sidm_ensure_neighbours(mode) when mode == 0, timers into All.CPU_Gravity / CPU_EnsureNgb. */

@@ -132,6 +132,18 @@ class HotPath:
         check(self.lib.b200_advance(ptr(a), 0 if a is None else len(a), t, C.byref(ns) if count else None), "b200_advance")
         return ns.value
 
+    def compute_potential(self):
+        """compute_potential(), potential.c:18: P[].Potential of every particle (rebuilds the tree)"""
+        out = np.empty(self.n, np.float32)
+        check(self.lib.b200_compute_potential(ptr(out)), "b200_compute_potential")
+        return out
+
+    def force_treeevaluate_potential(self, targets):
+        t = _i32(targets)
+        out = np.empty(len(t), np.float64)
+        check(self.lib.b200_potential_raw(ptr(t), len(t), ptr(out)), "b200_potential_raw")
+        return out
+
     def set_field(self, name, arr):
         arr = np.ascontiguousarray(arr)
         check(self.lib.b200_set_field(name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes), "b200_set_field")

@@ -33,9 +33,13 @@ def main(kind, out, n):
     R.set("HSML", (h0 * rng.choice(np.array([1, 1, 1, 0.8, 1.3], np.float32), n)).astype(np.float32))
     R.all_active(0.0, 0.01)
     R.compute_accelerations(0)                         # gravity (relative criterion) + sidm + ensure_neighbours
-    np.savez(out, h0=h0, ngb0=ngb0, acc1=acc1, old1=old1, acc2=R.get("ACCEL"), old2=R.get("OLDACC"),
-             h2=R.get("HSML"), ngb2=R.get("NGB"), dvel=R.get("DVEL"), pospred=R.get("POSPRED"),
-             nactive=len(R.active()))
+    res = dict(h0=h0, ngb0=ngb0, acc1=acc1, old1=old1, acc2=R.get("ACCEL"), old2=R.get("OLDACC"),
+               h2=R.get("HSML"), ngb2=R.get("NGB"), dvel=R.get("DVEL"), pospred=R.get("POSPRED"),
+               nactive=len(R.active()))
+    if kind != "b200":                                 # potential.c:18 (the symbol-by-symbol shim leaves potential.c's CPU walk out)
+        R.compute_potential()
+        res["pot"] = R.get("POT")
+    np.savez(out, **res)
 
 
 if __name__ == "__main__":

@@ -44,3 +44,5 @@ def test_reference_driver_on_gpu_path(tmp_path, refdrv_mod, kind):
     assert (cpu["h2"] == gpu["h2"]).mean() > 0.999
     assert not gpu["dvel"].any() and not cpu["dvel"].any()
     assert cpu["nactive"] == gpu["nactive"] == N
+    if kind == "b200f":                                # compute_potential() through the shim
+        np.testing.assert_allclose(gpu["pot"], cpu["pot"], rtol=3e-6)

@@ -66,3 +66,18 @@ def test_sidm_step_and_repair(pair, refdrv_mod):
     assert np.array_equal(R.get("DVEL"), O.dvel)
     log = refdrv_mod.read_scatlog("sct_000.0")
     assert len(log) >= res["sct"][2] > 0
+
+
+def test_potential(pair):
+    """force_treeevaluate_potential() (forcetree.c:1389-1755, both criteria) and compute_potential() (potential.c:18)"""
+    R, O, pos = pair
+    idx = np.arange(0, N, 19, dtype=np.int32)
+    R.set("OLDACC", np.zeros(N, np.float32))
+    assert np.array_equal(R.potential(idx), O.potential(idx, None)[0])
+    R.all_active(0.0, 0.0)
+    R.getvmax()
+    R.compute_accelerations(1)
+    old = R.get("OLDACC")
+    assert np.array_equal(R.potential(idx), O.potential(idx, old)[0])
+    R.compute_potential()
+    assert np.array_equal(R.get("POT"), O.potential(np.arange(N, dtype=np.int32), old)[1])
