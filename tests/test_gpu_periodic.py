@@ -125,3 +125,74 @@ assert err < 1e-4 and np.allclose(oa, orr, rtol=1e-3)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_comoving_periodic_sidm_replay(refdrv_mod):
+    """sidm() in a comoving periodic box (BASELINE config C4): the a^-2 cross-section, the dt/S(a) factor
+    (sidm.c:226-272) and the periodic neighbour search, against the -DPERIODIC reference with its own random
+    numbers replayed.  The reference's draw log is split into per-slot uniforms and directions with the
+    P_max / total probability the GPU reports per slot (a mismatch there derails the split and fails the test)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, tempfile, numpy as np
+sys.path.insert(0, "oracle"); sys.path.insert(0, "sidm-nbody_b200")
+import refdrv
+from sidm_b200 import HotPath, ic
+BOX, EPS, A, SIG = 100.0, 0.5, 0.25, 1.5e3
+pos, vel, mass, ids = ic.periodic_box(20, seed=6, box=BOX, vel_sigma=60.0)
+n = len(mass)
+root = os.getcwd(); os.chdir(tempfile.mkdtemp())
+R = refdrv.Reference("periodic")
+R.setup(n, BoxSize=BOX, SofteningHalo=EPS, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1, Time=A, CrossSectionInternal=SIG)
+R.init_rand(55)
+R.set_particles(pos, vel, mass, ids)
+R.treebuild()
+R.setup_smoothinglengths_sidm(30)
+h = R.get("HSML")
+R.all_active(A, A * 1.02)
+t = R.time
+vmax = R.getvmax()
+R.rng_log_begin(4 * n + 1000)
+R.sidm()
+log = R.rng_log_end()
+dv_ref, ngb_ref = R.get("DVEL"), R.get("NGB")
+os.chdir(root)
+assert (np.abs(dv_ref).sum(1) > 0).sum() >= 10, "fixture too quiet"
+kw = dict(BoxSize=BOX, PeriodicBoundariesOn=1, SofteningHalo=EPS, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7,
+          Hubble=0.1, CrossSectionInternal=SIG, ReferenceNgbOrder=1)
+act = np.arange(n, dtype=np.int32)
+with HotPath(n, **kw) as hp:
+    hp.set_particles(pos, vel, mass, ids, hsml=h, curtime=np.full(n, A, np.float32))
+    hp.force_treebuild()                   # the reference searched the unpredicted positions (no gravity_tree() before)
+    # pass A: any uniforms, only to read P_max and the total probability of every slot
+    hp.sidm(active=act, time=t, vmax=vmax, replay_rand=np.full(n, 1e-300), replay_dir=np.zeros((n, 3)))
+    sp, pmax, ptot, partner = hp.sidm_debug(n)
+    rand = np.zeros(n); dirs = np.zeros((n, 3)); k = 0
+    npass = nfound = 0
+    for s in range(n):                      # split the reference's draw log (sidm.c:341, sidm_rand.h:24-37)
+        if k >= len(log):
+            print("log exhausted at slot", s, "pass", npass, "found", nfound, "pmax", pmax[:5], "ptot", ptot[:5]); break
+        u = log[k]; k += 1; rand[s] = u
+        npass += int(not (pmax[s] < u)); nfound += int((not (pmax[s] < u)) and ptot[s] >= u)
+        if pmax[s] < u or not (ptot[s] >= u):
+            continue
+        while True:
+            y1 = 1.0 - 2.0 * log[k]; y2 = 1.0 - 2.0 * log[k + 1]; k += 2
+            r2 = y1 * y1 + y2 * y2
+            if r2 <= 1.0:
+                break
+        sq = np.sqrt(1.0 - r2); dirs[s] = (2.0 * y1 * sq, 2.0 * y2 * sq, 1.0 - 2.0 * r2)
+    print("draws", len(log), "used", k, "passed", int(((pmax >= rand) & (ptot >= rand)).sum()))
+    assert k == len(log), (k, len(log))     # every draw accounted for
+    hp.set_particles(hsml=h, dvel=np.zeros((n, 3), np.float32), curtime=np.full(n, A, np.float32))
+    hp.sidm(active=act, time=t, vmax=vmax, replay_rand=rand, replay_dir=dirs)
+    dv, ngb = hp.get("dVel", "NgbVelDisp")
+assert np.array_equal(ngb, ngb_ref), "neighbour counts"
+assert np.array_equal(dv != 0, dv_ref != 0), "who scattered"
+np.testing.assert_allclose(dv, dv_ref, rtol=3e-6, atol=1e-30)
+print("comoving sidm: scattered", int((np.abs(dv).sum(1) > 0).sum()))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
