@@ -142,7 +142,9 @@ const char *b200_version(void);
 /* run-time switches.  "overlap" (default 1): b200_compute_accelerations(0) issues the gravity walk and
  * the SIDM chain on two CUDA streams so the SIDM repair loop's small launches hide behind the walk
  * 0 runs the phases one after the other as accel.c:39-65 does.  "shard_overlap" (default 0): see
- * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes. */
+ * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes.  "shard_min_work"
+ * (default 262144): work lists shorter than this are done completely by every rank instead of being sharded
+ * (the repair passes and small active sets are latency-bound; an exchange per pass costs more than it saves). */
 int  b200_set_option(const char *name, int value);
 
 /* ---- particle state -------------------------------------------------------------- */

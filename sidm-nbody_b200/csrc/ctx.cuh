@@ -8,6 +8,9 @@
 
 namespace b200 {
 
+// work lists shorter than Ctx::shard_min_work are not sharded (every rank does all of it); option "shard_min_work"
+constexpr int kShardMinWorkDefault = 1 << 18;
+
 struct Ctx {
   bool ready = false;
   b200_params par{};
@@ -24,6 +27,7 @@ struct Ctx {
   bool opt_overlap = true;         // b200_set_option("overlap", 0|1)
   bool opt_shard_overlap = false;  // b200_set_option("shard_overlap", 1): the host's all-gather callback runs on
                                    // b200_current_stream(), so the two-stream overlap is also safe when sharded
+  int shard_min_work = kShardMinWorkDefault;
   cudaStream_t coll_stream = nullptr;   // stream the pending collective has to be ordered on
   bool opt_group_search = true;    // b200_set_option("group_search", 0|1): warp-shared neighbour search for all-active passes
   bool overlap_now = false;        // true while the SIDM chain is being issued on stream_sidm

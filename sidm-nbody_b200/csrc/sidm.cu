@@ -948,6 +948,9 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   cudaStream_t st = sidm_stream();
   const int na = nactive;
   if (na <= 0) return B200_OK;
+  // small passes (the repair loop, small active sets) are latency-bound: every rank does them completely -
+  // same inputs, counter-based random numbers, so same results - instead of paying an exchange per pass
+  const bool sharded = g.shard_world > 1 && na >= g.shard_min_work;
   const int B = 256;
   const double sainv = s_a_inverse_at(time);
   // C_Pmax, sidm.c:226-316 (types 0..3)
@@ -1032,12 +1035,12 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
     const bool group_mode = !act && nb == g.n && !periodic_box && S.ngroups > 0 && g.opt_group_search;
     const int *global_order = S.slot_of_sorted;      // all ranks' slots in processing order
-    if (group_mode && g.shard_world > 1) {           // sharded group search: processing order = leaf order
+    if (group_mode && sharded) {                     // sharded group search: processing order = leaf order
       k_order_leaf<<<G, B, 0, st>>>(nb, g.leaf_orig, slot_of_active, S.order_leaf);
       count_launch();
       global_order = S.order_leaf;
     }
-    if (g.shard_world > 1) { B200_TRY(shard_select(global_order, nb, S.x_shard, &nord, st)); order = S.x_shard; }
+    if (sharded) { B200_TRY(shard_select(global_order, nb, S.x_shard, &nord, st)); order = S.x_shard; }
     // pass 1
     Pass1 P1;
     P1.ns = nord; P1.order = order; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
@@ -1052,9 +1055,9 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       PG.ng = S.ngroups; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
       PG.dt = S.dt; PG.already = S.already; PG.replay_rand = d_rr; PG.C_Pmax = C_Pmax; PG.s_a_inverse = sainv; PG.k0 = k0; PG.k1 = k1;
       PG.ngb = g.s_ngb; PG.pmax = g.s_pmax; PG.rnd = g.s_rand; PG.pass = g.s_pass; PG.order_leaf = S.order_leaf; PG.count_only = count_only; PG.ctr = g.d_ctr;
-      PG.rank = g.shard_rank; PG.world = g.shard_world;
+      PG.rank = sharded ? g.shard_rank : 0; PG.world = sharded ? g.shard_world : 1;
       k_pass1_group<<<cdiv((long long)S.ngroups * 32, 128), 128, 0, st>>>(PG);
-      if (g.shard_world == 1) order = S.order_leaf;        // the pass flags are indexed by leaf position
+      if (!sharded) order = S.order_leaf;                  // the pass flags are indexed by leaf position
     } else if (nord > 0) {
       // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
       if (nord <= kWarpQueryMax && !periodic_box && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
@@ -1103,7 +1106,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         count_launch();
       }
     }
-    if (g.shard_world > 1) {
+    if (sharded) {
       // exchange {Ngb, partner, dv} of every slot (replaces the result + confirm hypercube
       // passes of sidm.c:463-553); the two write sweeps below then run identically on all ranks
       const int per_rank = shard_max_blocks(nb, g.shard_world) * kShardBlock;
@@ -1142,7 +1145,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   CUDA_TRY(cudaGetLastError());
   if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
   // totals since the last b200_sidm(): the sum of the reference's SCT lines for this step
-  if (g.shard_world > 1) tot_pass1 = (int)g.h_ctr[CT_PASS1];
+  if (sharded) tot_pass1 = (int)g.h_ctr[CT_PASS1];
   g.cnt.sct_ntot += na; g.cnt.sct_pass1 += tot_pass1;
   g.cnt.sct_scattered += (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected += (int)g.h_ctr[CT_REJECTED];
   g.cnt.ngb_candidates += (long long)g.h_ctr[CT_CAND];

@@ -71,6 +71,7 @@ extern "C" int b200_set_option(const char *name, int value) {
   if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
   if (!strcmp(name, "shard_overlap")) { g.opt_shard_overlap = value != 0; return B200_OK; }
+  if (!strcmp(name, "shard_min_work")) { g.shard_min_work = value; return B200_OK; }
   return B200_ERR_ARG;
 }
 

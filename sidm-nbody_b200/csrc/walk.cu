@@ -529,17 +529,18 @@ int gravity_impl(const int *active, int nactive, double time, bool defer_sync) {
   int *d_sorted = nullptr;
   B200_TRY(prepare_targets(active, nt, &d_sorted));
   const int *work = d_sorted; int nw = nt;
-  if (g.shard_world > 1) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw, g.stream)); work = g.d_shard_list; }
+  const bool sharded = g.shard_world > 1 && nt >= g.shard_min_work;
+  if (sharded) { B200_TRY(shard_select(d_sorted, nt, g.d_shard_list, &nw, g.stream)); work = g.d_shard_list; }
   B200_TRY(walk_impl(work, nw, active != nullptr, defer_sync));
   EpiParams E;
   // all particles on one rank: run the epilogue in particle order (coalesced) instead of key order
-  E.nt = nw; E.list = (!active && g.shard_world == 1) ? nullptr : work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
+  E.nt = nw; E.list = (!active && !sharded) ? nullptr : work; E.slot_part = active ? g.d_active : nullptr; E.acc = g.d_acc; E.cost = g.d_cost;
   E.posm = g.posm; E.velpred = g.velpred; E.accel = g.accel; E.oldacc = g.oldacc; E.gravcost = g.gravcost;
   E.criterion = g.par.TypeOfOpeningCriterion; E.comoving = g.par.ComovingIntegrationOn;
   E.periodic = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   E.G = g.par.G; E.H = g.par.Hubble; E.O0 = g.par.Omega0; E.OL = g.par.OmegaLambda; E.time = time;
   if (nw > 0) { k_grav_epilogue<<<cdiv(nw, 256), 256, 0, g.stream>>>(E); count_launch(); }
-  if (g.shard_world > 1) {
+  if (sharded) {
     // all-gather of the partial results (the reduce step of gravtree.c:208-222 becomes a gather:
     // every target is evaluated completely by exactly one rank).  When the SIDM chain runs next to
     // the walk the exchange is issued by gravity_finish(), after the SIDM collectives: collectives
