@@ -74,6 +74,7 @@ __device__ __forceinline__ double u01(uint32_t x) { return (double)x / 429496729
 
 // ------------------------------------------------------------------ range search
 struct SearchCtx {
+  int qcap;                        // usable entries of the warp-private cell queue (<= kQCap; tests shrink it)
   int M; const SearchNode *snode; const SearchNodeF *snodef; const float4 *leaf_posm; const int *leaf_orig;
   const int *nparent, *leaf_parent, *orig_leaf;
   double box;                      // > 0: periodic box (ngb_periodic(), forcetree.c:1999-2006)
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
     }
     const unsigned m1 = __ballot_sync(0xffffffffu, sib >= 0), m2 = __ballot_sync(0xffffffffu, child >= 0);
     const int n1 = __popc(m1), n2 = __popc(m2);
-    if (qn + n1 + n2 > kQCap) { overflow = true; break; }
+    if (qn + n1 + n2 > P.C.qcap) { overflow = true; break; }
     if (sib >= 0) q[qn + __popc(m1 & lt)] = make_int2(sib, it.y);
     if (child >= 0) q[qn + n1 + __popc(m2 & lt)] = make_int2(child, cstop);
     qn += n1 + n2;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
     }
     const unsigned m1 = __ballot_sync(0xffffffffu, sib >= 0), m2 = __ballot_sync(0xffffffffu, child >= 0);
     const int n1 = __popc(m1), n2 = __popc(m2);
-    if (qn + n1 + n2 > kQCap) { overflow = true; break; }
+    if (qn + n1 + n2 > P.C.qcap) { overflow = true; break; }
     if (sib >= 0) q[qn + __popc(m1 & lt)] = make_int2(sib, it.y);
     if (child >= 0) q[qn + n1 + __popc(m2 & lt)] = make_int2(child, cstop);
     qn += n1 + n2;
@@ -910,7 +911,7 @@ static int cub_scratch(size_t tb) {
 }
 
 static SearchCtx search_ctx() {
-  SearchCtx C; C.M = g.num_nodes; C.snode = S.snode; C.snodef = S.snodef; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
+  SearchCtx C; C.qcap = g.opt_queue_cap; C.M = g.num_nodes; C.snode = S.snode; C.snodef = S.snodef; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
   C.nparent = g.nparent; C.leaf_parent = g.leaf_parent; C.orig_leaf = g.orig_leaf;
   C.box = (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? g.par.BoxSize : 0.0;
   return C;

@@ -93,9 +93,10 @@ def test_group_search_equals_per_query_search():
     n = 60000
     pos, vel, mass, ids = ic.hernquist(n, seed=11)
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):                                     # 2: warp-shared search with a tiny cell queue = its overflow fallback
         with HotPath(n, CrossSectionInternal=208.9, Seed=9) as hp:
-            hp.set_option("group_search", mode)
+            hp.set_option("group_search", min(mode, 1))
+            hp.set_option("queue_cap", 6 if mode == 2 else 320)
             hp.set_particles(pos, vel, mass, ids)
             hp.predict_collisionless_only(0.0)
             hp.force_treebuild()
@@ -113,3 +114,5 @@ def test_group_search_equals_per_query_search():
     assert np.array_equal(out[0][3], out[1][3])
     assert out[0][4] == out[1][4] and out[0][5] == out[1][5]
     assert out[0][5] > 0
+    for k in range(6):
+        assert np.array_equal(out[1][k], out[2][k]), f"overflow fallback differs in item {k}"
