@@ -144,7 +144,9 @@ const char *b200_version(void);
  * 0 runs the phases one after the other as accel.c:39-65 does.  "shard_overlap" (default 0): see
  * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes.  "shard_min_work"
  * (default 262144): work lists shorter than this are done completely by every rank instead of being sharded
- * (the repair passes and small active sets are latency-bound; an exchange per pass costs more than it saves). */
+ * (the repair passes and small active sets are latency-bound; an exchange per pass costs more than it saves).
+ * "compact_exchange" (default 1): SIDM results travel between ranks as {uint16 count per slot + the few
+ * scatter proposals} instead of 32-byte records. */
 int  b200_set_option(const char *name, int value);
 
 /* ---- particle state -------------------------------------------------------------- */

@@ -28,6 +28,7 @@ struct Ctx {
   bool opt_shard_overlap = false;  // b200_set_option("shard_overlap", 1): the host's all-gather callback runs on
                                    // b200_current_stream(), so the two-stream overlap is also safe when sharded
   int shard_min_work = kShardMinWorkDefault;
+  bool opt_compact_exchange = true;   // option "compact_exchange": 2.5-byte instead of 32-byte slot records between ranks
   int opt_queue_cap = 320;         // = kQCap of sidm.cu; option "queue_cap" lets tests force the queue-overflow fallback
   cudaStream_t coll_stream = nullptr;   // stream the pending collective has to be ordered on
   bool opt_group_search = true;    // b200_set_option("group_search", 0|1): warp-shared neighbour search for all-active passes

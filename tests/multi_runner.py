@@ -25,6 +25,7 @@ def main(out, n, backend):
     hp = HotPath(n, device=dev, CrossSectionInternal=400.0, Seed=7)
     sh = Sharder(hp, world, rank)
     hp.set_option("shard_min_work", int(os.environ.get("B200_SHARD_MIN_WORK", "1")))   # shard even this small problem
+    hp.set_option("compact_exchange", int(os.environ.get("B200_COMPACT", "1")))
     hp.set_particles(pos, vel, mass, ids)
     hp.predict_collisionless_only(0.0)
     hp.force_treebuild()
