@@ -9,6 +9,7 @@
 // HBM traffic per particle (SURVEY.md section 8d "build bytes"): 16 B read + 16 B key write,
 // 8 radix passes over (8 B key + 4 B index), 16 B gather into leaf order; per node 64 B
 // record + 80 B double moments scratch.
+#include <stdlib.h>
 #include <cub/cub.cuh>
 #include "ctx.cuh"
 #include "build_logic.h"
@@ -129,6 +130,52 @@ __global__ void k_b5(BuildView v, int level) {
   const int m = min(v.nodestart[v.n], v.maxnodes);
   if (id < m && v.nlevel[id] == level) b5_body(v, id);
 }
+// Moments in ONE launch instead of one per level: threads start at the cells without child cells and
+// climb; a cell is finished by the thread of its last-arriving child (atomic arrival counter), which reads
+// the children's moments past the L1 (they were written by other SMs in this same launch).  The sums run
+// over the children in octant order whatever the arrival order, so the result equals the per-level version.
+__device__ __forceinline__ void b5_body_cg(const BuildView &v, int id) {
+  const float4 gm = v.geom[id];
+  Moments m; moments_zero(m);
+  const int np = v.nnp[id], ps = v.npstart[id];
+  for (int k = 0; k < np; k++) {
+    const float4 p = v.leaf_posm[ps + k];
+    moments_add_particle(m, p.x, p.y, p.z, p.w, gm.x, gm.y, gm.z);
+  }
+  int mn = v.nminidx[id];
+  const int end = v.nodes[id].skip;
+  for (int c = id + 1; c < end; c = v.nodes[c].skip) {     // child cells, in octant order
+    const float4 cg = v.geom[c];
+    Moments cm;
+    const double *src = reinterpret_cast<const double *>(v.nmom + c);
+    double *dst = reinterpret_cast<double *>(&cm);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(Moments) / sizeof(double)); k++) dst[k] = __ldcg(src + k);
+    moments_add_child(m, cm, (double)cg.x - (double)gm.x, (double)cg.y - (double)gm.y, (double)cg.z - (double)gm.z);
+    const int cmn = __ldcg(v.nminidx + c);
+    if (cmn < mn) mn = cmn;
+  }
+  v.nmom[id] = m;
+  v.nminidx[id] = mn;
+  NodeRec r = v.nodes[id];
+  moments_finish(m, gm.x, gm.y, gm.z, gm.w, r);
+  v.nodes[id] = r;
+}
+__global__ void k_b5_up(BuildView v) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = min(v.nodestart[v.n], v.maxnodes);
+  if (id >= m || v.nnchild[id] != 0) return;
+  int cur = id;
+  for (;;) {
+    b5_body_cg(v, cur);
+    const int par = v.nparent[cur];
+    if (par < 0) break;
+    __threadfence();                                        // this cell's moments before the arrival count
+    if (atomicAdd(&v.narrive[par], 1) + 1 < (int)v.nnchild[par]) break;
+    __threadfence();
+    cur = par;                                              // last child to arrive: finish the parent
+  }
+}
 __global__ void k_b6(BuildView v, int level) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = min(v.nodestart[v.n], v.maxnodes);
@@ -212,9 +259,14 @@ int tree_build_impl() {
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb3, np32, g.npstart, m + 1, st));
   k_b4<<<GM, B, 0, st>>>(v);
   count_launch(5);
-  // 5. moments, deepest level first (children before parents)
-  for (int lev = g.max_level; lev >= 0; lev--) k_b5<<<GM, B, 0, st>>>(v, lev);
-  count_launch(g.max_level + 1);
+  // 5. moments, children before parents
+  static const bool per_level = getenv("B200_MOMENTS_PER_LEVEL") != nullptr;     // the one-launch-per-level form, kept for A/B
+  if (per_level) { for (int lev = g.max_level; lev >= 0; lev--) k_b5<<<GM, B, 0, st>>>(v, lev); count_launch(g.max_level + 1); }
+  else {
+    CUDA_TRY(cudaMemsetAsync(g.narrive, 0, (size_t)(m + 1) * sizeof(int), st));
+    k_b5_up<<<cdiv(m + 1, 128), 128, 0, st>>>(v);
+    count_launch();
+  }
   // 6. the reference's next[] chain order (only needed to scan neighbours in its order)
   if (g.par.ReferenceNgbOrder) {
     for (int lev = 0; lev <= g.max_level; lev++) k_b6<<<GM, B, 0, st>>>(v, lev);
