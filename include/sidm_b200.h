@@ -213,6 +213,9 @@ int  b200_compute_accelerations(int mode, const int *active, int nactive, double
 /* advance(), predict.c:245-345 ("next" row f1 of SURVEY.md section 8): kick-drift of the active
  * particles with Accel*dt + dVel, dVel cleared; *num_scattered (may be NULL) = n_scat_particles. */
 int  b200_advance(const int *active, int nactive, double time, int *num_scattered);
+/* reflect(), reflection.c:7-33 (-DREFLECTIONBOUNDARY, run.c:106; row f1): specular reflection of the active
+ * particles that are outside `radius` and moving outwards.  Acts on Pos / Vel as advance() left them. */
+int  b200_reflect(const int *active, int nactive, double radius, int *num_reflected);
 /* find_timesteps(mode), timestep.c:17-334 for collisionless particles ("next" row f1): new time step of
  * every active particle from the acceleration criterion (TypeOfTimestepCriterion 0 or 1), the SIDM
  * probability limit ProbabilityTol/(C_max m h^-3) and the G*rho limit (timestep.c:247-265), the 1.3*dtold

@@ -91,6 +91,8 @@ int    osidm_ensure(const otree *t, const oparams *p, int n, const float *vel, c
 /* force_treeevaluate_potential(), forcetree.c:1389-1755 and the epilogue of compute_potential(), potential.c:131-168 */
 void   otree_potential(const otree *t, const oparams *p, int nt, const int *targets, const float *oldacc, double *pot);
 void   opot_epilogue(const oparams *p, int nt, const double *pot, const float *mass, float *out);
+/* reflect(), reflection.c:7-33: specular reflection of outgoing active particles beyond the radius; returns how many */
+int    oreflect(int nactive, const int *active, double radius, const float *pos, float *vel);
 /* find_timesteps(mode), timestep.c:17-334, collisionless particles of type 1, no comoving integration,
  * steps that hit Max/MinSizeTimestep take the uniform jitter[a] (the reference: drand48()).  Writes
  * maxpred[i] = CurrentTime + dt/2 for the active particles; returns the number of clamped steps. */

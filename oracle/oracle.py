@@ -223,6 +223,15 @@ class Oracle:
                                     _p(accel), _p(curtime), _p(mp), _p(self.hsml), _p(self.mass), _p(jit))
         return mp, nc
 
+    def reflect(self, active, radius, pos, vel):
+        """reflection.c:7-33; returns (new velocities, number reflected)"""
+        active = np.ascontiguousarray(active, np.int32)
+        pos = np.ascontiguousarray(pos, np.float32); v = np.ascontiguousarray(vel, np.float32).copy()
+        self.L.oreflect.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        self.L.oreflect.restype = C.c_int
+        n = self.L.oreflect(len(active), _p(active), float(radius), _p(pos), _p(v))
+        return v, n
+
     def sidm_ensure_neighbours(self, dt, vmax):
         dta = np.ascontiguousarray(np.broadcast_to(np.float32(dt), (self.n,)), np.float32)
         return self.L.osidm_ensure(self.tree, C.byref(self.par), self.n, _p(self.vel), _p(self.mass), _p(self.hsml),

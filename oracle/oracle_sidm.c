@@ -311,3 +311,24 @@ int ofind_timesteps(const oparams *p, const otimestep *ts, int nactive, const in
   }
   return clamped;
 }
+
+/* ------------------------------------------------------------------ reflect(), reflection.c:7-33 (all float arithmetic) */
+int oreflect(int nactive, const int *active, double radius, const float *pos, float *vel)
+{
+  const float r_ref2 = (float)(radius * radius);
+  int n = 0;
+  for (int a = 0; a < nactive; a++) {
+    int i = active[a];
+    float r2 = pos[3 * i] * pos[3 * i] + pos[3 * i + 1] * pos[3 * i + 1] + pos[3 * i + 2] * pos[3 * i + 2];
+    if (r2 > r_ref2) {
+      float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+      float rv = x * vel[3 * i] + y * vel[3 * i + 1] + z * vel[3 * i + 2];
+      if (rv > 0) {
+        float r2inv2 = 2.0f / r2;
+        vel[3 * i] -= rv * x * r2inv2; vel[3 * i + 1] -= rv * y * r2inv2; vel[3 * i + 2] -= rv * z * r2inv2;
+        n++;
+      }
+    }
+  }
+  return n;
+}

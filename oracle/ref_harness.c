@@ -351,6 +351,9 @@ void ref_sidm_ensure_neighbours(int mode) { sidm_ensure_neighbours(mode); }
 void ref_setup_smoothinglengths_sidm(int desngb) { setup_smoothinglengths_sidm(desngb); }
 void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
+#ifdef REFLECTIONBOUNDARY
+void ref_reflect(double radius) { All.ReflectionRadius = radius; reflect(); All.ReflectionRadius = 1e30; }   /* reflection.c:7 */
+#endif
 void ref_compute_potential(void) { compute_potential(); }   /* potential.c:18: rebuilds the tree, all particles */
 /* timestep.c:17 with the accuracy parameters of the parameter file set here; mode 2 = start-up (no growth limit) */
 void ref_find_timesteps(int mode, int crit, double eta, double velscale, double probtol, double dyntol, double dtmax, double dtmin)

@@ -242,6 +242,10 @@ class Reference:
         self.lib.ref_find_timesteps.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6
         self.lib.ref_find_timesteps(int(mode), int(crit), eta, velscale, probtol, dyntol, dtmax, dtmin)
 
+    def reflect(self, radius):
+        self.lib.ref_reflect.argtypes = [C.c_double]
+        self.lib.ref_reflect(float(radius))
+
     def advance(self):
         self.lib.ref_advance()
 

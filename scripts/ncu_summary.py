@@ -7,7 +7,7 @@ import json
 import subprocess
 import sys
 
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r1h"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1j"
 KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',

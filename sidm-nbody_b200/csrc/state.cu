@@ -569,6 +569,41 @@ extern "C" int b200_set_field(const char *name, const void *host, long long nbyt
   return B200_OK;
 }
 
+// ----------------------------------------------------------------------------- reflect
+// reflection.c:7-33: float arithmetic throughout, products and sums individually rounded
+__global__ void k_reflect(int na, const int *active, float r_ref2, const float *pos0, float4 *velh, int *count) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int i = active ? active[a] : a;
+  const float x = pos0[3 * (size_t)i], y = pos0[3 * (size_t)i + 1], z = pos0[3 * (size_t)i + 2];
+  const float r2 = fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z));
+  if (!(r2 > r_ref2)) return;
+  float4 v = velh[i];
+  const float rv = fadd(fadd(fmul(x, v.x), fmul(y, v.y)), fmul(z, v.z));
+  if (!(rv > 0)) return;
+  const float r2inv2 = __fdiv_rn(2.0f, r2);
+  v.x = fadd(v.x, -fmul(fmul(rv, x), r2inv2)); v.y = fadd(v.y, -fmul(fmul(rv, y), r2inv2)); v.z = fadd(v.z, -fmul(fmul(rv, z), r2inv2));
+  velh[i] = v;
+  atomicAdd(count, 1);
+}
+extern "C" int b200_reflect(const int *active, int nactive, double radius, int *num_reflected) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  const int na = active ? nactive : g.n;
+  if (na < 0 || na > g.n) return B200_ERR_ARG;
+  if (num_reflected) *num_reflected = 0;
+  if (na == 0) return B200_OK;
+  const int *d_act = nullptr;
+  if (active) { CUDA_TRY(cudaMemcpyAsync(g.d_active, active, (size_t)na * sizeof(int), cudaMemcpyHostToDevice, g.stream)); d_act = g.d_active; }
+  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_NSCATLOG, 0, sizeof(int), g.stream));
+  k_reflect<<<cdiv(na, 256), 256, 0, g.stream>>>(na, d_act, (float)(radius * radius), g.pos0, g.velh, g.d_flags + FL_NSCATLOG);
+  count_launch();
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags + FL_NSCATLOG, g.d_flags + FL_NSCATLOG, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  if (num_reflected) *num_reflected = g.h_flags[FL_NSCATLOG];
+  return B200_OK;
+}
+
 // ----------------------------------------------------------------------------- find_timesteps
 // timestep.c:17-334 for collisionless particles.  Types as in the C code: Accel, CurrentTime,
 // MaxPredTime, HsmlVelDisp, Mass are floats, |a|^2 and CurrentTime + MaxPredTime are formed in float,

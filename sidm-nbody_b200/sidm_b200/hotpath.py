@@ -144,6 +144,13 @@ class HotPath:
         check(self.lib.b200_potential_raw(ptr(t), len(t), ptr(out)), "b200_potential_raw")
         return out
 
+    def reflect(self, radius, active=None):
+        """reflect(), reflection.c:7: returns the number of reflected particles"""
+        a = _i32(active)
+        n = C.c_int(0)
+        check(self.lib.b200_reflect(ptr(a), 0 if a is None else len(a), float(radius), C.byref(n)), "b200_reflect")
+        return n.value
+
     def set_field(self, name, arr):
         arr = np.ascontiguousarray(arr)
         check(self.lib.b200_set_field(name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes), "b200_set_field")

@@ -78,3 +78,40 @@ def test_gpu_matches_oracle_timesteps(mode, crit, clamp):
     assert nc == nclamp and (nclamp > 0) == clamp
     assert np.array_equal(out, want[active])
     assert np.array_equal(allmp, want)                     # inactive particles untouched
+
+
+def test_oracle_matches_reference_reflect(refdrv_mod):
+    """reflect(), reflection.c:7-33"""
+    import oracle
+    from sidm_b200 import ic
+    pos, vel, mass, ids = ic.hernquist(N, seed=33)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        R = refdrv_mod.Reference("diag")
+        R.setup(N)
+        R.set_particles(pos, vel, mass, ids)
+        R.all_active(0.0, 0.01)
+        R.reflect(40.0)
+        ref = R.get("VEL")
+    finally:
+        os.chdir(cwd)
+    O = oracle.Oracle(pos, vel, mass)
+    got, nref = O.reflect(np.arange(N, dtype=np.int32), 40.0, pos, vel)
+    assert nref > 50 and np.array_equal(got, ref) and not np.array_equal(got, vel)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_reflect():
+    import oracle
+    from sidm_b200 import HotPath, ic
+    pos, vel, mass, ids = ic.hernquist(N, seed=33)
+    O = oracle.Oracle(pos, vel, mass)
+    active = np.arange(0, N, 2, dtype=np.int32)
+    want, nref = O.reflect(active, 40.0, pos, vel)
+    with HotPath(N) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        n = hp.reflect(40.0, active=active)
+        got = hp.peek("velh", np.float32, (N, 4))[:, :3]
+    assert n == nref > 20
+    assert np.array_equal(got, want)
