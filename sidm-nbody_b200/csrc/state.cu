@@ -665,23 +665,29 @@ extern "C" int b200_find_timesteps(const int *active, int nactive, int mode, dou
   // constants of timestep.c:45-131
   const double ball = (3. / 4. / 3.14159265358979323846) * (g.par.DesNumNgb + g.par.MaxNumNgbDeviation);
   const int X = g.par.CrossSectionType;
-  double sig = g.par.CrossSectionInternal, vc = g.par.YukawaVelocity, s_a = 1, a3inv = 1, hubble_a = 0, tail = 1;
-  if (T.comoving) {
+  const double sig = g.par.CrossSectionInternal;
+  double vc = g.par.YukawaVelocity, s_a = 1, a3inv = 1, hubble_a = 0;
+  double C_max;
+  if (T.comoving) {                     // timestep.c:47-93, operations in the reference's order
     hubble_a = g.par.Hubble * sqrt(g.par.Omega0 / pow(time, 3) + (1 - g.par.Omega0 - g.par.OmegaLambda) / pow(time, 2) + g.par.OmegaLambda);
     s_a = g.par.Hubble * sqrt(g.par.Omega0 + time * (1 - g.par.Omega0 - g.par.OmegaLambda) + pow(time, 3) * g.par.OmegaLambda);
     a3inv = 1 / (time * time * time);
-    sig = sig / pow(time, X == 1 ? 2.5 : 2.0); vc = vc / sqrt(time); tail = 1 / s_a;
+    if (X == 1) C_max = 1.0 * ball * sig / pow(time, 2.5) / s_a;
+    else if (X == 2) {
+      vc = g.par.YukawaVelocity / sqrt(time);
+      if (2.0 * vmax < vc / sqrt(3.0)) { const double beta = 2.0 * vmax / vc, v_dep = 1.0 / (1.0 + beta * beta); C_max = 1.0 * ball * 2.0 * vmax * v_dep * v_dep * sig / pow(time, 2) / s_a; }
+      else C_max = 1.0 * ball * (3.0 * sqrt(3.0) / 16.0) * vc * sig / pow(time, 2) / s_a;
+    } else if (X == 3) C_max = 1.0 * ball * sig / pow(time, 2.0) * 2 * g.par.CrossSectionVelScale / s_a;
+    else C_max = 1.0 * ball * 2 * vmax * sig / pow(time, 2) / s_a;
+  } else {                              // timestep.c:95-130
+    if (X == 1) C_max = 1.0 * ball * sig;
+    else if (X == 2) {
+      // NB this branch of the reference uses v_dep = 1/(1 + 2 vmax/vc), not 1/(1 + beta^2) (timestep.c:108)
+      if (2.0 * vmax < vc / sqrt(3.0)) { const double v_dep = 1.0 / (1.0 + 2.0 * vmax / vc); C_max = 1.0 * ball * 2.0 * vmax * v_dep * v_dep * sig; }
+      else C_max = 1.0 * ball * (3.0 * sqrt(3.0) / 16.0) * vc * sig;
+    } else if (X == 3) C_max = 1.0 * ball * 2 * g.par.CrossSectionVelScale * sig;
+    else C_max = 1.0 * ball * 2 * vmax * sig;
   }
-  double C_max;
-  if (X == 1) C_max = 1.0 * ball * sig * tail;
-  else if (X == 2) {
-    if (2.0 * vmax < vc / sqrt(3.0)) {
-      // NB the non-comoving branch of the reference uses v_dep = 1/(1 + 2 vmax/vc) here, not 1/(1+beta^2) (timestep.c:108)
-      const double beta = 2.0 * vmax / vc, v_dep = T.comoving ? 1.0 / (1.0 + beta * beta) : 1.0 / (1.0 + 2.0 * vmax / vc);
-      C_max = 1.0 * ball * 2.0 * vmax * v_dep * v_dep * sig * tail;
-    } else C_max = 1.0 * ball * (3.0 * sqrt(3.0) / 16.0) * vc * sig * tail;
-  } else if (X == 3) C_max = T.comoving ? 1.0 * ball * sig * 2 * g.par.CrossSectionVelScale * tail : 1.0 * ball * 2 * g.par.CrossSectionVelScale * sig;
-  else C_max = 1.0 * ball * 2 * vmax * sig * tail;
   T.C_max = C_max; T.C_Grho = ball; T.s_a = s_a; T.hubble_a = hubble_a; T.a3inv = a3inv;
   T.eta = tp->ErrTolIntAccuracy; T.velscale = tp->ErrTolVelScale; T.probtol = tp->ProbabilityTol; T.dyntol = tp->ErrTolDynamicalAccuracy;
   T.dtmax = tp->MaxSizeTimestep; T.dtmin = tp->MinSizeTimestep;

@@ -115,3 +115,50 @@ def test_gpu_matches_oracle_reflect():
         got = hp.peek("velh", np.float32, (N, 4))[:, :3]
     assert n == nref > 20
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_comoving_timesteps_match_reference(refdrv_mod):
+    """the comoving branch of find_timesteps() (timestep.c:45-93: hubble_a, S(a), a^-2 cross-section, comoving
+    G*rho limit) directly against the -DPERIODIC reference build (fresh process: one configuration per library)"""
+    if not refdrv_mod.available("periodic"):
+        pytest.skip("oracle/_ref/libsidmref_per.so not built")
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, tempfile, numpy as np
+sys.path.insert(0, "oracle"); sys.path.insert(0, "sidm-nbody_b200")
+import refdrv
+from sidm_b200 import HotPath, ic
+BOX, EPS, A, SIG = 100.0, 0.5, 0.25, 1.5e3
+pos, vel, mass, ids = ic.periodic_box(16, seed=8, box=BOX, vel_sigma=60.0)
+n = len(mass)
+rng = np.random.default_rng(2)
+accel = (rng.normal(size=(n, 3)) * 40.0).astype(np.float32)
+hsml = (BOX / 16 * rng.uniform(1.0, 2.0, n)).astype(np.float32)
+maxpred = np.full(n, A, np.float32)
+curtime = (maxpred + rng.choice(np.array([1e-5, 2e-4, 3e-3], np.float32), n)).astype(np.float32)
+ts = dict(crit=0, eta=0.02, velscale=10.0, probtol=0.2, dyntol=0.05)
+root = os.getcwd(); os.chdir(tempfile.mkdtemp())
+R = refdrv.Reference("periodic")
+cos = dict(ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1)
+R.setup(n, BoxSize=BOX, SofteningHalo=EPS, Time=A, CrossSectionInternal=SIG, **cos)
+R.set_particles(pos, vel, mass, ids)
+R.all_active(A, A * 1.01)
+R.set("ACCEL", accel); R.set("HSML", hsml); R.set("CURTIME", curtime); R.set("MAXPRED", maxpred)
+R.set_time(A)
+vmax = R.getvmax()
+R.find_timesteps(1, **ts)
+ref = R.get("MAXPRED")
+os.chdir(root)
+with HotPath(n, BoxSize=BOX, PeriodicBoundariesOn=1, SofteningHalo=EPS, CrossSectionInternal=SIG, **cos) as hp:
+    hp.set_particles(pos, vel, mass, ids, curtime=curtime, accel=accel, hsml=hsml)
+    hp.set_field("maxpred", maxpred)
+    out, nc = hp.find_timesteps(1, time=A, vmax=vmax, **ts)
+assert nc == 0 and len(np.unique(out - curtime)) > 100
+assert np.array_equal(out, ref), float(np.abs(out.astype(np.float64) - ref).max())
+print("comoving timesteps bit-exact")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
