@@ -236,7 +236,7 @@ int  b200_find_timesteps(const int *active, int nactive, int mode, double time, 
  * walks it for ALL particles with force_treeevaluate_potential() (forcetree.c:1389-1755, same opening
  * decisions as the force walk), adds the self energy back and applies G and the Lambda / comoving terms.
  * P[].Potential on the device (downloaded when the layout binds it) and, if not NULL, pot_out[n].
- * Open boundaries only (the periodic ewald_pot_corr() table is not built: B200_ERR_ARG). */
+ * Periodic boxes add ewald_pot_corr() (ewald.c:246-285) per interaction. */
 int  b200_compute_potential(float *pot_out);
 /* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
 int  b200_potential_raw(const int *targets, int n, double *pot_out);

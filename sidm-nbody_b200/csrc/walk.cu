@@ -58,6 +58,21 @@ __device__ __forceinline__ void ewald_corr(const float4 *tab, float fac, float d
   cy = sy * (t000.y * f1 + t001.y * f2 + t010.y * f3 + t011.y * f4 + t100.y * f5 + t101.y * f6 + t110.y * f7 + t111.y * f8);
   cz = sz * (t000.z * f1 + t001.z * f2 + t010.z * f3 + t011.z * f4 + t100.z * f5 + t101.z * f6 + t110.z * f7 + t111.z * f8);
 }
+// ewald_pot_corr(), ewald.c:246-285: same trilinear lookup on the potential table (component w)
+__device__ __forceinline__ float ewald_pot_corr(const float4 *tab, float fac, float dx, float dy, float dz) {
+  float u = fabsf(dx) * fac, v = fabsf(dy) * fac, w = fabsf(dz) * fac;
+  int i = (int)u, j = (int)v, k = (int)w;
+  if (i >= kEwaldD) i = kEwaldD - 1;
+  if (j >= kEwaldD) j = kEwaldD - 1;
+  if (k >= kEwaldD) k = kEwaldD - 1;
+  u -= i; v -= j; w -= k;
+  const int S1 = kEwaldD + 1, S2 = S1 * S1;
+  const float4 *b = tab + (i * S2 + j * S1 + k);
+  const float p000 = __ldg(&b->w), p001 = __ldg(&(b + 1)->w), p010 = __ldg(&(b + S1)->w), p011 = __ldg(&(b + S1 + 1)->w);
+  const float p100 = __ldg(&(b + S2)->w), p101 = __ldg(&(b + S2 + 1)->w), p110 = __ldg(&(b + S2 + S1)->w), p111 = __ldg(&(b + S2 + S1 + 1)->w);
+  return p000 * ((1 - u) * (1 - v) * (1 - w)) + p001 * ((1 - u) * (1 - v) * w) + p010 * ((1 - u) * v * (1 - w)) + p011 * ((1 - u) * v * w) +
+         p100 * (u * (1 - v) * (1 - w)) + p101 * (u * (1 - v) * w) + p110 * (u * v * (1 - w)) + p111 * (u * v * w);
+}
 __device__ __forceinline__ float wrap_image(float d, float box, float boxhalf) {
   while (d > boxhalf) d -= box;
   while (d < -boxhalf) d += box;
@@ -219,7 +234,7 @@ static float h_inv_of_type1();
 // decisions as the force walk, scalar accumulator.  Leaf: -m/r, or m/h * knlpot(r/h) inside the softening
 // radius (no u > 1e-4 guard here: the target's own particle contributes -m/eps, which compute_potential()
 // adds back, potential.c:135).  Cell: -M/r + (-3 potq/r^2 + P/2)/r^3, softened form below h.  Open boundaries.
-template <int MODE>
+template <bool PER, int MODE>
 __device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no, double &pot) {
   const float h_inv = P.h_inv, theta2 = P.theta2;
   const float h2 = 1.0f / (h_inv * h_inv);
@@ -232,7 +247,8 @@ __device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 
     for (int it = 0; it < kFlushEvery && cur < M; it++) {
       const float4 *nd = nodes4 + 4 * (size_t)cur;
       const float4 A = __ldg(nd), Bv = __ldg(nd + 1), Cv = __ldg(nd + 2), Dv = __ldg(nd + 3);
-      const float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+      float dx = A.x - tp.x, dy = A.y - tp.y, dz = A.z - tp.z;
+      if (PER) { dx = wrap_image(dx, P.box, P.boxhalf); dy = wrap_image(dy, P.box, P.boxhalf); dz = wrap_image(dz, P.box, P.boxhalf); }
       const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       bool crit;
       if (MODE == 1) crit = (Bv.x > oac * r2 * r2 * r2) || (r2 < Bv.y);
@@ -254,6 +270,7 @@ __device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 
           soft_w234(u, w2, w3, w4);
           f += A.w * h_inv * soft_pot(u) + potq * w2 * h5i + 0.5f * Dv.z * soft_force(u) * h3i;   // :1722-1723
         }
+        if (PER) f += A.w * ewald_pot_corr(P.ewald, P.ewald_fac, dx, dy, dz);        // :1726-1728
       }
       no = acc ? __float_as_int(Bv.w) : (open ? cur + 1 : no);
       if (__any_sync(0xffffffffu, open)) {
@@ -263,10 +280,12 @@ __device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 
         for (int k = 0; k < np; k++) {
           const float4 q = __ldg(lp + k);
           if (open) {
-            const float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
+            float px = q.x - tp.x, py = q.y - tp.y, pz = q.z - tp.z;
+            if (PER) { px = wrap_image(px, P.box, P.boxhalf); py = wrap_image(py, P.box, P.boxhalf); pz = wrap_image(pz, P.box, P.boxhalf); }
             const float pr2 = fmaf(pz, pz, fmaf(py, py, px * px));
             if (pr2 >= h2) f -= q.w * rsqrt_fast(pr2);                       // forcetree.c:1625
             else f += q.w * h_inv * soft_pot(sqrtf(pr2) * h_inv);            // :1629-1631
+            if (PER) f += q.w * ewald_pot_corr(P.ewald, P.ewald_fac, px, py, pz);   // :1633-1635 (the target itself included)
           }
         }
       }
@@ -276,6 +295,7 @@ __device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 
   }
 }
 
+template <bool PER>
 __global__ void __launch_bounds__(128) k_walk_pot(WalkParams P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < P.nt;
@@ -288,15 +308,15 @@ __global__ void __launch_bounds__(128) k_walk_pot(WalkParams P) {
   int no = valid ? 0 : 0x7fffffff;
   double pot = 0;
   const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
-  if (all_rel) walk_loop_pot<1>(P, tp, bh, oac, no, pot);
-  else if (all_bh) walk_loop_pot<2>(P, tp, bh, oac, no, pot);
-  else walk_loop_pot<0>(P, tp, bh, oac, no, pot);
+  if (all_rel) walk_loop_pot<PER, 1>(P, tp, bh, oac, no, pot);
+  else if (all_bh) walk_loop_pot<PER, 2>(P, tp, bh, oac, no, pot);
+  else walk_loop_pot<PER, 0>(P, tp, bh, oac, no, pot);
   if (valid) P.acc[slot] = pot;                                  // raw potential per target slot (GravDataPotential)
 }
 
 // compute_potential(), potential.c:131-168: float Potential <- raw; += m/eps (self energy); *G; Lambda / comoving terms
 __global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, float *potential, double eps, double G,
-                               int comoving, double H, double O0, double OL) {
+                               int comoving, int periodic, double H, double O0, double OL) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = posm[i];
@@ -306,7 +326,7 @@ __global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, flo
   r2 += (double)fmul(p.x, p.x); r2 += (double)fmul(p.y, p.y); r2 += (double)fmul(p.z, p.z);
   if (comoving) {
     const double fac = 0.5 * O0 * H * H;
-    v = (float)(G * (double)v - fac * r2);
+    v = periodic ? (float)(G * (double)v) : (float)(G * (double)v - fac * r2);        // potential.c:141-150
   } else {
     const double fac = -0.5 * OL * H * H;
     v = (float)((double)v * G);
@@ -316,15 +336,19 @@ __global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, flo
 }
 
 static int potential_walk(const int *d_sorted, int nt, bool with_slots) {
-  if (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) return B200_ERR_ARG;    // ewald_pot_corr(): not built
+  const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   WalkParams P;
   P.nt = nt; P.num_nodes = g.num_nodes; P.tsorted = d_sorted; P.slot_part = with_slots ? g.d_active : nullptr;
   P.posm = g.posm; P.oldacc = g.oldacc; P.nodes = g.nodes; P.leaf_posm = g.leaf_posm;
   P.acc = g.d_acc; P.cost = g.d_cost;
   P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
-  P.box = 0; P.boxhalf = 0; P.ewald_fac = 0; P.ewald = nullptr;
-  if (nt > 0) { k_walk_pot<<<cdiv(nt, 128), 128, 0, g.stream>>>(P); count_launch(); }
+  P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
+  if (per) { B200_TRY(ewald_tables(&P.ewald)); }
+  if (nt > 0) {
+    if (per) k_walk_pot<true><<<cdiv(nt, 128), 128, 0, g.stream>>>(P); else k_walk_pot<false><<<cdiv(nt, 128), 128, 0, g.stream>>>(P);
+    count_launch();
+  }
   return B200_OK;
 }
 
@@ -333,7 +357,7 @@ static int potential_walk(const int *d_sorted, int nt, bool with_slots) {
 // of a unit point mass in a unit box (alpha = 2, |n|,|h| <= 4 per axis), tabulated on the
 // (ED+1)^3 grid of the first octant, then scaled by 1/L^2 (ewald.c:145-155).  One thread per
 // grid point, double precision, stored as float like the reference's tables.
-__global__ void k_ewald_table(float4 *tab, double inv_box2) {
+__global__ void k_ewald_table(float4 *tab, double inv_box2, double inv_box) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int S1 = kEwaldD + 1;
   if (idx >= S1 * S1 * S1) return;
@@ -342,6 +366,21 @@ __global__ void k_ewald_table(float4 *tab, double inv_box2) {
   const double x[3] = {(double)i / kEwaldN, (double)j / kEwaldN, (double)k / kEwaldN};
   double f[3] = {0, 0, 0};
   const double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  // ewald_psi(), ewald.c:291-325: potential correction; the origin holds the constant 2.8372975 (ewald.c:102-103)
+  double psi = 2.8372975;
+  if (idx != 0) {
+    double sum1 = 0, sum2 = 0;
+    for (int n0 = -4; n0 <= 4; n0++) for (int n1 = -4; n1 <= 4; n1++) for (int n2 = -4; n2 <= 4; n2++) {
+      const double d[3] = {x[0] - n0, x[1] - n1, x[2] - n2};
+      const double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      sum1 += erfc(alpha * r) / r;
+    }
+    for (int h0 = -4; h0 <= 4; h0++) for (int h1 = -4; h1 <= 4; h1++) for (int h2_ = -4; h2_ <= 4; h2_++) {
+      const int hh = h0 * h0 + h1 * h1 + h2_ * h2_;
+      if (hh > 0) sum2 += 1 / (PI * hh) * exp(-PI * PI * hh / (alpha * alpha)) * cos(2 * PI * (x[0] * h0 + x[1] * h1 + x[2] * h2_));
+    }
+    psi = PI / (alpha * alpha) - sum1 - sum2 + 1 / sqrt(r2);
+  }
   if (r2 != 0) {
     for (int a = 0; a < 3; a++) f[a] += x[a] / (r2 * sqrt(r2));
     for (int n0 = -4; n0 <= 4; n0++) for (int n1 = -4; n1 <= 4; n1++) for (int n2 = -4; n2 <= 4; n2++) {
@@ -360,14 +399,15 @@ __global__ void k_ewald_table(float4 *tab, double inv_box2) {
     }
   }
   // the reference stores the unit-box value as float, then divides the float by L^2 (a double)
-  tab[idx] = make_float4((float)((double)(float)f[0] * inv_box2), (float)((double)(float)f[1] * inv_box2), (float)((double)(float)f[2] * inv_box2), 0.f);
+  tab[idx] = make_float4((float)((double)(float)f[0] * inv_box2), (float)((double)(float)f[1] * inv_box2), (float)((double)(float)f[2] * inv_box2),
+                         (float)((double)(float)psi * inv_box));
 }
 
 int ewald_tables(const float4 **out) {
   const int S1 = kEwaldD + 1, n = S1 * S1 * S1;
   if (!g.d_ewald && cudaMalloc((void **)&g.d_ewald, (size_t)n * sizeof(float4)) != cudaSuccess) return B200_ERR_ALLOC;
   if (g.ewald_box != g.par.BoxSize) {
-    k_ewald_table<<<cdiv(n, 128), 128, 0, g.stream>>>(g.d_ewald, 1.0 / (g.par.BoxSize * g.par.BoxSize));
+    k_ewald_table<<<cdiv(n, 128), 128, 0, g.stream>>>(g.d_ewald, 1.0 / (g.par.BoxSize * g.par.BoxSize), 1.0 / g.par.BoxSize);
     count_launch();
     g.ewald_box = g.par.BoxSize;
   }
@@ -658,7 +698,7 @@ extern "C" int b200_compute_potential(float *pot_out) {
   double eps = 0;
   for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
   k_pot_epilogue<<<cdiv(g.n, 256), 256, 0, g.stream>>>(g.n, g.d_acc, g.posm, g.potential, eps, g.par.G, g.par.ComovingIntegrationOn,
-                                                     g.par.Hubble, g.par.Omega0, g.par.OmegaLambda);
+                                                     (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? 1 : 0, g.par.Hubble, g.par.Omega0, g.par.OmegaLambda);
   count_launch();
   if (pot_out) CUDA_TRY(cudaMemcpyAsync(pot_out, g.potential, (size_t)g.n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));

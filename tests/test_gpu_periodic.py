@@ -47,6 +47,8 @@ def test_ewald_table(world):
     ref = np.stack([tab[0], tab[1], tab[2]], axis=-1) / np.float32(BOX * BOX)
     scale = np.abs(ref).max()
     assert np.max(np.abs(mine[..., :3] - ref)) < 2e-6 * scale
+    pot_ref = tab[3] / np.float32(BOX)                   # potcorr, ewald.c:102-105,148
+    assert np.max(np.abs(mine[..., 3] - pot_ref)) < 2e-6 * np.abs(pot_ref).max()
 
 
 def test_periodic_forces(world):
@@ -71,6 +73,23 @@ def test_periodic_forces(world):
     acc, cost = hp.force_treeevaluate(idx)
     assert rel_rms(acc, acc_r) < 1e-4
     assert (cost == cost_r).all(axis=1).mean() > 0.995
+
+
+def test_periodic_potential(world):
+    """force_treeevaluate_potential() + ewald_pot_corr() and compute_potential() in the periodic box.  The periodic
+    potential is a small difference of large sums (-m/r terms against the Ewald corrections), so the float
+    interaction arithmetic shows up amplified: up to 3.4e-5 relative here (tolerance 1e-4, that of the forces) against 2e-6 for the open halo."""
+    R, hp, n = world["R"], world["hp"], world["n"]
+    idx = np.arange(0, n, 17, dtype=np.int32)
+    R.set("OLDACC", np.zeros(n, np.float32))
+    hp.set_particles(oldacc=np.zeros(n, np.float32))
+    np.testing.assert_allclose(hp.force_treeevaluate_potential(idx), R.potential(idx), rtol=1e-4)       # BH
+    oa = R.get("OLDACC") * 0 + np.float32(1e-4)
+    R.set("OLDACC", oa); hp.set_particles(oldacc=oa)
+    np.testing.assert_allclose(hp.force_treeevaluate_potential(idx), R.potential(idx), rtol=1e-4)       # relative criterion
+    R.compute_potential()
+    pot = hp.compute_potential()
+    np.testing.assert_allclose(pot, R.get("POT"), rtol=1e-4)
 
 
 def test_periodic_neighbours(world):
