@@ -293,10 +293,12 @@ void ref_force_tree(int n, const int *idx, double *acc, int *cost)
     for (int k = 0; k < 3; k++) GravDataIn[0].Pos[k] = p->PosPred[k];
     GravDataIn[0].Type = p->Type;
     GravDataIn[0].OldAcc = p->OldAcc;
-    int c0 = treecost[1], c1 = treecost_quadru[1];
+    int c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+    for (int tr = 0; tr < 6; tr++) { c0 += treecost[tr]; c1 += treecost_quadru[tr]; }      /* one tree per particle type */
     force_treeevaluate(0, 1.0);
     for (int k = 0; k < 3; k++) acc[3 * t + k] = GravDataResult[0].Acc[k];
-    if (cost) { cost[2 * t] = treecost[1] - c0; cost[2 * t + 1] = treecost_quadru[1] - c1; }
+    for (int tr = 0; tr < 6; tr++) { d0 += treecost[tr]; d1 += treecost_quadru[tr]; }
+    if (cost) { cost[2 * t] = d0 - c0; cost[2 * t + 1] = d1 - c1; }
   }
 }
 void ref_potential(int n, const int *idx, double *pot)     /* forcetree.c:1389, tree already built */
@@ -351,6 +353,8 @@ void ref_sidm_ensure_neighbours(int mode) { sidm_ensure_neighbours(mode); }
 void ref_setup_smoothinglengths_sidm(int desngb) { setup_smoothinglengths_sidm(desngb); }
 void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
+/* several particle types (one tree per type, forcetree.c:90-158): softening per type; types go in through ref_set_field(F_TYPE) */
+void ref_set_softening(int type, double eps) { All.SofteningTable[type] = All.SofteningTableMaxPhys[type] = eps; }
 #ifdef REFLECTIONBOUNDARY
 void ref_reflect(double radius) { All.ReflectionRadius = radius; reflect(); All.ReflectionRadius = 1e30; }   /* reflection.c:7 */
 #endif

@@ -246,6 +246,10 @@ class Reference:
         self.lib.ref_reflect.argtypes = [C.c_double]
         self.lib.ref_reflect(float(radius))
 
+    def set_softening(self, ptype, eps):
+        self.lib.ref_set_softening.argtypes = [C.c_int, C.c_double]
+        self.lib.ref_set_softening(int(ptype), float(eps))
+
     def advance(self):
         self.lib.ref_advance()
 

@@ -20,7 +20,8 @@ struct BuildView {
   const int *sidx;            // sorted position -> original index
   signed char *clev;          // [n]
   int *nodestart;             // [n+1]
-  const RootBox *root;
+  const RootBox *root;        // one root cell; with several particle types: root[type]
+  const unsigned char *stype = nullptr;   // several types (one tree per type, forcetree.c:90-158): type of every sorted particle
   // per node
   NodeRec *nodes; float4 *geom; int *nstart, *nend, *nparent, *npstart;
   unsigned char *nlevel, *nnp, *nnchild; int *ndp; int *narrive; int *nminidx; int *nlstart; Moments *nmom;
@@ -30,8 +31,13 @@ struct BuildView {
 };
 
 // ---- B1: shared levels with the next particle, and how many nodes start here
+// levels two sorted particles share; particles of different types share none (they live in different trees)
+B200_HD int common_of(const BuildView &v, int a, int b) {
+  if (v.stype && v.stype[a] != v.stype[b]) return -1;
+  return common_levels(v.shi[a], v.slo[a], v.shi[b], v.slo[b]);
+}
 B200_HD int b1_common(const BuildView &v, int i) {
-  return (i + 1 < v.n) ? common_levels(v.shi[i], v.slo[i], v.shi[i + 1], v.slo[i + 1]) : -1;
+  return (i + 1 < v.n) ? common_of(v, i, i + 1) : -1;
 }
 B200_HD int b1_count_from(int c_prev, int c_here, int i, int n) {
   int cnt = (i == 0) ? c_here + 1 : (c_here > c_prev ? c_here - c_prev : 0);
@@ -54,14 +60,13 @@ B200_HD void b2_body(const BuildView &v, int i) {
 
 // last sorted index that shares `level` leading octants with sorted particle a
 B200_HD int range_end(const BuildView &v, int a, int level) {
-  if (level == 0) return v.n - 1;
-  const uint64_t ahi = v.shi[a], alo = v.slo[a];
+  if (level == 0 && !v.stype) return v.n - 1;
   int lo = a, step = 1;                       // invariant: lo is inside
-  while (lo + step < v.n && common_levels(ahi, alo, v.shi[lo + step], v.slo[lo + step]) >= level) { lo += step; step <<= 1; }
+  while (lo + step < v.n && common_of(v, a, lo + step) >= level) { lo += step; step <<= 1; }
   int hi = lo + step; if (hi > v.n) hi = v.n;  // hi is outside (or n)
   while (hi - lo > 1) {
     const int mid = lo + ((hi - lo) >> 1);
-    if (common_levels(ahi, alo, v.shi[mid], v.slo[mid]) >= level) lo = mid; else hi = mid;
+    if (common_of(v, a, mid) >= level) lo = mid; else hi = mid;
   }
   return lo;
 }
@@ -82,7 +87,8 @@ B200_HD void b3_body(const BuildView &v, int id) {
   const int b = range_end(v, a, level);
   v.nend[id] = b;
   // cell: descend from the root along the first `level` octants of particle a
-  float cx = v.root->cx, cy = v.root->cy, cz = v.root->cz, len = v.root->len;
+  const RootBox &rb = v.stype ? v.root[v.stype[a]] : v.root[0];
+  float cx = rb.cx, cy = rb.cy, cz = rb.cz, len = rb.len;
   const uint64_t ahi = v.shi[a], alo = v.slo[a];
   for (int l = 0; l < level; l++) child_cell(digit_at(ahi, alo, l), cx, cy, cz, len);
   v.geom[id] = make_float4(cx, cy, cz, len);
@@ -105,7 +111,7 @@ B200_HD void b3_body(const BuildView &v, int id) {
   for (int k = np; k < 8; k++) v.ndp[8 * id + k] = -1;
   v.nnp[id] = (unsigned char)np; v.nnchild[id] = (unsigned char)nch;
   v.narrive[id] = 0;
-  if (id == 0) v.nparent[0] = -1;
+  if (level == 0) v.nparent[id] = -1;          // a root (one per particle type)
   v.nodes[id].skip = v.nodestart[b + 1];
 }
 
@@ -154,7 +160,7 @@ B200_HD void b5_body(const BuildView &v, int id) {
 // inside every node the groups (children) are ordered by the smallest original index they
 // contain; recursively that fixes the whole chain.  One thread per node, parents first.
 B200_HD void b6_body(const BuildView &v, int id) {
-  const int base = (id == 0) ? 0 : v.nlstart[id];
+  const int base = (v.nparent[id] < 0) ? v.nstart[id] : v.nlstart[id];   // a root starts its tree's chain
   // gather children: direct particles (size 1, minidx = own index) and child nodes
   int cmin[8], csize[8], cref[8], nc = 0;   // cref >= 0: node id, < 0: ~original particle index
   const int np = v.nnp[id];

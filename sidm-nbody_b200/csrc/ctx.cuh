@@ -50,6 +50,10 @@ struct Ctx {
   float  *potential = nullptr; // Potential (written by b200_compute_potential)
   float  *curtime = nullptr, *oldacc = nullptr, *gravcost = nullptr, *left = nullptr, *right = nullptr;
   int    *ngb = nullptr, *pid = nullptr, *ptype = nullptr;
+  // particle types present (one tree per type, forcetree.c:90-158): refreshed by the tree build when dirty
+  bool types_dirty = true; int type_count[6] = {0, 0, 0, 0, 0, 0}; int ntypes = 1;
+  unsigned char *stype = nullptr;  // several types: type of every sorted particle
+  int ntrees = 1; int tree_type[6] = {1, 0, 0, 0, 0, 0}; int tree_root[7] = {0, 0, 0, 0, 0, 0, 0};   // roots in node order, [ntrees] = num_nodes
 
   // ---- tree (rebuilt by b200_tree_build)
   bool tree_valid = false;
@@ -149,7 +153,7 @@ inline void count_launch(int k = 1) { g.cnt.kernel_launches += k; }
 
 // device status words (d_flags)
 enum { FL_ERR_COINCIDENT = 0, FL_NUM_NODES = 1, FL_MAX_LEVEL = 2, FL_ERR_NGB = 3, FL_NPASS = 4,
-       FL_NREPAIR = 5, FL_NSCATLOG = 6, FL_NEXPORT = 7, FL_MULTITYPE = 8, FL_COUNT = 16 };
+       FL_NREPAIR = 5, FL_NSCATLOG = 6, FL_NEXPORT = 7, FL_MULTITYPE = 8, FL_TROOT0 = 9 /* .. 15 */, FL_COUNT = 16 };
 // device counters (d_ctr)
 enum { CT_PART = 0, CT_NODE = 1, CT_LIST_NODES = 2, CT_LIST_PARTS = 3, CT_CAND = 4, CT_PASS1 = 5,
        CT_SCATTERED = 6, CT_REJECTED = 7, CT_COUNT = 8 };

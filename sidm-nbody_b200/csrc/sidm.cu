@@ -107,9 +107,9 @@ __device__ __forceinline__ int search_start(const SearchCtx &C, int i, float x, 
   const double lox = (double)fadd(x, -h), loy = (double)fadd(y, -h), loz = (double)fadd(z, -h);
   const double hix = (double)fadd(x, h), hiy = (double)fadd(y, h), hiz = (double)fadd(z, h);
   const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h);
-  if (C.box > 0) return 0;
   int no = C.leaf_parent[C.orig_leaf[i]];
-  while (no > 0) {
+  if (C.box > 0) { while (C.nparent[no] >= 0) no = C.nparent[no]; return no; }   // periodic: the root of the particle's own tree
+  while (C.nparent[no] >= 0) {                 // stop at the root of the particle's tree (one tree per type)
     const SearchNode &nd = C.snode[no];
     if (nd.lo[0] + m <= lox && nd.lo[1] + m <= loy && nd.lo[2] + m <= loz && nd.hi[0] - m >= hix && nd.hi[1] - m >= hiy && nd.hi[2] - m >= hiz) break;
     no = C.nparent[no];
@@ -134,8 +134,9 @@ __device__ __forceinline__ void range_search(const SearchCtx &C, bool valid, int
     const double box = C.box;
     const double sminx = fadd(lox, -x), sminy = fadd(loy, -y), sminz = fadd(loz, -z);
     const double smaxx = fadd(hix, -x), smaxy = fadd(hiy, -y), smaxz = fadd(hiz, -z);
-    int no = 0;
-    while (no < C.M) {
+    int no = start;                                    // the root of the query's own tree
+    const int stop_p = C.snode[start].skip;
+    while (no < stop_p) {
       const double2 *q = reinterpret_cast<const double2 *>(C.snode + no);
       const double2 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
       const int4 info = __ldg(reinterpret_cast<const int4 *>(q + 3));
@@ -218,7 +219,7 @@ __device__ __forceinline__ void range_search_fast(const SearchCtx &C, bool valid
   }
 }
 
-__global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, const int *npstart, const unsigned char *nnp, SearchNode *out, SearchNodeF *outf) {
+__global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, const int *npstart, const unsigned char *nnp, const int *nparent, SearchNode *out, SearchNodeF *outf) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= m) return;
   const float4 gm = geom[id]; const int skip = nodes[id].skip;
@@ -236,7 +237,7 @@ __global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, 
     t.lo[k] = l; t.hi[k] = h;
   }
   const int cnt = s.pend - s.pstart;
-  const int bucket = (cnt <= kBucket && id > 0) ? 1 : 0;
+  const int bucket = (cnt <= kBucket && nparent[id] >= 0) ? 1 : 0;     // roots are never buckets
   t.skip = skip; t.pinfo = (s.pstart << 5) | (bucket << 4) | (bucket ? cnt : s.np);
   outf[id] = t;
   if (id == m - 1) { SearchNodeF e; for (int k = 0; k < 3; k++) { e.lo[k] = 0; e.hi[k] = 0; } e.skip = m; e.pinfo = npstart[m] << 5; outf[m] = e; }
@@ -244,10 +245,11 @@ __global__ void k_search_nodes(int m, const NodeRec *nodes, const float4 *geom, 
 
 // ------------------------------------------------------------------ slots
 // sidm.c:141-161: particles within h of the domain box are flagged for export and placed first
-__global__ void k_export_flag(int na, const int *active, const float4 *posm, const float4 *velh, const float *domain, int *flag) {
+__global__ void k_export_flag(int na, const int *active, const float4 *posm, const float4 *velh, const float *domain_all, int *flag, const int *ptype) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= na) return;
   const int i = active ? active[a] : a;
+  const float *domain = ptype ? domain_all + 6 * (ptype[i] & 7) : domain_all;     // DomainMin/Max[type], forcetree.c:192-198
   const float4 p = posm[i]; const float h = velh[i].w;
   const float pp[3] = {p.x, p.y, p.z};
   int j;
@@ -337,7 +339,7 @@ __global__ void k_group_flag(int m, const SearchNode *sn, const int *nparent, in
   const int2 r = group_range(sn[id]);
   int f = 0;
   if (r.y > r.x) f = aligned ? ((r.y - 1) >> 5) - (r.x >> 5) + 1 : (r.y - r.x + 31) >> 5;
-  if (cnt <= kGroupCell && id > 0) { const int par = nparent[id]; if (sn[par].pend - sn[par].pstart <= kGroupCell) f = 0; }
+  if (cnt <= kGroupCell && nparent[id] >= 0) { const int par = nparent[id]; if (sn[par].pend - sn[par].pstart <= kGroupCell) f = 0; }
   flag[id] = f;
 }
 __global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const int *pos, int2 *groups, int *gnode, int aligned) {
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   {
     const double mg = 1.0e-5 * (fmax(fabs((double)U.lx), fabs((double)U.hx)) + fmax(fabs((double)U.ly), fabs((double)U.hy)) +
                                 fmax(fabs((double)U.lz), fabs((double)U.hz)) + ((double)U.hx - (double)U.lx));
-    while (A > 0) {
+    while (P.C.nparent[A] >= 0) {
       const SearchNode &nd = P.C.snode[A];
       if (nd.lo[0] + mg <= (double)U.lx && nd.lo[1] + mg <= (double)U.ly && nd.lo[2] + mg <= (double)U.lz &&
           nd.hi[0] - mg >= (double)U.hx && nd.hi[1] - mg >= (double)U.hy && nd.hi[2] - mg >= (double)U.hz) break;
@@ -973,7 +975,7 @@ int refresh_search_nodes() {
   g.search_epoch = g.tree_epoch;
   cudaStream_t st = sidm_stream();
   const int m = g.num_nodes;
-  k_search_nodes<<<cdiv(m, 256), 256, 0, st>>>(m, g.nodes, g.geom, g.npstart, g.nnp, S.snode, S.snodef);
+  k_search_nodes<<<cdiv(m, 256), 256, 0, st>>>(m, g.nodes, g.geom, g.npstart, g.nnp, g.nparent, S.snode, S.snodef);
   // query groups of the warp-shared search
   const int aligned = g.shard_world > 1;
   k_group_flag<<<cdiv(m + 1, 256), 256, 0, st>>>(m, S.snode, g.nparent, S.gflag, aligned);
@@ -1033,7 +1035,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     if (!d_active && b0 > 0) return B200_ERR_ARG;     // bunches need an explicit list
     const int G = cdiv(nb, B);
     // slots: exported-first buffer order
-    k_export_flag<<<G, B, 0, st>>>(nb, act, g.posm, g.velh, g.d_domain, g.s_flag);
+    k_export_flag<<<G, B, 0, st>>>(nb, act, g.posm, g.velh, g.d_domain, g.s_flag, g.ntypes > 1 ? g.ptype : nullptr);
     CUDA_TRY(cudaMemsetAsync(g.s_flag + nb, 0, sizeof(int), st));
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, g.s_flag, g.s_pos, nb + 1, st);
@@ -1242,7 +1244,8 @@ __global__ void __launch_bounds__(128) k_knn(KnnParams P) {
   if (valid) {
     // starting radius from the local density: descend while the cell holds > 200 particles
     // (forcetree.c:2327-2347)
-    int th = 0;
+    int th = P.C.leaf_parent[P.C.orig_leaf[i]];
+    while (P.C.nparent[th] >= 0) th = P.C.nparent[th];      // the root of the particle's own tree
     for (;;) {
       const int skip = P.snode[th].skip;
       const float4 gc = P.geom[th];
@@ -1319,8 +1322,9 @@ __global__ void k_flag_repair(int n, int lo, int hi, int ensure_variant, const i
   flag[i] = f;
 }
 // sidm.c:917-929: new smoothing length for the flagged particles (h from k-NN where asked)
+struct TypeCount { int n[8]; };
 __global__ void k_new_hsml(int nr, const int *redo, const int *ngb, const float *left, const float *right, float4 *velh, int des,
-                           int ensure_variant, int ntype, int *want_knn) {
+                           int ensure_variant, TypeCount tc, const int *ptype, int *want_knn) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nr) return;
   const int i = redo[a];
@@ -1328,7 +1332,7 @@ __global__ void k_new_hsml(int nr, const int *redo, const int *ngb, const float 
   const float L = left[i], R = right[i];
   int knn = 0;
   if (L == 0 || R == 0) {
-    if (ensure_variant && R == 0 && ngb[i] < 15 && ntype > des) knn = 1;
+    if (ensure_variant && R == 0 && ngb[i] < 15 && tc.n[ptype[i] & 7] > des) knn = 1;    // NtypeLocal[P[i].Type], sidm.c:919
     else v.w = (float)((double)v.w * (0.5 + 0.5 * pow(ngb[i] / ((double)des), -1.0 / 3)));
   } else v.w = (float)(0.5 * ((double)L + (double)R));
   velh[i] = v;
@@ -1379,7 +1383,9 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     count_launch(4);
     const int nr = g.h_flags[FL_NREPAIR];
     if (nr == 0) break;
-    k_new_hsml<<<cdiv(nr, B), B, 0, st>>>(nr, redo, g.ngb, g.left, g.right, g.velh, g.par.DesNumNgb, ensure_variant, n, want);
+    TypeCount tc;
+    for (int t = 0; t < 8; t++) tc.n[t] = t < 6 ? g.type_count[t] : 0;
+    k_new_hsml<<<cdiv(nr, B), B, 0, st>>>(nr, redo, g.ngb, g.left, g.right, g.velh, g.par.DesNumNgb, ensure_variant, tc, g.ptype, want);
     count_launch();
     if (ensure_variant) {
       // exact k-th neighbour distance where sidm.c:918-922 asks for it (rare: Ngb < 15 with no upper bracket)

@@ -28,7 +28,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.curtime, n)); B200_TRY(dalloc(&g.oldacc, n)); B200_TRY(dalloc(&g.gravcost, n));
   B200_TRY(dalloc(&g.left, n)); B200_TRY(dalloc(&g.right, n)); B200_TRY(dalloc(&g.maxpred, n)); B200_TRY(dalloc(&g.potential, n));
   B200_TRY(dalloc(&g.ngb, n)); B200_TRY(dalloc(&g.pid, n)); B200_TRY(dalloc(&g.ptype, n));
-  B200_TRY(dalloc(&g.d_bbox, 8)); B200_TRY(dalloc(&g.d_root, 1)); B200_TRY(dalloc(&g.d_domain, 8));
+  B200_TRY(dalloc(&g.d_bbox, 8)); B200_TRY(dalloc(&g.d_root, 8)); B200_TRY(dalloc(&g.d_domain, 48));   // root cell and DomainMin/Max per particle type
   B200_TRY(dalloc(&g.key_hi, n)); B200_TRY(dalloc(&g.key_lo, n));
   B200_TRY(dalloc(&g.skey_hi, n)); B200_TRY(dalloc(&g.skey_lo, n)); B200_TRY(dalloc(&g.key_tmp, n));
   B200_TRY(dalloc(&g.sidx, n)); B200_TRY(dalloc(&g.sidx_tmp, n)); B200_TRY(dalloc(&g.krank, n));
@@ -167,6 +167,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.d_aos); g.aos_cap = 0;
   dfree(&g.posm); dfree(&g.velh); dfree(&g.pos0); dfree(&g.velpred); dfree(&g.accel); dfree(&g.dvel);
   dfree(&g.maxpred); dfree(&g.potential);
+  if (g.stype) cudaFree(g.stype); g.stype = nullptr; g.types_dirty = true; g.ntypes = 1; g.ntrees = 1;
   dfree(&g.curtime); dfree(&g.oldacc); dfree(&g.gravcost); dfree(&g.left); dfree(&g.right);
   dfree(&g.ngb); dfree(&g.pid); dfree(&g.ptype);
   dfree(&g.d_bbox); dfree(&g.d_root); dfree(&g.d_domain);
@@ -252,6 +253,7 @@ extern "C" int b200_set_soa(int n, const float *pos, const float *vel, const flo
     CUDA_TRY(cudaMemsetAsync(g.ngb, 0, n * sizeof(int), g.stream));
     CUDA_TRY(cudaMemsetAsync(g.pid, 0, n * sizeof(int), g.stream));
     k_fill_i<<<G, B, 0, g.stream>>>(n, g.ptype, 1);
+    g.types_dirty = true;
     k_fill_f<<<G, B, 0, g.stream>>>(n, g.gravcost, 1.0f);
     count_launch(2);
   }
@@ -394,7 +396,7 @@ extern "C" int b200_upload(void) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
-  g.tree_valid = false;
+  g.tree_valid = false; g.types_dirty = true;
   return B200_OK;
 }
 
@@ -446,7 +448,7 @@ extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
-  g.tree_valid = false;
+  g.tree_valid = false; g.types_dirty = true;
   return B200_OK;
 }
 
@@ -566,6 +568,7 @@ extern "C" int b200_set_field(const char *name, const void *host, long long nbyt
   if (!host || nbytes <= 0 || nbytes > nb || !d) return B200_ERR_ARG;
   CUDA_TRY(cudaMemcpyAsync(d, host, (size_t)nbytes, cudaMemcpyHostToDevice, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (!strcmp(name, "ptype")) { g.types_dirty = true; g.tree_valid = false; }
   return B200_OK;
 }
 
@@ -756,7 +759,7 @@ extern "C" int b200_device_buffer(const char *name, void **dptr, long long *nbyt
       {"posm", g.posm, n * 16}, {"velh", g.velh, n * 16}, {"accel", g.accel, n * 12}, {"dvel", g.dvel, n * 12},
       {"oldacc", g.oldacc, n * 4}, {"ngb", g.ngb, n * 4}, {"acc_raw", g.d_acc, n * 24}, {"cost", g.d_cost, n * 8},
       {"velpred", g.velpred, n * 12}, {"pos0", g.pos0, n * 12}, {"curtime", g.curtime, n * 4},
-      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4}, {"potential", g.potential, n * 4},
+      {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4}, {"potential", g.potential, n * 4}, {"ptype", g.ptype, n * 4},
       {"ewald", g.d_ewald, g.d_ewald ? 33LL * 33 * 33 * 16 : 0}};
   for (auto &t : tab) if (!strcmp(t.nm, name)) { *dptr = t.p; *nbytes = t.b; return B200_OK; }
   return B200_ERR_ARG;

@@ -17,18 +17,21 @@
 namespace b200 {
 
 // ------------------------------------------------------------------ bounding box
-__global__ void k_bbox_partial(int n, const float4 *posm, const int *ptype, float *part, int *flags) {
+// only_type >= 0: bounding box of the particles of that type (one tree per type)
+__global__ void k_bbox_partial(int n, const float4 *posm, const int *ptype, float *part, int *flags, int only_type) {
   __shared__ float sm[6][256];
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  const int t0 = ptype[0];
+  const int t0 = only_type >= 0 ? only_type : (ptype[0] & 7);
   bool multi = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool mine = (ptype[i] & 7) == t0;
+    multi |= !mine;
+    if (only_type >= 0 && !mine) continue;
     const float4 p = posm[i];
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
-    multi |= (ptype[i] != t0);
   }
-  if (multi) flags[FL_MULTITYPE] = 1;
+  if (multi && only_type < 0) flags[FL_MULTITYPE] = 1;
   for (int k = 0; k < 3; k++) { sm[k][threadIdx.x] = mn[k]; sm[3 + k][threadIdx.x] = mx[k]; }
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -59,10 +62,10 @@ __global__ void k_bbox_final(int nblk, const float *part, double *bbox, RootBox 
 }
 
 // ------------------------------------------------------------------ keys
-__global__ void k_keys(int n, const float4 *posm, const RootBox *root, uint64_t *hi, uint64_t *lo, int *iota) {
+__global__ void k_keys(int n, const float4 *posm, const RootBox *root, uint64_t *hi, uint64_t *lo, int *iota, const int *ptype) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const RootBox rb = *root;
+  const RootBox rb = ptype ? root[ptype[i] & 7] : root[0];    // several types: the key is the path through the particle's own tree
   const float4 p = posm[i];
   uint64_t h, l;
   make_key(p.x, p.y, p.z, rb, h, l);
@@ -76,19 +79,38 @@ __global__ void k_gather_lo(int n, const int *sidx, const uint64_t *lo, uint64_t
 
 // particles whose first 21 octants agree are ordered by the next 21 (rare: a few pairs in a
 // 1e7-particle cusp); one thread per run of equal high words, insertion sort on the low word
-__global__ void k_fix_ties(int n, const uint64_t *shi, uint64_t *slo, int *sidx) {
+__global__ void k_fix_ties(int n, const uint64_t *shi, uint64_t *slo, int *sidx, const unsigned char *stype) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n - 1) return;
   const uint64_t h = shi[j];
-  if ((j > 0 && shi[j - 1] == h) || shi[j + 1] != h) return;   // not the start of a run
+  auto same = [&](int a, int b) { return shi[a] == shi[b] && (!stype || stype[a] == stype[b]); };   // runs never cross a type boundary
+  if ((j > 0 && same(j - 1, j)) || !same(j + 1, j)) return;   // not the start of a run
   int e = j + 1;
-  while (e + 1 < n && shi[e + 1] == h) e++;
+  while (e + 1 < n && same(e + 1, j)) e++;
   for (int a = j + 1; a <= e; a++) {
     const uint64_t l = slo[a]; const int s = sidx[a];
     int b = a - 1;
     while (b >= j && (slo[b] > l || (slo[b] == l && sidx[b] > s))) { slo[b + 1] = slo[b]; sidx[b + 1] = sidx[b]; b--; }
     slo[b + 1] = l; sidx[b + 1] = s;
   }
+}
+
+// several particle types: after the key sort, a stable 3-bit sort by type puts the trees one after the other
+__global__ void k_type_hist(int n, const int *ptype, int *hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[ptype[i] & 7], 1);
+}
+__global__ void k_type_keys(int n, const int *sidx, const int *ptype, unsigned char *tkey, int *pos) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) { tkey[j] = (unsigned char)(ptype[sidx[j]] & 7); pos[j] = j; }
+}
+__global__ void k_type_gather(int n, const int *perm, const int *sidx_in, const uint64_t *shi_in, int *sidx_out, uint64_t *shi_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) { const int p = perm[j]; sidx_out[j] = sidx_in[p]; shi_out[j] = shi_in[p]; }
+}
+__global__ void k_troots(int ntrees, const int *first, const int *nodestart, int *flags) {
+  const int t = threadIdx.x;
+  if (t < ntrees) flags[FL_TROOT0 + t] = nodestart[first[t]];
 }
 
 // ------------------------------------------------------------------ construction kernels
@@ -195,7 +217,7 @@ static int ensure_cub(size_t bytes) {
 BuildView make_view() {
   BuildView v;
   v.n = g.n; v.maxnodes = g.maxnodes; v.posm = g.posm; v.shi = g.skey_hi; v.slo = g.skey_lo; v.sidx = g.sidx;
-  v.clev = g.clev; v.nodestart = g.nodestart; v.root = g.d_root;
+  v.clev = g.clev; v.nodestart = g.nodestart; v.root = g.d_root; v.stype = g.ntypes > 1 ? g.stype : nullptr;
   v.nodes = g.nodes; v.geom = g.geom; v.nstart = g.nstart; v.nend = g.nend; v.nparent = g.nparent; v.npstart = g.npstart;
   v.nlevel = g.nlevel; v.nnp = g.nnp; v.nnchild = g.nnchild; v.ndp = g.ndp; v.narrive = g.narrive;
   v.nminidx = g.nminidx; v.nlstart = g.nlstart; v.nmom = g.nmom;
@@ -211,21 +233,61 @@ int tree_build_impl() {
   CUDA_TRY(cudaEventRecord(g.ev0, st));
   CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), st));
 
-  // 1. bounding box -> root cell (forcetree.c:179-212)
+  // which particle types are present (one tree per type, forcetree.c:90-158)
+  if (g.types_dirty) {
+    int *hist = g.d_flags + FL_TROOT0;        // scratch: overwritten below
+    CUDA_TRY(cudaMemsetAsync(hist, 0, 8 * sizeof(int), st));
+    k_type_hist<<<G, B, 0, st>>>(n, g.ptype, hist);
+    CUDA_TRY(cudaMemcpyAsync(g.h_flags + FL_TROOT0, hist, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    g.ntypes = 0;
+    for (int t = 0; t < 6; t++) { g.type_count[t] = g.h_flags[FL_TROOT0 + t]; if (g.type_count[t] > 0) g.ntypes++; }
+    g.types_dirty = false;
+    count_launch();
+    CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), st));
+  }
+  const bool multi = g.ntypes > 1;
+  if (multi && !g.stype && cudaMalloc((void **)&g.stype, (size_t)g.maxpart + 256) != cudaSuccess) return B200_ERR_ALLOC;
+  // 1. bounding box -> root cell (forcetree.c:179-212), per type when there are several
   const int GB = 296;
   float *part = (float *)g.d_cost;
-  k_bbox_partial<<<GB, 256, 0, st>>>(n, g.posm, g.ptype, part, g.d_flags);
-  k_bbox_final<<<1, 32, 0, st>>>(GB, part, g.d_bbox, g.d_root, g.d_domain);
+  if (!multi) {
+    k_bbox_partial<<<GB, 256, 0, st>>>(n, g.posm, g.ptype, part, g.d_flags, -1);
+    k_bbox_final<<<1, 32, 0, st>>>(GB, part, g.d_bbox, g.d_root, g.d_domain);
+    count_launch(2);
+  } else {
+    for (int t = 0; t < 6; t++) if (g.type_count[t] > 0) {
+      k_bbox_partial<<<GB, 256, 0, st>>>(n, g.posm, g.ptype, part, g.d_flags, t);
+      k_bbox_final<<<1, 32, 0, st>>>(GB, part, g.d_bbox, g.d_root + t, g.d_domain + 6 * t);
+      count_launch(2);
+    }
+  }
   // 2. keys + sort
-  k_keys<<<G, B, 0, st>>>(n, g.posm, g.d_root, g.key_hi, g.key_lo, g.iota);
-  count_launch(3);
+  k_keys<<<G, B, 0, st>>>(n, g.posm, g.d_root, g.key_hi, g.key_lo, g.iota, multi ? g.ptype : nullptr);
+  count_launch();
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, g.key_hi, g.skey_hi, g.iota, g.sidx, n, 0, 63, st);
   B200_TRY(ensure_cub(tb));
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tb, g.key_hi, g.skey_hi, g.iota, g.sidx, n, 0, 63, st));
+  count_launch(9);
+  if (multi) {
+    // stable sort of the key order by type: tree after tree, each in its own key order
+    unsigned char *tkey = g.stype, *tkey2 = (unsigned char *)g.clev;          // clev is written later (k_b1)
+    int *pos = g.sidx_tmp, *perm = g.krank;                                     // krank is written later (k_b2)
+    k_type_keys<<<G, B, 0, st>>>(n, g.sidx, g.ptype, tkey, pos);
+    size_t tbt = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tbt, tkey, tkey2, pos, perm, n, 0, 3, st);
+    B200_TRY(ensure_cub(tbt));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tbt, tkey, tkey2, pos, perm, n, 0, 3, st));
+    k_type_gather<<<G, B, 0, st>>>(n, perm, g.sidx, g.skey_hi, g.sidx_tmp, g.key_tmp);
+    CUDA_TRY(cudaMemcpyAsync(g.sidx, g.sidx_tmp, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g.skey_hi, g.key_tmp, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g.stype, tkey2, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    count_launch(4);
+  }
   k_gather_lo<<<G, B, 0, st>>>(n, g.sidx, g.key_lo, g.skey_lo);
-  k_fix_ties<<<G, B, 0, st>>>(n, g.skey_hi, g.skey_lo, g.sidx);
-  count_launch(2 + 9);
+  k_fix_ties<<<G, B, 0, st>>>(n, g.skey_hi, g.skey_lo, g.sidx, multi ? g.stype : nullptr);
+  count_launch(2);
   // 3. prefix lengths, node counts, scan
   BuildView v = make_view();
   int *cnt = g.sidx_tmp;
@@ -237,10 +299,22 @@ int tree_build_impl() {
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb2, cnt, g.nodestart, n + 1, st));
   k_b2<<<G, B, 0, st>>>(v);
   count_launch(4);
+  // tree roots (node ids) in node order
+  g.ntrees = 0;
+  {
+    int first[6], at = 0;
+    for (int t = 0; t < 6; t++) if (g.type_count[t] > 0) { first[g.ntrees] = at; g.tree_type[g.ntrees] = t; g.ntrees++; at += g.type_count[t]; }
+    if (multi) {
+      int *d_first = (int *)g.d_bbox;          // 8 doubles of scratch, free again by now
+      CUDA_TRY(cudaMemcpyAsync(d_first, first, g.ntrees * sizeof(int), cudaMemcpyHostToDevice, st));
+      k_troots<<<1, 32, 0, st>>>(g.ntrees, d_first, g.nodestart, g.d_flags);
+      count_launch();
+    }
+  }
   // node count / depth / error flags back to the host (the only sync of the build)
   CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (g.h_flags[FL_MULTITYPE]) return B200_ERR_TYPES;
+  if (g.h_flags[FL_MULTITYPE] && !multi) { g.types_dirty = true; return B200_ERR_TYPES; }   // stale type census
   if (g.h_flags[FL_ERR_COINCIDENT]) return B200_ERR_COINCIDENT;
   const int m = g.h_flags[FL_NUM_NODES];
   if (m >= g.maxnodes) {   // forcetree.c:233-239
@@ -248,6 +322,9 @@ int tree_build_impl() {
     return B200_ERR_NODES;
   }
   g.num_nodes = m; g.max_level = g.h_flags[FL_MAX_LEVEL];
+  if (multi) { for (int t = 0; t < g.ntrees; t++) g.tree_root[t] = g.h_flags[FL_TROOT0 + t]; }
+  else { g.ntrees = 1; g.tree_root[0] = 0; }
+  g.tree_root[g.ntrees] = m;
   const int GM = cdiv(m + 1, B);
   // 4. ranges, geometry, children
   k_b3<<<GM, B, 0, st>>>(v);

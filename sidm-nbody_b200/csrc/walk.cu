@@ -34,8 +34,12 @@ struct WalkParams {
   unsigned long long *ctr;
   // periodic box (forcetree.c:870-877,921-930): nearest image + Ewald correction table
   float box, boxhalf, ewald_fac; const float4 *ewald;
+  // one tree per particle type, laid out one after the other in the node array (forcetree.c:90-158, 798-808):
+  // tree t = nodes [troot[t], troot[t+1]); softening of an interaction = max(eps of the tree's type, eps of the target's type)
+  int ntrees; int troot[7]; int ttype[6]; float eps[6]; const int *ptype;
 };
 
+struct EpsTab { double e[8]; };             // SofteningTable by particle type
 constexpr int kEwaldN = 64, kEwaldD = 32;        // EN, ED of ewald.c:12-14
 
 // ewald_corr(), ewald.c:171-238: fold into the first octant, trilinear interpolation of the
@@ -103,10 +107,10 @@ __device__ __forceinline__ float pp_soft(float r2, float mass, float h_inv) {
 // 2 = all BH (forcetree.c:817); the choice is warp-uniform, the arithmetic identical.
 template <bool PER, int MODE>
 __device__ __forceinline__ void walk_loop(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no,
-                                          double &ax, double &ay, double &az, int &npart, int &nnode, unsigned &wnodes, unsigned &wparts) {
-  const float h_inv = P.h_inv, theta2 = P.theta2;
+                                          double &ax, double &ay, double &az, int &npart, int &nnode, unsigned &wnodes, unsigned &wparts,
+                                          const float h_inv, const int M) {
+  const float theta2 = P.theta2;
   const float h2 = 1.0f / (h_inv * h_inv);
-  const int M = P.num_nodes;
   const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
   int cur = __reduce_min_sync(0xffffffffu, no);
   while (cur < M) {
@@ -195,7 +199,7 @@ __device__ __forceinline__ void walk_loop(const WalkParams &P, const float4 tp, 
 #ifndef WALK_MINBLOCKS
 #define WALK_MINBLOCKS 10
 #endif
-template <bool PER>
+template <bool PER, bool MULTI>
 __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParams P) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,9 +215,18 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParam
   int npart = 0, nnode = 0;
   unsigned wnodes = 0, wparts = 0;
   const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
-  if (all_rel) walk_loop<PER, 1>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
-  else if (all_bh) walk_loop<PER, 2>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
-  else walk_loop<PER, 0>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts);
+  if (!MULTI) {
+    if (all_rel) walk_loop<PER, 1>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts, P.h_inv, P.num_nodes);
+    else if (all_bh) walk_loop<PER, 2>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts, P.h_inv, P.num_nodes);
+    else walk_loop<PER, 0>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts, P.h_inv, P.num_nodes);
+  } else {
+    const float eps_t = valid ? P.eps[P.ptype[part] & 7] : 0.f;
+    for (int t = 0; t < P.ntrees; t++) {                       // forcetree.c:798-808: every tree in turn
+      const float h_inv = 1.0f / (2.8f * fmaxf(P.eps[P.ttype[t]], eps_t));
+      no = valid ? P.troot[t] : 0x7fffffff;
+      walk_loop<PER, 0>(P, tp, bh, oac, no, ax, ay, az, npart, nnode, wnodes, wparts, h_inv, P.troot[t + 1]);
+    }
+  }
   if (valid) {
     P.acc[3 * (size_t)slot] = ax; P.acc[3 * (size_t)slot + 1] = ay; P.acc[3 * (size_t)slot + 2] = az;
     P.cost[2 * (size_t)slot] = npart; P.cost[2 * (size_t)slot + 1] = nnode;
@@ -228,6 +241,7 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParam
 }
 
 static float h_inv_of_type1();
+static void fill_trees(WalkParams &P);
 
 // ------------------------------------------------------------------ potential walk
 // force_treeevaluate_potential(), forcetree.c:1389-1755: the same lock-step walk and the same open/accept
@@ -235,11 +249,11 @@ static float h_inv_of_type1();
 // radius (no u > 1e-4 guard here: the target's own particle contributes -m/eps, which compute_potential()
 // adds back, potential.c:135).  Cell: -M/r + (-3 potq/r^2 + P/2)/r^3, softened form below h.  Open boundaries.
 template <bool PER, int MODE>
-__device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no, double &pot) {
-  const float h_inv = P.h_inv, theta2 = P.theta2;
+__device__ __forceinline__ void walk_loop_pot(const WalkParams &P, const float4 tp, const bool bh, const float oac, int &no, double &pot,
+                                              const float h_inv, const int M) {
+  const float theta2 = P.theta2;
   const float h2 = 1.0f / (h_inv * h_inv);
   const float h3i = h_inv * h_inv * h_inv, h5i = h3i * h_inv * h_inv;
-  const int M = P.num_nodes;
   const float4 *nodes4 = reinterpret_cast<const float4 *>(P.nodes);
   int cur = __reduce_min_sync(0xffffffffu, no);
   while (cur < M) {
@@ -308,20 +322,25 @@ __global__ void __launch_bounds__(128) k_walk_pot(WalkParams P) {
   int no = valid ? 0 : 0x7fffffff;
   double pot = 0;
   const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
-  if (all_rel) walk_loop_pot<PER, 1>(P, tp, bh, oac, no, pot);
-  else if (all_bh) walk_loop_pot<PER, 2>(P, tp, bh, oac, no, pot);
-  else walk_loop_pot<PER, 0>(P, tp, bh, oac, no, pot);
+  const float eps_t = valid ? P.eps[P.ptype[part] & 7] : 0.f;
+  for (int t = 0; t < P.ntrees; t++) {                         // forcetree.c:1397-1409: every tree in turn
+    const float h_inv = P.ntrees > 1 ? 1.0f / (2.8f * fmaxf(P.eps[P.ttype[t]], eps_t)) : P.h_inv;
+    no = valid ? P.troot[t] : 0x7fffffff;
+    if (all_rel) walk_loop_pot<PER, 1>(P, tp, bh, oac, no, pot, h_inv, P.troot[t + 1]);
+    else if (all_bh) walk_loop_pot<PER, 2>(P, tp, bh, oac, no, pot, h_inv, P.troot[t + 1]);
+    else walk_loop_pot<PER, 0>(P, tp, bh, oac, no, pot, h_inv, P.troot[t + 1]);
+  }
   if (valid) P.acc[slot] = pot;                                  // raw potential per target slot (GravDataPotential)
 }
 
 // compute_potential(), potential.c:131-168: float Potential <- raw; += m/eps (self energy); *G; Lambda / comoving terms
-__global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, float *potential, double eps, double G,
+__global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, float *potential, const int *ptype, EpsTab tab, double G,
                                int comoving, int periodic, double H, double O0, double OL) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = posm[i];
   float v = (float)raw[i];
-  v = (float)((double)v + (double)p.w / eps);
+  v = (float)((double)v + (double)p.w / tab.e[ptype[i] & 7]);      // P[i].Mass / All.SofteningTable[P[i].Type]
   double r2 = 0;
   r2 += (double)fmul(p.x, p.x); r2 += (double)fmul(p.y, p.y); r2 += (double)fmul(p.z, p.z);
   if (comoving) {
@@ -343,6 +362,7 @@ static int potential_walk(const int *d_sorted, int nt, bool with_slots) {
   P.acc = g.d_acc; P.cost = g.d_cost;
   P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
+  fill_trees(P);
   P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
   if (per) { B200_TRY(ewald_tables(&P.ewald)); }
   if (nt > 0) {
@@ -440,10 +460,17 @@ int prepare_targets(const int *active_host, int nactive, int **d_sorted_out) {
   return B200_OK;
 }
 
+static void fill_trees(WalkParams &P) {
+  P.ntrees = g.ntrees; P.ptype = g.ptype;
+  for (int t = 0; t < 7; t++) P.troot[t] = g.tree_root[t];
+  for (int t = 0; t < 6; t++) { P.ttype[t] = g.tree_type[t]; P.eps[t] = (float)g.par.SofteningTable[t]; }
+  if (g.ntrees == 1) { P.troot[0] = 0; P.troot[1] = g.num_nodes; }
+}
+
 static float h_inv_of_type1() {
   // epsilon = max(eps_tree, eps_target) (forcetree.c:800); one collisionless type => its own eps
-  double eps = 0;
-  for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
+  double eps = g.par.SofteningTable[g.tree_type[0]];
+  if (!(eps > 0)) for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
   return (float)(1.0 / (2.8 * eps));
 }
 
@@ -462,13 +489,17 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots, bool defer_sync) {
   P.acc = g.d_acc; P.cost = g.d_cost;
   P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
+  fill_trees(P);
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, 4 * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
   if (per) { B200_TRY(ewald_tables(&P.ewald)); }
   if (nt > 0) {
-    if (per) k_walk<true><<<cdiv(nt, WALK_THREADS), WALK_THREADS, 0, g.stream>>>(P); else k_walk<false><<<cdiv(nt, WALK_THREADS), WALK_THREADS, 0, g.stream>>>(P);
+    const int GW = cdiv(nt, WALK_THREADS);
+    if (g.ntrees > 1) { if (per) k_walk<true, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); else k_walk<false, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); }
+    else if (per) k_walk<true, false><<<GW, WALK_THREADS, 0, g.stream>>>(P);
+    else k_walk<false, false><<<GW, WALK_THREADS, 0, g.stream>>>(P);
     count_launch();
   }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -599,16 +630,19 @@ __device__ __forceinline__ double soft_force_d(double u) {
   if (u <= 0.5) return 32.0 * (1.0 / 3 - 6.0 / 5 * u * u + u * u * u);
   return 64.0 * (1.0 / 3 - 3.0 / 4 * u + 3.0 / 5 * u * u - u * u * u / 6) - 1.0 / 15 / (u * u * u);
 }
-__global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int n, const float4 *posm, double h_inv, double *acc,
-                                                double box, const float4 *ewald, float ewald_fac) {
+__global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int n, const float4 *posm, double h_inv_one, double *acc,
+                                                double box, const float4 *ewald, float ewald_fac, const int *ptype, EpsTab tab, int ntypes) {
   __shared__ float4 tile[128];
+  __shared__ int ttile[128];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   float4 tp = make_float4(0, 0, 0, 0);
-  if (t < nt) tp = posm[targets[t]];
+  double eps_t = 0;
+  if (t < nt) { tp = posm[targets[t]]; eps_t = tab.e[ptype[targets[t]] & 7]; }
   double ax = 0, ay = 0, az = 0;
   for (int base = 0; base < n; base += 128) {
     const int j = base + threadIdx.x;
     tile[threadIdx.x] = j < n ? posm[j] : make_float4(0, 0, 0, 0);
+    ttile[threadIdx.x] = j < n ? (ptype[j] & 7) : 0;
     __syncthreads();
     const int lim = min(128, n - base);
     for (int k = 0; k < lim; k++) {
@@ -620,6 +654,8 @@ __global__ void __launch_bounds__(128) k_direct(int nt, const int *targets, int 
         while (dx < -bh) dx += box; while (dy < -bh) dy += box; while (dz < -bh) dz += box;
       }
       const double r2 = dx * dx + dy * dy + dz * dz;
+      // forcetree.c:1910: epsilon = max(eps of the source's type, eps of the target's type)
+      const double h_inv = ntypes > 1 ? 1.0 / (2.8 * fmax(tab.e[ttile[k]], eps_t)) : h_inv_one;
       const double r = sqrt(r2), u = r * h_inv;
       double fac = 0;
       if (u >= 1) fac = (double)q.w / (r2 * r);
@@ -643,8 +679,10 @@ int direct_impl(const int *targets, int nt, double *acc_out) {
   const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   const float4 *ew = nullptr;
   if (per) { B200_TRY(ewald_tables(&ew)); }
+  EpsTab tab;
+  for (int t = 0; t < 8; t++) tab.e[t] = t < 6 ? g.par.SofteningTable[t] : 0.0;
   k_direct<<<cdiv(nt, 128), 128, 0, g.stream>>>(nt, g.d_active, g.n, g.posm, (double)h_inv_of_type1(), g.d_acc,
-                                                per ? g.par.BoxSize : 0.0, ew, per ? (float)(kEwaldN / g.par.BoxSize) : 0.f);
+                                                per ? g.par.BoxSize : 0.0, ew, per ? (float)(kEwaldN / g.par.BoxSize) : 0.f, g.ptype, tab, g.ntypes);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(acc_out, g.d_acc, (size_t)nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -695,9 +733,9 @@ extern "C" int b200_compute_potential(float *pot_out) {
   if (!g.ready || g.n <= 0) return B200_ERR_STATE;
   B200_TRY(b200_tree_build());                                   // potential.c:47 force_treebuild()
   B200_TRY(potential_walk(g.sidx, g.n, false));
-  double eps = 0;
-  for (int t = 0; t < 6; t++) if (g.par.SofteningTable[t] > eps) eps = g.par.SofteningTable[t];
-  k_pot_epilogue<<<cdiv(g.n, 256), 256, 0, g.stream>>>(g.n, g.d_acc, g.posm, g.potential, eps, g.par.G, g.par.ComovingIntegrationOn,
+  EpsTab tab;
+  for (int t = 0; t < 8; t++) tab.e[t] = t < 6 ? g.par.SofteningTable[t] : 0.0;
+  k_pot_epilogue<<<cdiv(g.n, 256), 256, 0, g.stream>>>(g.n, g.d_acc, g.posm, g.potential, g.ptype, tab, g.par.G, g.par.ComovingIntegrationOn,
                                                      (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? 1 : 0, g.par.Hubble, g.par.Omega0, g.par.OmegaLambda);
   count_launch();
   if (pot_out) CUDA_TRY(cudaMemcpyAsync(pot_out, g.potential, (size_t)g.n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
