@@ -48,7 +48,7 @@ extern "C" {
 #define B200_ERR_COINCIDENT 9005  /* >1 particle at one position to 42 octree levels;
                                      the reference randomises such pairs with rand()
                                      (forcetree.c:320-326), which cannot be reproduced */
-#define B200_ERR_TYPES      9006  /* more than one collisionless particle type present */
+#define B200_ERR_TYPES      9006  /* particle types changed behind the library's back (set them through b200_set_field / b200_upload) */
 
 /* The `All` fields the path reads (allvars.h:164-420).  Filled by the shim from `All`. */
 typedef struct b200_params {
@@ -146,7 +146,9 @@ const char *b200_version(void);
  * (default 262144): work lists shorter than this are done completely by every rank instead of being sharded
  * (the repair passes and small active sets are latency-bound; an exchange per pass costs more than it saves).
  * "compact_exchange" (default 1): SIDM results travel between ranks as {uint16 count per slot + the few
- * scatter proposals} instead of 32-byte records. */
+ * scatter proposals} instead of 32-byte records.  "cand_cap" (default 1024): candidates kept per slot in the
+ * ReferenceNgbOrder parity mode (the search cube of a particle in the outskirts can clip the dense centre);
+ * more than that returns B200_ERR_NGBOVERFLOW like the reference's endrun(78). */
 int  b200_set_option(const char *name, int value);
 
 /* ---- particle state -------------------------------------------------------------- */

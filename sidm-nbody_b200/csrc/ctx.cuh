@@ -31,6 +31,7 @@ struct Ctx {
   bool opt_compact_exchange = true;   // option "compact_exchange": 2.5-byte instead of 32-byte slot records between ranks
   int opt_queue_cap = 320;         // = kQCap of sidm.cu; option "queue_cap" lets tests force the queue-overflow fallback
   cudaStream_t coll_stream = nullptr;   // stream the pending collective has to be ordered on
+  int opt_cand_cap = 1024;        // option "cand_cap": per-slot candidate capacity of the reference-order mode (parity runs)
   bool opt_group_search = true;    // b200_set_option("group_search", 0|1): warp-shared neighbour search for all-active passes
   bool overlap_now = false;        // true while the SIDM chain is being issued on stream_sidm
   bool walk_pending = false;       // a deferred walk whose counters / timing are still to be read

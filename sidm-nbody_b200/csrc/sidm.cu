@@ -57,7 +57,6 @@ struct SidmState {
   int2 *groups = nullptr; int *gnode = nullptr, *gflag = nullptr, *gpos = nullptr, *order_leaf = nullptr; int ngroups = 0;
 } S;
 
-constexpr int kCandCap = 1024;      // per-slot candidate capacity in reference-order mode
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
@@ -643,7 +642,7 @@ struct Pass2 {
   const double *kernel;            // begrun.c:968-992 table, 1002 doubles
   int *partner; float *dv; double *prob, *ptot;
   // reference-order mode
-  int ref_order; int *cand; unsigned long long *candkey; int cand_stride; const int *krank, *lrank, *nstart; int *flags;
+  int ref_order; int *cand; unsigned long long *candkey; int cand_stride, cand_cap; const int *krank, *lrank, *nstart; int *flags;
 };
 
 __device__ __forceinline__ double kernel_w(const double *K, double u, double hinv3) {
@@ -731,7 +730,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
     int nc = 0; bool over = false;
     int *cl = P.cand + t; unsigned long long *ck = P.candkey + t; const int st = P.cand_stride;
     range_search(P.C, valid, start, p.x, p.y, p.z, h, [&](int L, const float4 &, float, bool bulk, int node) {
-      if (nc >= kCandCap) { over = true; return; }
+      if (nc >= P.cand_cap) { over = true; return; }
       const int o = P.C.leaf_orig[L];
       const unsigned long long key = bulk ? (((unsigned long long)P.nstart[node] << 32) | (unsigned)P.lrank[o])
                                           : ((unsigned long long)P.krank[o] << 32);
@@ -1133,9 +1132,11 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       count_launch(3);
       tot_pass1 += npass;
       const bool ref_order = g.par.ReferenceNgbOrder != 0;
-      const int chunk = ref_order ? 131072 : npass;
+      // reference-order mode: per-slot candidate lists in scratch (option "cand_cap" entries each), about 1.6 GB at most
+      const int cand_cap = g.opt_cand_cap;
+      const int chunk = ref_order ? (int)(((size_t)131072 * 1024 / cand_cap + 127) / 128 * 128) : npass;
       if (ref_order && npass > 0) {
-        const size_t need = (size_t)(npass < chunk ? npass : chunk) * kCandCap;
+        const size_t need = (size_t)(npass < chunk ? npass : chunk) * cand_cap;
         if (g.s_cand_cap < need) {
           if (g.s_cand) cudaFree(g.s_cand); if (g.s_candkey) cudaFree(g.s_candkey);
           g.s_cand = nullptr; g.s_candkey = nullptr; g.s_cand_cap = 0;
@@ -1153,7 +1154,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         P2.pl_n = g.par.CrossSectionPowLaw; P2.pl_v0 = g.par.CrossSectionVelScale; P2.kernel = d_kernel_table;
         P2.extra = d_rx; P2.extra_off = d_ro;
         P2.partner = g.s_partner; P2.dv = g.s_dv; P2.prob = g.s_prob; P2.ptot = S.ptot;
-        P2.ref_order = ref_order; P2.cand = g.s_cand; P2.candkey = g.s_candkey; P2.cand_stride = nc;
+        P2.ref_order = ref_order; P2.cand = g.s_cand; P2.candkey = g.s_candkey; P2.cand_stride = nc; P2.cand_cap = cand_cap;
         P2.krank = g.krank; P2.lrank = g.lrank; P2.nstart = g.nstart; P2.flags = g.d_flags;
         k_pass2<<<cdiv(nc, 128), 128, 0, st>>>(P2);
         count_launch();

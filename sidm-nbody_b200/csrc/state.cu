@@ -73,6 +73,7 @@ extern "C" int b200_set_option(const char *name, int value) {
   if (!strcmp(name, "shard_overlap")) { g.opt_shard_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "shard_min_work")) { g.shard_min_work = value; return B200_OK; }
   if (!strcmp(name, "compact_exchange")) { g.opt_compact_exchange = value != 0; return B200_OK; }
+  if (!strcmp(name, "cand_cap")) { g.opt_cand_cap = value < 64 ? 64 : (value > (1 << 20) ? (1 << 20) : value); return B200_OK; }
   if (!strcmp(name, "queue_cap")) { g.opt_queue_cap = value < 2 ? 2 : (value > 320 ? 320 : value); return B200_OK; }
   return B200_ERR_ARG;
 }

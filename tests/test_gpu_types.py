@@ -92,3 +92,70 @@ def test_smoothing_lengths_and_step_three_types(world):
     assert rel_rms(acc.astype(np.float64), R.get("ACCEL").astype(np.float64)) < 1e-4
     assert np.array_equal(ngb, R.get("NGB"))
     assert (hh == R.get("HSML")).mean() > 0.999
+
+
+def test_scatter_replay_three_types(world):
+    """sidm() with three types: neighbours and partners come from the particle's own type only (sidm.c:319-330,
+    one search tree per type), slots in exported-first order with DomainMin/Max of the particle's type.  The
+    reference's own random numbers are replayed: its draw log is split into per-slot uniforms and directions
+    with the P_max / total probability the GPU reports per slot (a mismatch derails the split and fails)."""
+    R, hp, types = world["R"], world["hp"], world["types"]
+    pos, vel, mass, ids = world["pos"], world["vel"], world["mass"], world["ids"]
+    SIG, DT = 20.89, 0.02
+    R.setup(N, CrossSectionInternal=SIG)
+    for t, e in EPS.items():
+        R.set_softening(t, e)
+    R.init_rand(55)
+    R.set_particles(pos, vel, mass, ids)
+    R.set("TYPE", types)
+    R.treebuild()
+    R.setup_smoothinglengths_sidm(30)
+    h = R.get("HSML")
+    R.all_active(0.0, DT)
+    t = R.time
+    vmax = R.getvmax()
+    R.rng_log_begin(4 * N + 1000)
+    R.sidm()
+    log = R.rng_log_end()
+    dv_ref, ngb_ref = R.get("DVEL"), R.get("NGB")
+    nscat = int((np.abs(dv_ref).sum(1) > 0).sum())
+    assert nscat >= 10, "fixture too quiet"
+    act = np.arange(N, dtype=np.int32)
+    hp.set_params(CrossSectionInternal=SIG)
+    hp.set_option("cand_cap", 16384)       # pass A runs every slot through pass 2: a search cube in the outskirts can clip the centre
+    hp.set_particles(pos, vel, mass, ids, hsml=h, curtime=np.zeros(N, np.float32), dvel=np.zeros((N, 3), np.float32))
+    hp.set_field("ptype", types)
+    hp.force_treebuild()
+    # pass A: any uniforms, only to read P_max and the total probability of every slot
+    hp.sidm(active=act, time=t, vmax=vmax, replay_rand=np.full(N, 1e-300), replay_dir=np.zeros((N, 3)))
+    sp, pmax, ptot, partner = hp.sidm_debug(N)
+    rand = np.zeros(N)
+    dirs = np.zeros((N, 3))
+    k = 0
+    for s in range(N):                      # split the reference's draw log (sidm.c:341, sidm_rand.h:24-37)
+        assert k < len(log), f"draw log exhausted at slot {s}"
+        u = log[k]
+        k += 1
+        rand[s] = u
+        if pmax[s] < u or not (ptot[s] >= u):
+            continue
+        while True:
+            y1 = 1.0 - 2.0 * log[k]
+            y2 = 1.0 - 2.0 * log[k + 1]
+            k += 2
+            r2 = y1 * y1 + y2 * y2
+            if r2 <= 1.0:
+                break
+        sq = np.sqrt(1.0 - r2)
+        dirs[s] = (2.0 * y1 * sq, 2.0 * y2 * sq, 1.0 - 2.0 * r2)
+    assert k == len(log), (k, len(log))     # every draw accounted for
+    hp.set_particles(hsml=h, dvel=np.zeros((N, 3), np.float32), curtime=np.zeros(N, np.float32))
+    hp.sidm(active=act, time=t, vmax=vmax, replay_rand=rand, replay_dir=dirs)
+    sp, pmax, ptot, partner = hp.sidm_debug(N)
+    hit = partner >= 0
+    assert hit.sum() >= 5
+    assert np.array_equal(types[sp[hit]], types[partner[hit]]), "a pair across particle types"
+    dv, ngb = hp.get("dVel", "NgbVelDisp")
+    assert np.array_equal(ngb, ngb_ref), "neighbour counts"
+    assert np.array_equal(dv != 0, dv_ref != 0), "who scattered"
+    np.testing.assert_allclose(dv, dv_ref, rtol=3e-6, atol=1e-30)
