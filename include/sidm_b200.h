@@ -240,6 +240,18 @@ int  b200_find_timesteps(const int *active, int nactive, int mode, double time, 
  * P[].Potential on the device (downloaded when the layout binds it) and, if not NULL, pot_out[n].
  * Periodic boxes add ewald_pot_corr() (ewald.c:246-285) per interaction. */
 int  b200_compute_potential(float *pot_out);
+/* compute_global_quantities_of_system(), global.c:18-135 ("next" row f2): mass, kinetic and potential energy,
+ * momentum, angular momentum and centre of mass per particle type and in total, from PosPred / VelPred / Mass /
+ * Potential / Type on the device (P[].Potential as the last b200_compute_potential left it).  The struct has the
+ * layout of the reference's `struct state_of_system` (allvars.h:517-537) so that a drop-in can copy it into
+ * SysState.  Products are formed in float like the reference's expressions, sums in double (tree order instead
+ * of particle order: equal to rounding of the double sums).  EnergyInt is 0 (no gas on this path). */
+typedef struct b200_sysstate {
+  double Mass, EnergyKin, EnergyPot, EnergyInt, EnergyTot, Momentum[4], AngMomentum[4], CenterOfMass[4];
+  double MassComp[5], EnergyKinComp[5], EnergyPotComp[5], EnergyIntComp[5], EnergyTotComp[5];
+  double MomentumComp[5][4], AngMomentumComp[5][4], CenterOfMassComp[5][4];
+} b200_sysstate;
+int  b200_compute_global_quantities(b200_sysstate *out);
 /* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
 int  b200_potential_raw(const int *targets, int n, double *pot_out);
 /* host -> device copy into a named internal buffer (see b200_device_buffer), e.g. "maxpred" */

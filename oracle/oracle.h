@@ -99,4 +99,13 @@ int    oreflect(int nactive, const int *active, double radius, const float *pos,
 typedef struct otimestep { int crit; double eta, velscale, probtol, dyntol, dtmax, dtmin; } otimestep;
 int    ofind_timesteps(const oparams *p, const otimestep *ts, int nactive, const int *active, int mode, double time, double vmax,
                        const float *accel, const float *curtime, float *maxpred, const float *hsml, const float *mass, const double *jitter);
+/* compute_global_quantities_of_system(), global.c:18-135, one rank, no gas: per-type and total mass, energies,
+ * momentum, angular momentum, centre of mass.  Field order of `struct state_of_system` (allvars.h:517-537). */
+typedef struct osysstate {
+  double Mass, EnergyKin, EnergyPot, EnergyInt, EnergyTot, Momentum[4], AngMomentum[4], CenterOfMass[4];
+  double MassComp[5], EnergyKinComp[5], EnergyPotComp[5], EnergyIntComp[5], EnergyTotComp[5];
+  double MomentumComp[5][4], AngMomentumComp[5][4], CenterOfMassComp[5][4];
+} osysstate;
+void   oglobal_quantities(int n, const float *pospred, const float *velpred, const float *mass, const float *potential,
+                          const int *type, osysstate *out);
 #endif

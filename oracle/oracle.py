@@ -67,6 +67,20 @@ def lib():
     return _lib
 
 
+def global_quantities(pospred, velpred, mass, potential, types=None):
+    """compute_global_quantities_of_system(), global.c:18-135: SysState as a flat array of 102 doubles
+    (field order of allvars.h:517-537)"""
+    L = lib()
+    pp = np.ascontiguousarray(pospred, np.float32); vp = np.ascontiguousarray(velpred, np.float32)
+    m = np.ascontiguousarray(mass, np.float32); pot = np.ascontiguousarray(potential, np.float32)
+    ty = None if types is None else np.ascontiguousarray(types, np.int32)
+    out = np.zeros(102, np.float64)
+    L.oglobal_quantities.argtypes = [C.c_int] + [C.c_void_p] * 6
+    L.oglobal_quantities.restype = None
+    L.oglobal_quantities(len(m), _p(pp), _p(vp), _p(m), _p(pot), None if ty is None else _p(ty), _p(out))
+    return out
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

@@ -462,3 +462,41 @@ float ongb_treefind(const otree *t, const float xyz[3], int desngb)   /* forcetr
 }
 
 const float *otree_positions(const otree *t) { return t->pos; }
+
+/* ---- global quantities (global.c:18-135) -------------------------------------------------------
+ * Particle order, float products and double sums exactly as the reference's expressions. */
+static void onorm3(double *v) { v[3] = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+void oglobal_quantities(int n, const float *pp, const float *vp, const float *mass, const float *potential,
+                        const int *type, osysstate *S)
+{
+  memset(S, 0, sizeof(*S));
+  for (int i = 0; i < n; i++) {
+    const int t = type ? type[i] : 1;
+    const float m = mass[i];
+    const float *x = pp + 3 * (size_t)i, *v = vp + 3 * (size_t)i;
+    if (t < 0 || t > 4) continue;
+    S->MassComp[t] += m;                                                         /* :33 */
+    S->EnergyPotComp[t] += 0.5 * m * potential[i];                               /* :35 */
+    S->EnergyKinComp[t] += 0.5 * m * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);  /* :40-42 */
+    for (int j = 0; j < 3; j++) {                                                /* :44-48 */
+      S->MomentumComp[t][j] += m * v[j];
+      S->CenterOfMassComp[t][j] += m * x[j];
+    }
+    S->AngMomentumComp[t][0] += m * (x[1] * v[2] - x[2] * v[1]);                 /* :50-55 */
+    S->AngMomentumComp[t][1] += m * (x[2] * v[0] - x[0] * v[2]);
+    S->AngMomentumComp[t][2] += m * (x[0] * v[1] - x[1] * v[0]);
+  }
+  for (int i = 0; i < 5; i++) {                                                  /* :71-93 */
+    S->EnergyTotComp[i] = S->EnergyKinComp[i] + S->EnergyPotComp[i] + S->EnergyIntComp[i];
+    S->Mass += S->MassComp[i]; S->EnergyKin += S->EnergyKinComp[i]; S->EnergyPot += S->EnergyPotComp[i];
+    S->EnergyInt += S->EnergyIntComp[i]; S->EnergyTot += S->EnergyTotComp[i];
+    for (int j = 0; j < 3; j++) {
+      S->Momentum[j] += S->MomentumComp[i][j]; S->AngMomentum[j] += S->AngMomentumComp[i][j];
+      S->CenterOfMass[j] += S->CenterOfMassComp[i][j];
+    }
+  }
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 3; j++) if (S->MassComp[i] > 0) S->CenterOfMassComp[i][j] /= S->MassComp[i];
+  for (int j = 0; j < 3; j++) if (S->Mass > 0) S->CenterOfMass[j] /= S->Mass;    /* :95-102 */
+  for (int i = 0; i < 5; i++) { onorm3(S->CenterOfMassComp[i]); onorm3(S->MomentumComp[i]); onorm3(S->AngMomentumComp[i]); }
+  onorm3(S->CenterOfMass); onorm3(S->Momentum); onorm3(S->AngMomentum);          /* :104-130 */
+}

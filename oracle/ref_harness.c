@@ -355,6 +355,8 @@ void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
 /* several particle types (one tree per type, forcetree.c:90-158): softening per type; types go in through ref_set_field(F_TYPE) */
 void ref_set_softening(int type, double eps) { All.SofteningTable[type] = All.SofteningTableMaxPhys[type] = eps; }
+/* global.c:18: SysState as 102 doubles (allvars.h:517-537) */
+int ref_global_quantities(double *out) { compute_global_quantities_of_system(); memcpy(out, &SysState, sizeof(SysState)); return (int)(sizeof(SysState) / sizeof(double)); }
 #ifdef REFLECTIONBOUNDARY
 void ref_reflect(double radius) { All.ReflectionRadius = radius; reflect(); All.ReflectionRadius = 1e30; }   /* reflection.c:7 */
 #endif

@@ -246,6 +246,12 @@ class Reference:
         self.lib.ref_reflect.argtypes = [C.c_double]
         self.lib.ref_reflect(float(radius))
 
+    def global_quantities(self):
+        """compute_global_quantities_of_system(), global.c:18: SysState as a flat array of 102 doubles"""
+        out = np.zeros(128, np.float64)
+        n = self.lib.ref_global_quantities(out.ctypes)
+        return out[:n]
+
     def set_softening(self, ptype, eps):
         self.lib.ref_set_softening.argtypes = [C.c_int, C.c_double]
         self.lib.ref_set_softening(int(ptype), float(eps))

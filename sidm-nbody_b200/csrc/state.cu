@@ -744,6 +744,82 @@ extern "C" int b200_getvmax(double *vmax) {
   return B200_OK;
 }
 
+// ----------------------------------------------------------------------------- global quantities
+// compute_global_quantities_of_system(), global.c:18-135.  12 sums per particle type: mass, E_kin, E_pot,
+// momentum[3], angular momentum[3], mass-weighted position[3].  One pass per type present (one in every BASELINE
+// config); per-thread double accumulators over a grid-stride loop, warp shuffle + shared-memory block reduction,
+// per-block partials summed in block order by the host: deterministic, no atomics.  Streaming, 48 B per particle.
+constexpr int kGQ = 12, kGQBlocks = 296;
+__global__ void __launch_bounds__(256) k_global_quantities(int n, int type, const float4 *posm, const float *velpred, const float *potential,
+                                                           const int *ptype, double *part) {
+  double a[kGQ];
+  for (int k = 0; k < kGQ; k++) a[k] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if ((ptype[i] & 7) != type) continue;
+    const float4 p = posm[i];
+    const float vx = velpred[3 * (size_t)i], vy = velpred[3 * (size_t)i + 1], vz = velpred[3 * (size_t)i + 2];
+    const float m = p.w;
+    a[0] += (double)m;                                                           // global.c:33
+    a[2] += 0.5 * (double)m * (double)potential[i];                              // :35
+    const float v2 = fadd(fadd(fmul(vx, vx), fmul(vy, vy)), fmul(vz, vz));       // float expression, :40-42
+    a[1] += 0.5 * (double)m * (double)v2;
+    a[3] += (double)fmul(m, vx); a[4] += (double)fmul(m, vy); a[5] += (double)fmul(m, vz);          // :46
+    a[9] += (double)fmul(m, p.x); a[10] += (double)fmul(m, p.y); a[11] += (double)fmul(m, p.z);     // :47
+    a[6] += (double)fmul(m, fadd(fmul(p.y, vz), -fmul(p.z, vy)));                // :50-55
+    a[7] += (double)fmul(m, fadd(fmul(p.z, vx), -fmul(p.x, vz)));
+    a[8] += (double)fmul(m, fadd(fmul(p.x, vy), -fmul(p.y, vx)));
+  }
+  __shared__ double sm[8][kGQ];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = 0; k < kGQ; k++) {
+    double v = a[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kGQ) {
+    double v = 0;
+    for (int q = 0; q < 8; q++) v += sm[q][threadIdx.x];
+    part[(size_t)blockIdx.x * kGQ + threadIdx.x] = v;
+  }
+}
+
+extern "C" int b200_compute_global_quantities(b200_sysstate *out) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  if (!out) return B200_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  double *part = g.d_acc;                                   // scratch: 296 x 12 doubles
+  static double h[kGQBlocks * kGQ];
+  for (int t = 0; t < 5; t++) {                             // types 0..4 as global.c:24 (type 5 is not summed there either)
+    if (!g.types_dirty && g.type_count[t] == 0) continue;
+    k_global_quantities<<<kGQBlocks, 256, 0, g.stream>>>(g.n, t, g.posm, g.velpred, g.potential, g.ptype, part);
+    count_launch();
+    CUDA_TRY(cudaMemcpyAsync(h, part, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    double s[kGQ];
+    for (int k = 0; k < kGQ; k++) { s[k] = 0; for (int b = 0; b < kGQBlocks; b++) s[k] += h[b * kGQ + k]; }
+    out->MassComp[t] = s[0]; out->EnergyKinComp[t] = s[1]; out->EnergyPotComp[t] = s[2];
+    for (int j = 0; j < 3; j++) { out->MomentumComp[t][j] = s[3 + j]; out->AngMomentumComp[t][j] = s[6 + j]; out->CenterOfMassComp[t][j] = s[9 + j]; }
+  }
+  CUDA_TRY(cudaGetLastError());
+  // totals, centre-of-mass normalisation and vector norms, global.c:71-130
+  for (int i = 0; i < 5; i++) {
+    out->EnergyTotComp[i] = out->EnergyKinComp[i] + out->EnergyPotComp[i] + out->EnergyIntComp[i];
+    out->Mass += out->MassComp[i]; out->EnergyKin += out->EnergyKinComp[i]; out->EnergyPot += out->EnergyPotComp[i];
+    out->EnergyInt += out->EnergyIntComp[i]; out->EnergyTot += out->EnergyTotComp[i];
+    for (int j = 0; j < 3; j++) {
+      out->Momentum[j] += out->MomentumComp[i][j]; out->AngMomentum[j] += out->AngMomentumComp[i][j];
+      out->CenterOfMass[j] += out->CenterOfMassComp[i][j];
+    }
+  }
+  for (int i = 0; i < 5; i++) for (int j = 0; j < 3; j++) if (out->MassComp[i] > 0) out->CenterOfMassComp[i][j] /= out->MassComp[i];
+  for (int j = 0; j < 3; j++) if (out->Mass > 0) out->CenterOfMass[j] /= out->Mass;
+  auto norm3 = [](double *v) { v[3] = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+  for (int i = 0; i < 5; i++) { norm3(out->CenterOfMassComp[i]); norm3(out->MomentumComp[i]); norm3(out->AngMomentumComp[i]); }
+  norm3(out->CenterOfMass); norm3(out->Momentum); norm3(out->AngMomentum);
+  return B200_OK;
+}
+
 // ----------------------------------------------------------------------------- counters / buffers
 
 extern "C" int b200_get_counters(b200_counters *c) {

@@ -82,7 +82,6 @@ __global__ void k_gather_lo(int n, const int *sidx, const uint64_t *lo, uint64_t
 __global__ void k_fix_ties(int n, const uint64_t *shi, uint64_t *slo, int *sidx, const unsigned char *stype) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n - 1) return;
-  const uint64_t h = shi[j];
   auto same = [&](int a, int b) { return shi[a] == shi[b] && (!stype || stype[a] == stype[b]); };   // runs never cross a type boundary
   if ((j > 0 && same(j - 1, j)) || !same(j + 1, j)) return;   // not the start of a run
   int e = j + 1;

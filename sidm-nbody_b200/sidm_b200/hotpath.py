@@ -138,6 +138,14 @@ class HotPath:
         check(self.lib.b200_compute_potential(ptr(out)), "b200_compute_potential")
         return out
 
+    def compute_global_quantities_of_system(self):
+        """global.c:18: SysState (energies, momenta, centre of mass per type and in total) from the device state;
+        P[].Potential as the last compute_potential() left it"""
+        from .capi import SysState
+        st = SysState()
+        check(self.lib.b200_compute_global_quantities(C.byref(st)), "b200_compute_global_quantities")
+        return st
+
     def force_treeevaluate_potential(self, targets):
         t = _i32(targets)
         out = np.empty(len(t), np.float64)

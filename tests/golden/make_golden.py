@@ -89,5 +89,34 @@ def main():
     print("wrote hernquist3k.npz:", len(nd["len"]), "nodes,", len(log), "scatter events,", len(draws), "draws")
 
 
+def main_global():
+    """global3k.npz: compute_potential() + compute_global_quantities_of_system() (potential.c:18, global.c:18) on the
+    same halo half a step into a run (PosPred != Pos), with three particle types of different softening."""
+    pos, vel, mass, ids = ic.hernquist(N, seed=11)
+    types = np.random.default_rng(12).choice(np.array([1, 2, 3], np.int32), N, p=[0.6, 0.3, 0.1]).astype(np.int32)
+    eps = {1: 0.3, 2: 0.6, 3: 0.2}
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    R = refdrv.Reference("diag")
+    R.setup(N, CrossSectionInternal=0.0)
+    for t, e in eps.items():
+        R.set_softening(t, e)
+    R.set_particles(pos, vel, mass, ids)
+    R.set("TYPE", types)
+    R.all_active(0.0, 0.0)
+    R.getvmax()
+    R.compute_accelerations(1)
+    R.compute_potential()
+    sys_state = R.global_quantities()
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "global3k.npz"), types=types, eps=np.array([0, 0.3, 0.6, 0.2, 0, 0]),
+                        pospred=R.get("POSPRED"), velpred=R.get("VELPRED"), mass=R.get("MASS"), oldacc=R.get("OLDACC"),
+                        pot=R.get("POT"), sys=sys_state)
+    print("wrote global3k.npz: E_kin", sys_state[1], "E_pot", sys_state[2])
+
+
 if __name__ == "__main__":
-    main()
+    if "global" in sys.argv[1:]:
+        main_global()
+    else:
+        main()

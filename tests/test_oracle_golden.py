@@ -106,3 +106,14 @@ def _check_stream(res, draws):
             sq = np.sqrt(1.0 - r2)
             assert np.allclose(res["dir"][s], [2 * y1 * sq, 2 * y2 * sq, 1 - 2 * r2], rtol=0, atol=1e-15)
     assert pos == len(draws)
+
+
+def test_global_quantities_golden():
+    """compute_global_quantities_of_system() (global.c:18-135) with three particle types: the 102 doubles of the
+    reference's SysState, bit for bit (fixture: make_golden.py global)"""
+    import oracle
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "global3k.npz")))
+    got = oracle.global_quantities(g["pospred"], g["velpred"], g["mass"], g["pot"], g["types"])
+    assert np.array_equal(got, g["sys"])
+    # virial sanity of the fixture itself: a Hernquist halo in equilibrium, 2T + W ~ 0
+    assert abs(2 * g["sys"][1] + g["sys"][2]) < 0.15 * abs(g["sys"][2])

@@ -81,3 +81,19 @@ def test_potential(pair):
     assert np.array_equal(R.potential(idx), O.potential(idx, old)[0])
     R.compute_potential()
     assert np.array_equal(R.get("POT"), O.potential(np.arange(N, dtype=np.int32), old)[1])
+
+
+def test_global_quantities(pair):
+    """compute_global_quantities_of_system() (global.c:18-135) after compute_potential(): every one of the 102
+    doubles of SysState bit for bit, with one and with three particle types"""
+    import oracle
+    R, O, pos = pair
+    R.compute_potential()
+    for types in (np.ones(N, np.int32), np.random.default_rng(8).choice(np.array([1, 2, 4], np.int32), N)):
+        R.set("TYPE", types)
+        ref = R.global_quantities()
+        assert len(ref) == 102
+        got = oracle.global_quantities(R.get("POSPRED"), R.get("VELPRED"), R.get("MASS"), R.get("POT"), types)
+        assert np.array_equal(got, ref)
+        assert ref[0] > 0 and ref[1] > 0 and ref[2] < 0          # Mass, EnergyKin, EnergyPot
+    R.set("TYPE", np.ones(N, np.int32))
