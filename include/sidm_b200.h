@@ -50,6 +50,8 @@ extern "C" {
                                      (forcetree.c:320-326), which cannot be reproduced */
 #define B200_ERR_TYPES      9006  /* particle types changed behind the library's back (set them through b200_set_field / b200_upload) */
 
+#define B200_ERR_IO         9007  /* snapshot file could not be opened / written (io.c:98-102 endrun(10), io.c:594-605) */
+
 /* The `All` fields the path reads (allvars.h:164-420).  Filled by the shim from `All`. */
 typedef struct b200_params {
   int    device;                   /* CUDA device ordinal (rank-local)                 */
@@ -252,6 +254,16 @@ typedef struct b200_sysstate {
   double MomentumComp[5][4], AngMomentumComp[5][4], CenterOfMassComp[5][4];
 } b200_sysstate;
 int  b200_compute_global_quantities(b200_sysstate *out);
+/* savepositions(), io.c:16-590 ("next" row f3): one snapshot file in GADGET format 1 (NumFilesPerSnapshot = 1) written
+ * from the device state - header (struct io_header_1, allvars.h:727-746), then PosPred, VelPred, ID and the masses of
+ * the types whose mass_table entry is 0, particles in TYPE order and particle order inside a type, every block
+ * between 4-byte length markers; positions wrapped into [0, BoxSize] in periodic runs (io.c:275-283).  The blocks
+ * are gathered on the device and streamed to the file through pinned buffers; the host AoS is not touched.
+ * `time` = All.Time, `mass_table` = All.MassTable[6] (NULL: all 0), `hubble_param` = All.HubbleParam; BoxSize / Omega0 /
+ * OmegaLambda / ComovingIntegrationOn come from b200_params.  npart_out[6] (may be NULL) = header1.npart.  Byte-identical
+ * to the file the reference writes from the same state.  Gas particles (type 0: u / rho / hsml blocks) are not on
+ * this path: B200_ERR_ARG.  The 84 fill bytes of the header are zero (the reference leaves what read_ic() put there). */
+int  b200_savepositions(const char *path, double time, const double *mass_table, double hubble_param, int *npart_out);
 /* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
 int  b200_potential_raw(const int *targets, int n, double *pot_out);
 /* host -> device copy into a named internal buffer (see b200_device_buffer), e.g. "maxpred" */

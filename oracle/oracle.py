@@ -81,6 +81,75 @@ def global_quantities(pospred, velpred, mass, potential, types=None):
     return out
 
 
+def snapshot_bytes(pospred, velpred, ids, mass, types=None, time=0.0, mass_table=None, box=0.0, omega0=0.0,
+                   omega_lambda=0.0, hubble_param=0.0, comoving=False, periodic=False):
+    """savepositions_ioformat1(), io.c:54-590, one rank, one file, no gas: the bytes of the snapshot file.
+    Header struct io_header_1 (allvars.h:727-746, fill bytes zero), then PosPred, VelPred, ID, and the masses of the types
+    whose MassTable entry is 0 - particles in type order (0..4; type 5 is not written, io.c:265), particle order
+    inside a type - every block between int32 byte counts (io.c:207-210,261-262,576-578)."""
+    pp = np.ascontiguousarray(pospred, np.float32).copy(); vp = np.ascontiguousarray(velpred, np.float32)
+    ids = np.ascontiguousarray(ids, np.int32); m = np.ascontiguousarray(mass, np.float32)
+    ty = np.ones(len(m), np.int32) if types is None else np.ascontiguousarray(types, np.int32)
+    mt = np.zeros(6) if mass_table is None else np.asarray(mass_table, np.float64)
+    if periodic:                                                    # io.c:275-283, float += double, one wrap per trip
+        b = np.float64(box)
+        for _ in range(64):
+            lo = pp < 0
+            if not lo.any():
+                break
+            pp[lo] = (pp[lo].astype(np.float64) + b).astype(np.float32)
+        for _ in range(64):
+            hi = pp.astype(np.float64) > b
+            if not hi.any():
+                break
+            pp[hi] = (pp[hi].astype(np.float64) - b).astype(np.float32)
+    order = np.concatenate([np.nonzero(ty == t)[0] for t in range(5)])
+    cnt = np.array([(ty == t).sum() for t in range(5)] + [0], np.int32)
+    assert cnt[0] == 0, "gas blocks are not part of this path"
+    hdr = np.zeros(1, np.dtype([("npart", "<i4", 6), ("mass", "<f8", 6), ("time", "<f8"), ("redshift", "<f8"),
+                                ("flag_sfr", "<i4"), ("flag_feedback", "<i4"), ("npartTotal", "<i4", 6),
+                                ("flag_cooling", "<i4"), ("num_files", "<i4"), ("BoxSize", "<f8"), ("Omega0", "<f8"),
+                                ("OmegaLambda", "<f8"), ("HubbleParam", "<f8"), ("flag_multiphase", "<i4"),
+                                ("flag_stellarage", "<i4"), ("flag_sfrhistogram", "<i4"), ("fill", "S84")]))
+    assert hdr.itemsize == 256
+    hdr["npart"] = cnt; hdr["npartTotal"] = cnt; hdr["mass"] = mt; hdr["time"] = time
+    hdr["redshift"] = (1.0 / time - 1) if comoving else 0.0
+    hdr["num_files"] = 1; hdr["BoxSize"] = box; hdr["Omega0"] = omega0; hdr["OmegaLambda"] = omega_lambda
+    hdr["HubbleParam"] = hubble_param
+    withmass = np.concatenate([np.nonzero(ty == t)[0] for t in range(5) if mt[t] == 0] + [np.zeros(0, np.int64)]).astype(np.int64)
+
+    def rec(payload):
+        if len(payload) == 0:
+            return b""
+        mark = np.array([len(payload)], np.uint32).astype(np.int32, casting="unsafe").tobytes() if len(payload) >= 2**31 \
+            else np.array([len(payload)], np.int32).tobytes()
+        return mark + payload + mark
+    return (rec(hdr.tobytes()) + rec(pp[order].tobytes()) + rec(vp[order].tobytes()) + rec(ids[order].tobytes())
+            + rec(m[withmass].tobytes()))
+
+
+def read_snapshot(path):
+    """format-1 reader for round trips (read_ic.c:32-481 block order): header fields, pos, vel, id, mass (None if absent)"""
+    raw = open(path, "rb").read()
+    o = 0
+
+    def block():
+        nonlocal o
+        nb = int(np.frombuffer(raw, "<i4", 1, o)[0]); o += 4
+        body = raw[o:o + nb]; o += nb
+        assert int(np.frombuffer(raw, "<i4", 1, o)[0]) == nb; o += 4
+        return body
+    h = block()
+    npart = np.frombuffer(h, "<i4", 6, 0); mt = np.frombuffer(h, "<f8", 6, 24); time = float(np.frombuffer(h, "<f8", 1, 72)[0])
+    n = int(npart.sum())
+    pos = np.frombuffer(block(), "<f4").reshape(n, 3); vel = np.frombuffer(block(), "<f4").reshape(n, 3)
+    ids = np.frombuffer(block(), "<i4")
+    nm = int(sum(npart[t] for t in range(6) if mt[t] == 0))
+    mass = np.frombuffer(block(), "<f4") if nm > 0 else None
+    assert o == len(raw)
+    return dict(npart=npart.copy(), mass_table=mt.copy(), time=time, pos=pos, vel=vel, ids=ids, mass=mass)
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

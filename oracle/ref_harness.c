@@ -357,6 +357,15 @@ void ref_advance(void) { advance(); }
 void ref_set_softening(int type, double eps) { All.SofteningTable[type] = All.SofteningTableMaxPhys[type] = eps; }
 /* global.c:18: SysState as 102 doubles (allvars.h:517-537) */
 int ref_global_quantities(double *out) { compute_global_quantities_of_system(); memcpy(out, &SysState, sizeof(SysState)); return (int)(sizeof(SysState) / sizeof(double)); }
+/* savepositions(), io.c:16: one file <dir><base>_<num> in format 1 */
+void ref_savepositions(int num, const char *dir, const char *base, const double *mass_table, double hubble_param)
+{
+  strcpy(All.OutputDir, dir); strcpy(All.SnapshotFileBase, base);
+  All.NumFilesPerSnapshot = 1; All.CoolingOn = 0; All.StarformationOn = 0; All.MultiPhaseModelOn = 0;
+  for (int t = 0; t < 6; t++) All.MassTable[t] = mass_table[t];
+  All.HubbleParam = hubble_param;
+  savepositions(num);
+}
 #ifdef REFLECTIONBOUNDARY
 void ref_reflect(double radius) { All.ReflectionRadius = radius; reflect(); All.ReflectionRadius = 1e30; }   /* reflection.c:7 */
 #endif

@@ -252,6 +252,14 @@ class Reference:
         n = self.lib.ref_global_quantities(out.ctypes)
         return out[:n]
 
+    def savepositions(self, num, outdir, base="snap", mass_table=None, hubble_param=0.0):
+        """savepositions(), io.c:16; returns the path of the file written"""
+        mt = np.zeros(6) if mass_table is None else np.ascontiguousarray(mass_table, np.float64)
+        d = os.path.join(outdir, "")
+        self.lib.ref_savepositions.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_double]
+        self.lib.ref_savepositions(int(num), d.encode(), base.encode(), mt.ctypes, float(hubble_param))
+        return f"{d}{base}_{num:03d}"
+
     def set_softening(self, ptype, eps):
         self.lib.ref_set_softening.argtypes = [C.c_int, C.c_double]
         self.lib.ref_set_softening(int(ptype), float(eps))

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("B200_LIB") or os.path.join(PKG_DIR, "libsidm_b200.so"
 ERRORS = {1: "tree nodes exhausted (forcetree.c:233 endrun(1))", 3: "allocation failed (endrun(3))",
           78: "neighbour list overflow (endrun(78))", 1155: "smoothing-length iteration failed (endrun(1155))",
           9001: "CUDA error", 9002: "no CUDA device - this library has no CPU path", 9003: "bad argument",
-          9004: "bad state / not initialised", 9005: "coincident particles", 9006: "particle types changed behind the library's back"}
+          9004: "bad state / not initialised", 9005: "coincident particles", 9007: "snapshot file could not be opened or written", 9006: "particle types changed behind the library's back"}
 
 
 class B200Error(RuntimeError):
@@ -97,7 +97,7 @@ def layout_of(dtype=PARTICLE_DTYPE):
 
 
 EXPORTS = ["b200_init", "b200_set_params", "b200_finalize", "b200_last_cuda_error", "b200_set_stream", "b200_set_option", "b200_set_shard", "b200_current_stream", "b200_version",
-           "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_upload_shard", "b200_download_shard", "b200_advance", "b200_find_timesteps", "b200_reflect", "b200_set_field", "b200_compute_potential", "b200_compute_global_quantities", "b200_potential_raw", "b200_set_soa", "b200_get_soa", "b200_predict",
+           "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_upload_shard", "b200_download_shard", "b200_advance", "b200_find_timesteps", "b200_reflect", "b200_set_field", "b200_compute_potential", "b200_compute_global_quantities", "b200_savepositions", "b200_potential_raw", "b200_set_soa", "b200_get_soa", "b200_predict",
            "b200_tree_build", "b200_gravity", "b200_sidm", "b200_setup_nbr_sidm", "b200_sidm_ensure_neighbours",
            "b200_setup_smoothinglengths_sidm", "b200_compute_accelerations", "b200_getvmax", "b200_ngb_treefind",
            "b200_direct", "b200_walk_raw", "b200_get_tree", "b200_ngb_lists", "b200_sidm_debug", "b200_get_scatlog",
@@ -142,6 +142,7 @@ def load():
         _lib.b200_set_field.argtypes = [C.c_char_p, C.c_void_p, C.c_longlong]
         _lib.b200_compute_potential.argtypes = [C.c_void_p]
         _lib.b200_compute_global_quantities.argtypes = [C.c_void_p]
+        _lib.b200_savepositions.argtypes = [C.c_char_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p]
         _lib.b200_potential_raw.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.b200_download_to.argtypes = [C.c_void_p]
         _lib.b200_upload_shard.argtypes = [C.c_int, C.c_int, C.c_int]

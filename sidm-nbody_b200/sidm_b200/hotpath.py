@@ -146,6 +146,15 @@ class HotPath:
         check(self.lib.b200_compute_global_quantities(C.byref(st)), "b200_compute_global_quantities")
         return st
 
+    def savepositions(self, path, time=None, mass_table=None, hubble_param=0.0):
+        """savepositions(), io.c:16: GADGET format-1 snapshot file from the device state; returns header1.npart"""
+        t = self.time if time is None else float(time)
+        mt = None if mass_table is None else np.ascontiguousarray(mass_table, np.float64)
+        assert mt is None or mt.size == 6
+        npart = np.zeros(6, np.int32)
+        check(self.lib.b200_savepositions(str(path).encode(), t, ptr(mt), float(hubble_param), ptr(npart)), "b200_savepositions")
+        return npart
+
     def force_treeevaluate_potential(self, targets):
         t = _i32(targets)
         out = np.empty(len(t), np.float64)

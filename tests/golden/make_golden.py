@@ -108,10 +108,17 @@ def main_global():
     R.compute_accelerations(1)
     R.compute_potential()
     sys_state = R.global_quantities()
+    # the snapshot file of this state (savepositions(), io.c:16): type 2 has tabulated masses
+    import hashlib
+    mt = [0, 0, float(2 * mass[0]), 0, 0, 0]
+    snap = open(R.savepositions(3, os.getcwd(), mass_table=mt, hubble_param=0.7), "rb").read()
     os.chdir(cwd)
     np.savez_compressed(os.path.join(HERE, "global3k.npz"), types=types, eps=np.array([0, 0.3, 0.6, 0.2, 0, 0]),
                         pospred=R.get("POSPRED"), velpred=R.get("VELPRED"), mass=R.get("MASS"), oldacc=R.get("OLDACC"),
-                        pot=R.get("POT"), sys=sys_state)
+                        pot=R.get("POT"), sys=sys_state,
+                        ids=R.get("ID"), snap_mass_table=np.array(mt), snap_time=R.time, snap_len=len(snap),
+                        snap_sha256=hashlib.sha256(snap).hexdigest(), snap_head=np.frombuffer(snap[:264], np.uint8),
+                        snap_omega0=R.cfg["Omega0"])
     print("wrote global3k.npz: E_kin", sys_state[1], "E_pot", sys_state[2])
 
 

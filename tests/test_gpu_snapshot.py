@@ -1,0 +1,90 @@
+"""GPU: savepositions() (io.c:16-590) - the GADGET format-1 snapshot written from the device state
+through b200_savepositions, byte for byte against (a) the reference's own file of the golden three-type fixture
+(SHA-256 in tests/golden/global3k.npz) and (b) the oracle's writer, which tests/test_oracle_vs_reference.py pins on
+the files the unmodified reference writes (incl. the -DPERIODIC wrap)."""
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_snapshot_golden_three_types():
+    from sidm_b200 import HotPath
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "global3k.npz")))
+    n = len(g["mass"])
+    out = tempfile.mkdtemp()
+    with HotPath(n, Omega0=float(g["snap_omega0"])) as hp:
+        hp.set_particles(g["pospred"], g["velpred"], g["mass"], g["ids"])
+        hp.set_field("ptype", g["types"])
+        hp.predict_collisionless_only(0.0)
+        path = os.path.join(out, "snap_003")
+        npart = hp.savepositions(path, time=float(g["snap_time"]), mass_table=g["snap_mass_table"], hubble_param=0.7)
+        assert npart.tolist() == [int((g["types"] == t).sum()) for t in range(5)] + [0]
+        raw = open(path, "rb").read()
+        assert len(raw) == int(g["snap_len"])
+        assert raw[:264] == g["snap_head"].tobytes()
+        assert hashlib.sha256(raw).hexdigest() == str(g["snap_sha256"])
+        # error behaviour: unwritable path (io.c:98-102), gas particles (not on this path)
+        from sidm_b200.capi import B200Error
+        with pytest.raises(B200Error) as e:
+            hp.savepositions(os.path.join(out, "no_such_dir", "snap"), time=0.0)
+        assert e.value.code == 9007
+        ty = g["types"].copy(); ty[5] = 0
+        hp.set_field("ptype", ty)
+        with pytest.raises(B200Error) as e:
+            hp.savepositions(path, time=0.0)
+        assert e.value.code == 9003
+
+
+def test_snapshot_mid_run_against_oracle():
+    """3.2e6 particles of one type half a step into a run (PosPred != Pos; the 38 MB blocks cross the 32 MB staging
+    chunks), then the same particles as four types with a type-5 remainder that the file leaves out"""
+    import oracle
+    from sidm_b200 import HotPath, ic
+    n = 3200000
+    pos, vel, mass, ids = ic.hernquist(n, seed=13)
+    out = tempfile.mkdtemp()
+    with HotPath(n) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.compute_accelerations(1, time=0.0, vmax=0.0)
+        hp.predict_collisionless_only(0.003)
+        pp, vp = hp.get("PosPred", "VelPred")
+        assert not np.array_equal(pp, pos)
+        path = os.path.join(out, "snap_000")
+        hp.savepositions(path, time=0.003, hubble_param=0.7)
+        assert open(path, "rb").read() == oracle.snapshot_bytes(pp, vp, ids, mass, None, time=0.003, hubble_param=0.7, omega0=1.0)
+        back = oracle.read_snapshot(path)
+        assert np.array_equal(back["ids"], ids) and np.array_equal(back["pos"], pp) and np.array_equal(back["mass"], mass)
+        types = np.random.default_rng(1).choice(np.array([1, 2, 3, 4, 5], np.int32), n).astype(np.int32)
+        hp.set_field("ptype", types)
+        mt = [0, 0, float(mass[0]), 0, 0.5, 0]
+        npart = hp.savepositions(path, time=0.003, mass_table=mt, hubble_param=0.7)
+        assert npart.sum() == (types != 5).sum()
+        assert open(path, "rb").read() == oracle.snapshot_bytes(pp, vp, ids, mass, types, time=0.003, mass_table=mt, hubble_param=0.7, omega0=1.0)
+
+
+def test_snapshot_periodic_wrap():
+    import oracle
+    from sidm_b200 import HotPath, ic
+    BOX, A = 100.0, 0.25
+    pos, vel, mass, ids = ic.periodic_box(24, seed=4, box=BOX, vel_sigma=60.0)
+    n = len(mass)
+    rng = np.random.default_rng(2)
+    pos = (pos + rng.choice(np.array([0, 0, 0, -BOX, BOX, 2 * BOX], np.float32), (n, 3))).astype(np.float32)
+    out = tempfile.mkdtemp()
+    kw = dict(BoxSize=BOX, PeriodicBoundariesOn=1, SofteningHalo=0.5, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1)
+    with HotPath(n, **kw) as hp:
+        hp.set_particles(pos, vel, mass, ids, curtime=np.full(n, A, np.float32))
+        hp.predict_collisionless_only(A)
+        pp, vp = hp.get("PosPred", "VelPred")
+        path = os.path.join(out, "snap_007")
+        hp.savepositions(path, time=A, mass_table=[0, float(mass[0]), 0, 0, 0, 0], hubble_param=0.7)
+        want = oracle.snapshot_bytes(pp, vp, ids, mass, None, time=A, mass_table=[0, float(mass[0]), 0, 0, 0, 0], box=BOX,
+                                     omega0=0.3, omega_lambda=0.7, hubble_param=0.7, comoving=True, periodic=True)
+        assert open(path, "rb").read() == want
+        back = oracle.read_snapshot(path)
+        assert back["mass"] is None and back["pos"].min() >= 0 and back["pos"].max() <= BOX

@@ -117,3 +117,16 @@ def test_global_quantities_golden():
     assert np.array_equal(got, g["sys"])
     # virial sanity of the fixture itself: a Hernquist halo in equilibrium, 2T + W ~ 0
     assert abs(2 * g["sys"][1] + g["sys"][2]) < 0.15 * abs(g["sys"][2])
+
+
+def test_snapshot_golden():
+    """savepositions() (io.c:16-590): the oracle's format-1 writer reproduces the reference's snapshot file of the
+    three-type fixture (header bytes and the SHA-256 of the whole file)"""
+    import hashlib
+    import oracle
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "global3k.npz")))
+    got = oracle.snapshot_bytes(g["pospred"], g["velpred"], g["ids"], g["mass"], g["types"], time=float(g["snap_time"]),
+                                mass_table=g["snap_mass_table"], hubble_param=0.7, omega0=float(g["snap_omega0"]))
+    assert len(got) == int(g["snap_len"])
+    assert got[:264] == g["snap_head"].tobytes()
+    assert hashlib.sha256(got).hexdigest() == str(g["snap_sha256"])

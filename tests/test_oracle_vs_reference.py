@@ -97,3 +97,59 @@ def test_global_quantities(pair):
         assert np.array_equal(got, ref)
         assert ref[0] > 0 and ref[1] > 0 and ref[2] < 0          # Mass, EnergyKin, EnergyPot
     R.set("TYPE", np.ones(N, np.int32))
+
+
+def test_snapshot_file_bytes(pair, refdrv_mod):
+    """savepositions() (io.c:16-590): the oracle's snapshot writer against the file the reference writes - one type
+    with and without a MassTable entry, three types of which one has tabulated masses"""
+    import oracle
+    R, O, pos = pair
+    out = tempfile.mkdtemp()
+    R.all_active(0.0, 0.004)
+    R.getvmax()
+    R.compute_accelerations(0)                       # PosPred / VelPred half a step ahead of Pos / Vel
+    pp, vp, ids, m = R.get("POSPRED"), R.get("VELPRED"), R.get("ID"), R.get("MASS")
+    assert not np.array_equal(pp, R.get("POS"))
+    three = np.random.default_rng(8).choice(np.array([1, 2, 4], np.int32), N)
+    cases = [(np.ones(N, np.int32), None), (np.ones(N, np.int32), [0, float(m[0]), 0, 0, 0, 0]), (three, [0, 0, 0.25, 0, 0, 0])]
+    for k, (types, mt) in enumerate(cases):
+        R.set("TYPE", types)
+        path = R.savepositions(k, out, mass_table=mt, hubble_param=0.7)
+        want = open(path, "rb").read()
+        got = oracle.snapshot_bytes(pp, vp, ids, m, types, time=R.time, mass_table=mt, hubble_param=0.7, omega0=R.cfg["Omega0"])
+        assert got == want, f"case {k}: {len(got)} vs {len(want)} bytes"
+        back = oracle.read_snapshot(path)
+        assert back["npart"].sum() == N and np.array_equal(np.sort(back["ids"]), np.sort(ids))
+    R.set("TYPE", np.ones(N, np.int32))
+
+
+def test_snapshot_periodic_wrap(refdrv_mod):
+    """io.c:275-283 under -DPERIODIC: positions outside [0, BoxSize] are wrapped in the file (float += double);
+    comoving header (redshift = 1/a - 1)"""
+    import oracle
+    from sidm_b200 import ic
+    if not refdrv_mod.available("periodic"):
+        pytest.skip("periodic reference build absent")
+    BOX, A = 100.0, 0.25
+    pos, vel, mass, ids = ic.periodic_box(12, seed=4, box=BOX, vel_sigma=60.0)
+    n = len(mass)
+    rng = np.random.default_rng(2)
+    pos = (pos + rng.choice(np.array([0, 0, 0, -BOX, BOX, 2 * BOX], np.float32), (n, 3))).astype(np.float32)   # images
+    cwd = os.getcwd()
+    out = tempfile.mkdtemp()
+    os.chdir(out)
+    try:
+        R = refdrv_mod.Reference("periodic")
+        R.setup(n, BoxSize=BOX, SofteningHalo=0.5, ComovingIntegrationOn=1, Omega0=0.3, OmegaLambda=0.7, Hubble=0.1, Time=A)
+        R.set_particles(pos, vel, mass, ids)
+        path = R.savepositions(7, out, mass_table=[0, float(mass[0]), 0, 0, 0, 0], hubble_param=0.7)
+        want = open(path, "rb").read()
+        pp = R.get("POSPRED")
+        assert (pp < 0).any() and (pp > BOX).any()
+        got = oracle.snapshot_bytes(pp, R.get("VELPRED"), ids, mass, None, time=R.time, mass_table=[0, float(mass[0]), 0, 0, 0, 0],
+                                    box=BOX, omega0=0.3, omega_lambda=0.7, hubble_param=0.7, comoving=True, periodic=True)
+        assert got == want
+        back = oracle.read_snapshot(path)
+        assert back["mass"] is None and back["pos"].min() >= 0 and back["pos"].max() <= BOX
+    finally:
+        os.chdir(cwd)
