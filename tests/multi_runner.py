@@ -22,11 +22,16 @@ def main(out, n, backend):
     if world > 1:
         dist.init_process_group(backend)
     pos, vel, mass, ids = ic.hernquist(n, seed=13)
-    hp = HotPath(n, device=dev, CrossSectionInternal=400.0, Seed=7)
+    multi_type = os.environ.get("B200_TYPES", "0") == "1"          # three particle types: one tree per type
+    types = np.random.default_rng(17).choice(np.array([1, 2, 3], np.int32), n, p=[0.5, 0.3, 0.2]).astype(np.int32) if multi_type else np.ones(n, np.int32)
+    kw = dict(SofteningTable=[0, 0.3, 0.6, 0.2, 0, 0]) if multi_type else {}
+    hp = HotPath(n, device=dev, CrossSectionInternal=400.0, Seed=7, **kw)
     sh = Sharder(hp, world, rank)
     hp.set_option("shard_min_work", int(os.environ.get("B200_SHARD_MIN_WORK", "1")))   # shard even this small problem
     hp.set_option("compact_exchange", int(os.environ.get("B200_COMPACT", "1")))
     hp.set_particles(pos, vel, mass, ids)
+    if multi_type:
+        hp.set_field("ptype", types)
     hp.predict_collisionless_only(0.0)
     hp.force_treebuild()
     hp.setup_smoothinglengths_sidm(30)
@@ -50,7 +55,7 @@ def main(out, n, backend):
     aos = np.zeros(n, capi.PARTICLE_DTYPE)
     aos["Pos"] = hp.peek("pos0", np.float32, (n, 3)); aos["PosPred"] = aos["Pos"]
     aos["Vel"] = velh[:, :3]; aos["VelPred"] = aos["Vel"]; aos["HsmlVelDisp"] = velh[:, 3]
-    aos["Mass"] = mass; aos["ID"] = ids; aos["Type"] = 1; aos["Potential"] = 7.0; aos["ForceFlag"] = 3
+    aos["Mass"] = mass; aos["ID"] = ids; aos["Type"] = types; aos["Potential"] = 7.0; aos["ForceFlag"] = 3
     aos["CurrentTime"] = hp.peek("curtime", np.float32, (n,))
     aos["Accel"], aos["OldAcc"], aos["NgbVelDisp"] = hp.get("Accel", "OldAcc", "NgbVelDisp")
     back = aos.copy()

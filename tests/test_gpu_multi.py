@@ -14,14 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 N = 30000
 
 
-def _launch(world, out, backend, min_work="1", compact="1"):
+def _launch(world, out, backend, min_work="1", compact="1", types="0"):
     runner = os.path.join(HERE, "multi_runner.py")
     if world == 1:
         cmd = [sys.executable, runner, out, str(N), backend]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", runner, out, str(N), backend]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, B200_SHARD_MIN_WORK=min_work, B200_COMPACT=compact))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, B200_SHARD_MIN_WORK=min_work, B200_COMPACT=compact, B200_TYPES=types))
     assert r.returncode == 0, (r.stdout[-1500:] + "\n".join(l for l in r.stderr.splitlines() if "Error" in l or "assert" in l or "File" in l)[-3000:])
     return np.load(out)
 
@@ -35,6 +35,14 @@ def test_two_ranks_equal_one_rank(tmp_path):
     one = _launch(1, str(tmp_path / "one.npz"), "gloo")
     assert one["sct0"][2] + one["sct1"][2] > 0, "no scatterings - fixture too quiet"
     two = _launch(2, str(tmp_path / "two.npz"), "gloo")
+    _same(one, two)
+
+
+def test_two_ranks_three_types(tmp_path):
+    """three particle types (one tree per type, query groups and 32-aligned leaf blocks per tree) sharded over two ranks"""
+    one = _launch(1, str(tmp_path / "one.npz"), "gloo", types="1")
+    assert one["sct0"][2] + one["sct1"][2] > 0, "no scatterings - fixture too quiet"
+    two = _launch(2, str(tmp_path / "two.npz"), "gloo", types="1")
     _same(one, two)
 
 

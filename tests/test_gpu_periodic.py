@@ -215,3 +215,53 @@ print("comoving sidm: scattered", int((np.abs(dv).sum(1) > 0).sum()))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_periodic_two_types(refdrv_mod):
+    """two collisionless types with different softening in a periodic box: two trees walked in turn with the
+    nearest-image / Ewald terms (forcetree.c:798-808, 870-930), neighbour searches inside the particle's own tree"""
+    import subprocess
+    import sys
+    if not refdrv_mod.available("periodic"):
+        pytest.skip("oracle/_ref/libsidmref_per.so not built")
+    code = r'''
+import sys, os, tempfile, numpy as np
+sys.path.insert(0, "oracle"); sys.path.insert(0, "sidm-nbody_b200")
+import refdrv
+from sidm_b200 import HotPath, ic
+BOX = 100.0
+pos, vel, mass, ids = ic.periodic_box(20, seed=9, box=BOX, vel_sigma=50.0)
+n = len(mass)
+types = np.random.default_rng(5).choice(np.array([1, 2], np.int32), n, p=[0.7, 0.3]).astype(np.int32)
+root = os.getcwd(); os.chdir(tempfile.mkdtemp())
+R = refdrv.Reference("periodic")
+R.setup(n, BoxSize=BOX, SofteningHalo=0.5, CrossSectionInternal=0.0)
+R.set_softening(1, 0.5); R.set_softening(2, 1.1)
+R.set_particles(pos, vel, mass, ids)
+R.set("TYPE", types)
+R.treebuild()
+idx = np.arange(0, n, 5, dtype=np.int32)
+acc_r, cost_r = R.force_tree(idx)
+pot_r = R.potential(idx)
+R.setup_smoothinglengths_sidm(30)
+h_r, n_r = R.get("HSML"), R.get("NGB")
+os.chdir(root)
+with HotPath(n, BoxSize=BOX, PeriodicBoundariesOn=1, SofteningTable=[0, 0.5, 1.1, 0, 0, 0], CrossSectionInternal=0.0, ReferenceNgbOrder=1) as hp:
+    hp.set_particles(pos, vel, mass, ids)
+    hp.set_field("ptype", types)
+    hp.force_treebuild()
+    acc, cost = hp.force_treeevaluate(idx)
+    err = float(np.sqrt(((acc - acc_r) ** 2).sum() / (acc_r ** 2).sum()))
+    same = float((cost.sum(1) == cost_r.sum(1)).mean())
+    print("periodic two types: rel rms", err, "same counts", same)
+    assert err < 1e-4 and same > 0.99
+    pot = hp.force_treeevaluate_potential(idx)
+    assert np.allclose(pot, pot_r, rtol=1e-4, atol=1e-4 * np.abs(pot_r).max())
+    hp.setup_smoothinglengths_sidm(30)
+    h, ngb = hp.get("HsmlVelDisp", "NgbVelDisp")
+    assert np.array_equal(ngb, n_r), "neighbour counts"
+    assert (h == h_r).mean() > 0.999 and np.allclose(h, h_r, rtol=3e-7)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
