@@ -305,6 +305,47 @@ void compute_potential(void)
   All.CPU_Potential += timediff(t0, t1);
 }
 
+/* compute_global_quantities_of_system(), global.c:18-135 (linked instead of global.c): the sums come from the
+ * device state that compute_potential() / compute_accelerations() left there; b200_sysstate has the field order
+ * of struct state_of_system (allvars.h:517-537). */
+void compute_global_quantities_of_system(void)
+{
+  b200_sysstate s;
+  sync_params_and_particles();                          /* the host may have advanced P[] since the last device call */
+  b200_check(b200_compute_global_quantities(&s), "b200_compute_global_quantities");
+  memcpy(&SysState, &s, sizeof(SysState) < sizeof(s) ? sizeof(SysState) : sizeof(s));
+}
+
+/* savepositions(), io.c:16-590 (linked instead of io.c): one format-1 file written from the device state */
+size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE *stream)          /* io.c:594-605, used by ewald.c:136 */
+{
+  size_t nwritten = fwrite(ptr, size, nmemb, stream);
+  if (nwritten != nmemb) { printf("I/O error (fwrite) on task=%d has occured.\n", ThisTask); fflush(stdout); endrun(777); }
+  return nwritten;
+}
+size_t my_fread(void *ptr, size_t size, size_t nmemb, FILE *stream)           /* io.c:611-622, used by read_ic.c, ewald.c */
+{
+  size_t nread = fread(ptr, size, nmemb, stream);
+  if (nread != nmemb) { printf("I/O error (fread) on task=%d has occured.\n", ThisTask); fflush(stdout); endrun(778); }
+  return nread;
+}
+void savepositions(int num)
+{
+  char buf[500];
+  double t0 = second(), t1;
+  if (ThisTask == 0) printf("\nwriting snapshot file... \n");
+  if (num < 0) num = 1000 + num;                                                /* io.c:77-78 */
+  if (All.NumFilesPerSnapshot != 1 || NTask != 1 || All.TotN_gas > 0) {
+    printf("savepositions: the device writer covers one file, one task, no gas\n"); endrun(9003);
+  }
+  sprintf(buf, "%s%s_%03d", All.OutputDir, All.SnapshotFileBase, num);         /* io.c:96 */
+  sync_params_and_particles();
+  b200_check(b200_savepositions(buf, All.Time, All.MassTable, All.HubbleParam, 0), "b200_savepositions");
+  if (ThisTask == 0) printf("done with snapshot.\n");
+  t1 = second();
+  All.CPU_Snapshot += timediff(t0, t1);
+}
+
 /* accel.c:27-132 for collisionless runs, as one coarse call.  Same order of effects as the CPU code:
  * gravity_tree() bookkeeping (gravtree.c:42-60), forces, determine_interior(), sidm() +
  * sidm_ensure_neighbours(mode) when mode == 0, timers into All.CPU_Gravity / CPU_EnsureNgb. */

@@ -39,6 +39,9 @@ def main(kind, out, n):
     if kind != "b200":                                 # potential.c:18 (the symbol-by-symbol shim leaves potential.c's CPU walk out)
         R.compute_potential()
         res["pot"] = R.get("POT")
+        res["sys"] = R.global_quantities()             # global.c:18 (b200f: the shim's, from the device state)
+        snap = R.savepositions(5, os.getcwd(), mass_table=[0, float(mass[0]), 0, 0, 0, 0], hubble_param=0.7)   # io.c:16
+        res["snap"] = np.frombuffer(open(snap, "rb").read(), np.uint8)
     np.savez(out, **res)
 
 

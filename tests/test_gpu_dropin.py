@@ -46,3 +46,19 @@ def test_reference_driver_on_gpu_path(tmp_path, refdrv_mod, kind):
     assert cpu["nactive"] == gpu["nactive"] == N
     if kind == "b200f":                                # compute_potential() through the shim
         np.testing.assert_allclose(gpu["pot"], cpu["pot"], rtol=3e-6)
+        # compute_global_quantities_of_system() and savepositions() through the shim (global.c / io.c replaced)
+        s_cpu, s_gpu = cpu["sys"], gpu["sys"]
+        # (VelPred carries the 2e-6 different start-up accelerations of the two runs: E_kin to 1e-8, not to rounding)
+        assert abs(s_gpu[0] - s_cpu[0]) <= 1e-12 * s_cpu[0] and abs(s_gpu[1] - s_cpu[1]) <= 1e-8 * s_cpu[1]       # Mass, EnergyKin
+        assert abs(s_gpu[2] - s_cpu[2]) <= 3e-6 * abs(s_cpu[2])                                                      # EnergyPot
+        np.testing.assert_allclose(s_gpu, s_cpu, rtol=1e-5, atol=1e-6 * np.abs(s_cpu).max())
+        # same file layout; VelPred carries the (2e-6 different) start-up accelerations, everything else is bit-equal
+        import oracle
+        snaps = {}
+        for k, r in (("cpu", cpu), ("gpu", gpu)):
+            (tmp_path / f"snap_{k}").write_bytes(r["snap"].tobytes())
+            snaps[k] = oracle.read_snapshot(str(tmp_path / f"snap_{k}"))
+        assert len(gpu["snap"]) == len(cpu["snap"]) and gpu["snap"][:264].tobytes() == cpu["snap"][:264].tobytes()
+        assert np.array_equal(snaps["gpu"]["pos"], snaps["cpu"]["pos"]) and np.array_equal(snaps["gpu"]["ids"], snaps["cpu"]["ids"])
+        assert snaps["gpu"]["mass"] is None and snaps["cpu"]["mass"] is None
+        np.testing.assert_allclose(snaps["gpu"]["vel"], snaps["cpu"]["vel"], rtol=1e-5, atol=1e-4)
