@@ -264,6 +264,12 @@ int  b200_compute_global_quantities(b200_sysstate *out);
  * to the file the reference writes from the same state.  Gas particles (type 0: u / rho / hsml blocks) are not on
  * this path: B200_ERR_ARG.  The 84 fill bytes of the header are zero (the reference leaves what read_ic() put there). */
 int  b200_savepositions(const char *path, double time, const double *mass_table, double hubble_param, int *npart_out);
+/* read_ic() + the start-up loop of init() (read_ic.c:32-481, init.c:76-100) for one format-1 file without gas, straight
+ * into the device state: types from the header's block ranges, masses from MassTable or the mass block, PosPred = Pos,
+ * VelPred = Vel, CurrentTime = header time, Accel = dVel = OldAcc = Potential = 0, GravCost = 1, Hsml = 0.  The file is
+ * streamed through pinned buffers; the particle count becomes the file's (<= MaxPart).  Block markers are checked
+ * (B200_ERR_IO).  time_out, mass_table_out[6], npart_out[6] may be NULL. */
+int  b200_load_snapshot(const char *path, double *time_out, double *mass_table_out, int *npart_out);
 /* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
 int  b200_potential_raw(const int *targets, int n, double *pot_out);
 /* host -> device copy into a named internal buffer (see b200_device_buffer), e.g. "maxpred" */

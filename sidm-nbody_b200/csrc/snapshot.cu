@@ -52,6 +52,29 @@ __global__ void k_snap_gather(int nout, const int *perm, const float4 *posm, con
   id[j] = pid[i]; mass[j] = p.w;
 }
 
+// read_ic() + the start-up loop of init() (read_ic.c:32-481, init.c:76-100) for one format-1 file without gas:
+// particle j of the file is of the type whose block range holds j; its mass is the MassTable entry of the type or
+// the next entry of the mass block; PosPred = Pos, VelPred = Vel, Accel = dVel = OldAcc = Potential = 0, GravCost = 1.
+struct SnapTypes { int cum[7]; int moff[6]; float mtab[6]; };
+__global__ void k_snap_scatter(int n, SnapTypes T, const float *pos, const float *vel, const int *id, const float *mass, float time,
+                               float4 *posm, float4 *velh, float *pos0, float *velpred, int *pid, int *ptype, float *accel, float *dvel,
+                               float *curtime, float *oldacc, float *gravcost, float *left, float *right, int *ngb, float *maxpred,
+                               float *potential) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int t = 0;
+  while (t < 5 && j >= T.cum[t + 1]) t++;
+  const float m = T.moff[t] >= 0 ? mass[T.moff[t] + (j - T.cum[t])] : T.mtab[t];
+  const float x = pos[3 * (size_t)j], y = pos[3 * (size_t)j + 1], z = pos[3 * (size_t)j + 2];
+  const float vx = vel[3 * (size_t)j], vy = vel[3 * (size_t)j + 1], vz = vel[3 * (size_t)j + 2];
+  posm[j] = make_float4(x, y, z, m); velh[j] = make_float4(vx, vy, vz, 0.f);
+  pos0[3 * (size_t)j] = x; pos0[3 * (size_t)j + 1] = y; pos0[3 * (size_t)j + 2] = z;
+  velpred[3 * (size_t)j] = vx; velpred[3 * (size_t)j + 1] = vy; velpred[3 * (size_t)j + 2] = vz;
+  for (int k = 0; k < 3; k++) { accel[3 * (size_t)j + k] = 0.f; dvel[3 * (size_t)j + k] = 0.f; }
+  pid[j] = id[j]; ptype[j] = t;
+  curtime[j] = time; maxpred[j] = time; oldacc[j] = 0.f; gravcost[j] = 1.f; left[j] = 0.f; right[j] = 0.f; ngb[j] = 0; potential[j] = 0.f;
+}
+
 namespace {
 constexpr size_t kChunk = 32u << 20;
 struct Stager {
@@ -79,6 +102,22 @@ struct Stager {
       const size_t off = c * kChunk, len = bytes - off < kChunk ? bytes - off : kChunk;
       if (fwrite(pin[c & 1], 1, len, fd) != len) return B200_ERR_IO;           // my_fwrite(), io.c:594-605
     }
+    return B200_OK;
+  }
+};
+// file bytes -> device, double buffered (the fread of chunk c+1 runs while chunk c is on the bus)
+struct Loader {
+  Stager &sg; explicit Loader(Stager &s) : sg(s) {}
+  int read(FILE *fd, void *d_dst, size_t bytes) {
+    const size_t nch = (bytes + kChunk - 1) / kChunk;
+    for (size_t c = 0; c < nch; c++) {
+      const size_t off = c * kChunk, len = bytes - off < kChunk ? bytes - off : kChunk;
+      if (c >= 2) CUDA_TRY(cudaEventSynchronize(sg.ev[c & 1]));           // the copy that last used this buffer
+      if (fread(sg.pin[c & 1], 1, len, fd) != len) return B200_ERR_IO;     // my_fread(), io.c:611-622
+      CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, sg.pin[c & 1], len, cudaMemcpyHostToDevice, g.stream));
+      CUDA_TRY(cudaEventRecord(sg.ev[c & 1], g.stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
     return B200_OK;
   }
 };
@@ -175,5 +214,57 @@ extern "C" int b200_savepositions(const char *path, double time, const double *m
   // u, rho, hsml: sizeof(float)*ntot_type[0] == 0 -> nothing written (io.c:254-262)
   fc.fd = nullptr;
   if (fclose(fd) != 0) return B200_ERR_IO;
+  return B200_OK;
+}
+
+extern "C" int b200_load_snapshot(const char *path, double *time_out, double *mass_table_out, int *npart_out) {
+  if (!g.ready) return B200_ERR_STATE;
+  if (!path) return B200_ERR_ARG;
+  FileCloser fc{fopen(path, "r")};
+  FILE *fd = fc.fd;
+  if (!fd) return B200_ERR_IO;
+  auto marker = [&](long long expect) -> int {              // SKIP of read_ic.c:35, checked
+    int d = 0;
+    if (fread(&d, sizeof(d), 1, fd) != 1) return B200_ERR_IO;
+    return d == (int)expect ? B200_OK : B200_ERR_IO;
+  };
+  SnapHeader h;
+  B200_TRY(marker(256));
+  if (fread(&h, sizeof(h), 1, fd) != 1) return B200_ERR_IO;
+  B200_TRY(marker(256));
+  if (h.num_files > 1) return B200_ERR_ARG;                 // one file per snapshot on this path
+  if (h.npart[0] > 0) return B200_ERR_ARG;                  // gas blocks are not on this path
+  SnapTypes T;
+  long long ntot = 0, nmass = 0;
+  for (int t = 0; t < 6; t++) {
+    if (h.npart[t] < 0) return B200_ERR_IO;
+    T.cum[t] = (int)ntot; T.mtab[t] = (float)h.mass[t];
+    T.moff[t] = (h.mass[t] == 0 && h.npart[t] > 0) ? (int)nmass : -1;      // read_ic.c:126,260
+    if (h.mass[t] == 0) nmass += h.npart[t];
+    ntot += h.npart[t];
+  }
+  T.cum[6] = (int)ntot;
+  if (ntot <= 0 || ntot > g.maxpart) return B200_ERR_ARG;
+  const int n = (int)ntot;
+  float *d_pos = (float *)g.d_acc, *d_vel = d_pos + 3 * (size_t)n;
+  int *d_id = g.d_cost; float *d_mass = (float *)(g.d_cost + n);
+  Stager sg;
+  B200_TRY(sg.init());
+  Loader ld(sg);
+  B200_TRY(marker(12 * ntot)); B200_TRY(ld.read(fd, d_pos, 12 * (size_t)ntot)); B200_TRY(marker(12 * ntot));
+  B200_TRY(marker(12 * ntot)); B200_TRY(ld.read(fd, d_vel, 12 * (size_t)ntot)); B200_TRY(marker(12 * ntot));
+  B200_TRY(marker(4 * ntot));  B200_TRY(ld.read(fd, d_id, 4 * (size_t)ntot));   B200_TRY(marker(4 * ntot));
+  if (nmass > 0) { B200_TRY(marker(4 * nmass)); B200_TRY(ld.read(fd, d_mass, 4 * (size_t)nmass)); B200_TRY(marker(4 * nmass)); }
+  g.n = n;
+  k_snap_scatter<<<cdiv(n, 256), 256, 0, g.stream>>>(n, T, d_pos, d_vel, d_id, d_mass, (float)h.time, g.posm, g.velh, g.pos0, g.velpred,
+                                                     g.pid, g.ptype, g.accel, g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right,
+                                                     g.ngb, g.maxpred, g.potential);
+  count_launch();
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  g.tree_valid = false; g.types_dirty = true;
+  if (time_out) *time_out = h.time;
+  if (mass_table_out) for (int t = 0; t < 6; t++) mass_table_out[t] = h.mass[t];
+  if (npart_out) for (int t = 0; t < 6; t++) npart_out[t] = h.npart[t];
   return B200_OK;
 }

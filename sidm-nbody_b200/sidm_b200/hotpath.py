@@ -155,6 +155,17 @@ class HotPath:
         check(self.lib.b200_savepositions(str(path).encode(), t, ptr(mt), float(hubble_param), ptr(npart)), "b200_savepositions")
         return npart
 
+    def read_ic(self, path):
+        """read_ic() + init() start-up state (read_ic.c:32, init.c:76-100) from one format-1 file into the device state;
+        returns (time, mass_table, npart)"""
+        t = C.c_double(0.0)
+        mt = np.zeros(6, np.float64)
+        npart = np.zeros(6, np.int32)
+        check(self.lib.b200_load_snapshot(str(path).encode(), C.byref(t), ptr(mt), ptr(npart)), "b200_load_snapshot")
+        self.n = int(npart.sum())
+        self.time = t.value
+        return t.value, mt, npart
+
     def force_treeevaluate_potential(self, targets):
         t = _i32(targets)
         out = np.empty(len(t), np.float64)

@@ -64,7 +64,14 @@ def test_snapshot_mid_run_against_oracle():
         mt = [0, 0, float(mass[0]), 0, 0.5, 0]
         npart = hp.savepositions(path, time=0.003, mass_table=mt, hubble_param=0.7)
         assert npart.sum() == (types != 5).sum()
-        assert open(path, "rb").read() == oracle.snapshot_bytes(pp, vp, ids, mass, types, time=0.003, mass_table=mt, hubble_param=0.7, omega0=1.0)
+        raw = open(path, "rb").read()
+        assert raw == oracle.snapshot_bytes(pp, vp, ids, mass, types, time=0.003, mass_table=mt, hubble_param=0.7, omega0=1.0)
+        # and back: read_ic() of that file (38 MB blocks through the 32 MB staging buffers), written again -> the same bytes
+        t, mt2, npart2 = hp.read_ic(path)
+        assert t == 0.003 and np.array_equal(npart2, npart) and np.array_equal(mt2, mt) and hp.n == npart.sum()
+        path2 = os.path.join(out, "snap_001")
+        hp.savepositions(path2, time=t, mass_table=mt2, hubble_param=0.7)
+        assert open(path2, "rb").read() == raw
 
 
 def test_snapshot_periodic_wrap():
@@ -88,3 +95,53 @@ def test_snapshot_periodic_wrap():
         assert open(path, "rb").read() == want
         back = oracle.read_snapshot(path)
         assert back["mass"] is None and back["pos"].min() >= 0 and back["pos"].max() <= BOX
+
+
+def test_read_ic_golden_three_types():
+    """read_ic() + init() start-up state (read_ic.c:32-481, init.c:76-100) from the reference's snapshot of the golden
+    fixture (the oracle writer reproduces that file, SHA-256 checked): types from the block ranges, masses from the
+    MassTable or the mass block, PosPred = Pos, VelPred = Vel, zeroed accelerations; then a full step on that state"""
+    import oracle
+    from sidm_b200 import HotPath
+    from sidm_b200.capi import B200Error
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "global3k.npz")))
+    n = len(g["mass"])
+    raw = oracle.snapshot_bytes(g["pospred"], g["velpred"], g["ids"], g["mass"], g["types"], time=float(g["snap_time"]),
+                                mass_table=g["snap_mass_table"], hubble_param=0.7, omega0=float(g["snap_omega0"]))
+    assert hashlib.sha256(raw).hexdigest() == str(g["snap_sha256"])
+    out = tempfile.mkdtemp()
+    path = os.path.join(out, "snap_003")
+    open(path, "wb").write(raw)
+    order = np.concatenate([np.nonzero(g["types"] == t)[0] for t in range(5)])
+    with HotPath(n + 100, Omega0=float(g["snap_omega0"]), SofteningTable=[float(e) for e in g["eps"]]) as hp:
+        t, mt, npart = hp.read_ic(path)
+        assert t == float(g["snap_time"]) and np.array_equal(mt, g["snap_mass_table"]) and hp.n == n
+        posm = hp.peek("posm", np.float32, (n, 4))
+        velh = hp.peek("velh", np.float32, (n, 4))
+        assert np.array_equal(posm[:, :3], g["pospred"][order]) and np.array_equal(velh[:, :3], g["velpred"][order])
+        assert np.array_equal(hp.peek("pos0", np.float32, (n, 3)), posm[:, :3])
+        assert np.array_equal(hp.peek("pid", np.int32, (n,)), g["ids"][order])
+        ty = hp.peek("ptype", np.int32, (n,))
+        assert np.array_equal(ty, g["types"][order])
+        want_m = np.where(ty == 2, np.float32(g["snap_mass_table"][2]), g["mass"][order]).astype(np.float32)
+        assert np.array_equal(posm[:, 3], want_m)
+        pp, vp, acc, oa, gc, dv = hp.get("PosPred", "VelPred", "Accel", "OldAcc", "GravCost", "dVel")
+        assert np.array_equal(pp, posm[:, :3]) and np.array_equal(vp, velh[:, :3])
+        assert not acc.any() and not oa.any() and not dv.any() and (gc == 1).all() and not velh[:, 3].any()
+        # the loaded state runs: start-up smoothing lengths and one full step over the three trees
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        hp.compute_accelerations(1, time=t, vmax=hp.getvmax())
+        assert np.isfinite(hp.get("Accel")).all() and hp.get("NgbVelDisp").min() >= 28
+        # written again: the same file
+        path2 = os.path.join(out, "snap_004")
+        hp.savepositions(path2, time=t, mass_table=mt, hubble_param=0.7)
+        assert open(path2, "rb").read() == raw
+        # error behaviour: truncated file, missing file
+        open(path, "wb").write(raw[:len(raw) // 2])
+        with pytest.raises(B200Error) as e:
+            hp.read_ic(path)
+        assert e.value.code == 9007
+        with pytest.raises(B200Error) as e:
+            hp.read_ic(os.path.join(out, "absent"))
+        assert e.value.code == 9007
