@@ -76,3 +76,55 @@ def test_scatter_conserves_momentum_and_pair_energy():
     h1 = log["h1"]
     r = np.sqrt(((log["x1"].astype(np.float64) - log["x2"]) ** 2).sum(1))
     assert (r < h1).all()                                  # partners lie inside the scatterer's kernel
+
+
+def test_run_from_snapshot_with_device_statistics(tmp_path):
+    """the reference's run loop with every per-step piece on the device: read_ic() of a format-1 file, start-up
+    smoothing lengths and forces, 40 x [compute_accelerations(0) + advance()], energy statistics through
+    compute_potential() + compute_global_quantities_of_system() (run.c:51-60 -> energy_out), savepositions().
+    Checks: SysState energy conserved, linear momentum conserved by gravity + SIDM kicks, the statistics agree
+    with a host evaluation of the same sums, the written snapshot reloads to the same state."""
+    import oracle
+    from sidm_b200 import HotPath, ic
+    n, dt, steps = 20000, 0.001, 40
+    pos, vel, mass, ids = ic.hernquist(n, seed=43)
+    ic_file = str(tmp_path / "ic_000")
+    open(ic_file, "wb").write(oracle.snapshot_bytes(pos, vel, ids, mass, None, time=0.0, mass_table=[0, float(mass[0]), 0, 0, 0, 0], omega0=1.0))
+    with HotPath(n, CrossSectionInternal=20.89, Seed=5) as hp:
+        t, mt, npart = hp.read_ic(ic_file)
+        assert t == 0.0 and npart[1] == n
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        vmax = hp.getvmax()
+        hp.compute_accelerations(1, time=0.0, vmax=vmax)
+
+        def stats(time):
+            hp.predict_collisionless_only(time)
+            pot = hp.compute_potential()
+            return hp.compute_global_quantities_of_system(), pot
+        s0, pot0 = stats(0.0)
+        # the statistics against a host evaluation of the same sums
+        pp, vp = hp.get("PosPred", "VelPred")
+        want = oracle.global_quantities(pp, vp, mass, pot0)
+        np.testing.assert_allclose(s0.flat()[:5], want[:5], rtol=1e-12)
+        assert 0.35 < -s0.EnergyKin / s0.EnergyPot < 0.65
+        scat = 0
+        for _ in range(steps):
+            hp.compute_accelerations(0, time=t + dt / 2, vmax=vmax)
+            scat += hp.counters().sct_scattered
+            hp.advance(time=t + dt / 2)
+            t += dt
+        s1, _ = stats(t)
+        assert scat > 0, "fixture too quiet"
+        assert abs(s1.EnergyTot - s0.EnergyTot) < 2e-3 * abs(s0.EnergyTot), (s0.EnergyTot, s1.EnergyTot)
+        assert s1.Mass == s0.Mass
+        pscale = float((mass.astype(np.float64) * np.sqrt((vel.astype(np.float64) ** 2).sum(1))).sum())
+        for j in range(3):
+            assert abs(s1.Momentum[j] - s0.Momentum[j]) < 1e-4 * pscale
+        # snapshot of the end state, reloaded: the same predicted positions / velocities
+        snap = str(tmp_path / "snap_001")
+        hp.savepositions(snap, time=t, mass_table=mt)
+        pp1, vp1 = hp.get("PosPred", "VelPred")
+        hp.read_ic(snap)
+        pp2, vp2 = hp.get("PosPred", "VelPred")
+        assert np.array_equal(pp1, pp2) and np.array_equal(vp1, vp2)
