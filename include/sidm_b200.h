@@ -152,6 +152,13 @@ const char *b200_version(void);
  * ReferenceNgbOrder parity mode (the search cube of a particle in the outskirts can clip the dense centre);
  * more than that returns B200_ERR_NGBOVERFLOW like the reference's endrun(78). */
 int  b200_set_option(const char *name, int value);
+/* Generator state for restarts ("next" row f3; the reference's restart files, restart.c:37-154, do not save its
+ * MT19937 state, so a restarted reference run draws different scatterings).  Here every random number is a function
+ * of (Seed, call counter, particle index): state[0] = sidm() calls so far, state[1] = find_timesteps() calls so far.
+ * Saving the two words with the particle data and setting them after b200_init makes a restarted run bit-identical
+ * to the uninterrupted one. */
+int  b200_get_rng_state(unsigned long long *state);
+int  b200_set_rng_state(const unsigned long long *state);
 
 /* ---- particle state -------------------------------------------------------------- */
 /* Bind the host AoS (the reference's &P[1]).  pin!=0 page-locks it for async DMA. */

@@ -108,7 +108,8 @@ struct Ctx {
   int *s_repair = nullptr;
   b200_scatlog *d_scatlog = nullptr; int scatlog_cap = 0; int scatlog_n = 0;
   int last_nslot = 0;
-  unsigned long long sidm_calls = 0;
+  unsigned long long sidm_calls = 0;   // counter-based RNG: the key of a sidm() call is (Seed, sidm_calls); b200_get/set_rng_state
+  unsigned long long ts_calls = 0;     // same for the Max/MinSizeTimestep jitter of find_timesteps()
 
   // ---- sharding across the GPUs of one box (b200_set_shard): this rank works on the 32-entry
   // blocks b of every sorted work list with b % world == rank; results are all-gathered

@@ -78,6 +78,19 @@ extern "C" int b200_set_option(const char *name, int value) {
   return B200_ERR_ARG;
 }
 
+// restart support (restart.c:37-154 dumps All and P[] but not the generator state): the random numbers of this
+// path are a pure function of (Seed, call counter, particle index), so two counters are the whole generator state
+extern "C" int b200_get_rng_state(unsigned long long *state) {
+  if (!state) return B200_ERR_ARG;
+  state[0] = g.sidm_calls; state[1] = g.ts_calls;
+  return B200_OK;
+}
+extern "C" int b200_set_rng_state(const unsigned long long *state) {
+  if (!state) return B200_ERR_ARG;
+  g.sidm_calls = state[0]; g.ts_calls = state[1];
+  return B200_OK;
+}
+
 extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes, b200_allgather_fn fn, void *user) {
   if (world < 1 || rank < 0 || rank >= world) return B200_ERR_ARG;
   if (world > 1 && (!send || !recv || !fn || cap_bytes <= 0)) return B200_ERR_ARG;
@@ -156,7 +169,7 @@ extern "C" int b200_init(const b200_params *p) {
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, CT_COUNT * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   memset(&g.cnt, 0, sizeof(g.cnt));
-  g.n = 0; g.tree_valid = false; g.sidm_calls = 0;
+  g.n = 0; g.tree_valid = false; g.sidm_calls = 0; g.ts_calls = 0;
   g.ready = true;
   return B200_OK;
 }
@@ -697,7 +710,7 @@ extern "C" int b200_find_timesteps(const int *active, int nactive, int mode, dou
   T.dtmax = tp->MaxSizeTimestep; T.dtmin = tp->MinSizeTimestep;
   for (int t = 0; t < 6; t++) T.soft[t] = g.par.SofteningTable[t];
   T.accel = g.accel; T.curtime = g.curtime; T.maxpred = g.maxpred; T.velh = g.velh; T.posm = g.posm; T.ptype = g.ptype;
-  static unsigned long long calls = 0; calls++;
+  const unsigned long long calls = ++g.ts_calls;
   T.k0 = (uint32_t)(g.par.Seed ^ (calls * 0x9E3779B97F4A7C15ull)); T.k1 = (uint32_t)(calls >> 7) ^ 0x51ED270Bu;
   T.jitter = nullptr; T.out = nullptr; T.nclamped = g.d_flags + FL_NSCATLOG;
   if (jitter) { CUDA_TRY(cudaMemcpyAsync(g.d_acc, jitter, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, g.stream)); T.jitter = g.d_acc; }

@@ -155,6 +155,17 @@ class HotPath:
         check(self.lib.b200_savepositions(str(path).encode(), t, ptr(mt), float(hubble_param), ptr(npart)), "b200_savepositions")
         return npart
 
+    def rng_state(self):
+        """the whole generator state of the path: (sidm() calls, find_timesteps() calls) - save it with a restart file"""
+        st = np.zeros(2, np.uint64)
+        check(self.lib.b200_get_rng_state(ptr(st)), "b200_get_rng_state")
+        return st
+
+    def set_rng_state(self, state):
+        st = np.ascontiguousarray(state, np.uint64)
+        assert st.size == 2
+        check(self.lib.b200_set_rng_state(ptr(st)), "b200_set_rng_state")
+
     def read_ic(self, path):
         """read_ic() + init() start-up state (read_ic.c:32, init.c:76-100) from one format-1 file into the device state;
         returns (time, mass_table, npart)"""

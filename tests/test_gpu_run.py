@@ -128,3 +128,62 @@ def test_run_from_snapshot_with_device_statistics(tmp_path):
         hp.read_ic(snap)
         pp2, vp2 = hp.get("PosPred", "VelPred")
         assert np.array_equal(pp1, pp2) and np.array_equal(vp1, vp2)
+
+
+def test_restart_is_bit_identical():
+    """restart.c:37-154 writes All + P[] but not the generator state, so a restarted reference run scatters
+    differently.  Here the generator state is two counters (b200_get_rng_state): a run stopped after 3 steps,
+    dumped as particle arrays + those counters and continued in a fresh context equals the uninterrupted run
+    bit for bit (positions, velocities, smoothing lengths, scatter kicks, the scatter log)."""
+    from sidm_b200 import HotPath, ic
+    n, dt = 30000, 0.002
+    pos, vel, mass, ids = ic.hernquist(n, seed=44)
+    kw = dict(CrossSectionInternal=150.0, Seed=11)
+
+    def steps(hp, t, k, vmax):
+        ev = []
+        for _ in range(k):
+            hp.compute_accelerations(0, time=t + dt / 2, vmax=vmax)
+            log = hp.scatlog()
+            ev.append(np.stack([log["id1"], log["id2"]], 1).astype(np.int64))
+            hp.advance(time=t + dt / 2)
+            t += dt
+        return t, np.concatenate(ev)
+
+    def dump(hp):
+        velh = hp.peek("velh", np.float32, (n, 4))
+        acc, oa, dv, ngb = hp.get("Accel", "OldAcc", "dVel", "NgbVelDisp")
+        return dict(pos=hp.peek("pos0", np.float32, (n, 3)), vel=velh[:, :3].copy(), hsml=velh[:, 3].copy(), accel=acc, oldacc=oa,
+                    dvel=dv, curtime=hp.peek("curtime", np.float32, (n,)), rng=hp.rng_state(), ngb=ngb)
+
+    with HotPath(n, **kw) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.predict_collisionless_only(0.0)
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        vmax = hp.getvmax()
+        hp.compute_accelerations(1, time=0.0, vmax=vmax)
+        t, _ = steps(hp, 0.0, 3, vmax)
+        rst = dump(hp)                                      # the "restart file"
+        assert rst["rng"][0] >= 3
+        t_end, ev_a = steps(hp, t, 3, vmax)
+        end_a = dump(hp)
+    assert len(ev_a) >= 20, "fixture too quiet"
+    with HotPath(n, **kw) as hp:                            # fresh context, state from the dump
+        hp.set_particles(rst["pos"], rst["vel"], mass, ids, curtime=rst["curtime"], accel=rst["accel"], oldacc=rst["oldacc"],
+                         hsml=rst["hsml"], dvel=rst["dvel"])
+        hp.set_field("ngb", rst["ngb"])
+        hp.set_rng_state(rst["rng"])
+        _, ev_b = steps(hp, t, 3, vmax)
+        end_b = dump(hp)
+        # control: without the generator state the continuation scatters other pairs
+        hp.set_particles(rst["pos"], rst["vel"], mass, ids, curtime=rst["curtime"], accel=rst["accel"], oldacc=rst["oldacc"],
+                         hsml=rst["hsml"], dvel=rst["dvel"])
+        hp.set_field("ngb", rst["ngb"])
+        hp.set_rng_state([0, 0])
+        _, ev_c = steps(hp, t, 3, vmax)
+    assert np.array_equal(ev_a, ev_b), "scattered pairs differ after the restart"
+    for k in ("pos", "vel", "hsml", "accel", "oldacc", "dvel", "curtime", "ngb"):
+        assert np.array_equal(end_a[k], end_b[k]), k
+    assert np.array_equal(end_a["rng"], end_b["rng"])
+    assert not (len(ev_c) == len(ev_a) and np.array_equal(ev_a, ev_c))
