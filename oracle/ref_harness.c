@@ -377,6 +377,24 @@ void ref_find_timesteps(int mode, int crit, double eta, double velscale, double 
   All.ProbabilityTol = probtol; All.ErrTolDynamicalAccuracy = dyntol; All.MaxSizeTimestep = dtmax; All.MinSizeTimestep = dtmin;
   find_timesteps(mode);
 }
+/* k iterations of the main loop of run.c:34-150 (no statistics / snapshots / domain decomposition):
+ * find_next_time(), compute_accelerations(0), advance(), reflect(), update_node_sidm(), find_timesteps(0).
+ * time_out[s], nactive_out[s] = All.Time and NumForceUpdate of iteration s. */
+void ref_run_steps(int k, double *time_out, int *nactive_out)
+{
+  for (int s = 0; s < k; s++) {
+    find_next_time();
+    time_out[s] = All.Time; nactive_out[s] = NumForceUpdate;
+    compute_accelerations(0);
+    advance();
+#ifdef REFLECTIONBOUNDARY
+    reflect();
+#endif
+    update_node_sidm();
+    find_timesteps(0);
+    All.NumCurrentTiStep++;
+  }
+}
 void ref_force_rebuild_next(void)
 { All.NumForcesSinceLastTreeConstruction = 1 << 30; }
 void ref_set_snapcount(int c) { All.SnapshotFileCount = c; }

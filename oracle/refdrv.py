@@ -260,6 +260,14 @@ class Reference:
         self.lib.ref_savepositions(int(num), d.encode(), base.encode(), mt.ctypes, float(hubble_param))
         return f"{d}{base}_{num:03d}"
 
+    def run_steps(self, k):
+        """k iterations of the main loop of run.c:34-150; returns (All.Time, NumForceUpdate) per iteration"""
+        t = np.zeros(k, np.float64)
+        na = np.zeros(k, np.int32)
+        self.lib.ref_run_steps.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ref_run_steps(int(k), t.ctypes, na.ctypes)
+        return t, na
+
     def set_softening(self, ptype, eps):
         self.lib.ref_set_softening.argtypes = [C.c_int, C.c_double]
         self.lib.ref_set_softening(int(ptype), float(eps))

@@ -45,5 +45,32 @@ def main(kind, out, n):
     np.savez(out, **res)
 
 
+def main_run(kind, out, n, k=60):
+    """the reference's own main loop (run.c:34-150) with individual time steps: start-up as init.c:120-185, then k
+    iterations of find_next_time / compute_accelerations(0) / advance / find_timesteps(0) on small active sets"""
+    import refdrv
+    from sidm_b200 import ic
+    pos, vel, mass, ids = ic.hernquist(n, seed=10)
+    os.chdir(tempfile.mkdtemp())
+    R = refdrv.Reference(kind)
+    R.setup(n, CrossSectionInternal=0.0)      # no scatterings: the two runs can be compared particle by particle
+    R.init_rand(55)
+    R.set_particles(pos, vel, mass, ids)
+    R.treebuild()
+    R.setup_smoothinglengths_sidm(30)
+    R.all_active(0.0, 0.0)
+    R.getvmax()
+    R.compute_accelerations(1)
+    ts = dict(crit=0, eta=0.02, velscale=10.0, probtol=0.2, dyntol=0.05, dtmax=0.02, dtmin=0.0)
+    R.find_timesteps(2, **ts)                          # init.c:177: first steps + construct_timetree()
+    mp0 = R.get("MAXPRED")
+    t, na = R.run_steps(k)
+    np.savez(out, maxpred0=mp0, time=t, nactive=na, pos=R.get("POS"), vel=R.get("VEL"), curtime=R.get("CURTIME"),
+             maxpred=R.get("MAXPRED"), hsml=R.get("HSML"), ngb=R.get("NGB"))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]))
+    if len(sys.argv) > 4 and sys.argv[4] == "run":
+        main_run(sys.argv[1], sys.argv[2], int(sys.argv[3]))
+    else:
+        main(sys.argv[1], sys.argv[2], int(sys.argv[3]))

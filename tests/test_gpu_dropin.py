@@ -62,3 +62,34 @@ def test_reference_driver_on_gpu_path(tmp_path, refdrv_mod, kind):
         assert np.array_equal(snaps["gpu"]["pos"], snaps["cpu"]["pos"]) and np.array_equal(snaps["gpu"]["ids"], snaps["cpu"]["ids"])
         assert snaps["gpu"]["mass"] is None and snaps["cpu"]["mass"] is None
         np.testing.assert_allclose(snaps["gpu"]["vel"], snaps["cpu"]["vel"], rtol=1e-5, atol=1e-4)
+
+
+def _run_loop(kind, out):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_runner.py"), kind, out, str(N), "run"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return np.load(out)
+
+
+@pytest.mark.parametrize("kind", ["b200", "b200f"])
+def test_reference_main_loop_individual_timesteps(tmp_path, refdrv_mod, kind):
+    """BASELINE config C5 ingredients through the reference's own driver: 60 iterations of the main loop of run.c
+    (find_next_time -> compute_accelerations(0) -> advance -> find_timesteps(0), timeline.c / predict.c / timestep.c
+    unmodified) with individual time steps, i.e. active sets of 10^2..10^4 of 2e4 particles taken from the ForceFlag
+    chain, all-CPU against the GPU drop-in.  sigma = 0 so that the runs can be compared particle by particle; forces
+    differ by ~2e-6, so steps (sqrt(eps/|a|)) and with them the time line drift apart at that level."""
+    if not refdrv_mod.available(kind):
+        pytest.skip(f"oracle/_ref/libsidmref_{kind}.so not built")
+    cpu = _run_loop("diag", str(tmp_path / "cpu.npz"))
+    gpu = _run_loop(kind, str(tmp_path / "gpu.npz"))
+    np.testing.assert_allclose(gpu["maxpred0"], cpu["maxpred0"], rtol=1e-5)          # first steps from the start-up forces
+    np.testing.assert_allclose(gpu["time"], cpu["time"], rtol=2e-5)                  # the same sequence of system times
+    assert cpu["nactive"].min() < N // 20 and cpu["nactive"].max() > N // 4          # small and large active sets occur
+    # the same particles are advanced in (nearly) every iteration: near-ties in MaxPredTime may swap between iterations
+    assert np.abs(gpu["nactive"] - cpu["nactive"]).sum() <= 0.01 * cpu["nactive"].sum()
+    same = gpu["curtime"] == cpu["curtime"]
+    assert same.mean() > 0.98
+    np.testing.assert_allclose(gpu["pos"][same], cpu["pos"][same], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(gpu["vel"][same], cpu["vel"][same], rtol=0, atol=2e-3)
+    assert (gpu["ngb"][same] == cpu["ngb"][same]).mean() > 0.99
+    assert (np.abs(gpu["ngb"] - 30) <= 2).all()                                      # the repair loop kept every count in range
