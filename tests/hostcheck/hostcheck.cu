@@ -22,23 +22,36 @@ struct Host {
   std::vector<NodeRec> nodes;
   std::vector<Moments> nmom;
   RootBox root;
+  RootBox roots[8];                       // several particle types: one root cell per type
+  std::vector<unsigned char> stype;       // type of every sorted particle (empty: one type)
   int flags[16];
 } H;
 }
 
-extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lorder) {
+// types == nullptr: one tree.  Otherwise one tree per particle type as csrc/tree_build.cu lays them out: a root
+// cell per type, keys along the particle's own tree, key order, then a stable sort by type.
+static int hc_build_impl(int n, const float *pos, const float *mass, const int *types, int want_lorder) {
   H.n = n;
   H.posm.resize(n);
-  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  double mn[8][3], mx[8][3];
+  for (int t = 0; t < 8; t++) for (int k = 0; k < 3; k++) { mn[t][k] = 1e300; mx[t][k] = -1e300; }
   for (int i = 0; i < n; i++) {
     H.posm[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]);
-    for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], (double)pos[3 * i + k]); mx[k] = std::max(mx[k], (double)pos[3 * i + k]); }
+    const int t = types ? (types[i] & 7) : 0;
+    for (int k = 0; k < 3; k++) { mn[t][k] = std::min(mn[t][k], (double)pos[3 * i + k]); mx[t][k] = std::max(mx[t][k], (double)pos[3 * i + k]); }
   }
-  H.root = make_root(mn, mx);
+  for (int t = 0; t < 8; t++) if (mn[t][0] <= mx[t][0]) H.roots[t] = make_root(mn[t], mx[t]);
+  H.root = H.roots[0];
   H.hi.resize(n); H.lo.resize(n);
-  for (int i = 0; i < n; i++) make_key(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], H.root, H.hi[i], H.lo[i]);
+  for (int i = 0; i < n; i++) make_key(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], H.roots[types ? (types[i] & 7) : 0], H.hi[i], H.lo[i]);
   H.sidx.resize(n); std::iota(H.sidx.begin(), H.sidx.end(), 0);
   std::stable_sort(H.sidx.begin(), H.sidx.end(), [&](int a, int b) { return key_less(H.hi[a], H.lo[a], H.hi[b], H.lo[b]); });
+  H.stype.clear();
+  if (types) {
+    std::stable_sort(H.sidx.begin(), H.sidx.end(), [&](int a, int b) { return (types[a] & 7) < (types[b] & 7); });
+    H.stype.resize(n);
+    for (int j = 0; j < n; j++) H.stype[j] = (unsigned char)(types[H.sidx[j]] & 7);
+  }
   H.shi.resize(n); H.slo.resize(n);
   for (int j = 0; j < n; j++) { H.shi[j] = H.hi[H.sidx[j]]; H.slo[j] = H.lo[H.sidx[j]]; }
   const int cap = 4 * n + 64;
@@ -50,7 +63,8 @@ extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lor
   for (int k = 0; k < 16; k++) H.flags[k] = 0;
   BuildView v;
   v.n = n; v.maxnodes = cap; v.posm = H.posm.data(); v.shi = H.shi.data(); v.slo = H.slo.data(); v.sidx = H.sidx.data();
-  v.clev = H.clev.data(); v.nodestart = H.nodestart.data(); v.root = &H.root;
+  v.clev = H.clev.data(); v.nodestart = H.nodestart.data(); v.root = types ? H.roots : &H.root;
+  v.stype = types ? H.stype.data() : nullptr;
   v.nodes = H.nodes.data(); v.geom = H.geom.data(); v.nstart = H.nstart.data(); v.nend = H.nend.data(); v.nparent = H.nparent.data();
   v.npstart = H.npstart.data(); v.nlevel = H.nlevel.data(); v.nnp = H.nnp.data(); v.nnchild = H.nnchild.data(); v.ndp = H.ndp.data();
   v.narrive = H.narrive.data(); v.nminidx = H.nminidx.data(); v.nlstart = H.nlstart.data(); v.nmom = H.nmom.data();
@@ -83,6 +97,10 @@ extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lor
   return 0;
 }
 
+extern "C" int hc_build(int n, const float *pos, const float *mass, int want_lorder) { return hc_build_impl(n, pos, mass, nullptr, want_lorder); }
+extern "C" int hc_build_types(int n, const float *pos, const float *mass, const int *types, int want_lorder) {
+  return hc_build_impl(n, pos, mass, types, want_lorder);
+}
 extern "C" int hc_num_nodes() { return H.m; }
 extern "C" int hc_max_level() { return H.maxlev; }
 extern "C" void hc_get_root(float *out) { out[0] = H.root.cx; out[1] = H.root.cy; out[2] = H.root.cz; out[3] = H.root.len; }

@@ -69,3 +69,49 @@ def test_key_tree_equals_insertion_tree(hc):
     hc.hc_walk(len(idx), idx.ctypes, oa.ctypes, 1, C.c_float(0.5), C.c_float(0.005), C.c_float(0.3), acc.ctypes, cost.ctypes)
     assert (cost == g["cost_rel"]).all(axis=1).mean() > 0.995
     assert np.sqrt(((acc - g["acc_rel"]) ** 2).sum() / (g["acc_rel"] ** 2).sum()) < 1e-5
+
+
+def _tree(hc):
+    m = hc.hc_num_nodes()
+    d = dict(center=np.empty((m, 3), np.float32), len=np.empty(m, np.float32), mass=np.empty(m, np.float32),
+             s=np.empty((m, 3), np.float32), Q=np.empty((m, 7), np.float32), oc=np.empty(m, np.float32),
+             bmax2=np.empty(m, np.float32), count=np.empty(m, np.int32), level=np.empty(m, np.int32),
+             skip=np.empty(m, np.int32), parent=np.empty(m, np.int32), minidx=np.empty(m, np.int32))
+    hc.hc_get_tree(*[d[k].ctypes for k in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count", "level", "skip",
+                                           "parent", "minidx")])
+    return d
+
+
+def test_forest_of_types_equals_one_tree_per_type(hc):
+    """several particle types (forcetree.c:90-158: one tree per type): the forest the build lays out in one node array
+    - root cell per type, keys along the particle's own tree, trees one after the other - is, tree by tree, exactly the
+    single tree of that type's particles alone (which test_key_tree_equals_insertion_tree pins on the reference)"""
+    g = np.load(os.path.join(HERE, "golden", "global3k.npz"))
+    pos, mass, types = np.ascontiguousarray(g["pospred"]), np.ascontiguousarray(g["mass"]), np.ascontiguousarray(g["types"])
+    n = len(mass)
+    assert hc.hc_build_types(n, pos.ctypes, mass.ctypes, types.ctypes, 1) == 0
+    forest = _tree(hc)
+    sidx, lo, lr = (np.empty(n, np.int32) for _ in range(3))
+    hc.hc_get_orders(sidx.ctypes, lo.ctypes, lr.ctypes)
+    roots = np.nonzero(forest["parent"] < 0)[0]
+    present = [t for t in range(6) if (types == t).any()]
+    assert len(roots) == len(present) == 3 and roots[0] == 0
+    bounds = list(roots) + [len(forest["len"])]
+    assert np.array_equal(types[sidx], np.sort(types))                     # tree after tree in the sorted order
+    at = 0
+    for k, t in enumerate(present):
+        sel = np.nonzero(types == t)[0]
+        p_t, m_t = np.ascontiguousarray(pos[sel]), np.ascontiguousarray(mass[sel])
+        assert hc.hc_build(len(sel), p_t.ctypes, m_t.ctypes, 1) == 0
+        one = _tree(hc)
+        s1, l1, r1 = (np.empty(len(sel), np.int32) for _ in range(3))
+        hc.hc_get_orders(s1.ctypes, l1.ctypes, r1.ctypes)
+        a, b = bounds[k], bounds[k + 1]
+        assert b - a == len(one["len"]), t
+        for f in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count", "level"):
+            assert np.array_equal(forest[f][a:b], one[f]), (t, f)
+        assert np.array_equal(forest["skip"][a:b] - a, one["skip"])       # the root's skip is the next tree's root
+        assert np.array_equal(np.where(forest["parent"][a:b] < 0, -1, forest["parent"][a:b] - a), one["parent"])
+        assert np.array_equal(sidx[at:at + len(sel)], sel[s1])             # the same particle order inside the tree
+        assert np.array_equal(np.argsort(lr[sel], kind="stable"), np.argsort(r1, kind="stable"))   # and the same next[] chain
+        at += len(sel)
