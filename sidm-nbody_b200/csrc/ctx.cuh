@@ -170,5 +170,6 @@ int direct_impl(const int *targets, int n, double *acc_out);
 int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only);
 int prepare_targets(const int *active_host, int nactive, int **d_sorted_out);
 void sidm_release();
+void snapshot_release();
 
 }  // namespace b200

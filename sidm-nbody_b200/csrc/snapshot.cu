@@ -77,13 +77,15 @@ __global__ void k_snap_scatter(int n, SnapTypes T, const float *pos, const float
 
 namespace {
 constexpr size_t kChunk = 32u << 20;
-struct Stager {
+struct Stager {                         // two pinned staging buffers, kept between calls (page-locking 64 MB costs ~30 ms)
   char *pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
-  ~Stager() { for (int k = 0; k < 2; k++) { if (pin[k]) cudaFreeHost(pin[k]); if (ev[k]) cudaEventDestroy(ev[k]); } }
+  void release() {
+    for (int k = 0; k < 2; k++) { if (pin[k]) cudaFreeHost(pin[k]); if (ev[k]) cudaEventDestroy(ev[k]); pin[k] = nullptr; ev[k] = nullptr; }
+  }
   int init() {
     for (int k = 0; k < 2; k++) {
-      if (cudaHostAlloc((void **)&pin[k], kChunk, cudaHostAllocDefault) != cudaSuccess) return B200_ERR_ALLOC;
-      if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) return B200_ERR_CUDA;
+      if (!pin[k] && cudaHostAlloc((void **)&pin[k], kChunk, cudaHostAllocDefault) != cudaSuccess) { pin[k] = nullptr; return B200_ERR_ALLOC; }
+      if (!ev[k] && cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { ev[k] = nullptr; return B200_ERR_CUDA; }
     }
     return B200_OK;
   }
@@ -126,7 +128,10 @@ struct DevTmp {
   ~DevTmp() { for (auto q : p) if (q) cudaFree(q); }
 };
 struct FileCloser { FILE *fd; ~FileCloser() { if (fd) fclose(fd); } };
+Stager g_stager;
 }  // namespace
+
+void snapshot_release() { g_stager.release(); }      // b200_finalize
 
 }  // namespace b200
 
@@ -191,7 +196,7 @@ extern "C" int b200_savepositions(const char *path, double time, const double *m
   FileCloser fc{fopen(path, "w")};
   FILE *fd = fc.fd;
   if (!fd) return B200_ERR_IO;                                // io.c:98-102 endrun(10)
-  Stager sg;
+  Stager &sg = g_stager;
   B200_TRY(sg.init());
   auto marker = [&](long long bytes) -> int { const int d = (int)bytes; return fwrite(&d, sizeof(d), 1, fd) == 1 ? B200_OK : B200_ERR_IO; };
   B200_TRY(marker(256));
@@ -248,7 +253,7 @@ extern "C" int b200_load_snapshot(const char *path, double *time_out, double *ma
   const int n = (int)ntot;
   float *d_pos = (float *)g.d_acc, *d_vel = d_pos + 3 * (size_t)n;
   int *d_id = g.d_cost; float *d_mass = (float *)(g.d_cost + n);
-  Stager sg;
+  Stager &sg = g_stager;
   B200_TRY(sg.init());
   Loader ld(sg);
   B200_TRY(marker(12 * ntot)); B200_TRY(ld.read(fd, d_pos, 12 * (size_t)ntot)); B200_TRY(marker(12 * ntot));

@@ -201,7 +201,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.s_prob); dfree(&g.s_dv); dfree(&g.s_winner); dfree(&g.s_repair);
   dfree(&g.s_cand); dfree(&g.s_candkey); g.s_cand_cap = 0;
   dfree(&g.d_scatlog);
-  sidm_release();
+  sidm_release(); snapshot_release();
   g.search_epoch = ~0ull; g.tree_epoch = 0;
   dfree(&g.d_ewald); g.ewald_box = -1;
   if (g.h_flags) cudaFreeHost(g.h_flags); g.h_flags = nullptr;
