@@ -130,3 +130,30 @@ def test_snapshot_golden():
     assert len(got) == int(g["snap_len"])
     assert got[:264] == g["snap_head"].tobytes()
     assert hashlib.sha256(got).hexdigest() == str(g["snap_sha256"])
+
+
+def test_snapshot_writer_reader_edge_cases(tmp_path):
+    """format-1 round trips of the oracle writer / reader: a single particle, every type with a MassTable entry (no
+    mass block at all), type-5 particles left out of the file (io.c:265 loops over types 0..4)"""
+    import oracle
+    rng = np.random.default_rng(3)
+    for n, types, mt in ((1, np.array([1], np.int32), None),
+                         (50, rng.choice(np.array([1, 2, 3, 4], np.int32), 50), [0, 0.5, 0.25, 2.0, 1.0, 0]),
+                         (64, rng.choice(np.array([1, 3, 5], np.int32), 64), [0, 0, 0, 0.125, 0, 0])):
+        pos = rng.standard_normal((n, 3)).astype(np.float32); vel = rng.standard_normal((n, 3)).astype(np.float32)
+        mass = rng.random(n).astype(np.float32); ids = np.arange(1, n + 1, dtype=np.int32)
+        raw = oracle.snapshot_bytes(pos, vel, ids, mass, types, time=0.5, mass_table=mt)
+        p = tmp_path / f"snap_{n}"
+        p.write_bytes(raw)
+        b = oracle.read_snapshot(str(p))
+        order = np.concatenate([np.nonzero(types == t)[0] for t in range(5)])
+        assert b["npart"].tolist() == [int((types == t).sum()) for t in range(5)] + [0] and b["time"] == 0.5
+        assert np.array_equal(b["pos"], pos[order]) and np.array_equal(b["vel"], vel[order]) and np.array_equal(b["ids"], ids[order])
+        table = np.zeros(6) if mt is None else np.asarray(mt, np.float64)
+        with_mass = order[table[types[order]] == 0]
+        if len(with_mass):
+            assert np.array_equal(b["mass"], mass[with_mass])
+        else:
+            assert b["mass"] is None
+        nblocks = 4 + (1 if len(with_mass) else 0)
+        assert len(raw) == 256 + 28 * len(order) + 4 * len(with_mass) + 8 * nblocks
