@@ -145,3 +145,51 @@ def test_read_ic_golden_three_types():
         with pytest.raises(B200Error) as e:
             hp.read_ic(os.path.join(out, "absent"))
         assert e.value.code == 9007
+
+
+def test_snapshot_edge_cases():
+    """three particles; every type with a MassTable entry (no mass block in the file, masses come from the table on
+    load); a file that holds type-5 particles (other codes write them; io.c's writer leaves them out)"""
+    import oracle
+    from sidm_b200 import HotPath
+    rng = np.random.default_rng(3)
+    out = tempfile.mkdtemp()
+    for n, types, mt in ((3, np.array([1, 1, 1], np.int32), None),
+                         (500, rng.choice(np.array([1, 2, 3, 4], np.int32), 500), [0, 0.5, 0.25, 2.0, 1.0, 0])):
+        pos = rng.standard_normal((n, 3)).astype(np.float32); vel = rng.standard_normal((n, 3)).astype(np.float32)
+        mass = rng.random(n).astype(np.float32); ids = np.arange(1, n + 1, dtype=np.int32)
+        want = oracle.snapshot_bytes(pos, vel, ids, mass, types, time=0.5, mass_table=mt, omega0=1.0)
+        with HotPath(n) as hp:
+            hp.set_particles(pos, vel, mass, ids)
+            hp.set_field("ptype", types)
+            hp.predict_collisionless_only(0.0)
+            path = os.path.join(out, f"snap_{n}")
+            hp.savepositions(path, time=0.5, mass_table=mt)
+            assert open(path, "rb").read() == want
+            t, mt2, npart = hp.read_ic(path)
+            assert hp.n == n and t == 0.5
+            ty = hp.peek("ptype", np.int32, (n,))
+            assert np.array_equal(ty, np.sort(types))
+            if mt is not None:                                   # masses from the table
+                assert np.array_equal(hp.peek("posm", np.float32, (n, 4))[:, 3], np.asarray(mt, np.float32)[ty])
+            hp.savepositions(path + "b", time=0.5, mass_table=mt)
+            assert open(path + "b", "rb").read() == want
+    # a file with type-5 particles: header and blocks by hand (the oracle writer follows io.c and drops them)
+    n1, n5 = 40, 24
+    n = n1 + n5
+    pos = rng.standard_normal((n, 3)).astype(np.float32); vel = rng.standard_normal((n, 3)).astype(np.float32)
+    mass = rng.random(n).astype(np.float32); ids = np.arange(1, n + 1, dtype=np.int32)
+    base = oracle.snapshot_bytes(pos[:n1], vel[:n1], ids[:n1], mass[:n1], None, time=0.25, omega0=1.0)
+    hdr = bytearray(base[4:260])
+    hdr[20:24] = np.array([n5], np.int32).tobytes(); hdr[96 + 20:96 + 24] = np.array([n5], np.int32).tobytes()   # npart[5], npartTotal[5]
+    rec = lambda b: np.array([len(b)], np.int32).tobytes() + b + np.array([len(b)], np.int32).tobytes()
+    raw = rec(bytes(hdr)) + rec(pos.tobytes()) + rec(vel.tobytes()) + rec(ids.tobytes()) + rec(mass.tobytes())
+    path = os.path.join(out, "snap_t5")
+    open(path, "wb").write(raw)
+    with HotPath(n) as hp:
+        t, mt2, npart = hp.read_ic(path)
+        assert npart.tolist() == [0, n1, 0, 0, 0, n5] and hp.n == n
+        assert np.array_equal(hp.peek("ptype", np.int32, (n,)), np.r_[np.ones(n1, np.int32), np.full(n5, 5, np.int32)])
+        assert np.array_equal(hp.peek("posm", np.float32, (n, 4)), np.c_[pos, mass])
+        hp.savepositions(path + "b", time=t)                    # written back without the type-5 particles, like io.c
+        assert open(path + "b", "rb").read() == base
