@@ -102,6 +102,19 @@ class Sharder:
     def compute_accelerations(self, mode, time, vmax, active=None):
         self.hp.compute_accelerations(mode, active, time, vmax)
 
+    # statistics and snapshots (global.c:18, io.c:16): the particle state is replicated, so every rank computes the same
+    # SysState (deterministic block sums) and ONE rank writes the file - the reference reduces / sends to task 0 instead
+    # (global.c:59-66, io.c:90-103,390-470)
+    def compute_global_quantities_of_system(self):
+        return self.hp.compute_global_quantities_of_system()
+
+    def savepositions(self, path, **kw):
+        npart = self.hp.savepositions(path, **kw) if self.rank == 0 else None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        return npart
+
     # host array-of-structs sharded over the ranks (the reference's per-rank P[]): rank r owns rows
     # [r*rows, (r+1)*rows); PCIe carries only the own rows, NVLink replicates them
     def rows(self):

@@ -69,7 +69,13 @@ def main(out, n, backend):
         res["aos_" + f] = back[f][lo:hi].copy()
     if world > 1 and rank == 0:
         assert np.array_equal(back["Accel"][hi:], aos["Accel"][hi:]), "rows of other ranks must stay untouched"
+    # statistics on every rank (replicated state), snapshot by rank 0 only
+    res["sys"] = sh.compute_global_quantities_of_system().flat()
+    snap = out + ".snap"
+    sh.savepositions(snap, time=t, mass_table=[0, 0, 0.25, 0, 0, 0])
+    assert os.path.exists(snap)
     if rank == 0:
+        res["snap"] = np.frombuffer(open(snap, "rb").read(), np.uint8)
         np.savez(out, acc_start=acc1, old_start=old1, **res)
     hp.close()
     if world > 1:
