@@ -112,10 +112,24 @@ def main_global():
     import hashlib
     mt = [0, 0, float(2 * mass[0]), 0, 0, 0]
     snap = open(R.savepositions(3, os.getcwd(), mass_table=mt, hubble_param=0.7), "rb").read()
+    # three trees: forces (both criteria), interaction counts, raw potentials, start-up smoothing lengths
+    oldacc = R.get("OLDACC")
+    posp, velp, massp, potp = R.get("POSPRED"), R.get("VELPRED"), R.get("MASS"), R.get("POT")
+    idx = np.arange(0, N, 7, dtype=np.int32)
+    R.treebuild()
+    R.set("OLDACC", np.zeros(N, np.float32))
+    acc_bh, cost_bh = R.force_tree(idx)
+    R.set("OLDACC", oldacc)
+    acc_rel, cost_rel = R.force_tree(idx)
+    pot_raw = R.potential(idx)
+    R.setup_smoothinglengths_sidm(30)
+    hsml, ngb = R.get("HSML"), R.get("NGB")
     os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "types3k.npz"), idx=idx, acc_bh=acc_bh, cost_bh=cost_bh, acc_rel=acc_rel, cost_rel=cost_rel,
+                        pot_raw=pot_raw, hsml=hsml, ngb=ngb)
     np.savez_compressed(os.path.join(HERE, "global3k.npz"), types=types, eps=np.array([0, 0.3, 0.6, 0.2, 0, 0]),
-                        pospred=R.get("POSPRED"), velpred=R.get("VELPRED"), mass=R.get("MASS"), oldacc=R.get("OLDACC"),
-                        pot=R.get("POT"), sys=sys_state,
+                        pospred=posp, velpred=velp, mass=massp, oldacc=oldacc,
+                        pot=potp, sys=sys_state,
                         ids=R.get("ID"), snap_mass_table=np.array(mt), snap_time=R.time, snap_len=len(snap),
                         snap_sha256=hashlib.sha256(snap).hexdigest(), snap_head=np.frombuffer(snap[:264], np.uint8),
                         snap_omega0=R.cfg["Omega0"])
