@@ -1,7 +1,9 @@
 """Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built from
 /root/reference by oracle/Makefile) on small seeded inputs.  Run in the build container:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # hernquist3k.npz: one particle type, tree / forces / neighbours / sidm
+    python tests/golden/make_golden.py global     # global3k.npz + types3k.npz: three types - SysState, snapshot file hash,
+                                                  # forces, potentials, start-up smoothing lengths
 
 The reference ships no golden vectors of its own; these fixtures pin the
 oracle restatement (oracle/*.c) and, through it, the CUDA path, on machines where
