@@ -22,7 +22,7 @@ typedef struct oparams {
   double theta;            /* All.ErrTolTheta */
   double alpha;            /* All.ErrTolForceAcc */
   int    criterion;        /* All.TypeOfOpeningCriterion */
-  double eps;              /* Plummer softening of the (single) particle type */
+  double eps;              /* Plummer softening: of the particle type, or max(tree type, target type) in a forest */
   double G;
   int    des_ngb, max_dev; /* All.DesNumNgb, All.MaxNumNgbDeviation */
   double sigma;            /* All.CrossSectionInternal */
@@ -45,6 +45,11 @@ void   otree_domain(const otree *t, float *mn, float *mx);
 void   otree_force(const otree *t, const oparams *p, int nt, const int *targets, const float *oldacc,
                    double *acc, int *cost /*[nt][2] particle,node*/);
 void   otree_direct(const otree *t, const oparams *p, int nt, const int *targets, double *acc);
+/* several particle types = one tree per type (forcetree.c:90-158, 798-808, 1397-1409): the same walks for targets given
+ * by position, with p->eps = max(eps of the tree's type, eps of the target's type); keep != 0 adds to acc / cost / pot
+ * (second and later trees of a target, in ascending type order like the reference's loop) */
+void   otree_force_at(const otree *t, const oparams *p, int nt, const float *xyz, const float *oldacc, double *acc, int *cost, int keep);
+void   otree_potential_at(const otree *t, const oparams *p, int nt, const float *xyz, const float *oldacc, double *pot, int keep);
 /* gravtree.c:230-324 epilogue for non-comoving runs */
 void   ograv_epilogue(const oparams *p, int nt, const double *acc, float *accel, float *oldacc);
 

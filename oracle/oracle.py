@@ -320,3 +320,63 @@ class Oracle:
         return self.L.osidm_ensure(self.tree, C.byref(self.par), self.n, _p(self.vel), _p(self.mass), _p(self.hsml),
                                    _p(dta), _p(self.dvel), _p(self.ngb), _p(self.left), _p(self.right), float(vmax),
                                    self.rng)
+
+
+class OracleForest:
+    """Several collisionless particle types: one tree per type present (forcetree.c:90-158), every target walks all of
+    them in ascending type order into the same accumulators with epsilon = max(eps of the tree's type, eps of the
+    target's type) (forcetree.c:798-808 forces, :1397-1409 potentials).  Each tree is the single-type oracle tree of
+    that type's particles in index order (the reference inserts them in that order)."""
+
+    def __init__(self, pos, vel, mass, types, eps_table, **kw):
+        self.pos = np.ascontiguousarray(pos, np.float32)
+        self.types = np.ascontiguousarray(types, np.int32)
+        self.eps = np.asarray(eps_table, np.float64)
+        self.n = len(self.types)
+        self.members, self.trees = {}, {}
+        for t in sorted(set(self.types.tolist())):
+            sel = np.nonzero(self.types == t)[0]
+            self.members[t] = sel
+            o = Oracle(self.pos[sel], np.ascontiguousarray(vel, np.float32)[sel], np.ascontiguousarray(mass, np.float32)[sel],
+                       eps=float(self.eps[t]), **kw)
+            o.treebuild()
+            self.trees[t] = o
+        L = lib()
+        L.otree_force_at.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.otree_force_at.restype = None
+        L.otree_potential_at.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.otree_potential_at.restype = None
+        self.L = L
+
+    def _walk(self, idx, oldacc, fn, out_width):
+        idx = np.ascontiguousarray(idx, np.int32)
+        oa_all = np.zeros(self.n, np.float32) if oldacc is None else np.ascontiguousarray(oldacc, np.float32)
+        out = np.zeros((len(idx), out_width), np.float64)
+        cost = np.zeros((len(idx), 2), np.int32)
+        first = True
+        for t, o in self.trees.items():                                   # ascending type order
+            for s in sorted(set(self.types[idx].tolist())):               # targets grouped by their own type: one epsilon each
+                rows = np.nonzero(self.types[idx] == s)[0]
+                xyz = np.ascontiguousarray(self.pos[idx[rows]])
+                oa = np.ascontiguousarray(oa_all[idx[rows]])
+                a = np.ascontiguousarray(out[rows])
+                c = np.ascontiguousarray(cost[rows])
+                eps_save = o.par.eps
+                o.par.eps = max(float(self.eps[t]), float(self.eps[s]))
+                fn(o, len(rows), xyz, oa, a, c, 0 if first else 1)
+                o.par.eps = eps_save
+                out[rows] = a
+                cost[rows] = c
+            first = False
+        return out, cost
+
+    def force_tree(self, idx, oldacc=None):
+        """double accelerations and (particle, node) interaction counts of force_treeevaluate() over all trees"""
+        return self._walk(idx, oldacc, lambda o, n, xyz, oa, a, c, keep: self.L.otree_force_at(
+            o.tree, C.byref(o.par), n, _p(xyz), _p(oa), _p(a), _p(c), keep), 3)
+
+    def potential(self, idx, oldacc=None):
+        """raw potentials as force_treeevaluate_potential() leaves them over all trees"""
+        out, _ = self._walk(idx, oldacc, lambda o, n, xyz, oa, a, c, keep: self.L.otree_potential_at(
+            o.tree, C.byref(o.par), n, _p(xyz), _p(oa), _p(a), keep), 1)
+        return out[:, 0]

@@ -226,13 +226,15 @@ static double lerp_tab(const double *tab, double u, int *ii, double *ff)
 { *ii = (int)(u * KLEN); *ff = (u - ((double)*ii) / KLEN) * KLEN; return tab[*ii] + (tab[*ii + 1] - tab[*ii]) * *ff; }
 
 /* one target; forcetree.c:817-1089 (BH) and :1097-1377 (relative), dt = 0 */
-static void walk_one(const otree *t, const oparams *p, const float *tp, float oldacc, double *acc, int *cost)
+/* keep != 0: add to acc / cost instead of starting from zero - the second and later trees of a target when there is
+ * one tree per particle type (forcetree.c:798-808: the accumulators are zeroed once, then every tree is walked) */
+static void walk_one(const otree *t, const oparams *p, const float *tp, float oldacc, double *acc, int *cost, int keep)
 {
   const int bh = (p->criterion == 0 || oldacc == 0);
   const double h = 2.8 * p->eps, h_inv = 1 / h;
   const double h2_inv = h_inv * h_inv, h3_inv = h2_inv * h_inv, h4_inv = h2_inv * h2_inv, h5_inv = h2_inv * h3_inv, h6_inv = h3_inv * h3_inv;
   const double oac = oldacc * p->alpha;
-  acc[0] = acc[1] = acc[2] = 0; cost[0] = cost[1] = 0;
+  if (!keep) { acc[0] = acc[1] = acc[2] = 0; cost[0] = cost[1] = 0; }
   int item = t->n;                                          /* root */
   while (item >= 0) {
     if (item < t->n) {                                      /* a particle */
@@ -288,19 +290,24 @@ void otree_force(const otree *t, const oparams *p, int nt, const int *targets, c
 {
   for (int i = 0; i < nt; i++) {
     int c[2];
-    walk_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f, acc + 3 * i, c);
+    walk_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f, acc + 3 * i, c, 0);
     if (cost) { cost[2 * i] = c[0]; cost[2 * i + 1] = c[1]; }
   }
 }
+/* the same walk for targets given by position (particles of another type's tree, forcetree.c:798-808); oldacc and the
+ * results are per target entry */
+void otree_force_at(const otree *t, const oparams *p, int nt, const float *xyz, const float *oldacc, double *acc, int *cost, int keep)
+{
+  for (int i = 0; i < nt; i++) walk_one(t, p, xyz + 3 * i, oldacc ? oldacc[i] : 0.0f, acc + 3 * i, cost + 2 * i, keep);
+}
 
 /* potential of one target: forcetree.c:1417-1577 (BH) and :1585-1755 (relative criterion) */
-static double pot_one(const otree *t, const oparams *p, const float *tp, float oldacc)
+static double pot_one(const otree *t, const oparams *p, const float *tp, float oldacc, double pot)
 {
   const int bh = (p->criterion == 0 || oldacc == 0);        /* forcetree.c:1404 */
   const double h = 2.8 * p->eps, h_inv = 1 / h;
   const double h2_inv = h_inv * h_inv, h3_inv = h2_inv * h_inv, h5_inv = h2_inv * h3_inv;
   const double oac = oldacc * p->alpha;
-  double pot = 0;
   int item = t->n;
   while (item >= 0) {
     if (item < t->n) {
@@ -340,7 +347,11 @@ static double pot_one(const otree *t, const oparams *p, const float *tp, float o
 /* raw potentials as force_treeevaluate_potential() leaves them in GravDataPotential (forcetree.c:1389) */
 void otree_potential(const otree *t, const oparams *p, int nt, const int *targets, const float *oldacc, double *pot)
 {
-  for (int i = 0; i < nt; i++) pot[i] = pot_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f);
+  for (int i = 0; i < nt; i++) pot[i] = pot_one(t, p, t->pos + 3 * targets[i], oldacc ? oldacc[targets[i]] : 0.0f, 0.0);
+}
+void otree_potential_at(const otree *t, const oparams *p, int nt, const float *xyz, const float *oldacc, double *pot, int keep)
+{
+  for (int i = 0; i < nt; i++) pot[i] = pot_one(t, p, xyz + 3 * i, oldacc ? oldacc[i] : 0.0f, keep ? pot[i] : 0.0);
 }
 /* potential.c:131-168 without comoving integration and Lambda: float Potential = raw; += m/eps (self energy); *= G */
 void opot_epilogue(const oparams *p, int nt, const double *pot, const float *mass, float *out)

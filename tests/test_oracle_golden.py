@@ -157,3 +157,19 @@ def test_snapshot_writer_reader_edge_cases(tmp_path):
             assert b["mass"] is None
         nblocks = 4 + (1 if len(with_mass) else 0)
         assert len(raw) == 256 + 28 * len(order) + 4 * len(with_mass) + 8 * nblocks
+
+
+def test_forest_of_types_golden():
+    """three particle types (one tree per type, epsilon = max(eps_tree, eps_target), forcetree.c:90-158, 798-808): the
+    oracle forest against the reference's golden vectors - double accelerations with both criteria, interaction
+    counts and raw potentials, bit for bit"""
+    import oracle
+    here = os.path.dirname(__file__)
+    g = dict(np.load(os.path.join(here, "golden", "global3k.npz")))
+    t = dict(np.load(os.path.join(here, "golden", "types3k.npz")))
+    F = oracle.OracleForest(g["pospred"], g["velpred"], g["mass"], g["types"], g["eps"])
+    acc, cost = F.force_tree(t["idx"], None)
+    assert np.array_equal(acc, t["acc_bh"]) and np.array_equal(cost, t["cost_bh"])
+    acc, cost = F.force_tree(t["idx"], g["oldacc"])
+    assert np.array_equal(acc, t["acc_rel"]) and np.array_equal(cost, t["cost_rel"])
+    assert np.array_equal(F.potential(t["idx"], g["oldacc"]), t["pot_raw"])
