@@ -380,3 +380,10 @@ class OracleForest:
         out, _ = self._walk(idx, oldacc, lambda o, n, xyz, oa, a, c, keep: self.L.otree_potential_at(
             o.tree, C.byref(o.par), n, _p(xyz), _p(oa), _p(a), keep), 1)
         return out[:, 0]
+
+    def ngb_variable(self, i, h):
+        """ngb_treefind_variable(P[i].PosPred, h, P[i].Type), forcetree.c:2163: neighbours of particle i inside its own
+        type's tree, as global particle indices in the reference's list order"""
+        t = int(self.types[i])
+        lst, r2 = self.trees[t].ngb_variable(self.pos[i], h)
+        return self.members[t][lst], r2

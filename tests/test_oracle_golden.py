@@ -173,3 +173,7 @@ def test_forest_of_types_golden():
     acc, cost = F.force_tree(t["idx"], g["oldacc"])
     assert np.array_equal(acc, t["acc_rel"]) and np.array_equal(cost, t["cost_rel"])
     assert np.array_equal(F.potential(t["idx"], g["oldacc"]), t["pot_raw"])
+    # neighbour searches stay inside the particle's own type (sidm.c:319-330): the counts the reference ended with
+    for i in t["idx"][::3]:
+        lst, r2 = F.ngb_variable(int(i), t["hsml"][i])
+        assert len(lst) == t["ngb"][i] and (g["types"][lst] == g["types"][i]).all()
