@@ -53,3 +53,20 @@ def test_particle_layout_matches_reference():
     import refdrv
     if refdrv.available("diag"):
         assert refdrv.Reference("diag").psize == 124
+
+
+def test_header_is_plain_c_and_structs_match(tmp_path):
+    """include/sidm_b200.h compiles as C99 (the reference and its shim are C), and the structs the Python mirror passes
+    have the sizes the header declares: b200_sysstate = struct state_of_system (allvars.h:517-537, 102 doubles)"""
+    import ctypes as C
+    import subprocess
+    from sidm_b200 import capi
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "sidm_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(b200_sysstate), sizeof(b200_params), sizeof(b200_layout), '
+                   'sizeof(b200_counters)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes[0] == 102 * 8 == C.sizeof(capi.SysState)
+    assert sizes[1] == C.sizeof(capi.Params) and sizes[2] == C.sizeof(capi.Layout) and sizes[3] == C.sizeof(capi.Counters)
