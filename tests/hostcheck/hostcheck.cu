@@ -149,3 +149,42 @@ extern "C" void hc_walk(int nt, const int *targets, const float *oldacc, int cri
     acc[3 * t] = ax; acc[3 * t + 1] = ay; acc[3 * t + 2] = az; cost[2 * t] = npart; cost[2 * t + 1] = nnode;
   }
 }
+
+// the same lane arithmetic over a forest (one tree per particle type, k_walk<PER, MULTI> of csrc/walk.cu): every tree in
+// turn from its root to the next root, h = 2.8 max(eps of the tree's type, eps of the target's type)
+extern "C" void hc_walk_types(int nt, const int *targets, const float *oldacc, const int *types, const float *eps_table, int criterion,
+                              float theta, float alpha, double *acc, int *cost) {
+  const float theta2 = theta * theta;
+  std::vector<int> roots;
+  for (int id = 0; id < H.m; id++) if (H.nparent[id] < 0) roots.push_back(id);
+  roots.push_back(H.m);
+  for (int t = 0; t < nt; t++) {
+    const float4 tp = H.posm[targets[t]];
+    const float oa = oldacc[targets[t]];
+    const bool bh = criterion == 0 || oa == 0.0f;
+    const float oac = oa * alpha;
+    const float eps_t = eps_table[types[targets[t]] & 7];
+    double ax = 0, ay = 0, az = 0; int npart = 0, nnode = 0;
+    for (size_t r = 0; r + 1 < roots.size(); r++) {
+      const int ttype = H.stype[H.nstart[roots[r]]];                 // type of the tree's first sorted particle
+      const float h_inv = 1.0f / (2.8f * std::max(eps_table[ttype], eps_t));
+      float fx = 0, fy = 0, fz = 0; int it = 0;
+      int no = roots[r];
+      while (no < roots[r + 1]) {
+        const NodeRec &n = H.nodes[no];
+        const float dx = n.sx - tp.x, dy = n.sy - tp.y, dz = n.sz - tp.z;
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        const bool open = bh ? open_bh(n.len2, r2, theta2) : open_rel(n.oc, n.bmax2, r2, oac);
+        if (!open) { pn_force(dx, dy, dz, r2, n, h_inv, fx, fy, fz); nnode++; no = n.skip; }
+        else {
+          const int np = n.pinfo & 15, ps = n.pinfo >> 4;
+          for (int k = 0; k < np; k++) { const float4 q = H.leaf_posm[ps + k]; pp_force(q.x - tp.x, q.y - tp.y, q.z - tp.z, q.w, h_inv, fx, fy, fz); npart++; }
+          no = no + 1;
+        }
+        if (++it == 8) { ax += fx; ay += fy; az += fz; fx = fy = fz = 0; it = 0; }
+      }
+      ax += fx; ay += fy; az += fz;
+    }
+    acc[3 * t] = ax; acc[3 * t + 1] = ay; acc[3 * t + 2] = az; cost[2 * t] = npart; cost[2 * t + 1] = nnode;
+  }
+}

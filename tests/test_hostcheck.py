@@ -115,3 +115,25 @@ def test_forest_of_types_equals_one_tree_per_type(hc):
         assert np.array_equal(sidx[at:at + len(sel)], sel[s1])             # the same particle order inside the tree
         assert np.array_equal(np.argsort(lr[sel], kind="stable"), np.argsort(r1, kind="stable"))   # and the same next[] chain
         at += len(sel)
+
+
+def test_forest_walk_matches_reference_golden(hc):
+    """the walk's lane arithmetic over three trees (k_walk<PER, MULTI>: every tree in turn, h = 2.8 max(eps_tree,
+    eps_target)) against the reference's three-type golden vectors: identical interaction counts, float-level forces"""
+    g = np.load(os.path.join(HERE, "golden", "global3k.npz"))
+    t = np.load(os.path.join(HERE, "golden", "types3k.npz"))
+    pos, mass, types = np.ascontiguousarray(g["pospred"]), np.ascontiguousarray(g["mass"]), np.ascontiguousarray(g["types"])
+    n = len(mass)
+    assert hc.hc_build_types(n, pos.ctypes, mass.ctypes, types.ctypes, 0) == 0
+    idx = np.ascontiguousarray(t["idx"])
+    eps = np.ascontiguousarray(g["eps"], np.float32)
+    acc = np.empty((len(idx), 3))
+    cost = np.empty((len(idx), 2), np.int32)
+    zero = np.zeros(n, np.float32)
+    hc.hc_walk_types(len(idx), idx.ctypes, zero.ctypes, types.ctypes, eps.ctypes, 1, C.c_float(0.5), C.c_float(0.005), acc.ctypes, cost.ctypes)
+    assert (cost == t["cost_bh"]).all(axis=1).mean() > 0.995
+    assert np.sqrt(((acc - t["acc_bh"]) ** 2).sum() / (t["acc_bh"] ** 2).sum()) < 1e-6
+    oa = np.ascontiguousarray(g["oldacc"])
+    hc.hc_walk_types(len(idx), idx.ctypes, oa.ctypes, types.ctypes, eps.ctypes, 1, C.c_float(0.5), C.c_float(0.005), acc.ctypes, cost.ctypes)
+    assert (cost == t["cost_rel"]).all(axis=1).mean() > 0.995
+    assert np.sqrt(((acc - t["acc_rel"]) ** 2).sum() / (t["acc_rel"] ** 2).sum()) < 1e-5
