@@ -353,6 +353,9 @@ void ref_sidm_ensure_neighbours(int mode) { sidm_ensure_neighbours(mode); }
 void ref_setup_smoothinglengths_sidm(int desngb) { setup_smoothinglengths_sidm(desngb); }
 void ref_compute_accelerations(int mode) { compute_accelerations(mode); }
 void ref_advance(void) { advance(); }
+#ifdef SIDM
+int  ref_n_scat_particles(void) { return n_scat_particles; }   /* predict.c:258,268-269: particles that carried a kick into advance() */
+#endif
 /* several particle types (one tree per type, forcetree.c:90-158): softening per type; types go in through ref_set_field(F_TYPE) */
 void ref_set_softening(int type, double eps) { All.SofteningTable[type] = All.SofteningTableMaxPhys[type] = eps; }
 /* global.c:18: SysState as 102 doubles (allvars.h:517-537) */

@@ -274,6 +274,7 @@ class Reference:
 
     def advance(self):
         self.lib.ref_advance()
+        return int(self.lib.ref_n_scat_particles())
 
     # -- RNG log ------------------------------------------------------------
     def rng_log_begin(self, cap):

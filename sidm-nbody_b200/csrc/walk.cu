@@ -343,13 +343,14 @@ __global__ void k_pot_epilogue(int n, const double *raw, const float4 *posm, flo
   v = (float)((double)v + (double)p.w / tab.e[ptype[i] & 7]);      // P[i].Mass / All.SofteningTable[P[i].Type]
   double r2 = 0;
   r2 += (double)fmul(p.x, p.x); r2 += (double)fmul(p.y, p.y); r2 += (double)fmul(p.z, p.z);
+  // products and sums individually rounded like the reference's C expressions (no DFMA contraction)
   if (comoving) {
     const double fac = 0.5 * O0 * H * H;
-    v = periodic ? (float)(G * (double)v) : (float)(G * (double)v - fac * r2);        // potential.c:141-150
+    v = periodic ? (float)__dmul_rn(G, (double)v) : (float)__dsub_rn(__dmul_rn(G, (double)v), __dmul_rn(fac, r2));        // potential.c:141-150
   } else {
     const double fac = -0.5 * OL * H * H;
-    v = (float)((double)v * G);
-    if (fac != 0) v = (float)((double)v + fac * r2);
+    v = (float)__dmul_rn((double)v, G);
+    if (fac != 0) v = (float)__dadd_rn((double)v, __dmul_rn(fac, r2));
   }
   potential[i] = v;
 }
@@ -533,20 +534,20 @@ __global__ void k_grav_epilogue(EpiParams E) {
     if (E.criterion == 1)
       E.oldacc[p] = (float)sqrt((double)fadd(fadd(fmul(a[0], a[0]), fmul(a[1], a[1])), fmul(a[2], a[2])));
     const double fac1 = E.OL * E.H * E.H;
-    for (int k = 0; k < 3; k++) E.accel[3 * (size_t)p + k] = (float)(E.G * (double)a[k] + fac1 * (double)pos[k]);
+    for (int k = 0; k < 3; k++) E.accel[3 * (size_t)p + k] = (float)__dadd_rn(__dmul_rn(E.G, (double)a[k]), __dmul_rn(fac1, (double)pos[k]));
   } else {
     if (E.criterion == 1) {
       const double fac3 = 0.5 * E.H * E.H * E.O0 / E.G;
       double a2 = 0;
-      for (int k = 0; k < 3; k++) { const double x = E.periodic ? (double)a[k] : (double)a[k] + fac3 * (double)pos[k]; a2 += x * x; }
+      for (int k = 0; k < 3; k++) { const double x = E.periodic ? (double)a[k] : __dadd_rn((double)a[k], __dmul_rn(fac3, (double)pos[k])); a2 = __dadd_rn(a2, __dmul_rn(x, x)); }
       E.oldacc[p] = (float)sqrt(a2);
     }
     const double t = E.time;
     const double s_a = sqrt(E.O0 + t * (1 - E.O0 - E.OL) + t * t * t * E.OL);
     const double fac1 = E.G / (E.H * t * t * s_a), fac2 = -1.5 / t, fac3 = 0.5 * E.H * E.O0 / (t * t * s_a);
     for (int k = 0; k < 3; k++) {
-      double v = fac1 * (double)a[k] + fac2 * (double)E.velpred[3 * (size_t)p + k];
-      if (!E.periodic) v += fac3 * (double)pos[k];
+      double v = __dadd_rn(__dmul_rn(fac1, (double)a[k]), __dmul_rn(fac2, (double)E.velpred[3 * (size_t)p + k]));
+      if (!E.periodic) v = __dadd_rn(v, __dmul_rn(fac3, (double)pos[k]));
       E.accel[3 * (size_t)p + k] = (float)v;
     }
   }
