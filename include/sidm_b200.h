@@ -150,7 +150,9 @@ const char *b200_version(void);
  * "compact_exchange" (default 1): SIDM results travel between ranks as {uint16 count per slot + the few
  * scatter proposals} instead of 32-byte records.  "cand_cap" (default 1024): candidates kept per slot in the
  * ReferenceNgbOrder parity mode (the search cube of a particle in the outskirts can clip the dense centre);
- * more than that returns B200_ERR_NGBOVERFLOW like the reference's endrun(78). */
+ * more than that returns B200_ERR_NGBOVERFLOW like the reference's endrun(78).  "walk_pairs" (default 0): 1 selects the packed
+ * sibling-pair form of the gravity walk (f32x2 arithmetic over two child cells at a time, same interaction lists; open boundaries,
+ * one particle type), "walkp_minb" (8 / 6 / 4) its occupancy variant. */
 int  b200_set_option(const char *name, int value);
 /* Generator state for restarts ("next" row f3; the reference's restart files, restart.c:37-154, do not save its
  * MT19937 state, so a restarted reference run draws different scatterings).  Here every random number is a function
@@ -168,6 +170,16 @@ int  b200_download(void);                      /* device -> host AoS (fields the
                                                   PosPred VelPred Accel GravCost OldAcc Left
                                                   Right NgbVelDisp HsmlVelDisp dVel)      */
 int  b200_download_to(void *dst);              /* same, into another array of the bound layout */
+/* Partial transfers for small active sets (the reference moves 20 bytes in / 24 bytes out per ACTIVE particle,
+ * gravtree.c:149-166,230-238; allvars.h:547-559).  b200_upload_active: the fields the host driver changes between two
+ * force computations - advance() (predict.c:245-345: Pos, Vel, VelPred = Vel, dVel = 0, CurrentTime), reflect() (Vel),
+ * find_timesteps() (MaxPredTime) - of the listed particles (normally the previous step's active list), read from the bound
+ * array, 36 bytes each in one H2D copy.  b200_download_active: the fields the path writes (PosPred VelPred Accel OldAcc
+ * GravCost dVel NgbVelDisp HsmlVelDisp Left Right, 76 bytes each, one D2H copy) of the listed particles AND of every
+ * particle that received a partner kick since the last download (the partner of a scattering need not be active,
+ * sidm.c:559-601), scattered into `dst` (NULL: the bound array).  A host that changes anything else uses b200_upload(). */
+int  b200_upload_active(const int *idx, int n);
+int  b200_download_active(const int *idx, int n, void *dst);
 /* Multi-GPU variants (after b200_set_shard): each rank owns host rows [first, first+count) of the
  * global particle order (the reference's per-rank P[] after its domain decomposition).  Upload
  * copies only those rows over PCIe and replicates them to every rank with one all-gather over

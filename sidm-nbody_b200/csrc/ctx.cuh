@@ -83,6 +83,11 @@ struct Ctx {
   int *nminidx = nullptr;          // min original index below the node (next[] order, forcetree.c:274-279)
   int *nlstart = nullptr;          // first position of the node's particles in next[] order
   Moments *nmom = nullptr;
+  // sibling-pair records of the packed walk (walk.cu k_walk_pairs): the child cells of a node are stored next to each
+  // other, two per 128-byte record, components interleaved for the f32x2 instructions
+  PairRec *pairs = nullptr; int *gbase = nullptr; bool pairs_valid = false;
+  bool opt_walk_pairs = false;     // b200_set_option("walk_pairs", 1): the packed sibling-pair walk (measured slower than k_walk: profiles/walk_pairs_r2_ncu_summary.txt)
+  int opt_walkp_minb = 6;          // resident 128-thread blocks per SM the packed walk is compiled for (8, 6, 5 or 4)
   // leaf order (particles sorted by (parent node, octant)): every subtree is a contiguous range
   float4 *leaf_posm = nullptr;
   int *leaf_orig = nullptr, *orig_leaf = nullptr, *leaf_parent = nullptr;
@@ -94,7 +99,7 @@ struct Ctx {
   int *d_active = nullptr, *d_tsorted = nullptr, *d_tkeys = nullptr, *d_tkeys2 = nullptr, *d_tvals2 = nullptr;
   double *d_acc = nullptr;         // [n][3] raw accelerations per target slot
   int *d_cost = nullptr;           // [n][2]
-  unsigned long long *d_ctr = nullptr;   // [8] device counters
+  unsigned long long *d_ctr = nullptr;   // [CT_COUNT] device counters
   unsigned long long *h_ctr = nullptr;
 
   // ---- sidm work buffers
@@ -108,6 +113,10 @@ struct Ctx {
   int *s_repair = nullptr;
   b200_scatlog *d_scatlog = nullptr; int scatlog_cap = 0; int scatlog_n = 0;
   int last_nslot = 0;
+  // particles that received a partner kick since the last download (b200_download_active sends them along)
+  int *kick_list = nullptr; int *d_nkick = nullptr;
+  // pinned / device staging of the partial transfers (b200_upload_active / b200_download_active)
+  char *h_stage = nullptr, *d_stage = nullptr; size_t stage_cap = 0;
   unsigned long long sidm_calls = 0;   // counter-based RNG: the key of a sidm() call is (Seed, sidm_calls); b200_get/set_rng_state
   unsigned long long ts_calls = 0;     // same for the Max/MinSizeTimestep jitter of find_timesteps()
 
@@ -157,8 +166,9 @@ inline void count_launch(int k = 1) { g.cnt.kernel_launches += k; }
 enum { FL_ERR_COINCIDENT = 0, FL_NUM_NODES = 1, FL_MAX_LEVEL = 2, FL_ERR_NGB = 3, FL_NPASS = 4,
        FL_NREPAIR = 5, FL_NSCATLOG = 6, FL_NEXPORT = 7, FL_MULTITYPE = 8, FL_TROOT0 = 9 /* .. 15 */, FL_COUNT = 16 };
 // device counters (d_ctr)
-enum { CT_PART = 0, CT_NODE = 1, CT_LIST_NODES = 2, CT_LIST_PARTS = 3, CT_CAND = 4, CT_PASS1 = 5,
-       CT_SCATTERED = 6, CT_REJECTED = 7, CT_COUNT = 8 };
+enum { CT_PART = 0, CT_NODE = 1, CT_LIST_NODES = 2, CT_LIST_PARTS = 3, CT_WALK_OVF = 4, CT_CAND = 5, CT_PASS1 = 6,
+       CT_SCATTERED = 7, CT_REJECTED = 8, CT_COUNT = 9 };
+constexpr int kWalkCounters = 5;   // [CT_PART, CT_CAND): written by the walk; [CT_CAND, CT_COUNT): by the SIDM chain
 
 // implemented across the .cu files
 int tree_build_impl();

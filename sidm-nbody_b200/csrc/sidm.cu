@@ -808,12 +808,14 @@ __global__ void k_resolve_own(int ns, const int *slot_part, const int *sngb, con
 // sidm.c:559-601: partner gets -dv; several slots naming one partner: the last in buffer order wins
 __global__ void k_resolve_partner(int ns, const int *confirm, const int *partner, const float *dv, const int *winner, float *dvel,
                                   const int *logpos, b200_scatlog *log, int logcap, int logbase, const int *slot_part,
-                                  const float4 *posm, const float4 *velh, const int *pid, float time) {
+                                  const float4 *posm, const float4 *velh, const int *pid, float time, int *kick_list, int *nkick, int kick_cap) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns || !confirm[s]) return;
   const int j = partner[s];
   if (winner[j] == s) {
     dvel[3 * (size_t)j] = -dv[3 * (size_t)s]; dvel[3 * (size_t)j + 1] = -dv[3 * (size_t)s + 1]; dvel[3 * (size_t)j + 2] = -dv[3 * (size_t)s + 2];
+    const int at = atomicAdd(nkick, 1);                    // the partner need not be active: b200_download_active() sends it along
+    if (at < kick_cap) kick_list[at] = j;
   }
   const int lp = logbase + logpos[s];
   if (lp < logcap) {
@@ -1207,7 +1209,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       B200_TRY(cub_scratch(tb4));
       CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
       k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
-                                         g.s_slot_part, g.posm, g.velh, g.pid, (float)time);
+                                         g.s_slot_part, g.posm, g.velh, g.pid, (float)time, g.kick_list, g.d_nkick, g.maxpart);
       int nlog = 0;
       CUDA_TRY(cudaMemcpyAsync(&nlog, S.logpos + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));

@@ -42,6 +42,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.ndp, 8 * (m + 1))); B200_TRY(dalloc(&g.narrive, m + 1));
   B200_TRY(dalloc(&g.nminidx, m + 1)); B200_TRY(dalloc(&g.nlstart, m + 1));
   B200_TRY(dalloc(&g.nmom, m + 1));
+  B200_TRY(dalloc(&g.pairs, m + 4)); B200_TRY(dalloc(&g.gbase, m + 2));
   B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n)); B200_TRY(dalloc(&g.leaf_parent, n));
   B200_TRY(dalloc(&g.lrank, n));
   B200_TRY(dalloc(&g.d_shard_list, n + 64));
@@ -54,6 +55,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.s_rand, n)); B200_TRY(dalloc(&g.s_dir, 3 * n)); B200_TRY(dalloc(&g.s_pmax, n));
   B200_TRY(dalloc(&g.s_prob, n)); B200_TRY(dalloc(&g.s_dv, 3 * n)); B200_TRY(dalloc(&g.s_winner, n));
   B200_TRY(dalloc(&g.s_repair, n));
+  B200_TRY(dalloc(&g.kick_list, n)); B200_TRY(dalloc(&g.d_nkick, (size_t)4));
   g.scatlog_cap = 1 << 20;
   B200_TRY(dalloc(&g.d_scatlog, (size_t)g.scatlog_cap));
   return B200_OK;
@@ -70,6 +72,8 @@ extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
   if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
+  if (!strcmp(name, "walkp_minb")) { g.opt_walkp_minb = value; return B200_OK; }
+  if (!strcmp(name, "walk_pairs")) { g.opt_walk_pairs = value != 0; g.tree_valid = false; return B200_OK; }
   if (!strcmp(name, "shard_overlap")) { g.opt_shard_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "shard_min_work")) { g.shard_min_work = value; return B200_OK; }
   if (!strcmp(name, "compact_exchange")) { g.opt_compact_exchange = value != 0; return B200_OK; }
@@ -167,6 +171,7 @@ extern "C" int b200_init(const b200_params *p) {
   CUDA_TRY(cudaMallocHost((void **)&g.h_ctr, CT_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), g.stream));
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, CT_COUNT * sizeof(unsigned long long), g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.d_nkick, 0, 4 * sizeof(int), g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   memset(&g.cnt, 0, sizeof(g.cnt));
   g.n = 0; g.tree_valid = false; g.sidm_calls = 0; g.ts_calls = 0;
@@ -191,7 +196,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.d_flags); dfree(&g.d_ctr);
   dfree(&g.nodes); dfree(&g.geom); dfree(&g.nstart); dfree(&g.nend); dfree(&g.nparent); dfree(&g.npstart);
   dfree(&g.nlevel); dfree(&g.nnp); dfree(&g.nnchild); dfree(&g.ndp); dfree(&g.narrive);
-  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom);
+  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
   dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.leaf_parent); dfree(&g.lrank);
   dfree(&g.d_shard_list);
   dfree(&g.d_active); dfree(&g.d_tsorted); dfree(&g.d_tkeys); dfree(&g.d_tkeys2); dfree(&g.d_tvals2);
@@ -200,7 +205,8 @@ extern "C" void b200_finalize(void) {
   dfree(&g.s_pass); dfree(&g.s_passlist); dfree(&g.s_rand); dfree(&g.s_dir); dfree(&g.s_pmax);
   dfree(&g.s_prob); dfree(&g.s_dv); dfree(&g.s_winner); dfree(&g.s_repair);
   dfree(&g.s_cand); dfree(&g.s_candkey); g.s_cand_cap = 0;
-  dfree(&g.d_scatlog);
+  dfree(&g.d_scatlog); dfree(&g.kick_list); dfree(&g.d_nkick);
+  if (g.h_stage) cudaFreeHost(g.h_stage); g.h_stage = nullptr; dfree(&g.d_stage); g.stage_cap = 0;
   sidm_release(); snapshot_release();
   g.search_epoch = ~0ull; g.tree_epoch = 0;
   dfree(&g.d_ewald); g.ewald_box = -1;
@@ -431,6 +437,7 @@ extern "C" int b200_download(void) {
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.d_nkick, 0, sizeof(int), g.stream));        // every partner kick has gone to the host
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
@@ -480,6 +487,121 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_download, g.ev0, g.ev1);
+  return B200_OK;
+}
+
+// ----------------------------------------------------------------------------- partial transfers (small active sets)
+// The reference moves 20 bytes in and 24 bytes out per ACTIVE particle (gravtree.c:149-166, 230-238; allvars.h:547-559).
+// Up: what the host driver changes between two force computations - advance() (predict.c:245-345: Pos, Vel, VelPred = Vel,
+// dVel = 0, CurrentTime), reflect() (Vel), find_timesteps() (MaxPredTime) - 32 bytes + index per listed particle.
+// Down: what the path writes - PosPred VelPred Accel OldAcc GravCost dVel NgbVelDisp HsmlVelDisp Left Right, 72 bytes +
+// index - for the listed particles and for every particle that received a partner kick since the last download (the
+// partner of a scattering need not be active, sidm.c:559-601).
+constexpr int kUpWords = 9, kDownWords = 19;
+
+static int ensure_stage(size_t bytes) {
+  if (bytes <= g.stage_cap) return B200_OK;
+  if (g.h_stage) cudaFreeHost(g.h_stage);
+  if (g.d_stage) cudaFree(g.d_stage);
+  g.h_stage = nullptr; g.d_stage = nullptr; g.stage_cap = 0;
+  bytes += bytes / 2 + 4096;
+  if (cudaMallocHost((void **)&g.h_stage, bytes) != cudaSuccess) return B200_ERR_ALLOC;
+  if (cudaMalloc((void **)&g.d_stage, bytes) != cudaSuccess) return B200_ERR_ALLOC;
+  g.stage_cap = bytes;
+  return B200_OK;
+}
+
+__global__ void k_scatter_up(int n, const int *rec, int nmax, float *pos0, float4 *posm, float4 *velh, float *velpred, float *dvel,
+                             float *curtime, float *maxpred) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int *r = rec + (size_t)a * kUpWords;
+  const int i = r[0];
+  if (i < 0 || i >= nmax) return;
+  float4 v = velh[i];
+  for (int k = 0; k < 3; k++) { pos0[3 * (size_t)i + k] = __int_as_float(r[1 + k]); velpred[3 * (size_t)i + k] = __int_as_float(r[4 + k]); dvel[3 * (size_t)i + k] = 0.0f; }
+  v.x = __int_as_float(r[4]); v.y = __int_as_float(r[5]); v.z = __int_as_float(r[6]);
+  velh[i] = v;
+  curtime[i] = __int_as_float(r[7]); maxpred[i] = __int_as_float(r[8]);
+}
+__global__ void k_gather_down(int n, const int *idx, int nk, const int *kicked, int *rec, const float4 *posm, const float4 *velh, const float *velpred,
+                              const float *accel, const float *oldacc, const float *gravcost, const float *dvel, const int *ngb,
+                              const float *left, const float *right) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n + nk) return;
+  const int i = a < n ? idx[a] : kicked[a - n];
+  int *r = rec + (size_t)a * kDownWords;
+  const float4 p = posm[i];
+  r[0] = i;
+  r[1] = __float_as_int(p.x); r[2] = __float_as_int(p.y); r[3] = __float_as_int(p.z);
+  for (int k = 0; k < 3; k++) {
+    r[4 + k] = __float_as_int(velpred[3 * (size_t)i + k]); r[7 + k] = __float_as_int(accel[3 * (size_t)i + k]); r[12 + k] = __float_as_int(dvel[3 * (size_t)i + k]);
+  }
+  r[10] = __float_as_int(oldacc[i]); r[11] = __float_as_int(gravcost[i]);
+  r[15] = ngb[i]; r[16] = __float_as_int(velh[i].w); r[17] = __float_as_int(left[i]); r[18] = __float_as_int(right[i]);
+}
+
+extern "C" int b200_upload_active(const int *idx, int n) {
+  if (!g.ready || !g.have_aos || g.n <= 0) return B200_ERR_STATE;
+  if (n < 0 || n > g.n || (n > 0 && !idx)) return B200_ERR_ARG;
+  if (n == 0) return B200_OK;
+  B200_TRY(ensure_stage((size_t)n * kUpWords * 4));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));             // the staging buffer may still be in flight
+  int *h = (int *)g.h_stage;
+  const b200_layout &L = g.lay;
+  for (int a = 0; a < n; a++) {
+    const int i = idx[a];
+    if (i < 0 || i >= g.n) return B200_ERR_ARG;
+    const char *p = g.h_base + (size_t)i * L.stride;
+    int *r = h + (size_t)a * kUpWords;
+    r[0] = i;
+    memcpy(r + 1, p + L.Pos, 12); memcpy(r + 4, p + L.Vel, 12); memcpy(r + 7, p + L.CurrentTime, 4);
+    if (L.MaxPredTime > 0) memcpy(r + 8, p + L.MaxPredTime, 4); else r[8] = 0;
+  }
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.d_stage, h, (size_t)n * kUpWords * 4, cudaMemcpyHostToDevice, g.stream));
+  k_scatter_up<<<cdiv(n, 256), 256, 0, g.stream>>>(n, (const int *)g.d_stage, g.n, g.pos0, g.posm, g.velh, g.velpred, g.dvel, g.curtime, g.maxpred);
+  count_launch();
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
+  g.tree_valid = false;
+  return B200_OK;
+}
+
+extern "C" int b200_download_active(const int *idx, int n, void *dst) {
+  if (!g.ready || !g.have_aos || g.n <= 0) return B200_ERR_STATE;
+  if (n < 0 || n > g.n || (n > 0 && !idx)) return B200_ERR_ARG;
+  char *out = dst ? (char *)dst : g.h_base;
+  int nk = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nk, g.d_nkick, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (nk > g.maxpart) nk = g.maxpart;
+  const int tot = n + nk;
+  if (tot == 0) return B200_OK;
+  B200_TRY(ensure_stage((size_t)tot * kDownWords * 4 + (size_t)n * 4));
+  int *d_rec = (int *)g.d_stage, *d_idx = d_rec + (size_t)tot * kDownWords;
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, g.stream));
+  k_gather_down<<<cdiv(tot, 256), 256, 0, g.stream>>>(n, d_idx, nk, g.kick_list, d_rec, g.posm, g.velh, g.velpred, g.accel, g.oldacc, g.gravcost, g.dvel,
+                                                      g.ngb, g.left, g.right);
+  count_launch();
+  CUDA_TRY(cudaMemcpyAsync(g.h_stage, d_rec, (size_t)tot * kDownWords * 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.d_nkick, 0, sizeof(int), g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_download, g.ev0, g.ev1);
+  const b200_layout &L = g.lay;
+  const int *h = (const int *)g.h_stage;
+  for (int a = 0; a < tot; a++) {
+    const int *r = h + (size_t)a * kDownWords;
+    char *p = out + (size_t)r[0] * L.stride;
+    memcpy(p + L.PosPred, r + 1, 12); memcpy(p + L.VelPred, r + 4, 12); memcpy(p + L.Accel, r + 7, 12);
+    memcpy(p + L.OldAcc, r + 10, 4); memcpy(p + L.GravCost, r + 11, 4); memcpy(p + L.dVel, r + 12, 12);
+    memcpy(p + L.NgbVelDisp, r + 15, 4); memcpy(p + L.HsmlVelDisp, r + 16, 4); memcpy(p + L.Left, r + 17, 4); memcpy(p + L.Right, r + 18, 4);
+  }
   return B200_OK;
 }
 

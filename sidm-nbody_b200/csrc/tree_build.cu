@@ -203,6 +203,40 @@ __global__ void k_b6(BuildView v, int level) {
   if (id < m && v.nlevel[id] == level) b6_body(v, id);
 }
 
+// ------------------------------------------------------------------ sibling-pair records of the packed walk
+// Child cells of node a occupy the slots 2 + gbase[a] .. of the record array (two slots per 128-byte PairRec), gbase =
+// exclusive scan of the child-cell counts rounded up to even; the root sits alone in pair 0.  A padding slot repeats
+// its sibling's position with zero mass / oc / bmax2 / len2: it is never opened and the walk does not count it.
+__global__ void k_pair_gsize(int m, const unsigned char *nnchild, int *gsize) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id <= m) gsize[id] = id < m ? ((nnchild[id] + 1) & ~1) : 0;
+}
+__global__ void k_pairs(int m, const NodeRec *nodes, const int *nparent, const unsigned char *nnchild, const int *gbase, PairRec *pairs) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= m) return;
+  const int par = nparent[id];
+  int slot = 0; bool pad = true;
+  if (par >= 0) {
+    int r = 0;
+    for (int c = par + 1; c != id; c = nodes[c].skip) r++;       // rank among the parent's child cells (octant order)
+    slot = 2 + gbase[par] + r;
+    const int kp = nnchild[par];
+    pad = (r == kp - 1) && (kp & 1);
+  }
+  const NodeRec n = nodes[id];
+  const int kc = nnchild[id];
+  const int cinfo = kc ? ((((2 + gbase[id]) >> 1) << 4) | kc) : 0;
+  float *f = pairs[slot >> 1].f + (slot & 1);
+  f[0] = n.sx; f[2] = n.sy; f[4] = n.sz; f[6] = n.mass;
+  f[8] = n.oc; f[10] = n.bmax2; f[12] = __int_as_float(cinfo); f[14] = __int_as_float(n.pinfo);
+  f[16] = fmul(-3.0f, n.q11); f[18] = fmul(-3.0f, n.q22); f[20] = fmul(-3.0f, n.q33); f[22] = fmul(-3.0f, n.q12);
+  f[24] = fmul(-3.0f, n.q13); f[26] = fmul(-3.0f, n.q23); f[28] = fmul(-1.5f, n.p); f[30] = n.len2;
+  if (pad) {
+    f[1] = n.sx; f[3] = n.sy; f[5] = n.sz;
+    for (int c = 3; c < 16; c++) f[2 * c + 1] = 0.0f;
+  }
+}
+
 static int ensure_cub(size_t bytes) {
   if (bytes <= g.cub_tmp_bytes) return B200_OK;
   if (g.cub_tmp) cudaFree(g.cub_tmp);
@@ -342,6 +376,19 @@ int tree_build_impl() {
     CUDA_TRY(cudaMemsetAsync(g.narrive, 0, (size_t)(m + 1) * sizeof(int), st));
     k_b5_up<<<cdiv(m + 1, 128), 128, 0, st>>>(v);
     count_launch();
+  }
+  // 5b. sibling-pair records for the packed walk (one tree, open boundaries)
+  g.pairs_valid = false;
+  if (g.opt_walk_pairs && !multi && !(g.par.PeriodicBoundariesOn && g.par.BoxSize > 0)) {
+    int *gsize = g.narrive;                      // free again after the moments
+    k_pair_gsize<<<GM, B, 0, st>>>(m, g.nnchild, gsize);
+    size_t tb4 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb4, gsize, g.gbase, m + 1, st);
+    B200_TRY(ensure_cub(tb4));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_tmp, tb4, gsize, g.gbase, m + 1, st));
+    k_pairs<<<cdiv(m, B), B, 0, st>>>(m, g.nodes, g.nparent, g.nnchild, g.gbase, g.pairs);
+    count_launch(4);
+    g.pairs_valid = true;
   }
   // 6. the reference's next[] chain order (only needed to scan neighbours in its order)
   if (g.par.ReferenceNgbOrder) {

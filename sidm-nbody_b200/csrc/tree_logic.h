@@ -129,6 +129,12 @@ struct __attribute__((aligned(16))) NodeRec {
 };
 // the first 32 bytes decide open/accept for the relative criterion (the BH test needs len2)
 
+// Record of the packed walk: two sibling cells, component c of cell h at f[2*c + h] (so that one 16-byte load yields
+// two (cell0, cell1) register pairs for the sm_100a f32x2 instructions).  Components:
+//   0 sx 1 sy 2 sz 3 mass | 4 oc 5 bmax2 6 cinfo 7 pinfo | 8 -3 Q11 9 -3 Q22 10 -3 Q33 11 -3 Q12 | 12 -3 Q13 13 -3 Q23 14 -1.5 P 15 len2
+// cinfo = (pair index of the first child cell << 4) | number of child cells; pinfo as in NodeRec.
+struct __attribute__((aligned(16))) PairRec { float f[32]; };
+
 // raw moments of a node about its geometric centre, in double (forcetree.c:433-571)
 struct Moments { double m, s[3], r[6]; };   // r: xx yy zz xy xz yz
 

@@ -240,6 +240,160 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) k_walk(WalkParam
   }
 }
 
+// ------------------------------------------------------------------ packed walk over sibling pairs
+// Same interaction lists as k_walk (every lane takes its own open/accept decision on every cell it reaches), other
+// order of work: when a lane opens a cell, ALL child cells of that cell will be visited by the warp, so they are
+// processed together, two at a time with the packed fp32 instructions of sm_100a (FADD2 / FMUL2 / FFMA2: one issue
+// slot for two cells).  The warp keeps a LIFO of pending sibling groups {first pair | number of cells, mask of the
+// lanes that opened the parent} in shared memory; a group is popped, its <= 4 cell pairs are loaded by broadcast
+// (one 128-byte record per pair), every lane of the mask decides and accumulates, opened cells contribute their
+// direct particles at once and push their own child group.  The quadrupole arrives pre-scaled (-3 Q, -1.5 P).
+// Open boundaries, one tree.  Results differ from k_walk only in the order of the float partial sums.
+constexpr int kPairStack = 160;
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+struct PairOut { double ax, ay, az; int npart, nnode; unsigned wnodes, wparts; bool overflow; };
+// the softened forms as real calls: rare, and out of the hot loop's register allocation
+__device__ __noinline__ float2 pn_soft_call(float r2, float potq, float mass, float pp, float h_inv) { return pn_soft(r2, potq, mass, pp, h_inv); }
+__device__ __noinline__ float pp_soft_call(float r2, float mass, float h_inv) { return pp_soft(r2, mass, h_inv); }
+
+template <int MODE>
+__device__ __forceinline__ void walk_pairs_body(const WalkParams &P, const PairRec *__restrict__ pairs, uint2 *stk, float4 *stage, const int lane, const bool valid,
+                                                const float4 tp, const bool bh, const float oac, PairOut &R) {
+  const float2 ntx = f2(-tp.x, -tp.x), nty = f2(-tp.y, -tp.y), ntz = f2(-tp.z, -tp.z), oac2 = f2(oac, oac);
+  const float theta2 = P.theta2, h_inv = P.h_inv, h2 = 1.0f / (h_inv * h_inv);
+  const float inf = __int_as_float(0x7f800000);
+  const unsigned lbit = 1u << lane;
+  float2 fx = f2(0, 0), fy = f2(0, 0), fz = f2(0, 0);
+  double ax = 0, ay = 0, az = 0;
+  int npart = 0, nvisit = 0, nopen = 0, pending = 0;            // accepted cells = cells this lane decided on - cells it opened
+  unsigned wnodes = 0, wparts = 0;
+  const unsigned vm = __ballot_sync(0xffffffffu, valid);
+  int sp = 0;
+  if (vm) { stk[0] = make_uint2(1u, vm); sp = 1; }              // the root: pair 0, one cell
+  bool overflow = false;
+  const float4 *recs = reinterpret_cast<const float4 *>(pairs);
+  while (sp > 0) {
+    const uint2 e = stk[--sp];
+    __syncwarp();                                               // every lane has read the entry before anyone overwrites the slot
+    const bool in = (e.y & lbit) != 0;
+    const int k = (int)(e.x & 15u);
+    // the whole group (<= 4 pair records = 512 bytes) in one coalesced load, staged in shared memory
+    if (lane < 4 * (k + 1)) stage[lane] = __ldg(recs + 8 * (size_t)(e.x >> 4) + lane);      // 8 float4 per pair, (k+1)/2 pairs
+    __syncwarp();
+    const float4 *rec = stage;
+    if (in) nvisit += k;
+    wnodes += k;
+    for (int j = 0; j < k; j += 2, rec += 8) {
+      const float4 A = rec[0], B = rec[1], Cv = rec[2], D = rec[3];
+      const float4 H = rec[7];                                  // -1.5 P (x2), len2 (x2)
+      const float2 dx = __fadd2_rn(f2(A.x, A.y), ntx), dy = __fadd2_rn(f2(A.z, A.w), nty), dz = __fadd2_rn(f2(B.x, B.y), ntz);
+      float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+      bool c0, c1;                                              // forcetree.c:967 / :1253-1257
+      if (MODE == 2) { c0 = H.z > r2.x * theta2; c1 = H.w > r2.y * theta2; }
+      else {
+        const float2 o = __fmul2_rn(__fmul2_rn(__fmul2_rn(oac2, r2), r2), r2);
+        c0 = (Cv.x > o.x) || (r2.x < Cv.z); c1 = (Cv.y > o.y) || (r2.y < Cv.w);
+        if (MODE == 0 && bh) { c0 = H.z > r2.x * theta2; c1 = H.w > r2.y * theta2; }
+      }
+      const bool in1 = in && (j + 1 < k);
+      const bool a0 = in && !c0, a1 = in1 && !c1, o0 = in && c0, o1 = in1 && c1;
+      if (a0 || a1) {
+        const float4 E = rec[4], F = rec[5], G = rec[6];
+        const float2 q11 = f2(E.x, E.y), q22 = f2(E.z, E.w), q33 = f2(F.x, F.y), q12 = f2(F.z, F.w), q13 = f2(G.x, G.y), q23 = f2(G.z, G.w);
+        const float2 qx = __ffma2_rn(q13, dz, __ffma2_rn(q12, dy, __fmul2_rn(q11, dx)));
+        const float2 qy = __ffma2_rn(q23, dz, __ffma2_rn(q22, dy, __fmul2_rn(q12, dx)));
+        const float2 qz = __ffma2_rn(q33, dz, __ffma2_rn(q23, dy, __fmul2_rn(q13, dx)));
+        const float2 tt = __ffma2_rn(dz, qz, __ffma2_rn(dy, qy, __fmul2_rn(dx, qx)));          // -3 y^T Q y
+        // a half this lane does not accept gets r^2 = inf: 1/r = 0 and every term of it vanishes
+        if (!a0) r2.x = inf;
+        if (!a1) r2.y = inf;
+        // fac = m/r^3 + (15 potq/r^2 - 1.5 P)/r^5, ff = -3/r^5 (forcetree.c:1262-1301) with -3 folded into Q
+        const float2 ri = f2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
+        const float2 r2i = __fmul2_rn(ri, ri), r3i = __fmul2_rn(r2i, ri);
+        float2 r5i = __fmul2_rn(r3i, r2i);
+        float2 fac = __ffma2_rn(__ffma2_rn(__fmul2_rn(tt, r2i), f2(-2.5f, -2.5f), f2(H.x, H.y)), r5i, __fmul2_rn(f2(B.z, B.w), r3i));
+        if (r2.x < h2 || r2.y < h2) {                            // softened cell (rare): forcetree.c:1026-1074
+          if (r2.x < h2) { const float2 v = pn_soft_call(r2.x, tt.x * (-1.0f / 6), B.z, H.x * (-2.0f / 3), h_inv); fac.x = v.x; r5i.x = v.y * (-1.0f / 3); }
+          if (r2.y < h2) { const float2 v = pn_soft_call(r2.y, tt.y * (-1.0f / 6), B.w, H.y * (-2.0f / 3), h_inv); fac.y = v.x; r5i.y = v.y * (-1.0f / 3); }
+        }
+        fx = __ffma2_rn(r5i, qx, __ffma2_rn(dx, fac, fx));
+        fy = __ffma2_rn(r5i, qy, __ffma2_rn(dy, fac, fy));
+        fz = __ffma2_rn(r5i, qz, __ffma2_rn(dz, fac, fz));
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, o0), m1 = __ballot_sync(0xffffffffu, o1);
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        const unsigned mo = hh ? m1 : m0;
+        if (!mo) continue;                                      // warp-uniform
+        const bool open = hh ? o1 : o0;
+        const int cinfo = __float_as_int(hh ? D.y : D.x), pinfo = __float_as_int(hh ? D.w : D.z);
+        const int np = pinfo & 15;
+        const float4 *lp = P.leaf_posm + (pinfo >> 4);
+        wparts += np;
+#pragma unroll 1
+        for (int q = 0; q < np; q++) {
+          const float4 pq = __ldg(lp + q);
+          if (open) {
+            const float px = pq.x - tp.x, py = pq.y - tp.y, pz = pq.z - tp.z;
+            const float pr2 = fmaf(pz, pz, fmaf(py, py, px * px));
+            const float pri = rsqrt_fast(pr2);
+            float pf = pq.w * pri * pri * pri;                  // m/r^3, forcetree.c:1135-1186
+            if (pr2 < h2) pf = pp_soft_call(pr2, pq.w, h_inv);
+            fx.x = fmaf(px, pf, fx.x); fy.x = fmaf(py, pf, fy.x); fz.x = fmaf(pz, pf, fz.x);
+          }
+        }
+        if (open) { npart += np; nopen++; }
+        if (cinfo & 15) {                                       // child cells: one more pending group (every lane writes the same words)
+          if (sp < kPairStack) { stk[sp] = make_uint2((unsigned)cinfo, mo); sp++; } else overflow = true;
+          // its records towards L1 while the rest of this group is processed (one 128-byte line per pair)
+          if (lane < (((cinfo & 15) + 1) >> 1)) asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + 8 * (size_t)((unsigned)cinfo >> 4) + 8 * lane));
+        }
+      }
+    }
+    pending += k;
+    if (pending >= 24) {                                        // float partial sums -> double accumulators
+      ax += (double)fx.x + (double)fx.y; ay += (double)fy.x + (double)fy.y; az += (double)fz.x + (double)fz.y;
+      fx = f2(0, 0); fy = f2(0, 0); fz = f2(0, 0); pending = 0;
+    }
+  }
+  ax += (double)fx.x + (double)fx.y; ay += (double)fy.x + (double)fy.y; az += (double)fz.x + (double)fz.y;
+  R.ax = ax; R.ay = ay; R.az = az; R.npart = npart; R.nnode = nvisit - nopen; R.wnodes = wnodes; R.wparts = wparts; R.overflow = overflow;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(WALK_THREADS, MINB) k_walk_pairs(WalkParams P, const PairRec *__restrict__ pairs) {
+  __shared__ uint2 s_stack[WALK_THREADS / 32][kPairStack];
+  __shared__ float4 s_stage[WALK_THREADS / 32][32];
+  const int lane = threadIdx.x & 31;
+  uint2 *stk = s_stack[threadIdx.x >> 5];
+  float4 *stage = s_stage[threadIdx.x >> 5];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < P.nt;
+  int slot = 0, part = 0;
+  if (valid) { slot = P.tsorted[t]; part = P.slot_part ? P.slot_part[slot] : slot; }
+  float4 tp = make_float4(0, 0, 0, 0); float oa = 0;
+  if (valid) { tp = P.posm[part]; oa = P.oldacc[part]; }
+  const bool bh = (P.criterion == 0) || (oa == 0.0f);          // forcetree.c:801
+  const float oac = oa * P.alpha;                               // forcetree.c:1129
+  const bool all_rel = __all_sync(0xffffffffu, !valid || !bh), all_bh = __all_sync(0xffffffffu, !valid || bh);
+  PairOut R;
+  if (all_rel) walk_pairs_body<1>(P, pairs, stk, stage, lane, valid, tp, bh, oac, R);
+  else if (all_bh) walk_pairs_body<2>(P, pairs, stk, stage, lane, valid, tp, bh, oac, R);
+  else walk_pairs_body<0>(P, pairs, stk, stage, lane, valid, tp, bh, oac, R);
+  if (valid) {
+    P.acc[3 * (size_t)slot] = R.ax; P.acc[3 * (size_t)slot + 1] = R.ay; P.acc[3 * (size_t)slot + 2] = R.az;
+    P.cost[2 * (size_t)slot] = R.npart; P.cost[2 * (size_t)slot + 1] = R.nnode;
+  }
+  unsigned long long spp = R.npart, sn = R.nnode;
+  for (int o = 16; o > 0; o >>= 1) { spp += __shfl_down_sync(0xffffffffu, spp, o); sn += __shfl_down_sync(0xffffffffu, sn, o); }
+  if (lane == 0) {
+    atomicAdd(&P.ctr[CT_PART], spp); atomicAdd(&P.ctr[CT_NODE], sn);
+    atomicAdd(&P.ctr[CT_LIST_NODES], (unsigned long long)R.wnodes); atomicAdd(&P.ctr[CT_LIST_PARTS], (unsigned long long)R.wparts);
+    if (R.overflow) atomicAdd(&P.ctr[CT_WALK_OVF], 1ull);
+  }
+}
+
 static float h_inv_of_type1();
 static void fill_trees(WalkParams &P);
 
@@ -480,6 +634,11 @@ static int walk_read_counters() {
   cudaEventElapsedTime(&g.cnt.ms_walk, g.ev0, g.ev1);
   g.cnt.part_interactions = (long long)g.h_ctr[CT_PART]; g.cnt.node_interactions = (long long)g.h_ctr[CT_NODE];
   g.cnt.list_nodes = (long long)g.h_ctr[CT_LIST_NODES]; g.cnt.list_parts = (long long)g.h_ctr[CT_LIST_PARTS];
+  if (g.h_ctr[CT_WALK_OVF]) {
+    fprintf(stderr, "libsidm_b200: %llu warps overflowed the %d-entry group stack of the packed walk; b200_set_option(\"walk_pairs\", 0) selects the stack-free walk\n",
+            g.h_ctr[CT_WALK_OVF], kPairStack);
+    return B200_ERR_STATE;
+  }
   return B200_OK;
 }
 
@@ -491,27 +650,34 @@ int walk_impl(const int *d_sorted, int nt, bool with_slots, bool defer_sync) {
   P.theta2 = (float)(g.par.ErrTolTheta * g.par.ErrTolTheta); P.alpha = (float)g.par.ErrTolForceAcc;
   P.h_inv = h_inv_of_type1(); P.criterion = g.par.TypeOfOpeningCriterion; P.ctr = g.d_ctr;
   fill_trees(P);
-  CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, 4 * sizeof(unsigned long long), g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, kWalkCounters * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   const bool per = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
   P.box = (float)g.par.BoxSize; P.boxhalf = (float)(g.par.BoxSize / 2); P.ewald_fac = per ? (float)(kEwaldN / g.par.BoxSize) : 0.f; P.ewald = nullptr;
   if (per) { B200_TRY(ewald_tables(&P.ewald)); }
   if (nt > 0) {
     const int GW = cdiv(nt, WALK_THREADS);
-    if (g.ntrees > 1) { if (per) k_walk<true, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); else k_walk<false, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); }
+    if (g.pairs_valid && g.opt_walk_pairs && g.ntrees == 1 && !per) {
+      switch (g.opt_walkp_minb) {                 // registers per thread: 64 / 80 / 96 / 128 (occupancy A/B, option "walkp_minb")
+        case 8: k_walk_pairs<8><<<GW, WALK_THREADS, 0, g.stream>>>(P, g.pairs); break;
+        case 5: k_walk_pairs<5><<<GW, WALK_THREADS, 0, g.stream>>>(P, g.pairs); break;
+        case 4: k_walk_pairs<4><<<GW, WALK_THREADS, 0, g.stream>>>(P, g.pairs); break;
+        default: k_walk_pairs<6><<<GW, WALK_THREADS, 0, g.stream>>>(P, g.pairs); break;
+      }
+    }
+    else if (g.ntrees > 1) { if (per) k_walk<true, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); else k_walk<false, true><<<GW, WALK_THREADS, 0, g.stream>>>(P); }
     else if (per) k_walk<true, false><<<GW, WALK_THREADS, 0, g.stream>>>(P);
     else k_walk<false, false><<<GW, WALK_THREADS, 0, g.stream>>>(P);
     count_launch();
   }
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctr, g.d_ctr, kWalkCounters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   g.cnt.num_targets = nt;
   g.cnt.num_lists = (nt + 31) / 32;
   if (defer_sync) { g.walk_pending = true; return B200_OK; }      // gravity_finish() reads the counters
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
-  walk_read_counters();
-  return B200_OK;
+  return walk_read_counters();
 }
 
 // gravtree.c:230-324: Accel <- (float)Acc; OldAcc = |Accel| before G (relative criterion);
@@ -590,7 +756,7 @@ int gravity_finish() {
   B200_TRY(gravity_exchange());
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
-  if (g.walk_pending) { walk_read_counters(); g.walk_pending = false; }
+  if (g.walk_pending) { g.walk_pending = false; return walk_read_counters(); }
   return B200_OK;
 }
 

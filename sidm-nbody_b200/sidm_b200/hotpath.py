@@ -124,6 +124,21 @@ class HotPath:
             assert into.dtype == self._aos.dtype and len(into) >= self.n and into.flags["C_CONTIGUOUS"]
             check(self.lib.b200_download_to(into.ctypes.data_as(C.c_void_p)), "b200_download_to")
 
+    def upload_active(self, idx):
+        """host -> device of what the driver changes between force computations (Pos Vel CurrentTime MaxPredTime; VelPred = Vel,
+        dVel = 0) for the listed particles only (gravtree.c:149-166 moves 20 bytes per active particle)"""
+        a = _i32(idx)
+        check(self.lib.b200_upload_active(ptr(a), len(a)), "b200_upload_active")
+
+    def download_active(self, idx, into=None):
+        """device -> host of the fields the path writes for the listed particles and the partners kicked since the last download"""
+        a = _i32(idx)
+        dst = None
+        if into is not None:
+            assert into.dtype == self._aos.dtype and len(into) >= self.n and into.flags["C_CONTIGUOUS"]
+            dst = into.ctypes.data_as(C.c_void_p)
+        check(self.lib.b200_download_active(ptr(a), len(a), dst), "b200_download_active")
+
     def advance(self, active=None, time=None, count=False):
         """advance(), predict.c:245: leap-frog kick+drift of the active particles, clears dVel"""
         t = self.time if time is None else float(time)

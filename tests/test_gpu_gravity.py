@@ -111,3 +111,28 @@ def test_gravity_tree_epilogue(setup):
     acc2_r = R.get("ACCEL")
     acc2 = hp.get("Accel")
     assert rel_rms(acc2.astype(np.float64), acc2_r.astype(np.float64)) < 1e-4
+
+
+def test_packed_walk_equals_stream_walk(setup):
+    """k_walk_pairs (sibling pairs, f32x2) and k_walk (pre-order stream) take the same decisions: identical interaction
+    counts for every target, accelerations equal up to the order of the float partial sums"""
+    hp = setup["hp"]
+    idx = np.arange(0, N, 7, dtype=np.int32)
+    for oa in (np.zeros(N, np.float32), None):               # BH start-up criterion, then the relative criterion
+        if oa is not None:
+            hp.set_particles(oldacc=oa)
+        hp.set_option("walk_pairs", 0)
+        hp.force_treebuild()
+        a0, c0 = hp.force_treeevaluate(idx)
+        hp.set_option("walk_pairs", 1)
+        for minb in (4, 6, 8):
+            hp.set_option("walkp_minb", minb)
+            hp.force_treebuild()
+            a1, c1 = hp.force_treeevaluate(idx)
+            assert np.array_equal(c0, c1)
+            assert rel_rms(a1, a0) < 1e-6
+        if oa is not None:
+            hp.gravity_tree()                                 # OldAcc for the second round
+    hp.set_option("walkp_minb", 6)
+    hp.set_option("walk_pairs", 0)
+    hp.force_treebuild()
