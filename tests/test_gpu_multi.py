@@ -14,13 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 N = 30000
 
 
-def _launch(world, out, backend, min_work="1", compact="1", types="0"):
+def _launch(world, out, backend, min_work="1", compact="1", types="0", n=N):
     runner = os.path.join(HERE, "multi_runner.py")
     if world == 1:
-        cmd = [sys.executable, runner, out, str(N), backend]
+        cmd = [sys.executable, runner, out, str(n), backend]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-               "--master-addr", "127.0.0.1", "--master-port", "29541", runner, out, str(N), backend]
+               "--master-addr", "127.0.0.1", "--master-port", "29541", runner, out, str(n), backend]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, B200_SHARD_MIN_WORK=min_work, B200_COMPACT=compact, B200_TYPES=types))
     assert r.returncode == 0, (r.stdout[-1500:] + "\n".join(l for l in r.stderr.splitlines() if "Error" in l or "assert" in l or "File" in l)[-3000:])
     return np.load(out)
@@ -68,3 +68,18 @@ def test_two_gpus_nccl(tmp_path):
     one = _launch(1, str(tmp_path / "one.npz"), "nccl")
     two = _launch(2, str(tmp_path / "two.npz"), "nccl")
     _same(one, two)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_default_threshold_large(tmp_path, world):
+    """NCCL over NVLink with everything at its defaults (shard_min_work = 2^18, compact exchange, SIDM chain on its own
+    stream next to the walk = shard_overlap): the all-active passes of 3e5 particles are sharded, the repair passes
+    (< 2^18 particles) run completely on every rank.  N-GPU state = 1-GPU state, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    big = 300000
+    one = _launch(1, str(tmp_path / "one.npz"), "nccl", min_work=str(1 << 18), n=big)
+    assert one["sct0"][2] + one["sct1"][2] > 0 and one["sct0"][4] > 0, "no scatterings / no repair pass - fixture too quiet"
+    many = _launch(world, str(tmp_path / "many.npz"), "nccl", min_work=str(1 << 18), n=big)
+    _same(one, many)
