@@ -532,15 +532,18 @@ def run_e2e(hp, sh, n, mass, ids, vmax, state, args, world, rank, step_fn, cfg, 
         one(0)
         up = down = nact = 0
         torch.cuda.synchronize()
-        tsum = 0.0
+        tsum = t_up = t_cmp = t_down = 0.0
         for k in range(steps):
             act = tl.active(state["it"]); t = tl.t(state["it"])
             t0 = time.perf_counter()
             hp.upload_active(prev)
+            t1 = time.perf_counter()
             hp.compute_accelerations(0, active=act, time=t, vmax=vmax)
+            t2 = time.perf_counter()
             hp.download_active(act)
             torch.cuda.synchronize()
-            tsum += time.perf_counter() - t0
+            t3 = time.perf_counter()
+            tsum += t3 - t0; t_up += t1 - t0; t_cmp += t2 - t1; t_down += t3 - t2
             up += len(prev) * 36; down += len(act) * 76; nact += len(act)
             hp.advance(active=act, time=t)
             host["Pos"][act] = hp.peek("pos0", np.float32, (n, 3))[act]
@@ -551,6 +554,7 @@ def run_e2e(hp, sh, n, mass, ids, vmax, state, args, world, rank, step_fn, cfg, 
         rt.cudaHostUnregister(host.ctypes.data)
         return {"value": nact / tsum, "unit": UNIT, "h2d_bytes_per_step": int(up / steps), "d2h_bytes_per_step": int(down / steps),
                 "steps": steps, "ms_per_step": tsum / steps * 1e3,
+                "ms_upload": t_up / steps * 1e3, "ms_compute": t_cmp / steps * 1e3, "ms_download": t_down / steps * 1e3,
                 "api": "b200_upload_active(previous active list: Pos Vel CurrentTime MaxPredTime, 36 B each) + b200_compute_accelerations(0, active) + "
                        "b200_download_active(active list + kicked partners, 76 B each) on a pinned 124-byte particle_data array"}
 

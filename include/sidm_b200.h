@@ -187,6 +187,12 @@ int  b200_download_active(const int *idx, int n, void *dst);
  * length of the all-gather (ceil(N/world)); the shard buffers must hold rows_per_rank*stride bytes. */
 int  b200_upload_shard(int first, int count, int rows_per_rank);
 int  b200_download_shard(void *dst, int first, int count);
+/* The same for a host array that holds ONLY the rank's own rows with any number of rows per rank (the reference's per-task P[]
+ * after DomainDecomposition(), domain.c:31-884): b200_bind_rows binds rows [first, first+count) of a global order of n_global
+ * particles = the tasks' arrays one after the other; b200_upload_rows(counts[world]) sends them up and replicates them;
+ * b200_download_shard(NULL, first, count) brings the own rows back into the bound array. */
+int  b200_bind_rows(void *base, int first, int count, int n_global, const b200_layout *layout, int pin);
+int  b200_upload_rows(const int *counts);
 /* Structure-of-arrays alternative used by the tests / bench (host pointers, float32/int32;
  * any pointer may be NULL = keep current).  pos/vel are [n][3]. */
 int  b200_set_soa(int num_part, const float *pos, const float *vel, const float *mass,
@@ -211,6 +217,10 @@ typedef int (*b200_allgather_fn)(long long bytes_per_rank, void *user);
 int  b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes,
                     b200_allgather_fn fn, void *user);
 void *b200_current_stream(void);               /* cudaStream_t of the collective being requested */
+/* for a C host without CUDA code of its own (the shim): send == recv == NULL in b200_set_shard lets the library allocate the
+ * exchange buffers (cap_bytes and world * cap_bytes); b200_shard_buffers returns them for the callback's ncclAllGather */
+int  b200_shard_buffers(void **send, void **recv, long long *cap_bytes);
+int  b200_device_count(void);                  /* CUDA devices visible to this process (0: none) */
 
 /* ---- the hot path ---------------------------------------------------------------- */
 /* predict_collisionless_only(time), predict.c:106: PosPred, VelPred for all particles. */

@@ -38,6 +38,7 @@ struct Ctx {
 
   // host binding (the reference's &P[1])
   char *h_base = nullptr; b200_layout lay{}; bool pinned = false; bool have_aos = false;
+  int h_first = 0, h_count = 0;    // the bound host array holds the rows [h_first, h_first + h_count) of the particle order (b200_bind_rows)
   char *d_aos = nullptr; size_t aos_cap = 0;
 
   // ---- particle state, original index order (struct particle_data fields, allvars.h:422-460)
@@ -124,7 +125,7 @@ struct Ctx {
   // blocks b of every sorted work list with b % world == rank; results are all-gathered
   int shard_rank = 0, shard_world = 1;
   void *shard_send = nullptr, *shard_recv = nullptr; long long shard_cap = 0;
-  b200_allgather_fn shard_fn = nullptr; void *shard_user = nullptr;
+  b200_allgather_fn shard_fn = nullptr; void *shard_user = nullptr; bool shard_own = false;
 
   float4 *d_ewald = nullptr; double ewald_box = -1;   // (ED+1)^3 correction table, scaled for ewald_box
 

@@ -68,6 +68,12 @@ extern "C" const char *b200_version(void) { return "sidm_b200 0.1 (sm_100a)"; }
 extern "C" int b200_last_cuda_error(void) { return g.last_cuda; }
 extern "C" int b200_set_stream(void *cuda_stream) { g.stream = (cudaStream_t)cuda_stream; return B200_OK; }
 extern "C" void *b200_current_stream(void) { return (void *)g.coll_stream; }
+extern "C" int b200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+extern "C" int b200_shard_buffers(void **send, void **recv, long long *cap_bytes) {
+  if (g.shard_world <= 1) return B200_ERR_STATE;
+  if (send) *send = g.shard_send; if (recv) *recv = g.shard_recv; if (cap_bytes) *cap_bytes = g.shard_cap;
+  return B200_OK;
+}
 extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
   if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
@@ -97,7 +103,13 @@ extern "C" int b200_set_rng_state(const unsigned long long *state) {
 
 extern "C" int b200_set_shard(int rank, int world, void *send, void *recv, long long cap_bytes, b200_allgather_fn fn, void *user) {
   if (world < 1 || rank < 0 || rank >= world) return B200_ERR_ARG;
-  if (world > 1 && (!send || !recv || !fn || cap_bytes <= 0)) return B200_ERR_ARG;
+  if (world > 1 && (!fn || cap_bytes <= 0 || (send == nullptr) != (recv == nullptr))) return B200_ERR_ARG;
+  if (g.shard_own) { cudaFree(g.shard_send); cudaFree(g.shard_recv); g.shard_own = false; g.shard_send = g.shard_recv = nullptr; }
+  if (world > 1 && !send) {                   // a C host without CUDA of its own (the shim): the library owns the exchange buffers
+    if (!g.ready) return B200_ERR_STATE;
+    if (cudaMalloc(&send, (size_t)cap_bytes) != cudaSuccess || cudaMalloc(&recv, (size_t)cap_bytes * world) != cudaSuccess) return B200_ERR_ALLOC;
+    g.shard_own = true;
+  }
   g.shard_rank = rank; g.shard_world = world; g.shard_send = send; g.shard_recv = recv; g.shard_cap = cap_bytes;
   g.shard_fn = fn; g.shard_user = user;
   g.search_epoch = ~0ull;        // the query groups of the SIDM search depend on the sharding (sidm.cu)
@@ -199,6 +211,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
   dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.leaf_parent); dfree(&g.lrank);
   dfree(&g.d_shard_list);
+  if (g.shard_own) { cudaFree(g.shard_send); cudaFree(g.shard_recv); g.shard_own = false; g.shard_send = g.shard_recv = nullptr; g.shard_world = 1; g.shard_rank = 0; }
   dfree(&g.d_active); dfree(&g.d_tsorted); dfree(&g.d_tkeys); dfree(&g.d_tkeys2); dfree(&g.d_tvals2);
   dfree(&g.d_acc); dfree(&g.d_cost);
   dfree(&g.s_slot_part); dfree(&g.s_flag); dfree(&g.s_pos); dfree(&g.s_ngb); dfree(&g.s_partner);
@@ -334,7 +347,7 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
   if (!g.ready) return B200_ERR_STATE;
   if (!base || !lay || num_part <= 0 || num_part > g.maxpart || lay->stride <= 0 || (lay->stride & 3)) return B200_ERR_ARG;
   if (g.pinned && g.h_base && g.h_base != (char *)base) { cudaHostUnregister(g.h_base); g.pinned = false; }
-  g.h_base = (char *)base; g.lay = *lay; g.n = num_part; g.tree_valid = false;
+  g.h_base = (char *)base; g.lay = *lay; g.n = num_part; g.tree_valid = false; g.h_first = 0; g.h_count = num_part;
   const size_t bytes = (size_t)g.maxpart * lay->stride;
   if (g.aos_cap < bytes) {
     dfree(&g.d_aos);
@@ -344,6 +357,27 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
   if (pin && !g.pinned) {
     // page-lock the caller's array once (the reference allocates P once, allocate.c:127-160)
     cudaError_t e = cudaHostRegister(base, (size_t)num_part * lay->stride, cudaHostRegisterDefault);
+    if (e == cudaSuccess) g.pinned = true; else (void)cudaGetLastError();
+  }
+  g.have_aos = true;
+  return B200_OK;
+}
+
+// The host array of one rank of a distributed run (the reference's per-task P[], domain.c): `base` holds the rows
+// [first, first+count) of the global particle order = the tasks' arrays one after the other.
+extern "C" int b200_bind_rows(void *base, int first, int count, int n_global, const b200_layout *lay, int pin) {
+  if (!g.ready) return B200_ERR_STATE;
+  if (!base || !lay || count < 0 || first < 0 || n_global <= 0 || first + count > n_global || n_global > g.maxpart || lay->stride <= 0 || (lay->stride & 3)) return B200_ERR_ARG;
+  if (g.pinned && g.h_base && (g.h_base != (char *)base || g.h_count != count)) { cudaHostUnregister(g.h_base); g.pinned = false; }
+  g.h_base = (char *)base; g.lay = *lay; g.n = n_global; g.tree_valid = false; g.h_first = first; g.h_count = count;
+  const size_t bytes = (size_t)g.maxpart * lay->stride;
+  if (g.aos_cap < bytes) {
+    dfree(&g.d_aos);
+    if (cudaMalloc((void **)&g.d_aos, bytes) != cudaSuccess) return B200_ERR_ALLOC;
+    g.aos_cap = bytes;
+  }
+  if (pin && !g.pinned && count > 0) {
+    cudaError_t e = cudaHostRegister(base, (size_t)count * lay->stride, cudaHostRegisterDefault);
     if (e == cudaSuccess) g.pinned = true; else (void)cudaGetLastError();
   }
   g.have_aos = true;
@@ -445,22 +479,23 @@ extern "C" int b200_download(void) {
   return B200_OK;
 }
 
-extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
-  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
-  if (g.shard_world <= 1) return b200_upload();
-  const int n = g.n; const size_t st = (size_t)g.lay.stride;
-  if (first < 0 || count < 0 || first + count > n || rows_per_rank < count || (long long)rows_per_rank * g.shard_world < n) return B200_ERR_ARG;
+// every rank's rows -> all ranks: own rows over PCIe, one all-gather over NVLink, compacted into the device image of the
+// whole array.  counts[q] = rows of rank q (their sum = the particle number), rank q's rows start at the sum of the counts before it.
+static int upload_rows_impl(const int *counts) {
+  const int n = g.n, W = g.shard_world; const size_t st = (size_t)g.lay.stride;
+  long long tot = 0; int rows_per_rank = 0, first = 0;
+  for (int q = 0; q < W; q++) { if (counts[q] < 0) return B200_ERR_ARG; if (q < g.shard_rank) first += counts[q]; tot += counts[q]; if (counts[q] > rows_per_rank) rows_per_rank = counts[q]; }
+  const int count = counts[g.shard_rank];
+  if (tot != n || first < g.h_first || first + count > g.h_first + g.h_count) return B200_ERR_ARG;
   const long long bytes = (long long)rows_per_rank * (long long)st;
   if (bytes > g.shard_cap) return B200_ERR_ARG;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  if (count > 0) CUDA_TRY(cudaMemcpyAsync((char *)g.shard_send, g.h_base + (size_t)first * st, (size_t)count * st, cudaMemcpyHostToDevice, g.stream));
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync((char *)g.shard_send, g.h_base + (size_t)(first - g.h_first) * st, (size_t)count * st, cudaMemcpyHostToDevice, g.stream));
   B200_TRY(shard_exchange(bytes, g.stream));             // every rank's rows -> all ranks, over NVLink
-  // rank q's rows start at q*rows_per_rank: compact them into the device image of the whole array
-  for (int q = 0; q < g.shard_world; q++) {
-    const long long f = (long long)q * rows_per_rank;
-    if (f >= n) break;
-    const long long c = (n - f < rows_per_rank) ? n - f : rows_per_rank;
-    CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)c * st, cudaMemcpyDeviceToDevice, g.stream));
+  long long f = 0;
+  for (int q = 0; q < W; q++) {
+    if (counts[q] > 0) CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)counts[q] * st, cudaMemcpyDeviceToDevice, g.stream));
+    f += counts[q];
   }
   k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
                                                    g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred, g.potential);
@@ -473,6 +508,24 @@ extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
   return B200_OK;
 }
 
+extern "C" int b200_upload_rows(const int *counts) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  if (!counts) return B200_ERR_ARG;
+  if (g.shard_world <= 1) return counts[0] == g.n ? b200_upload() : B200_ERR_ARG;
+  return upload_rows_impl(counts);
+}
+
+extern "C" int b200_upload_shard(int first, int count, int rows_per_rank) {
+  if (!g.ready || !g.have_aos) return B200_ERR_STATE;
+  if (g.shard_world <= 1) return b200_upload();
+  const int n = g.n;
+  if (first < 0 || count < 0 || first + count > n || rows_per_rank < count || (long long)rows_per_rank * g.shard_world < n || g.shard_world > 64) return B200_ERR_ARG;
+  int counts[64];
+  for (int q = 0; q < g.shard_world; q++) { const long long f = (long long)q * rows_per_rank; counts[q] = f >= n ? 0 : (int)((n - f < rows_per_rank) ? n - f : rows_per_rank); }
+  if ((long long)g.shard_rank * rows_per_rank != first && count > 0) return B200_ERR_ARG;
+  return upload_rows_impl(counts);
+}
+
 extern "C" int b200_download_shard(void *dst, int first, int count) {
   if (!g.ready || !g.have_aos) return B200_ERR_STATE;
   const int n = g.n; const size_t st = (size_t)g.lay.stride;
@@ -482,7 +535,9 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
-  if (count > 0) CUDA_TRY(cudaMemcpyAsync(out + (size_t)first * st, g.d_aos + (size_t)first * st, (size_t)count * st, cudaMemcpyDeviceToHost, g.stream));
+  if (!dst && (first < g.h_first || first + count > g.h_first + g.h_count)) return B200_ERR_ARG;
+  // `dst` (if given) is a whole-array image; the bound array may hold the rank's rows only (b200_bind_rows)
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync(out + (size_t)(first - (dst ? 0 : g.h_first)) * st, g.d_aos + (size_t)first * st, (size_t)count * st, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
@@ -504,7 +559,10 @@ static int ensure_stage(size_t bytes) {
   if (g.h_stage) cudaFreeHost(g.h_stage);
   if (g.d_stage) cudaFree(g.d_stage);
   g.h_stage = nullptr; g.d_stage = nullptr; g.stage_cap = 0;
-  bytes += bytes / 2 + 4096;
+  // grow rarely: pinned allocations cost milliseconds and the active sets of successive steps differ in size
+  bytes = 4 * bytes + ((size_t)16 << 20);
+  const size_t most = (size_t)g.maxpart * kDownWords * 4 + (size_t)g.maxpart * 4 + 4096;
+  if (bytes > most) bytes = most;
   if (cudaMallocHost((void **)&g.h_stage, bytes) != cudaSuccess) return B200_ERR_ALLOC;
   if (cudaMalloc((void **)&g.d_stage, bytes) != cudaSuccess) return B200_ERR_ALLOC;
   g.stage_cap = bytes;

@@ -18,7 +18,22 @@
  *   compute_accelerations()   accel.c:27        only with -DB200_SHIM_ACCEL, linked instead of accel.c:
  *                                               one upload, ONE library call for gravity + sidm + repair
  *                                               loop (walk and SIDM chain overlapped on two CUDA streams),
- *                                               one download - the fast form of the drop-in
+ *                                               one download - the fast form of the drop-in.  Between steps only
+ *                                               the particles the driver advanced go up and only the active
+ *                                               particles (+ kicked partners) come down (b200_upload_active /
+ *                                               b200_download_active; B200_SHIM_FULL_COPY=1 in the environment
+ *                                               restores whole-array copies)
+ *   setup_smoothinglengths_sidm()  init.c:431   only with -DB200_SHIM_ACCEL (init.o's own definition weakened with
+ *                                               objcopy): one batched library call instead of
+ *                                               NumPart ngb_treefind() round trips
+ *
+ * Several tasks (NTask > 1, one GPU per task; -DB200_SHIM_ACCEL form): every task keeps the particles the reference's own
+ * domain decomposition gave it (domain.c is linked unchanged and keeps moving whole particles between tasks); the
+ * shim sends each task's rows up and replicates them on all GPUs (b200_bind_rows / b200_upload_rows), hands the library
+ * the global active list (the tasks' lists one after the other), and brings each task's own rows back.  The library
+ * deals the work out over the GPUs and all-gathers the results through b200_comm.c (NCCL over NVLink, or MPI through
+ * the host).  Task-dependent quantities of the reference become global ones, because every GPU must compute the same
+ * thing: vmax is the maximum over ALL particles (sidm.c:970-990 takes the local one), the generator seed is task 0's.
  *
  * Error convention: a non-zero return of the C ABI becomes endrun(code) like the CPU code
  * (endrun.c:19-30).  Timers: elapsed device time goes into the same All.CPU_* fields.
@@ -37,10 +52,35 @@
 #include "allvars.h"
 #include "proto.h"
 #include "sidm_b200.h"
+#ifdef SCATTERLOG
+#include "sidm.h"                 /* struct scatlog */
+typedef char b200_scatlog_has_the_layout_of_struct_scatlog[sizeof(b200_scatlog) == sizeof(struct scatlog) ? 1 : -1];
+#endif
 
 static int shim_ready = 0;
 static int *active_list = 0;
 static int active_cap = 0;
+
+/* several tasks: global particle order = the tasks' P[] one after the other */
+#define B200_MAX_TASKS 64
+static int rows_of_task[B200_MAX_TASKS];
+static int first_row = 0, n_global = 0;
+int b200_comm_init(int rank, int world, int use_nccl);
+int b200_comm_allgather(long long bytes, void *user);
+int b200_comm_uses_nccl(void);
+
+static void rows_refresh(void)
+{
+  int q;
+  MPI_Allgather(&NumPart, 1, MPI_INT, rows_of_task, 1, MPI_INT, MPI_COMM_WORLD);
+  for (q = 0, first_row = 0, n_global = 0; q < NTask; q++) { if (q < ThisTask) first_row += rows_of_task[q]; n_global += rows_of_task[q]; }
+}
+
+/* partial transfers of the fast path: the device mirrors P[] except for what advance() / reflect() / find_timesteps()
+ * did to the particles of the previous force computation */
+static int  dev_mirrors_host = 0;
+static int *prev_active = 0;
+static int  prev_n = 0;
 
 static void b200_check(int rc, const char *what)
 {
@@ -54,8 +94,11 @@ static void fill_params(b200_params *p)
 {
   int t;
   memset(p, 0, sizeof(*p));
-  p->device = ThisTask;                       /* one rank per GPU of the box */
-  p->MaxPart = All.MaxPart;
+  {
+    const int ndev = b200_device_count();
+    p->device = ndev > 0 ? ThisTask % ndev : 0;         /* one task per GPU of the box (tasks share GPUs if there are fewer) */
+  }
+  p->MaxPart = NTask > 1 ? (int)(All.TotNumPart + 64) : All.MaxPart;   /* several tasks: every GPU holds all particles */
   p->TreeAllocFactor = All.TreeAllocFactor;
   p->ErrTolTheta = All.ErrTolTheta;
   p->ErrTolForceAcc = All.ErrTolForceAcc;
@@ -77,7 +120,7 @@ static void fill_params(b200_params *p)
   p->CrossSectionPowLaw = All.CrossSectionPowLaw;
   p->CrossSectionVelScale = All.CrossSectionVelScale;
 #endif
-  p->Seed = (unsigned long long)(All.Seed1 + All.Seed2 * ThisTask);
+  p->Seed = (unsigned long long)(All.Seed1 + All.Seed2 * (NTask > 1 ? 0 : ThisTask));   /* begrun.c:44; replicated work needs one seed */
   p->BunchSizeSidm = 0;
 #endif
 }
@@ -119,15 +162,47 @@ static int gather_active(void)
   return NumForceUpdate;
 }
 
+/* several tasks: the global active list every GPU works on = the tasks' lists one after the other, in global row numbers */
+static int gather_active_global(int **list)
+{
+  static int *glist = 0; static int gcap = 0;
+  int counts[B200_MAX_TASKS], q, tot = 0, at = 0, i;
+  int n = gather_active();
+  if (NTask == 1) { *list = active_list; return n; }
+  MPI_Allgather(&n, 1, MPI_INT, counts, 1, MPI_INT, MPI_COMM_WORLD);
+  for (q = 0; q < NTask; q++) tot += counts[q];
+  if (gcap < tot + 1) { free(glist); gcap = (int)All.TotNumPart + 64; glist = (int *)malloc(sizeof(int) * gcap); if (!glist) endrun(3); }
+  for (q = 0; q < NTask; q++) {
+    if (q == ThisTask) for (i = 0; i < n; i++) glist[at + i] = first_row + active_list[i];
+    if (counts[q] > 0) MPI_Bcast(glist + at, counts[q], MPI_INT, q, MPI_COMM_WORLD);
+    at += counts[q];
+  }
+  *list = glist;
+  return tot;
+}
+
 static void sync_params_and_particles(void)
 {
   b200_params p;
   b200_layout l;
+  prev_n = 0;                                   /* whole array goes up: nothing is pending from the previous step */
   fill_params(&p);
   b200_check(b200_set_params(&p), "b200_set_params");
   fill_layout(&l);
-  b200_check(b200_bind_particles(&P[1], NumPart, &l, 1), "b200_bind_particles");
-  b200_check(b200_upload(), "b200_upload");
+  if (NTask == 1) {
+    b200_check(b200_bind_particles(&P[1], NumPart, &l, 1), "b200_bind_particles");
+    b200_check(b200_upload(), "b200_upload");
+  } else {
+    rows_refresh();
+    b200_check(b200_bind_rows(&P[1], first_row, NumPart, n_global, &l, 1), "b200_bind_rows");
+    b200_check(b200_upload_rows(rows_of_task), "b200_upload_rows");      /* own rows over PCIe, replicated over NVLink */
+  }
+}
+
+static void download_particles(void)
+{
+  if (NTask == 1) b200_check(b200_download(), "b200_download");
+  else b200_check(b200_download_shard(0, first_row, NumPart), "b200_download_shard");
 }
 
 /* ---------------------------------------------------------------- forcetree.h surface */
@@ -139,6 +214,17 @@ void force_treeallocate(int maxnodes, int maxpart)      /* forcetree.c:1797 */
   if (shim_ready) return;
   fill_params(&p);
   b200_check(b200_init(&p), "b200_init");
+  if (NTask > 1) {
+    /* exchange buffers: one task's rows of the particle array, or its share of the 32-byte per-slot records */
+    const long long rows = All.MaxPart, slots = ((All.TotNumPart + 31) / 32 + NTask - 1) / NTask * 32;
+    long long cap = rows * (long long)sizeof(struct particle_data);
+    if (slots * 32 > cap) cap = slots * 32;
+    if (NTask > B200_MAX_TASKS) endrun(9003);
+    b200_check(b200_set_shard(ThisTask, NTask, 0, 0, cap, b200_comm_allgather, 0), "b200_set_shard");
+    if (b200_comm_init(ThisTask, NTask, b200_device_count() >= NTask) != 0) { printf("task %d: communicator set-up failed\n", ThisTask); endrun(9001); }
+    b200_check(b200_set_option("shard_overlap", 1), "b200_set_option");     /* b200_comm_allgather honours b200_current_stream() */
+    if (ThisTask == 0) printf("libsidm_b200 on %d tasks, %d GPU(s), all-gather through %s\n", NTask, b200_device_count(), b200_comm_uses_nccl() ? "NCCL" : "MPI (host staged)");
+  }
   shim_ready = 1;
 }
 void force_treefree(void) { b200_finalize(); shim_ready = 0; }
@@ -200,7 +286,7 @@ void set_softenings(void)                               /* gravtree.c:425-458 */
 void gravity_tree(void)                                 /* gravtree.c:18-419 */
 {
   b200_counters c;
-  int n, ntot;
+  int n, ntot, *glist;
   double t0 = second(), t1;
   if (All.ComovingIntegrationOn) set_softenings();
   MPI_Allreduce(&NumForceUpdate, &ntot, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
@@ -210,9 +296,9 @@ void gravity_tree(void)                                 /* gravtree.c:18-419 */
   sync_params_and_particles();
   b200_check(b200_predict(All.Time), "b200_predict");               /* gravtree.c:72 */
   b200_check(b200_tree_build(), "b200_tree_build");                 /* gravtree.c:76 */
-  n = gather_active();
-  b200_check(b200_gravity(active_list, n, All.Time), "b200_gravity"); /* gravtree.c:127-324 */
-  b200_check(b200_download(), "b200_download");
+  n = gather_active_global(&glist);
+  b200_check(b200_gravity(glist, n, All.Time), "b200_gravity");     /* gravtree.c:127-324 */
+  download_particles();
   b200_get_counters(&c);
   All.CPU_TreeConstruction += 1e-3 * (c.ms_build + c.ms_predict);
   All.CPU_TreeWalk += 1e-3 * c.ms_walk;
@@ -226,15 +312,46 @@ void gravity_tree(void)                                 /* gravtree.c:18-419 */
 /* ---------------------------------------------------------------- sidm.c */
 
 #ifdef SIDM
-double getvmax(void)                                    /* sidm.c:970-990 */
+double getvmax(void)                                    /* sidm.c:970-990; called before force_treeallocate() (init.c:74): host loop */
 {
-  double v = 0;
-  sync_params_and_particles();
-  b200_check(b200_getvmax(&v), "b200_getvmax");
+  int j, q;
+  double v2, v = 0.0, all[B200_MAX_TASKS];
+  for (j = 1; j <= NumPart; j++) {
+    v2 = P[j].Vel[0] * P[j].Vel[0] + P[j].Vel[1] * P[j].Vel[1] + P[j].Vel[2] * P[j].Vel[2];
+    if (v < v2) v = v2;
+  }
+  v = sqrt(v);
+  if (NTask > 1) {                                      /* every GPU works on all particles: the global maximum */
+    MPI_Allgather(&v, 1, MPI_DOUBLE, all, 1, MPI_DOUBLE, MPI_COMM_WORLD);
+    for (q = 0; q < NTask; q++) if (all[q] > v) v = all[q];
+  }
 #ifdef FINDNBRLOG
   if (ThisTask == 0) fprintf(stdout, "Vmax= %g Processor %d\n", v, ThisTask);
 #endif
   return v;
+}
+
+/* -DSCATTERLOG (sidm.c:96-104, 571-601, 622-624): the records of this call appended to sct_<snapshot count>.<task> */
+static void write_scatterlog(void)
+{
+#ifdef SCATTERLOG
+  static b200_scatlog *buf = 0;
+  static int cap = 0;
+  char filename[128];
+  FILE *fp;
+  int n = 0;
+  if (!buf) { cap = 1 << 16; buf = (b200_scatlog *)malloc(sizeof(b200_scatlog) * cap); if (!buf) endrun(3); }
+  b200_check(b200_get_scatlog(buf, cap, &n), "b200_get_scatlog");
+  if (n == cap) {                                        /* more than the buffer holds: take all the library keeps (2^20) */
+    free(buf); cap = 1 << 20; buf = (b200_scatlog *)malloc(sizeof(b200_scatlog) * cap); if (!buf) endrun(3);
+    b200_check(b200_get_scatlog(buf, cap, &n), "b200_get_scatlog");
+  }
+  sprintf(filename, "sct_%03d.%d", All.SnapshotFileCount, ThisTask);
+  fp = fopen(filename, "ab");
+  if (!fp) return;
+  if (n > 0) fwrite(buf, sizeof(struct scatlog), n, fp);   /* b200_scatlog has the layout of struct scatlog (sidm.h:1-10) */
+  fclose(fp);
+#endif
 }
 
 static void print_sct(void)
@@ -249,18 +366,20 @@ static void print_sct(void)
 void sidm(void)                                         /* sidm.c:57-627; tree + particles are on the device
                                                            since gravity_tree() of this step (accel.c:39,63) */
 {
-  int n = gather_active();
-  b200_check(b200_sidm(active_list, n, All.Time, vmax, 0), "b200_sidm");
+  int *glist, n = gather_active_global(&glist);
+  b200_check(b200_sidm(glist, n, All.Time, vmax, 0), "b200_sidm");
+  write_scatterlog();
   print_sct();
 }
 
 void setup_nbr_sidm(void)                               /* sidm.c:630-805 */
 {
-  int n = gather_active();
+  int *glist, n;
   sync_params_and_particles();
+  n = gather_active_global(&glist);
   b200_check(b200_tree_build(), "b200_tree_build");
-  b200_check(b200_setup_nbr_sidm(active_list, n), "b200_setup_nbr_sidm");
-  b200_check(b200_download(), "b200_download");
+  b200_check(b200_setup_nbr_sidm(glist, n), "b200_setup_nbr_sidm");
+  download_particles();
 }
 
 void sidm_ensure_neighbours(int mode)                   /* sidm.c:814-968 */
@@ -269,9 +388,10 @@ void sidm_ensure_neighbours(int mode)                   /* sidm.c:814-968 */
   double save;
   int i;
   b200_check(b200_sidm_ensure_neighbours(mode, All.Time, vmax, 0), "b200_sidm_ensure_neighbours");
-  b200_check(b200_download(), "b200_download");
+  download_particles();
   b200_get_counters(&c);
   print_sct();
+  dev_mirrors_host = 0;
   All.CPU_CommSum += 1e-3 * c.ms_download;
   if (c.ensure_iterations > 0) {
     if (mode == 0) {                                    /* sidm.c:943-955: restore the time line */
@@ -297,7 +417,7 @@ void compute_potential(void)
   if (ThisTask == 0) { printf("Start computation of potential for all particles...\n"); fflush(stdout); }
   sync_params_and_particles();
   b200_check(b200_compute_potential(0), "b200_compute_potential");
-  b200_check(b200_download(), "b200_download");
+  download_particles();
   All.NumForcesSinceLastTreeConstruction = All.TreeUpdateFrequency * All.TotNumPart;   /* potential.c:49 */
   NoCostFlag = 1;
   if (ThisTask == 0) { printf("potential done.\n"); fflush(stdout); }
@@ -335,12 +455,14 @@ void savepositions(int num)
   double t0 = second(), t1;
   if (ThisTask == 0) printf("\nwriting snapshot file... \n");
   if (num < 0) num = 1000 + num;                                                /* io.c:77-78 */
-  if (All.NumFilesPerSnapshot != 1 || NTask != 1 || All.TotN_gas > 0) {
-    printf("savepositions: the device writer covers one file, one task, no gas\n"); endrun(9003);
+  if (All.NumFilesPerSnapshot != 1 || All.TotN_gas > 0) {
+    printf("savepositions: the device writer covers one file, no gas\n"); endrun(9003);
   }
   sprintf(buf, "%s%s_%03d", All.OutputDir, All.SnapshotFileBase, num);         /* io.c:96 */
   sync_params_and_particles();
-  b200_check(b200_savepositions(buf, All.Time, All.MassTable, All.HubbleParam, 0), "b200_savepositions");
+  /* several tasks: every GPU holds all particles, task 0 writes the one file (the reference sends the blocks to task 0, io.c:390-470) */
+  if (ThisTask == 0) b200_check(b200_savepositions(buf, All.Time, All.MassTable, All.HubbleParam, 0), "b200_savepositions");
+  MPI_Barrier(MPI_COMM_WORLD);
   if (ThisTask == 0) printf("done with snapshot.\n");
   t1 = second();
   All.CPU_Snapshot += timediff(t0, t1);
@@ -352,7 +474,7 @@ void savepositions(int num)
 void compute_accelerations(int mode)
 {
   b200_counters c;
-  int n, ntot, i;
+  int n, ntot, i, partial, *glist;
   double save;
   if (ThisTask == 0) { printf("Start force computation...\n"); fflush(stdout); }
   if (All.TotN_gas > 0) { printf("compute_accelerations: gas particles are not on the GPU path\n"); endrun(9006); }
@@ -361,11 +483,27 @@ void compute_accelerations(int mode)
   All.NumForcesSinceLastDomainDecomp += ntot;
   All.NumForcesSinceLastTreeConstruction = 0;
   if (ThisTask == 0) printf("Tree construction.\n");
-  sync_params_and_particles();
-  n = gather_active();
-  b200_check(b200_compute_accelerations(mode, active_list, n, All.Time, vmax), "b200_compute_accelerations");
-  b200_check(b200_download(), "b200_download");
+  if (NTask > 1) rows_refresh();
+  n = gather_active_global(&glist);
+  /* small active sets: move only what changed.  Up: the particles of the previous force computation (advance(), reflect(),
+   * find_timesteps() touched nothing else); down: this call's active particles and the partners they kicked. */
+  partial = NTask == 1 && dev_mirrors_host && !getenv("B200_SHIM_FULL_COPY") && (long long)4 * (prev_n + n) < NumPart;
+  if (partial) {
+    b200_params p;
+    fill_params(&p);
+    b200_check(b200_set_params(&p), "b200_set_params");
+    b200_check(b200_upload_active(prev_active, prev_n), "b200_upload_active");
+  } else sync_params_and_particles();
+  b200_check(b200_compute_accelerations(mode, glist, n, All.Time, vmax), "b200_compute_accelerations");
+  if (partial) b200_check(b200_download_active(glist, n, 0), "b200_download_active");
+  else download_particles();
+  if (NTask == 1) {
+    if (!prev_active) { prev_active = (int *)malloc(sizeof(int) * (All.MaxPart + 1)); if (!prev_active) endrun(3); }
+    memcpy(prev_active, glist, sizeof(int) * n);
+    prev_n = n;
+  }
   b200_get_counters(&c);
+  if (mode == 0) write_scatterlog();
   All.CPU_TreeConstruction += 1e-3 * (c.ms_build + c.ms_predict);
   All.CPU_TreeWalk += 1e-3 * c.ms_walk;
   All.CPU_CommSum += 1e-3 * (c.ms_upload + c.ms_download);
@@ -383,7 +521,19 @@ void compute_accelerations(int mode)
     }
   }
   (void)i;
+  dev_mirrors_host = 1;
   if (ThisTask == 0) { printf("force computation done.\n"); fflush(stdout); }
+}
+
+/* setup_smoothinglengths_sidm(), init.c:431-512: k-th neighbour distance of every particle, then the count / bisection
+ * iteration - one batched library call (the per-particle ngb_treefind() above stays as the fall-back of the
+ * symbol-by-symbol form) */
+void setup_smoothinglengths_sidm(int desired_ngb)
+{
+  sync_params_and_particles();
+  b200_check(b200_tree_build(), "b200_tree_build");
+  b200_check(b200_setup_smoothinglengths_sidm(desired_ngb), "b200_setup_smoothinglengths_sidm");
+  download_particles();
 }
 #endif
 #endif

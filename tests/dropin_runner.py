@@ -69,8 +69,32 @@ def main_run(kind, out, n, k=60):
              maxpred=R.get("MAXPRED"), hsml=R.get("HSML"), ngb=R.get("NGB"))
 
 
+def main_sct(kind, out, n):
+    """-DSCATTERLOG through the drop-in (sidm.c:96-104, 571-601): one all-active compute_accelerations(0) with a large cross
+    section; the records the run appends to sct_<snapshot count>.<task> in its working directory"""
+    import refdrv
+    from sidm_b200 import ic
+    pos, vel, mass, ids = ic.hernquist(n, seed=11)
+    os.chdir(tempfile.mkdtemp())
+    R = refdrv.Reference(kind)
+    R.setup(n, CrossSectionInternal=400.0)
+    R.init_rand(55)
+    R.set_particles(pos, vel, mass, ids)
+    R.treebuild()
+    R.setup_smoothinglengths_sidm(30)
+    R.all_active(0.0, 0.0)
+    R.getvmax()
+    R.compute_accelerations(1)
+    R.all_active(0.0, 0.01)
+    R.compute_accelerations(0)
+    log = refdrv.read_scatlog("sct_000.0")
+    np.savez(out, log=log, dvel=R.get("DVEL"), ids=R.get("ID"), hsml=R.get("HSML"))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 4 and sys.argv[4] == "run":
+    if len(sys.argv) > 4 and sys.argv[4] == "sct":
+        main_sct(sys.argv[1], sys.argv[2], int(sys.argv[3]))
+    elif len(sys.argv) > 4 and sys.argv[4] == "run":
         main_run(sys.argv[1], sys.argv[2], int(sys.argv[3]))
     else:
         main(sys.argv[1], sys.argv[2], int(sys.argv[3]))

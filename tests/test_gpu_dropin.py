@@ -93,3 +93,29 @@ def test_reference_main_loop_individual_timesteps(tmp_path, refdrv_mod, kind):
     np.testing.assert_allclose(gpu["vel"][same], cpu["vel"][same], rtol=0, atol=2e-3)
     assert (gpu["ngb"][same] == cpu["ngb"][same]).mean() > 0.99
     assert (np.abs(gpu["ngb"] - 30) <= 2).all()                                      # the repair loop kept every count in range
+
+
+def test_scatterlog_file_through_the_shim(tmp_path, refdrv_mod):
+    """-DSCATTERLOG: the fast drop-in appends one struct scatlog per scattering to sct_<snapshot>.<task> like sidm.c:571-601.
+    The two runs draw different random numbers (MT19937 / Philox), so the files agree in format and in statistics: every
+    record is an elastic kick between two particles within each other's reach, one record per kicked pair, and the number
+    of records is the all-CPU run's within Poisson noise."""
+    if not refdrv_mod.available("b200f"):
+        pytest.skip("oracle/_ref/libsidmref_b200f.so not built")
+    runs = {}
+    for kind in ("diag", "b200f"):
+        out = str(tmp_path / f"{kind}.npz")
+        r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_runner.py"), kind, out, str(N), "sct"], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = np.load(out)
+    cpu, gpu = runs["diag"]["log"], runs["b200f"]["log"]
+    assert len(cpu) > 100 and abs(len(gpu) - len(cpu)) < 6 * np.sqrt(len(cpu) + len(gpu))
+    for log, r in ((cpu, runs["diag"]), (gpu, runs["b200f"])):
+        assert (log["id1"] != log["id2"]).all() and log["id1"].min() >= 1 and log["id2"].max() <= N
+        d = np.sqrt(((log["x1"].astype(np.float64) - log["x2"]) ** 2).sum(1))
+        assert (d < log["h1"]).all()                                              # the partner lies inside the scatterer's sphere
+        v_rel0 = np.sqrt(((log["v1"].astype(np.float64) - log["v2"]) ** 2).sum(1))
+        v_rel1 = np.sqrt(((log["v1"].astype(np.float64) + log["dv"] - (log["v2"].astype(np.float64) - log["dv"])) ** 2).sum(1))
+        np.testing.assert_allclose(v_rel1, v_rel0, rtol=2e-5)                     # elastic: equal masses keep |v1 - v2|
+        kicked = (r["dvel"] != 0).any(axis=1).sum()
+        assert len(log) <= kicked <= 2 * len(log)
