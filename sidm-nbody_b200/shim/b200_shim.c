@@ -82,6 +82,8 @@ static int  dev_mirrors_host = 0;
 static int *prev_active = 0;
 static int  prev_n = 0;
 
+void force_treeallocate(int maxnodes, int maxpart);
+
 static void b200_check(int rc, const char *what)
 {
   if (rc != B200_OK) {
@@ -186,6 +188,7 @@ static void sync_params_and_particles(void)
   b200_params p;
   b200_layout l;
   prev_n = 0;                                   /* whole array goes up: nothing is pending from the previous step */
+  if (!shim_ready) force_treeallocate(0, 0);    /* init.c:120 asks for the statistics before it allocates the tree (init.c:123) */
   fill_params(&p);
   b200_check(b200_set_params(&p), "b200_set_params");
   fill_layout(&l);
@@ -223,6 +226,7 @@ void force_treeallocate(int maxnodes, int maxpart)      /* forcetree.c:1797 */
     b200_check(b200_set_shard(ThisTask, NTask, 0, 0, cap, b200_comm_allgather, 0), "b200_set_shard");
     if (b200_comm_init(ThisTask, NTask, b200_device_count() >= NTask) != 0) { printf("task %d: communicator set-up failed\n", ThisTask); endrun(9001); }
     b200_check(b200_set_option("shard_overlap", 1), "b200_set_option");     /* b200_comm_allgather honours b200_current_stream() */
+    if (getenv("B200_SHARD_MIN_WORK")) b200_check(b200_set_option("shard_min_work", atoi(getenv("B200_SHARD_MIN_WORK"))), "b200_set_option");
     if (ThisTask == 0) printf("libsidm_b200 on %d tasks, %d GPU(s), all-gather through %s\n", NTask, b200_device_count(), b200_comm_uses_nccl() ? "NCCL" : "MPI (host staged)");
   }
   shim_ready = 1;

@@ -70,3 +70,21 @@ def test_header_is_plain_c_and_structs_match(tmp_path):
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert sizes[0] == 102 * 8 == C.sizeof(capi.SysState)
     assert sizes[1] == C.sizeof(capi.Params) and sizes[2] == C.sizeof(capi.Layout) and sizes[3] == C.sizeof(capi.Counters)
+
+
+def test_dropin_builds_resolve_their_symbols():
+    """the reference driver linked against the shim (oracle/_ref/libsidmref_b200*.so, sidm_b200_mpi): every symbol the shim
+    needs (b200_comm.c included) is there at load time - no compute call, runs without a GPU"""
+    import ctypes
+    import subprocess
+    import pytest
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    libs = [os.path.join(ref, f) for f in ("libsidmref_b200.so", "libsidmref_b200f.so")]
+    if not all(os.path.exists(p) for p in libs):
+        pytest.skip("oracle/_ref not built")
+    for p in libs:
+        ctypes.CDLL(p, mode=os.RTLD_NOW)
+    exe = os.path.join(ref, "sidm_b200_mpi")
+    if os.path.exists(exe):
+        r = subprocess.run(["ldd", "-r", exe], capture_output=True, text=True)
+        assert "undefined symbol" not in r.stdout + r.stderr, r.stdout + r.stderr

@@ -28,7 +28,8 @@ def test_real_main_on_two_and_four_tasks(tmp_path):
     for nt in (2, 4):
         w = str(tmp_path / f"gpu{nt}")
         mpi_case.write_case(w, N, TimeMax=0.01)
-        r = mpi_case.run_case(w, "sidm_b200_mpi", nt, timeout=900)
+        # 2 tasks: even this small problem is dealt out over the GPUs (exchanges in every phase); 4 tasks: default threshold
+        r = mpi_case.run_case(w, "sidm_b200_mpi", nt, timeout=900, env=dict(B200_SHARD_MIN_WORK="1") if nt == 2 else None)
         assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
         assert f"libsidm_b200 on {nt} tasks" in r.stdout
         runs[nt], logs[nt] = mpi_case.last_snapshot(w), r.stdout
