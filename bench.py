@@ -423,7 +423,7 @@ def main_b200(args, cfg):
         iso.append(c.ms_walk)
         r_nodes += c.list_nodes; r_parts += c.list_parts; r_targ += c.num_targets; r_lists += c.num_lists
         r_in += c.node_interactions; r_ip += c.part_interactions
-    hp.set_option("overlap", 1)
+    hp.set_option("overlap", -1)                          # back to the default mode
     wms = float(np.mean(iso))
     a_per_launch = r_targ / ROOF_STEPS
     lists = max(1.0, r_lists / ROOF_STEPS)                # interaction lists per launch (one per warp of 32 targets)

@@ -141,9 +141,11 @@ int  b200_last_cuda_error(void);
 /* run on the caller's CUDA stream (a cudaStream_t); default is the legacy default stream */
 int  b200_set_stream(void *cuda_stream);
 const char *b200_version(void);
-/* run-time switches.  "overlap" (default 1): b200_compute_accelerations(0) issues the gravity walk and
- * the SIDM chain on two CUDA streams so the SIDM repair loop's small launches hide behind the walk
- * 0 runs the phases one after the other as accel.c:39-65 does.  "shard_overlap" (default 0): see
+/* run-time switches.  "overlap": how b200_compute_accelerations(0) uses its two CUDA streams: 0 = the phases one after the
+ * other as accel.c:39-65 does; 1 = gravity walk and the whole SIDM chain (pass + repair loop) next to each other; 2 = walk and
+ * SIDM pass next to each other, the repair loop's many small launches after the walk.  Default (-1): 1 on one GPU, 2 when the
+ * work is sharded over several (the repair loop would outlast a walk that is split N ways).
+ * "shard_overlap" (default 0): see
  * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes.  "shard_min_work"
  * (default 262144): work lists shorter than this are done completely by every rank instead of being sharded
  * (the repair passes and small active sets are latency-bound; an exchange per pass costs more than it saves).

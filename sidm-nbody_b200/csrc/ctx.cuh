@@ -24,7 +24,7 @@ struct Ctx {
   // while the gravity walk fills the machine on `stream` (both only read the tree)
   cudaStream_t stream_sidm = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
-  bool opt_overlap = true;         // b200_set_option("overlap", 0|1)
+  int opt_overlap = -1;            // b200_set_option("overlap", 0|1|2); -1 = default: 1 on one GPU, 2 when sharded (sidm.cu, b200_compute_accelerations)
   bool opt_shard_overlap = false;  // b200_set_option("shard_overlap", 1): the host's all-gather callback runs on
                                    // b200_current_stream(), so the two-stream overlap is also safe when sharded
   int shard_min_work = kShardMinWorkDefault;
@@ -84,6 +84,7 @@ struct Ctx {
   int *nminidx = nullptr;          // min original index below the node (next[] order, forcetree.c:274-279)
   int *nlstart = nullptr;          // first position of the node's particles in next[] order
   Moments *nmom = nullptr;
+  int *lev_off = nullptr;          // [72] cells per level -> offsets of the level lists (k_b5_levels)
   // sibling-pair records of the packed walk (walk.cu k_walk_pairs): the child cells of a node are stored next to each
   // other, two per 128-byte record, components interleaved for the f32x2 instructions
   PairRec *pairs = nullptr; int *gbase = nullptr; bool pairs_valid = false;
@@ -109,7 +110,8 @@ struct Ctx {
   int *s_ngb = nullptr, *s_partner = nullptr, *s_pass = nullptr, *s_passlist = nullptr;
   double *s_rand = nullptr, *s_dir = nullptr, *s_pmax = nullptr, *s_prob = nullptr;
   float *s_dv = nullptr;           // [n][3]
-  int *s_winner = nullptr;         // per particle: last buffer slot that chose it as partner
+  unsigned long long *s_winner = nullptr;   // per particle: winner_base + last buffer slot that chose it as partner (never reset: the base grows with every call)
+  unsigned long long winner_base = 1;
   int *s_cand = nullptr; unsigned long long *s_candkey = nullptr; size_t s_cand_cap = 0;
   int *s_repair = nullptr;
   b200_scatlog *d_scatlog = nullptr; int scatlog_cap = 0; int scatlog_n = 0;

@@ -51,10 +51,11 @@ struct SidmState {
   int cap_nodes = 0, cap_part = 0;
   // scratch private to the SIDM chain (it may run on its own stream next to the gravity walk,
   // which owns S.x_redo / g.d_t* / S.cub_tmp)
-  int *x_redo = nullptr, *x_want = nullptr, *x_keys = nullptr, *x_keys2 = nullptr, *x_vals = nullptr, *x_shard = nullptr;
+  int *x_redo = nullptr, *x_redo2 = nullptr, *x_want = nullptr, *x_keys = nullptr, *x_keys2 = nullptr, *x_vals = nullptr, *x_shard = nullptr;
   void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
   // query groups of the warp-shared search (k_pass1_group): leaf range + tree node of each group
   int2 *groups = nullptr; int *gnode = nullptr, *gflag = nullptr, *gpos = nullptr, *order_leaf = nullptr; int ngroups = 0;
+  int *gown = nullptr, *gownflag = nullptr; int nown = 0;   // sharded: the groups this rank searches (compact list: no idle warps in k_pass1_group)
 } S;
 
 
@@ -260,9 +261,10 @@ __global__ void k_export_flag(int na, const int *active, const float4 *posm, con
 }
 __global__ void k_assign_slots(int na, const int *active, const int *flag, const int *scan, int *slot_part, int *slot_of_active,
                                const float *curtime, const float *dvel, double time, float *dt, unsigned char *already,
-                               const int *krank, int *keys, int *vals, int *flags_out) {
+                               const int *krank, int *keys, int *vals, int *flags_out, int *partner, float *dv, double *prob, double *ptot) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= na) return;
+  partner[a] = -1; dv[3 * (size_t)a] = dv[3 * (size_t)a + 1] = dv[3 * (size_t)a + 2] = 0; prob[a] = 0; ptot[a] = 0;   // slot a's results
   const int nexport = scan[na];
   const int i = active ? active[a] : a;
   const int place = flag[a] ? scan[a] : nexport + (a - scan[a]);
@@ -358,6 +360,11 @@ __global__ void k_group_emit(int m, const SearchNode *sn, const int *flag, const
   }
 }
 // sharded runs: the global processing order of the slots = leaf order
+// sharded runs: the groups of the 32-blocks b of the leaf order with b % world == rank
+__global__ void k_group_own(int ng, const int2 *groups, int world, int rank, int *flag) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < ng) flag[w] = ((groups[w].x >> 5) % world) == rank;
+}
 __global__ void k_order_leaf(int n, const int *leaf_orig, const int *slot_of_part, int *order_leaf) {
   const int L = blockIdx.x * blockDim.x + threadIdx.x;
   if (L < n) order_leaf[L] = slot_of_part[leaf_orig[L]];
@@ -367,7 +374,7 @@ __device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f);
 __device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
 struct Pass1G {
-  int ng; const int2 *groups; const int *gnode; SearchCtx C; const float4 *velh; const int *slot_of_part;
+  int ng; const int *own; const int2 *groups; const int *gnode; SearchCtx C; const float4 *velh; const int *slot_of_part;
   const float *dt; const unsigned char *already; const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
   int *ngb; double *pmax, *rnd; int *pass; int *order_leaf; int count_only; unsigned long long *ctr;
   int rank, world;     // sharded: this rank handles the groups of the 32-blocks b with b % world == rank
@@ -422,18 +429,20 @@ __device__ __forceinline__ void pass1_finish(const Pass1G &P, int L, int i, cons
   P.pass[k] = !(pm < r) && !P.already[s];                             // sidm.c:343-346
 }
 __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
-  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (w >= P.ng) return;                                   // warp-uniform
+  const int wi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wi >= P.ng) return;                                  // warp-uniform
+  const int w = P.own ? P.own[wi] : wi;                    // sharded: this rank's groups only
   const int2 gr = P.groups[w];
-  if (P.world > 1 && (gr.x >> 5) % P.world != P.rank) return;   // another rank's block
   const bool valid = lane < gr.y;
   const int L = gr.x + (valid ? lane : 0);
   const float4 p = P.C.leaf_posm[L];
   const int i = P.C.leaf_orig[L];
   const float h = valid ? P.velh[i].w : 0.0f;
   const float sr2 = fmul(h, h);
-  if (gr.y <= kGroupTiny) {
-    // a few stray particles (direct particles of a big cell): per-query tree walks, as k_pass1
+  // a few stray particles (direct particles of a big cell, far from each other): per-query tree walks, as k_pass1.  Short runs
+  // inside a small cell (the 32-aligned cuts of sharded runs leave many) stay on the warp-shared search: their cubes overlap.
+  const SearchNode &gn = P.C.snode[P.gnode[w]];
+  if (gr.y <= kGroupTiny && gn.pend - gn.pstart > kGroupCell) {
     int cnt = 0, cand = 0;
     const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
     range_search_fast(P.C, valid, start, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
@@ -780,14 +789,9 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
 }
 
 // ------------------------------------------------------------------ resolve sweeps
-__global__ void k_clear_slots(int ns, int *partner, float *dv, double *prob, double *ptot) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= ns) return;
-  partner[s] = -1; dv[3 * (size_t)s] = dv[3 * (size_t)s + 1] = dv[3 * (size_t)s + 2] = 0; prob[s] = 0; ptot[s] = 0;
-}
 // sidm.c:495-537: own result -> particle, in/out of range decides confirmation
 __global__ void k_resolve_own(int ns, const int *slot_part, const int *sngb, const float *dv, int lo, int hi, int count_only,
-                              int *ngb, float *dvel, int *confirm, int *winner, const int *partner, unsigned long long *ctr) {
+                              int *ngb, float *dvel, int *confirm, unsigned long long *winner, unsigned long long wbase, const int *partner, unsigned long long *ctr) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns) return;
   const int i = slot_part[s];
@@ -803,16 +807,16 @@ __global__ void k_resolve_own(int ns, const int *slot_part, const int *sngb, con
     conf = 1;
   }
   confirm[s] = conf;
-  if (conf) atomicMax(&winner[partner[s]], s);
+  if (conf) atomicMax(&winner[partner[s]], wbase + (unsigned long long)s);
 }
 // sidm.c:559-601: partner gets -dv; several slots naming one partner: the last in buffer order wins
-__global__ void k_resolve_partner(int ns, const int *confirm, const int *partner, const float *dv, const int *winner, float *dvel,
+__global__ void k_resolve_partner(int ns, const int *confirm, const int *partner, const float *dv, const unsigned long long *winner, unsigned long long wbase, float *dvel,
                                   const int *logpos, b200_scatlog *log, int logcap, int logbase, const int *slot_part,
                                   const float4 *posm, const float4 *velh, const int *pid, float time, int *kick_list, int *nkick, int kick_cap) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns || !confirm[s]) return;
   const int j = partner[s];
-  if (winner[j] == s) {
+  if (winner[j] == wbase + (unsigned long long)s) {
     dvel[3 * (size_t)j] = -dv[3 * (size_t)s]; dvel[3 * (size_t)j + 1] = -dv[3 * (size_t)s + 1]; dvel[3 * (size_t)j + 2] = -dv[3 * (size_t)s + 2];
     const int at = atomicAdd(nkick, 1);                    // the partner need not be active: b200_download_active() sends it along
     if (at < kick_cap) kick_list[at] = j;
@@ -828,10 +832,6 @@ __global__ void k_resolve_partner(int ns, const int *confirm, const int *partner
     e.dv[0] = dv[3 * (size_t)s]; e.dv[1] = dv[3 * (size_t)s + 1]; e.dv[2] = dv[3 * (size_t)s + 2];
     log[lp] = e;
   }
-}
-__global__ void k_reset_winner(int ns, const int *partner, int *winner) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < ns && partner[s] >= 0) winner[partner[s]] = -1;
 }
 
 // multi-GPU: per-slot results of this rank's share of the buffer -> all ranks
@@ -921,12 +921,13 @@ static int ensure_sidm_buffers() {
   B200_TRY(al((void **)&S.dt, n * sizeof(float)));
   B200_TRY(al((void **)&S.already, n));
   B200_TRY(al((void **)&S.ptot, n * sizeof(double)));
-  B200_TRY(al((void **)&S.x_redo, n * sizeof(int))); B200_TRY(al((void **)&S.x_want, n * sizeof(int)));
+  B200_TRY(al((void **)&S.x_redo, n * sizeof(int))); B200_TRY(al((void **)&S.x_redo2, n * sizeof(int))); B200_TRY(al((void **)&S.x_want, n * sizeof(int)));
   B200_TRY(al((void **)&S.x_keys, n * sizeof(int))); B200_TRY(al((void **)&S.x_keys2, n * sizeof(int)));
   B200_TRY(al((void **)&S.x_vals, n * sizeof(int))); B200_TRY(al((void **)&S.x_shard, (n + 64) * sizeof(int)));
   B200_TRY(al((void **)&S.groups, (n + m + 1) * sizeof(int2))); B200_TRY(al((void **)&S.gnode, (n + m + 1) * sizeof(int)));
   B200_TRY(al((void **)&S.gflag, (m + 2) * sizeof(int))); B200_TRY(al((void **)&S.gpos, (m + 2) * sizeof(int)));
   B200_TRY(al((void **)&S.order_leaf, n * sizeof(int)));
+  B200_TRY(al((void **)&S.gown, (n + m + 1) * sizeof(int))); B200_TRY(al((void **)&S.gownflag, (n + m + 1) * sizeof(int)));
   if (!d_kernel_table) {
     double K[1002];
     const double PI = 3.14159265358979323846;
@@ -945,8 +946,8 @@ static int ensure_sidm_buffers() {
 void sidm_release() {
   void **ptrs[] = {(void **)&S.snode, (void **)&S.snodef, (void **)&S.last_active, (void **)&S.slot_of_sorted, (void **)&S.passlist,
                    (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot,
-                   (void **)&S.x_redo, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp,
-                   (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf};
+                   (void **)&S.x_redo, (void **)&S.x_redo2, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp,
+                   (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf, (void **)&S.gown, (void **)&S.gownflag};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (S.rx) cudaFree(S.rx); if (S.ro) cudaFree(S.ro);
   S.rx = nullptr; S.ro = nullptr; S.rx_cap = S.ro_cap = 0;
@@ -988,6 +989,17 @@ int refresh_search_nodes() {
   CUDA_TRY(cudaMemcpyAsync(&S.ngroups, S.gpos + m, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   count_launch(5);
+  S.nown = 0;
+  if (aligned && S.ngroups > 0) {
+    k_group_own<<<cdiv(S.ngroups, 256), 256, 0, st>>>(S.ngroups, S.groups, g.shard_world, g.shard_rank, S.gownflag);
+    size_t tbo = 0;
+    cub::DeviceSelect::Flagged(nullptr, tbo, g.iota, S.gownflag, S.gown, g.d_flags + FL_NPASS, S.ngroups, st);
+    B200_TRY(cub_scratch(tbo));
+    CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tbo, g.iota, S.gownflag, S.gown, g.d_flags + FL_NPASS, S.ngroups, st));
+    CUDA_TRY(cudaMemcpyAsync(&S.nown, g.d_flags + FL_NPASS, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    count_launch(3);
+  }
   static const bool dbg = getenv("B200_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "libsidm_b200: %d query groups for %d particles (%.1f per warp)\n", S.ngroups, g.n, (double)g.n / (S.ngroups > 0 ? S.ngroups : 1));
   return B200_OK;
@@ -1026,6 +1038,13 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
 
   CUDA_TRY(cudaMemsetAsync(g.d_ctr + CT_CAND, 0, 4 * sizeof(unsigned long long), st));
   CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_ERR_NGB, 0, sizeof(int), st));
+  // B200_TIMING=1: device time of the phases of every large pass (development aid)
+  static const bool timing = getenv("B200_TIMING") != nullptr;
+  static cudaEvent_t tev[8]; static bool tev_ok = false;
+  const bool tm = timing && na >= (1 << 20);
+  if (tm && !tev_ok) { for (auto &e : tev) cudaEventCreate(&e); tev_ok = true; }
+  auto mark = [&](int k) { if (tm) cudaEventRecord(tev[k], st); };
+  mark(0);
 
   int bunch = g.par.BunchSizeSidm > 0 ? g.par.BunchSizeSidm : na;
   int logbase = g.scatlog_n, tot_pass1 = 0;
@@ -1045,7 +1064,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     int *slot_of_active = g.s_repair;     // scratch
     // processing order: slots sorted along the tree key order (spatial coherence inside a warp)
     k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
-                                    g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags);
+                                    g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags, g.s_partner, g.s_dv, g.s_prob, S.ptot);
     count_launch(4);
     if (act) {
       size_t tb2 = 0;
@@ -1095,22 +1114,22 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       global_order = S.order_leaf;
     }
     if (sharded) { B200_TRY(shard_select(global_order, nb, S.x_shard, &nord, st)); order = S.x_shard; }
+    mark(1);
     // pass 1
     Pass1 P1;
     P1.ns = nord; P1.order = order; P1.slot_part = g.s_slot_part; P1.C = search_ctx();
     P1.posm = g.posm; P1.velh = g.velh; P1.dt = S.dt; P1.already = S.already; P1.replay_rand = d_rr;
     P1.C_Pmax = C_Pmax; P1.s_a_inverse = sainv; P1.k0 = k0; P1.k1 = k1;
     P1.ngb = g.s_ngb; P1.pmax = g.s_pmax; P1.rnd = g.s_rand; P1.pass = g.s_pass; P1.count_only = count_only; P1.ctr = g.d_ctr;
-    k_clear_slots<<<G, B, 0, st>>>(nb, g.s_partner, g.s_dv, g.s_prob, S.ptot);
     // every particle is a query, open boundaries: warp-shared search over the query groups
     const bool grouped = group_mode;
     if (grouped) {
       Pass1G PG;
-      PG.ng = S.ngroups; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
+      PG.ng = sharded ? S.nown : S.ngroups; PG.own = sharded ? S.gown : nullptr; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
       PG.dt = S.dt; PG.already = S.already; PG.replay_rand = d_rr; PG.C_Pmax = C_Pmax; PG.s_a_inverse = sainv; PG.k0 = k0; PG.k1 = k1;
       PG.ngb = g.s_ngb; PG.pmax = g.s_pmax; PG.rnd = g.s_rand; PG.pass = g.s_pass; PG.order_leaf = S.order_leaf; PG.count_only = count_only; PG.ctr = g.d_ctr;
       PG.rank = sharded ? g.shard_rank : 0; PG.world = sharded ? g.shard_world : 1;
-      k_pass1_group<<<cdiv((long long)S.ngroups * 32, 128), 128, 0, st>>>(PG);
+      if (PG.ng > 0) k_pass1_group<<<cdiv((long long)PG.ng * 32, 128), 128, 0, st>>>(PG);
       if (!sharded) order = S.order_leaf;                  // the pass flags are indexed by leaf position
     } else if (nord > 0) {
       // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
@@ -1118,6 +1137,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       else k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     }
     count_launch(2);
+    mark(2);
     int npass = 0;
     if (!count_only) {
       // compact the slots that passed the first approximation, keeping the processing order
@@ -1162,6 +1182,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         count_launch();
       }
     }
+    mark(3);
     if (sharded) {
       // exchange {Ngb, partner, dv} of every slot (replaces the result + confirm hypercube
       // passes of sidm.c:463-553); the two write sweeps below then run identically on all ranks
@@ -1196,11 +1217,13 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         count_launch();
       }
     }
+    mark(4);
     // resolve
     int *confirm = g.s_pass;   // reuse (pass flags are consumed)
-    CUDA_TRY(cudaMemsetAsync(g.s_winner, 0xff, (size_t)g.n * sizeof(int), st));
+    const unsigned long long wbase = g.winner_base;        // entries of earlier calls are smaller than every entry of this one
+    g.winner_base += (unsigned long long)nb;
     k_resolve_own<<<G, B, 0, st>>>(nb, g.s_slot_part, g.s_ngb, g.s_dv, g.par.DesNumNgb - g.par.MaxNumNgbDeviation,
-                                   g.par.DesNumNgb + g.par.MaxNumNgbDeviation, count_only, g.ngb, g.dvel, confirm, g.s_winner, g.s_partner, g.d_ctr);
+                                   g.par.DesNumNgb + g.par.MaxNumNgbDeviation, count_only, g.ngb, g.dvel, confirm, g.s_winner, wbase, g.s_partner, g.d_ctr);
     count_launch();
     if (!count_only) {
       CUDA_TRY(cudaMemsetAsync(confirm + nb, 0, sizeof(int), st));
@@ -1208,7 +1231,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       cub::DeviceScan::ExclusiveSum(nullptr, tb4, confirm, S.logpos, nb + 1, st);
       B200_TRY(cub_scratch(tb4));
       CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
-      k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
+      k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, wbase, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
                                          g.s_slot_part, g.posm, g.velh, g.pid, (float)time, g.kick_list, g.d_nkick, g.maxpart);
       int nlog = 0;
       CUDA_TRY(cudaMemcpyAsync(&nlog, S.logpos + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1217,6 +1240,14 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       count_launch(3);
     }
     g.last_nslot = nb;
+    mark(5);
+    if (tm) {
+      cudaEventSynchronize(tev[5]);
+      float t[5];
+      for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t[k], tev[k], tev[k + 1]);
+      fprintf(stderr, "libsidm_b200 timing rank %d: sidm pass of %d slots (%d here, %d groups): slots %.3f | pass1 %.3f | select+pass2 %.3f | exchange %.3f | resolve %.3f ms\n",
+              g.shard_rank, nb, nord, S.ngroups, t[0], t[1], t[2], t[3], t[4]);
+    }
   }
   g.scatlog_n = logbase < g.scatlog_cap ? logbase : g.scatlog_cap;
   CUDA_TRY(cudaMemcpyAsync(g.h_ctr + CT_CAND, g.d_ctr + CT_CAND, (CT_COUNT - CT_CAND) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1302,9 +1333,10 @@ static int knn_device(const int *d_idx, int nq, int k, float *d_h2) {
 // ------------------------------------------------------------------ ensure_neighbours
 // sidm.c:862-888 (ensure==1) or init.c:456-478 (ensure==0): flag particles whose neighbour
 // count is out of range and not yet converged, update the bisection bracket
-__global__ void k_flag_repair(int n, int lo, int hi, int ensure_variant, const int *ngb, const float4 *velh, float *left, float *right, int *flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void k_flag_repair(int n, const int *list, int lo, int hi, int ensure_variant, const int *ngb, const float4 *velh, float *left, float *right, int *flag) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int i = list[a];
   int f = 0;
   const int nb = ngb[i];
   if (nb < lo || nb > hi) {
@@ -1322,7 +1354,7 @@ __global__ void k_flag_repair(int n, int lo, int hi, int ensure_variant, const i
       left[i] = L; right[i] = R;
     }
   }
-  flag[i] = f;
+  flag[a] = f;
 }
 // sidm.c:917-929: new smoothing length for the flagged particles (h from k-NN where asked)
 struct TypeCount { int n[8]; };
@@ -1367,20 +1399,23 @@ __global__ void k_set_hsml_from_h2(int n, const float *h2, float4 *velh, float *
 
 // shared repair loop; ensure_variant 1 = sidm_ensure_neighbours (runs sidm()), 0 = start-up
 // (counts only, setup_nbr_sidm)
-static int repair_loop(int ensure_variant, double time, double vmax, const b200_replay *replay, int maxiter) {
+// `list` (nlist entries): the particles the loop may touch - the active list of the step (sidm.c:862-874 walks the ForceFlag chain)
+// or every particle at start-up (init.c:456).  A pass can only flag particles of the pass before it (nobody else's count
+// changes), so every pass after the first works on the previous pass's list: no O(N) sweep per pass.
+static int repair_loop(int ensure_variant, double time, double vmax, const b200_replay *replay, int maxiter, const int *list, int nlist) {
   cudaStream_t st = sidm_stream();
-  const int n = g.n, B = 256, G = cdiv(n, B);
+  const int B = 256;
   const int lo = g.par.DesNumNgb - g.par.MaxNumNgbDeviation, hi = g.par.DesNumNgb + g.par.MaxNumNgbDeviation;
   int iter = 0;
   size_t roff = 0;
-  int *redo = S.x_redo;                 // compacted list (ascending index, like sidm.c:862)
+  int *redo = S.x_redo;                 // compacted list in list order (the reference's order, sidm.c:862)
   int *want = S.x_want; float *h2 = (float *)S.x_keys2;
   for (;;) {
-    k_flag_repair<<<G, B, 0, st>>>(n, lo, hi, ensure_variant, g.ngb, g.velh, g.left, g.right, g.s_flag);
+    k_flag_repair<<<cdiv(nlist, B), B, 0, st>>>(nlist, list, lo, hi, ensure_variant, g.ngb, g.velh, g.left, g.right, g.s_flag);
     size_t tb = 0;
-    cub::DeviceSelect::Flagged(nullptr, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st);
+    cub::DeviceSelect::Flagged(nullptr, tb, list, g.s_flag, redo, g.d_flags + FL_NREPAIR, nlist, st);
     B200_TRY(cub_scratch(tb));
-    CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tb, g.iota, g.s_flag, redo, g.d_flags + FL_NREPAIR, n, st));
+    CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tb, list, g.s_flag, redo, g.d_flags + FL_NREPAIR, nlist, st));
     CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     count_launch(4);
@@ -1413,6 +1448,8 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0));
     iter++;
     g.cnt.ensure_repaired += nr;
+    list = redo; nlist = nr;                                    // the next pass looks at these only
+    redo = (redo == S.x_redo) ? S.x_redo2 : S.x_redo;
     if (iter > maxiter) { fprintf(stderr, "libsidm_b200: failed to converge in ensure_neighbours\n"); return B200_ERR_HSML; }
   }
   g.cnt.ensure_iterations = iter;
@@ -1471,9 +1508,9 @@ extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, c
   int rc = B200_OK;
   if (g.h_flags[FL_NREPAIR] > 0) {
     k_zero_lr<<<cdiv(na, 256), 256, 0, st>>>(na, act, g.left, g.right);     // sidm.c:857-859
-    k_iota<<<cdiv(g.n, 256), 256, 0, st>>>(g.n, g.iota);
-    count_launch(2);
-    rc = repair_loop(1, time, vmax, replay, 30);
+    count_launch();
+    // all particles: iota[i] = i is what every tree build leaves there (k_keys)
+    rc = repair_loop(1, time, vmax, replay, 30, act ? act : g.iota, na);
   }
   cudaEventRecord(g.ev_s1, st); cudaEventSynchronize(g.ev_s1);
   cudaEventElapsedTime(&g.cnt.ms_ensure, g.ev_s0, g.ev_s1);
@@ -1492,7 +1529,7 @@ extern "C" int b200_setup_smoothinglengths_sidm(int desired_ngb) {
   count_launch(2);
   S.last_all = true; S.last_nactive = n;
   B200_TRY(sidm_impl(nullptr, n, 0.0, 0.0, nullptr, true));                  // setup_nbr_sidm(), init.c:446
-  return repair_loop(0, 0.0, 0.0, nullptr, 60);                              // init.c:453-509
+  return repair_loop(0, 0.0, 0.0, nullptr, 60, g.iota, n);                   // init.c:453-509
 }
 
 extern "C" int b200_compute_accelerations(int mode, const int *active, int nactive, double time, double vmax) {
@@ -1507,7 +1544,13 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   // of small launches with host round trips - on a second, high-priority stream, so the tail costs
   // no wall time.  Sharded over several GPUs this needs a host whose all-gather callback runs on
   // b200_current_stream() (option "shard_overlap"); the gravity exchange is then issued last.
-  const bool overlap = g.opt_overlap && (g.shard_world == 1 || g.opt_shard_overlap);
+  // Modes (option "overlap"): 0 = one phase after the other as accel.c:39-65; 1 = the whole SIDM chain next to the walk;
+  // 2 = only the SIDM pass next to the walk, the repair loop after it.  Next to the walk every small kernel of the chain
+  // waits ~0.1-0.2 ms for thread-block slots: free while a 20 ms walk runs anyway (one GPU: mode 1), but with the walk
+  // split over several GPUs the repair loop's ~100 launches would outlast it (default when sharded: mode 2).
+  int omode = g.opt_overlap < 0 ? (g.shard_world == 1 ? 1 : 2) : g.opt_overlap;
+  if (g.shard_world > 1 && !g.opt_shard_overlap) omode = 0;
+  const bool overlap = omode != 0;
   if (active && (nactive < 0 || nactive > g.n)) return B200_ERR_ARG;
   if (!overlap) {
     B200_TRY(b200_gravity(active, nactive, time));   // gravtree.c:127-324
@@ -1524,7 +1567,7 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   if (rc == B200_OK) {
     g.overlap_now = true;
     rs = b200_sidm(active, nactive, time, vmax, nullptr);
-    if (rs == B200_OK) rs = b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);
+    if (rs == B200_OK && omode == 1) rs = b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);
     g.overlap_now = false;
   }
   cudaStreamSynchronize(g.stream_sidm);
@@ -1533,6 +1576,8 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   cudaEventRecord(g.ev_join, g.stream_sidm); cudaStreamWaitEvent(g.stream, g.ev_join, 0);
   if (rc != B200_OK) return rc;
   if (rs != B200_OK) return rs;
+  if (rf != B200_OK) return rf;
+  if (omode == 2) return b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);   // on the main stream, the GPU to itself
   return rf;
 }
 

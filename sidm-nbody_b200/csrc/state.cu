@@ -41,7 +41,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.nlevel, m + 1)); B200_TRY(dalloc(&g.nnp, m + 1)); B200_TRY(dalloc(&g.nnchild, m + 1));
   B200_TRY(dalloc(&g.ndp, 8 * (m + 1))); B200_TRY(dalloc(&g.narrive, m + 1));
   B200_TRY(dalloc(&g.nminidx, m + 1)); B200_TRY(dalloc(&g.nlstart, m + 1));
-  B200_TRY(dalloc(&g.nmom, m + 1));
+  B200_TRY(dalloc(&g.nmom, m + 1)); B200_TRY(dalloc(&g.lev_off, (size_t)72));
   B200_TRY(dalloc(&g.pairs, m + 4)); B200_TRY(dalloc(&g.gbase, m + 2));
   B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n)); B200_TRY(dalloc(&g.leaf_parent, n));
   B200_TRY(dalloc(&g.lrank, n));
@@ -76,7 +76,7 @@ extern "C" int b200_shard_buffers(void **send, void **recv, long long *cap_bytes
 }
 extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
-  if (!strcmp(name, "overlap")) { g.opt_overlap = value != 0; return B200_OK; }
+  if (!strcmp(name, "overlap")) { g.opt_overlap = value < 0 ? -1 : (value > 2 ? 2 : value); return B200_OK; }
   if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
   if (!strcmp(name, "walkp_minb")) { g.opt_walkp_minb = value; return B200_OK; }
   if (!strcmp(name, "walk_pairs")) { g.opt_walk_pairs = value != 0; g.tree_valid = false; return B200_OK; }
@@ -176,7 +176,8 @@ extern "C" int b200_init(const b200_params *p) {
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
     CUDA_TRY(cudaStreamCreateWithPriority(&g.stream_sidm, cudaStreamNonBlocking, phi));
   }
-  g.opt_overlap = getenv("B200_NO_OVERLAP") == nullptr; g.overlap_now = false; g.walk_pending = false;
+  g.opt_overlap = getenv("B200_NO_OVERLAP") ? 0 : (getenv("B200_OVERLAP") ? atoi(getenv("B200_OVERLAP")) : -1); g.overlap_now = false; g.walk_pending = false;
+  g.winner_base = 1;
   int rc = alloc_all();
   if (rc != B200_OK) { b200_finalize(); return rc; }
   CUDA_TRY(cudaMallocHost((void **)&g.h_flags, FL_COUNT * sizeof(int)));
@@ -184,6 +185,7 @@ extern "C" int b200_init(const b200_params *p) {
   CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), g.stream));
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, CT_COUNT * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaMemsetAsync(g.d_nkick, 0, 4 * sizeof(int), g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.s_winner, 0, (size_t)g.maxpart * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   memset(&g.cnt, 0, sizeof(g.cnt));
   g.n = 0; g.tree_valid = false; g.sidm_calls = 0; g.ts_calls = 0;
@@ -208,7 +210,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.d_flags); dfree(&g.d_ctr);
   dfree(&g.nodes); dfree(&g.geom); dfree(&g.nstart); dfree(&g.nend); dfree(&g.nparent); dfree(&g.npstart);
   dfree(&g.nlevel); dfree(&g.nnp); dfree(&g.nnchild); dfree(&g.ndp); dfree(&g.narrive);
-  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
+  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.lev_off); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
   dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.leaf_parent); dfree(&g.lrank);
   dfree(&g.d_shard_list);
   if (g.shard_own) { cudaFree(g.shard_send); cudaFree(g.shard_recv); g.shard_own = false; g.shard_send = g.shard_recv = nullptr; g.shard_world = 1; g.shard_rank = 0; }

@@ -11,6 +11,7 @@
 // record + 80 B double moments scratch.
 #include <stdlib.h>
 #include <cub/cub.cuh>
+#include <cooperative_groups.h>
 #include "ctx.cuh"
 #include "build_logic.h"
 
@@ -197,6 +198,34 @@ __global__ void k_b5_up(BuildView v) {
     cur = par;                                              // last child to arrive: finish the parent
   }
 }
+// Moments level by level in ONE cooperative launch: the cells are listed by level (6-bit radix sort of the pre-order ids), the
+// grid works through the levels from the deepest up with a grid-wide barrier in between, a cell reads the finished moments of
+// its child cells.  No arrival counters, no fences, no uncached loads; same sums in the same (octant) order as b5_body.
+__global__ void k_level_hist(int m, const unsigned char *nlevel, int *hist) {
+  __shared__ int sh[64];
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < m) atomicAdd(&sh[nlevel[id] & 63], 1);
+  __syncthreads();
+  if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_level_offsets(int *hist) {          // counts [64] -> exclusive offsets [65], in place
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int at = 0;
+  for (int l = 0; l < 64; l++) { const int c = hist[l]; hist[l] = at; at += c; }
+  hist[64] = at;
+}
+__global__ void __launch_bounds__(256) k_b5_levels(BuildView v, const int *lev_ids, const int *lev_off) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  for (int lev = kMaxLevels; lev >= 0; lev--) {
+    const int a = lev_off[lev], b = lev_off[lev + 1];
+    if (b == a) continue;                                   // the same for every thread: no barrier needed
+    for (int k = a + gt; k < b; k += gs) b5_body(v, lev_ids[k]);
+    grid.sync();
+  }
+}
 __global__ void k_b6(BuildView v, int level) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = min(v.nodestart[v.n], v.maxnodes);
@@ -371,8 +400,31 @@ int tree_build_impl() {
   count_launch(5);
   // 5. moments, children before parents
   static const bool per_level = getenv("B200_MOMENTS_PER_LEVEL") != nullptr;     // the one-launch-per-level form, kept for A/B
+  static const bool climb = getenv("B200_MOMENTS_CLIMB") != nullptr;             // the last-arriver climb of round 1, kept for A/B
   if (per_level) { for (int lev = g.max_level; lev >= 0; lev--) k_b5<<<GM, B, 0, st>>>(v, lev); count_launch(g.max_level + 1); }
-  else {
+  else if (!climb) {
+    int *hist = g.lev_off, *lev_ids = g.sidx_tmp;           // sidx_tmp: scratch of the key sort, free by now
+    unsigned char *lkeys = (unsigned char *)g.key_tmp;
+    CUDA_TRY(cudaMemsetAsync(hist, 0, 72 * sizeof(int), st));
+    k_level_hist<<<cdiv(m, 256), 256, 0, st>>>(m, g.nlevel, hist);
+    k_level_offsets<<<1, 32, 0, st>>>(hist);
+    size_t tbl = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st);
+    B200_TRY(ensure_cub(tbl));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st));
+    static int coop_blocks = 0;
+    if (!coop_blocks) {
+      int per_sm = 0, dev = 0, sms = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels, 256, 0));
+      CUDA_TRY(cudaGetDevice(&dev));
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      coop_blocks = per_sm * sms;
+    }
+    const int *cl = lev_ids, *co = hist;
+    void *args[] = {(void *)&v, (void *)&cl, (void *)&co};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_b5_levels, dim3(coop_blocks), dim3(256), args, 0, st));
+    count_launch(6);
+  } else {
     CUDA_TRY(cudaMemsetAsync(g.narrive, 0, (size_t)(m + 1) * sizeof(int), st));
     k_b5_up<<<cdiv(m + 1, 128), 128, 0, st>>>(v);
     count_launch();
