@@ -295,6 +295,11 @@ int  b200_compute_global_quantities(b200_sysstate *out);
  * to the file the reference writes from the same state.  Gas particles (type 0: u / rho / hsml blocks) are not on
  * this path: B200_ERR_ARG.  The 84 fill bytes of the header are zero (the reference leaves what read_ic() put there). */
 int  b200_savepositions(const char *path, double time, const double *mass_table, double hubble_param, int *npart_out);
+/* one file of a snapshot split over NumFilesPerSnapshot > 1 files (io.c:90-103,127-160, file <base>_<num>.<i>): the rows
+ * [first, first+count) of the particle order (the particles of the tasks of one file group) in type order; header npart = the
+ * file's counts, npartTotal = the system's, num_files as given */
+int  b200_savepositions_part(const char *path, double time, const double *mass_table, double hubble_param,
+                             int first, int count, int num_files, int *npart_out);
 /* read_ic() + the start-up loop of init() (read_ic.c:32-481, init.c:76-100) for one format-1 file without gas, straight
  * into the device state: types from the header's block ranges, masses from MassTable or the mass block, PosPred = Pos,
  * VelPred = Vel, CurrentTime = header time, Accel = dVel = OldAcc = Potential = 0, GravCost = 1, Hsml = 0.  The file is

@@ -82,7 +82,7 @@ def global_quantities(pospred, velpred, mass, potential, types=None):
 
 
 def snapshot_bytes(pospred, velpred, ids, mass, types=None, time=0.0, mass_table=None, box=0.0, omega0=0.0,
-                   omega_lambda=0.0, hubble_param=0.0, comoving=False, periodic=False):
+                   omega_lambda=0.0, hubble_param=0.0, comoving=False, periodic=False, npart_total=None, num_files=1):
     """savepositions_ioformat1(), io.c:54-590, one rank, one file, no gas: the bytes of the snapshot file.
     Header struct io_header_1 (allvars.h:727-746, fill bytes zero), then PosPred, VelPred, ID, and the masses of the types
     whose MassTable entry is 0 - particles in type order (0..4; type 5 is not written, io.c:265), particle order
@@ -112,9 +112,10 @@ def snapshot_bytes(pospred, velpred, ids, mass, types=None, time=0.0, mass_table
                                 ("OmegaLambda", "<f8"), ("HubbleParam", "<f8"), ("flag_multiphase", "<i4"),
                                 ("flag_stellarage", "<i4"), ("flag_sfrhistogram", "<i4"), ("fill", "S84")]))
     assert hdr.itemsize == 256
-    hdr["npart"] = cnt; hdr["npartTotal"] = cnt; hdr["mass"] = mt; hdr["time"] = time
+    hdr["npart"] = cnt; hdr["npartTotal"] = cnt if npart_total is None else np.asarray(npart_total, np.int32); hdr["mass"] = mt; hdr["time"] = time
     hdr["redshift"] = (1.0 / time - 1) if comoving else 0.0
-    hdr["num_files"] = 1; hdr["BoxSize"] = box; hdr["Omega0"] = omega0; hdr["OmegaLambda"] = omega_lambda
+    # io.c:140-160: npartTotal / num_files of a snapshot split over several files
+    hdr["num_files"] = num_files; hdr["BoxSize"] = box; hdr["Omega0"] = omega0; hdr["OmegaLambda"] = omega_lambda
     hdr["HubbleParam"] = hubble_param
     withmass = np.concatenate([np.nonzero(ty == t)[0] for t in range(5) if mt[t] == 0] + [np.zeros(0, np.int64)]).astype(np.int64)
 

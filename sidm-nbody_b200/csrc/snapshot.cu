@@ -22,24 +22,29 @@ struct SnapHeader {
 };
 static_assert(sizeof(SnapHeader) == 256, "io_header_1 is 256 bytes");
 
-__global__ void k_snap_hist(int n, const int *ptype, int *hist) {
-  __shared__ int sh[8];
-  if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+// hist[0..6]: types of the rows [first, first+count); hist[8..14]: types of all n rows (header npartTotal of a multi-file snapshot)
+__global__ void k_snap_hist(int n, int first, int count, const int *ptype, int *hist) {
+  __shared__ int sh[16];
+  if (threadIdx.x < 16) sh[threadIdx.x] = 0;
   __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[ptype[i] & 7], 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = ptype[i] & 7;
+    atomicAdd(&sh[8 + t], 1);
+    if (i >= first && i < first + count) atomicAdd(&sh[t], 1);
+  }
   __syncthreads();
-  if (threadIdx.x < 7 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);   // 7 words of scratch
+  if (threadIdx.x < 16 && (threadIdx.x & 7) != 7 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-__global__ void k_snap_keys(int n, const int *ptype, unsigned char *key, int *iota) {
+__global__ void k_snap_keys(int count, int first, const int *ptype, unsigned char *key, int *iota) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { key[i] = (unsigned char)(ptype[i] & 7); iota[i] = i; }
+  if (i < count) { key[i] = (unsigned char)(ptype[first + i] & 7); iota[i] = first + i; }
 }
 // slot j of the file order holds particle perm[j] (perm == nullptr: identity, one type)
 __global__ void k_snap_gather(int nout, const int *perm, const float4 *posm, const float *velpred, const int *pid,
-                              float *pos, float *vel, int *id, float *mass, int periodic, double box) {
+                              float *pos, float *vel, int *id, float *mass, int periodic, double box, int first) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nout) return;
-  const int i = perm ? perm[j] : j;
+  const int i = perm ? perm[j] : first + j;
   const float4 p = posm[i];
   float x[3] = {p.x, p.y, p.z};
   if (periodic) {                                            // io.c:275-283
@@ -140,24 +145,33 @@ using namespace b200;
 extern "C" int b200_savepositions(const char *path, double time, const double *mass_table, double hubble_param,
                                   int *npart_out) {
   if (!g.ready || g.n <= 0) return B200_ERR_STATE;
-  if (!path) return B200_ERR_ARG;
-  const int n = g.n, B = 256, G = cdiv(n, B);
+  return b200_savepositions_part(path, time, mass_table, hubble_param, 0, g.n, 1, npart_out);
+}
+
+// One file of a snapshot split over `num_files` files (io.c:90-103, 127-160): the rows [first, first+count) of the particle
+// order in type order, header npart = this file's counts, npartTotal = the whole system's.
+extern "C" int b200_savepositions_part(const char *path, double time, const double *mass_table, double hubble_param,
+                                       int first, int count, int num_files, int *npart_out) {
+  if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  if (!path || first < 0 || count < 0 || first + count > g.n || num_files < 1) return B200_ERR_ARG;
+  const int nall = g.n, n = count, B = 256, G = cdiv(n > 0 ? n : 1, B);
   cudaStream_t st = g.stream;
-  // particles per type (io.c:107-111)
-  int cnt[8];
-  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_TROOT0, 0, 7 * sizeof(int), st));        // 7 scratch words; type & 7 == 7 lands in none
-  k_snap_hist<<<296, B, 0, st>>>(n, g.ptype, g.d_flags + FL_TROOT0);
+  // particles per type (io.c:107-111), of this file and of the system
+  int cnt[16];
+  int *d_hist = (int *)g.d_bbox;                             // 8 doubles of scratch = 16 ints (free outside the tree build)
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, 16 * sizeof(int), st));
+  k_snap_hist<<<296, B, 0, st>>>(nall, first, count, g.ptype, d_hist);
   count_launch();
-  CUDA_TRY(cudaMemcpyAsync(cnt, g.d_flags + FL_TROOT0, 7 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(cnt, d_hist, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (cnt[0] > 0) return B200_ERR_ARG;                       // gas blocks (u, rho, hsml of SphP) are not on this path
+  if (cnt[8] > 0) return B200_ERR_ARG;                       // gas blocks (u, rho, hsml of SphP) are not on this path
   long long ntot = 0, nmass = 0; int ntypes = 0;
   for (int t = 0; t < 5; t++) {                              // type 5 is not written (io.c:265)
     ntot += cnt[t]; if (cnt[t] > 0) ntypes++;
     if (!mass_table || mass_table[t] == 0) nmass += cnt[t];  // io.c:121-123
   }
   if (npart_out) for (int t = 0; t < 6; t++) npart_out[t] = t < 5 ? cnt[t] : 0;
-  const bool identity = (ntypes == 1 && ntot == n);
+  const bool identity = (ntypes == 1 && ntot == n) || n == 0;   // one type: the rows as they are
   DevTmp tmp;
   const int *perm = nullptr;
   if (!identity) {
@@ -166,7 +180,7 @@ extern "C" int b200_savepositions(const char *path, double time, const double *m
         cudaMalloc(&tmp.p[2], (size_t)n * sizeof(int)) != cudaSuccess || cudaMalloc(&tmp.p[3], (size_t)n * sizeof(int)) != cudaSuccess)
       return B200_ERR_ALLOC;
     key = (unsigned char *)tmp.p[0]; key2 = (unsigned char *)tmp.p[1]; iota = (int *)tmp.p[2]; order = (int *)tmp.p[3];
-    k_snap_keys<<<G, B, 0, st>>>(n, g.ptype, key, iota);
+    k_snap_keys<<<G, B, 0, st>>>(n, first, g.ptype, key, iota);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, iota, order, n, 0, 3, st);
     if (cudaMalloc(&tmp.p[4], tb) != cudaSuccess) return B200_ERR_ALLOC;
@@ -179,18 +193,18 @@ extern "C" int b200_savepositions(const char *path, double time, const double *m
   int *d_id = g.d_cost; float *d_mass = (float *)(g.d_cost + n);
   const int periodic = (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? 1 : 0;
   if (ntot > 0) {
-    k_snap_gather<<<cdiv(ntot, B), B, 0, st>>>((int)ntot, perm, g.posm, g.velpred, g.pid, d_pos, d_vel, d_id, d_mass, periodic, g.par.BoxSize);
+    k_snap_gather<<<cdiv(ntot, B), B, 0, st>>>((int)ntot, perm, g.posm, g.velpred, g.pid, d_pos, d_vel, d_id, d_mass, periodic, g.par.BoxSize, first);
     count_launch();
   }
   CUDA_TRY(cudaGetLastError());
 
   SnapHeader h;
   memset(&h, 0, sizeof(h));
-  for (int t = 0; t < 5; t++) { h.npart[t] = cnt[t]; h.npartTotal[t] = cnt[t]; }
+  for (int t = 0; t < 5; t++) { h.npart[t] = cnt[t]; h.npartTotal[t] = cnt[8 + t]; }        // io.c:140-160
   for (int t = 0; t < 6; t++) h.mass[t] = mass_table ? mass_table[t] : 0.0;
   h.time = time;
   h.redshift = g.par.ComovingIntegrationOn ? 1.0 / time - 1 : 0;                    // io.c:168-171
-  h.num_files = 1;
+  h.num_files = num_files;
   h.BoxSize = g.par.BoxSize; h.Omega0 = g.par.Omega0; h.OmegaLambda = g.par.OmegaLambda; h.HubbleParam = hubble_param;
 
   FileCloser fc{fopen(path, "w")};

@@ -347,7 +347,7 @@ extern "C" int b200_get_soa(float *pospred, float *velpred, float *accel, float 
 
 extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *lay, int pin) {
   if (!g.ready) return B200_ERR_STATE;
-  if (!base || !lay || num_part <= 0 || num_part > g.maxpart || lay->stride <= 0 || (lay->stride & 3)) return B200_ERR_ARG;
+  if (!base || !lay || num_part <= 0 || num_part > g.maxpart || lay->stride <= 0 || (lay->stride & 3) || lay->stride > 188) return B200_ERR_ARG;
   if (g.pinned && g.h_base && g.h_base != (char *)base) { cudaHostUnregister(g.h_base); g.pinned = false; }
   g.h_base = (char *)base; g.lay = *lay; g.n = num_part; g.tree_valid = false; g.h_first = 0; g.h_count = num_part;
   const size_t bytes = (size_t)g.maxpart * lay->stride;
@@ -369,7 +369,7 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
 // [first, first+count) of the global particle order = the tasks' arrays one after the other.
 extern "C" int b200_bind_rows(void *base, int first, int count, int n_global, const b200_layout *lay, int pin) {
   if (!g.ready) return B200_ERR_STATE;
-  if (!base || !lay || count < 0 || first < 0 || n_global <= 0 || first + count > n_global || n_global > g.maxpart || lay->stride <= 0 || (lay->stride & 3)) return B200_ERR_ARG;
+  if (!base || !lay || count < 0 || first < 0 || n_global <= 0 || first + count > n_global || n_global > g.maxpart || lay->stride <= 0 || (lay->stride & 3) || lay->stride > 188) return B200_ERR_ARG;
   if (g.pinned && g.h_base && (g.h_base != (char *)base || g.h_count != count)) { cudaHostUnregister(g.h_base); g.pinned = false; }
   g.h_base = (char *)base; g.lay = *lay; g.n = n_global; g.tree_valid = false; g.h_first = first; g.h_count = count;
   const size_t bytes = (size_t)g.maxpart * lay->stride;
@@ -391,12 +391,39 @@ struct Lay { int stride, Pos, Vel, Mass, ID, Type, CurrentTime, PosPred, VelPred
 __device__ __forceinline__ float ldf(const char *p, int off) { return *(const float *)(p + off); }
 __device__ __forceinline__ int ldi(const char *p, int off) { return *(const int *)(p + off); }
 
-__global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4 *velh, float *pos0, float *velpred,
+// AoS <-> SoA through shared memory: a block moves kAosRows records; the array-of-structs side is read / written as one
+// contiguous stream of 16-byte words, the field accesses go to shared memory (a 124-byte record is 31 words: the lanes of a
+// warp hit 32 different banks), the structure-of-arrays side is coalesced as before.
+constexpr int kAosRows = 256;
+__device__ __forceinline__ void aos_block_load(const char *aos, int stride, int r0, int nrec, int *sm) {
+  const size_t off = (size_t)r0 * stride;                    // kAosRows * stride is a multiple of 16 (stride % 4 == 0)
+  const int words = nrec * (stride >> 2);
+  const int4 *src4 = reinterpret_cast<const int4 *>(aos + off);
+  int4 *dst4 = reinterpret_cast<int4 *>(sm);
+  const int quads = words >> 2;
+  for (int q = threadIdx.x; q < quads; q += blockDim.x) dst4[q] = src4[q];
+  for (int w = (quads << 2) + threadIdx.x; w < words; w += blockDim.x) sm[w] = reinterpret_cast<const int *>(aos + off)[w];
+}
+__device__ __forceinline__ void aos_block_store(char *aos, int stride, int r0, int nrec, const int *sm) {
+  const size_t off = (size_t)r0 * stride;
+  const int words = nrec * (stride >> 2);
+  int4 *dst4 = reinterpret_cast<int4 *>(aos + off);
+  const int4 *src4 = reinterpret_cast<const int4 *>(sm);
+  const int quads = words >> 2;
+  for (int q = threadIdx.x; q < quads; q += blockDim.x) dst4[q] = src4[q];
+  for (int w = (quads << 2) + threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<int *>(aos + off)[w] = sm[w];
+}
+
+__global__ void __launch_bounds__(kAosRows) k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4 *velh, float *pos0, float *velpred,
                              float *accel, float *dvel, float *curtime, float *oldacc, float *gravcost,
                              float *left, float *right, int *ngb, int *pid, int *ptype, float *maxpred, float *potential) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const char *p = aos + (size_t)i * L.stride;
+  extern __shared__ __align__(16) int sm_aos[];
+  const int r0 = blockIdx.x * kAosRows, nrec = min(kAosRows, n - r0);
+  aos_block_load(aos, L.stride, r0, nrec, sm_aos);
+  __syncthreads();
+  if ((int)threadIdx.x >= nrec) return;
+  const int i = r0 + threadIdx.x;
+  const char *p = reinterpret_cast<const char *>(sm_aos) + (size_t)threadIdx.x * L.stride;
   if (L.Pot > 0) potential[i] = ldf(p, L.Pot);
   if (L.MaxPred > 0) maxpred[i] = ldf(p, L.MaxPred);
   float4 a, b;
@@ -404,34 +431,42 @@ __global__ void k_unpack_aos(int n, const char *aos, Lay L, float4 *posm, float4
   b.x = ldf(p, L.Vel); b.y = ldf(p, L.Vel + 4); b.z = ldf(p, L.Vel + 8); b.w = ldf(p, L.Hsml);
   posm[i] = a; velh[i] = b;
   for (int k = 0; k < 3; k++) {
-    pos0[3 * i + k] = ldf(p, L.Pos + 4 * k);
-    velpred[3 * i + k] = ldf(p, L.VelPred + 4 * k);
-    accel[3 * i + k] = ldf(p, L.Accel + 4 * k);
-    dvel[3 * i + k] = ldf(p, L.dVel + 4 * k);
+    pos0[3 * (size_t)i + k] = ldf(p, L.Pos + 4 * k);
+    velpred[3 * (size_t)i + k] = ldf(p, L.VelPred + 4 * k);
+    accel[3 * (size_t)i + k] = ldf(p, L.Accel + 4 * k);
+    dvel[3 * (size_t)i + k] = ldf(p, L.dVel + 4 * k);
   }
   curtime[i] = ldf(p, L.CurrentTime); oldacc[i] = ldf(p, L.OldAcc); gravcost[i] = ldf(p, L.GravCost);
   left[i] = ldf(p, L.Left); right[i] = ldf(p, L.Right);
   ngb[i] = ldi(p, L.Ngb); pid[i] = ldi(p, L.ID); ptype[i] = ldi(p, L.Type);
 }
 
-__global__ void k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
+// the device image keeps the fields the path does not write (Pos Vel Mass ID Type CurrentTime ForceFlag) as uploaded
+__global__ void __launch_bounds__(kAosRows) k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
                            const float *accel, const float *dvel, const float *oldacc, const float *gravcost,
                            const float *left, const float *right, const int *ngb, const float *maxpred, const float *potential) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  char *p = aos + (size_t)i * L.stride;
-  if (L.Pot > 0) *(float *)(p + L.Pot) = potential[i];
-  if (L.MaxPred > 0) *(float *)(p + L.MaxPred) = maxpred[i];
-  float4 a = posm[i];
-  *(float *)(p + L.PosPred) = a.x; *(float *)(p + L.PosPred + 4) = a.y; *(float *)(p + L.PosPred + 8) = a.z;
-  for (int k = 0; k < 3; k++) {
-    *(float *)(p + L.VelPred + 4 * k) = velpred[3 * i + k];
-    *(float *)(p + L.Accel + 4 * k) = accel[3 * i + k];
-    *(float *)(p + L.dVel + 4 * k) = dvel[3 * i + k];
+  extern __shared__ __align__(16) int sm_aos[];
+  const int r0 = blockIdx.x * kAosRows, nrec = min(kAosRows, n - r0);
+  aos_block_load(aos, L.stride, r0, nrec, sm_aos);
+  __syncthreads();
+  if ((int)threadIdx.x < nrec) {
+    const int i = r0 + threadIdx.x;
+    char *p = reinterpret_cast<char *>(sm_aos) + (size_t)threadIdx.x * L.stride;
+    if (L.Pot > 0) *(float *)(p + L.Pot) = potential[i];
+    if (L.MaxPred > 0) *(float *)(p + L.MaxPred) = maxpred[i];
+    const float4 a = posm[i];
+    *(float *)(p + L.PosPred) = a.x; *(float *)(p + L.PosPred + 4) = a.y; *(float *)(p + L.PosPred + 8) = a.z;
+    for (int k = 0; k < 3; k++) {
+      *(float *)(p + L.VelPred + 4 * k) = velpred[3 * (size_t)i + k];
+      *(float *)(p + L.Accel + 4 * k) = accel[3 * (size_t)i + k];
+      *(float *)(p + L.dVel + 4 * k) = dvel[3 * (size_t)i + k];
+    }
+    *(float *)(p + L.OldAcc) = oldacc[i]; *(float *)(p + L.GravCost) = gravcost[i];
+    *(float *)(p + L.Left) = left[i]; *(float *)(p + L.Right) = right[i];
+    *(int *)(p + L.Ngb) = ngb[i]; *(float *)(p + L.Hsml) = velh[i].w;
   }
-  *(float *)(p + L.OldAcc) = oldacc[i]; *(float *)(p + L.GravCost) = gravcost[i];
-  *(float *)(p + L.Left) = left[i]; *(float *)(p + L.Right) = right[i];
-  *(int *)(p + L.Ngb) = ngb[i]; *(float *)(p + L.Hsml) = velh[i].w;
+  __syncthreads();
+  aos_block_store(aos, L.stride, r0, nrec, sm_aos);
 }
 
 static Lay to_lay(const b200_layout &l) {
@@ -445,7 +480,7 @@ extern "C" int b200_upload(void) {
   const int n = g.n;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.d_aos, g.h_base, (size_t)n * g.lay.stride, cudaMemcpyHostToDevice, g.stream));
-  k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
+  k_unpack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
                                                    g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -469,7 +504,7 @@ extern "C" int b200_download(void) {
   if (!g.ready || !g.have_aos) return B200_ERR_STATE;
   const int n = g.n;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+  k_pack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
@@ -499,7 +534,7 @@ static int upload_rows_impl(const int *counts) {
     if (counts[q] > 0) CUDA_TRY(cudaMemcpyAsync(g.d_aos + (size_t)f * st, (char *)g.shard_recv + (size_t)q * bytes, (size_t)counts[q] * st, cudaMemcpyDeviceToDevice, g.stream));
     f += counts[q];
   }
-  k_unpack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
+  k_unpack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.pos0, g.velpred, g.accel,
                                                    g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.pid, g.ptype, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
@@ -534,7 +569,7 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   if (first < 0 || count < 0 || first + count > n) return B200_ERR_ARG;
   char *out = dst ? (char *)dst : g.h_base;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  k_pack_aos<<<cdiv(n, 256), 256, 0, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+  k_pack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   if (!dst && (first < g.h_first || first + count > g.h_first + g.h_count)) return B200_ERR_ARG;

@@ -83,6 +83,7 @@ static int *prev_active = 0;
 static int  prev_n = 0;
 
 void force_treeallocate(int maxnodes, int maxpart);
+static void rng_state_io(int write);
 
 static void b200_check(int rc, const char *what)
 {
@@ -230,8 +231,30 @@ void force_treeallocate(int maxnodes, int maxpart)      /* forcetree.c:1797 */
     if (ThisTask == 0) printf("libsidm_b200 on %d tasks, %d GPU(s), all-gather through %s\n", NTask, b200_device_count(), b200_comm_uses_nccl() ? "NCCL" : "MPI (host staged)");
   }
   shim_ready = 1;
+  if (RestartFlag == 1) rng_state_io(0);
 }
 void force_treefree(void) { b200_finalize(); shim_ready = 0; }
+
+/* The generator state of the path (two call counters, b200_get_rng_state) next to the reference's restart files, which do not
+ * hold its MT19937 state (restart.c:37-154): <OutputDir><RestartFile>.<task>.b200rng is rewritten after every force
+ * computation and read back when the run is started with RestartFlag = 1 (begrun.c:57), so that a restarted run draws the
+ * same random numbers as the uninterrupted one. */
+static void rng_state_io(int write)
+{
+#ifdef SIDM
+  char name[400];
+  unsigned long long st[2];
+  FILE *f;
+  sprintf(name, "%s%s.%d.b200rng", All.OutputDir, All.RestartFile, ThisTask);
+  if (write) {
+    if (b200_get_rng_state(st) != B200_OK) return;
+    if ((f = fopen(name, "wb"))) { fwrite(st, sizeof(st), 1, f); fclose(f); }
+  } else if ((f = fopen(name, "rb"))) {
+    if (fread(st, sizeof(st), 1, f) == 1) b200_check(b200_set_rng_state(st), "b200_set_rng_state");
+    fclose(f);
+  }
+#endif
+}
 
 int force_treebuild(void)                               /* forcetree.c:90 (uses P[].PosPred) */
 {
@@ -459,13 +482,24 @@ void savepositions(int num)
   double t0 = second(), t1;
   if (ThisTask == 0) printf("\nwriting snapshot file... \n");
   if (num < 0) num = 1000 + num;                                                /* io.c:77-78 */
-  if (All.NumFilesPerSnapshot != 1 || All.TotN_gas > 0) {
-    printf("savepositions: the device writer covers one file, no gas\n"); endrun(9003);
-  }
-  sprintf(buf, "%s%s_%03d", All.OutputDir, All.SnapshotFileBase, num);         /* io.c:96 */
+  if (All.TotN_gas > 0) { printf("savepositions: gas blocks are not on the GPU path\n"); endrun(9003); }
   sync_params_and_particles();
-  /* several tasks: every GPU holds all particles, task 0 writes the one file (the reference sends the blocks to task 0, io.c:390-470) */
-  if (ThisTask == 0) b200_check(b200_savepositions(buf, All.Time, All.MassTable, All.HubbleParam, 0), "b200_savepositions");
+  if (All.NumFilesPerSnapshot <= 1) {
+    /* several tasks: every GPU holds all particles, task 0 writes the one file (the reference sends the blocks to task 0, io.c:390-470) */
+    sprintf(buf, "%s%s_%03d", All.OutputDir, All.SnapshotFileBase, num);       /* io.c:96 */
+    if (ThisTask == 0) b200_check(b200_savepositions(buf, All.Time, All.MassTable, All.HubbleParam, 0), "b200_savepositions");
+  } else {
+    /* io.c:78-103: file i holds the particles of the tasks [i*nprocgroup, (i+1)*nprocgroup); its first task writes it - here from
+     * its own GPU's copy of those rows, all files at the same time */
+    const int nprocgroup = NTask / All.NumFilesPerSnapshot;
+    if (nprocgroup < 1 || (NTask % nprocgroup)) { printf("Fatal error.\nNumber of processors must be a multiple of All.NumFilesPerSnapshot.\n"); endrun(213); }
+    if (ThisTask % nprocgroup == 0) {
+      int q, rows = 0;
+      for (q = ThisTask; q < ThisTask + nprocgroup; q++) rows += rows_of_task[q];
+      sprintf(buf, "%s%s_%03d.%d", All.OutputDir, All.SnapshotFileBase, num, ThisTask / nprocgroup);      /* io.c:94 */
+      b200_check(b200_savepositions_part(buf, All.Time, All.MassTable, All.HubbleParam, first_row, rows, All.NumFilesPerSnapshot, 0), "b200_savepositions_part");
+    }
+  }
   MPI_Barrier(MPI_COMM_WORLD);
   if (ThisTask == 0) printf("done with snapshot.\n");
   t1 = second();
@@ -525,6 +559,7 @@ void compute_accelerations(int mode)
     }
   }
   (void)i;
+  if (mode == 0) rng_state_io(1);
   dev_mirrors_host = 1;
   if (ThisTask == 0) { printf("force computation done.\n"); fflush(stdout); }
 }

@@ -97,7 +97,7 @@ def layout_of(dtype=PARTICLE_DTYPE):
 
 
 EXPORTS = ["b200_init", "b200_set_params", "b200_finalize", "b200_last_cuda_error", "b200_set_stream", "b200_set_option", "b200_set_shard", "b200_current_stream", "b200_version",
-           "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_upload_shard", "b200_download_shard", "b200_upload_active", "b200_download_active", "b200_bind_rows", "b200_upload_rows", "b200_shard_buffers", "b200_device_count", "b200_advance", "b200_find_timesteps", "b200_reflect", "b200_set_field", "b200_compute_potential", "b200_compute_global_quantities", "b200_savepositions", "b200_get_rng_state", "b200_set_rng_state", "b200_load_snapshot", "b200_potential_raw", "b200_set_soa", "b200_get_soa", "b200_predict",
+           "b200_bind_particles", "b200_upload", "b200_download", "b200_download_to", "b200_upload_shard", "b200_download_shard", "b200_upload_active", "b200_download_active", "b200_bind_rows", "b200_upload_rows", "b200_shard_buffers", "b200_device_count", "b200_advance", "b200_find_timesteps", "b200_reflect", "b200_set_field", "b200_compute_potential", "b200_compute_global_quantities", "b200_savepositions", "b200_savepositions_part", "b200_get_rng_state", "b200_set_rng_state", "b200_load_snapshot", "b200_potential_raw", "b200_set_soa", "b200_get_soa", "b200_predict",
            "b200_tree_build", "b200_gravity", "b200_sidm", "b200_setup_nbr_sidm", "b200_sidm_ensure_neighbours",
            "b200_setup_smoothinglengths_sidm", "b200_compute_accelerations", "b200_getvmax", "b200_ngb_treefind",
            "b200_direct", "b200_walk_raw", "b200_get_tree", "b200_ngb_lists", "b200_sidm_debug", "b200_get_scatlog",
@@ -143,6 +143,9 @@ def load():
         _lib.b200_compute_potential.argtypes = [C.c_void_p]
         _lib.b200_compute_global_quantities.argtypes = [C.c_void_p]
         _lib.b200_savepositions.argtypes = [C.c_char_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p]
+        _lib.b200_savepositions_part.argtypes = [C.c_char_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.b200_upload_active.argtypes = [C.c_void_p, C.c_int]
+        _lib.b200_download_active.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.b200_load_snapshot.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.b200_get_rng_state.argtypes = [C.c_void_p]
         _lib.b200_set_rng_state.argtypes = [C.c_void_p]

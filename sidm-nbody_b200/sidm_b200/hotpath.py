@@ -170,6 +170,15 @@ class HotPath:
         check(self.lib.b200_savepositions(str(path).encode(), t, ptr(mt), float(hubble_param), ptr(npart)), "b200_savepositions")
         return npart
 
+    def savepositions_part(self, path, first, count, num_files, time=None, mass_table=None, hubble_param=0.0):
+        """one file of a snapshot split over NumFilesPerSnapshot files (io.c:90-103): rows [first, first+count) of the particle order"""
+        t = self.time if time is None else float(time)
+        mt = None if mass_table is None else np.ascontiguousarray(mass_table, np.float64)
+        npart = np.zeros(6, np.int32)
+        check(self.lib.b200_savepositions_part(str(path).encode(), t, ptr(mt), float(hubble_param), int(first), int(count), int(num_files), ptr(npart)),
+              "b200_savepositions_part")
+        return npart
+
     def rng_state(self):
         """the whole generator state of the path: (sidm() calls, find_timesteps() calls) - save it with a restart file"""
         st = np.zeros(2, np.uint64)

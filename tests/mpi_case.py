@@ -33,10 +33,18 @@ def write_case(workdir, n, seed=21, **over):
     from sidm_b200 import ic
     os.makedirs(workdir, exist_ok=True)
     pos, vel, mass, ids = ic.hernquist(n, seed=seed)
-    with open(os.path.join(workdir, "ic.dat"), "wb") as f:
-        f.write(oracle.snapshot_bytes(pos, vel, ids, mass))
     par = dict(PARAMS)
     par.update(over)
+    nf = int(par["NumFilesPerSnapshot"])
+    if nf <= 1:
+        with open(os.path.join(workdir, "ic.dat"), "wb") as f:
+            f.write(oracle.snapshot_bytes(pos, vel, ids, mass))
+    else:                                               # read_ic.c:62-75: the initial conditions are split like the snapshots
+        cuts = np.linspace(0, n, nf + 1).astype(int)
+        for k in range(nf):
+            a, b = cuts[k], cuts[k + 1]
+            with open(os.path.join(workdir, f"ic.dat.{k}"), "wb") as f:
+                f.write(oracle.snapshot_bytes(pos[a:b], vel[a:b], ids[a:b], mass[a:b], npart_total=[0, n, 0, 0, 0, 0], num_files=nf))
     with open(os.path.join(workdir, "param.txt"), "w") as f:
         for k, v in par.items():
             f.write(f"{k:28s} {v}\n")

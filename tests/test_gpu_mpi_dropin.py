@@ -46,3 +46,43 @@ def test_real_main_on_two_and_four_tasks(tmp_path):
         np.testing.assert_allclose(a["pos"], c["pos"], rtol=0, atol=2e-3)
         np.testing.assert_allclose(a["vel"], c["vel"], rtol=0, atol=0.5)
         assert np.abs(a["vel"] - c["vel"]).mean() < 5e-3
+
+
+@pytest.mark.skipif(not _have("sidm_b200_mpi"), reason="oracle/_ref/sidm_b200_mpi not built (needs /root/reference)")
+def test_restart_and_split_snapshot(tmp_path):
+    """restart.c through the drop-in, with scatterings (sigma/m = 38 cm^2/g): a run that is interrupted by the reference's
+    stop-file mechanism (run.c:152-176: restart files written after the current step) and continued with RestartFlag = 1 ends
+    bit-identical to the uninterrupted run - the restart files come from the host arrays the shim keeps current, the
+    generator state of the path travels in the .b200rng side file.  Initial conditions and snapshots are split over two
+    files (NumFilesPerSnapshot = 2, one per task: read_ic.c:62-75, io.c:78-103)."""
+    import subprocess
+    import oracle
+    kw = dict(CrossSection=38.2614, NumFilesPerSnapshot=2, TimeMax=0.006)
+    w1 = str(tmp_path / "straight")
+    mpi_case.write_case(w1, N, **kw)
+    r = mpi_case.run_case(w1, "sidm_b200_mpi", 2)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
+    w2 = str(tmp_path / "restarted")
+    mpi_case.write_case(w2, N, **kw)
+    open(os.path.join(w2, "stop"), "w").close()              # stop after the first step
+    r = mpi_case.run_case(w2, "sidm_b200_mpi", 2)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
+    assert os.path.exists(os.path.join(w2, "rst_out.0")) and os.path.exists(os.path.join(w2, "rst_out.0.b200rng"))
+    assert not any(f.startswith("snp_") for f in os.listdir(w2)), "the interrupted run must not have reached TimeMax"
+    os.remove(os.path.join(w2, "stop"))
+    e = dict(os.environ, MINIMPI_NP="2")
+    r = subprocess.run([os.path.join(mpi_case.ROOT, "oracle", "_ref", "sidm_b200_mpi"), "param.txt", "1"], cwd=w2, capture_output=True, text=True, timeout=900, env=e)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2500:]
+
+    def final(w):
+        files = sorted(f for f in os.listdir(w) if f.startswith("snp_") and f.count(".") == 1)
+        last = files[-1].split(".")[0]
+        parts = [oracle.read_snapshot(os.path.join(w, f"{last}.{k}")) for k in range(2)]
+        assert all(p["time"] == 0.006 for p in parts)
+        assert all(p["npart"][1] == len(p["ids"]) for p in parts)
+        ids = np.concatenate([p["ids"] for p in parts]); o = np.argsort(ids)
+        return ids[o], np.concatenate([p["pos"] for p in parts])[o], np.concatenate([p["vel"] for p in parts])[o]
+    a, b = final(w1), final(w2)
+    assert len(a[0]) == N and np.array_equal(a[0], b[0])
+    assert "SCT" in r.stdout and any(int(l.split()[3]) > 0 for l in r.stdout.splitlines() if l.startswith("SCT ")), "no scatterings after the restart"
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), "restarted run differs from the uninterrupted one"

@@ -193,3 +193,34 @@ def test_snapshot_edge_cases():
         assert np.array_equal(hp.peek("posm", np.float32, (n, 4)), np.c_[pos, mass])
         hp.savepositions(path + "b", time=t)                    # written back without the type-5 particles, like io.c
         assert open(path + "b", "rb").read() == base
+
+
+def test_snapshot_split_over_files():
+    """NumFilesPerSnapshot > 1 (io.c:78-103, 127-160): every file holds a contiguous range of rows (the particles of one group of
+    tasks) in type order, npart = the file's counts, npartTotal = the system's, num_files = F; byte for byte the oracle writer's
+    file of the same rows; the files together hold every particle once"""
+    import oracle
+    from sidm_b200 import HotPath, ic
+    n = 50000
+    pos, vel, mass, ids = ic.hernquist(n, seed=23)
+    types = np.random.default_rng(3).choice(np.array([1, 2, 4], np.int32), n, p=[0.6, 0.3, 0.1]).astype(np.int32)
+    mt = [0, 0, float(mass[0]), 0, 0, 0]
+    out = tempfile.mkdtemp()
+    cuts = [0, 17001, 17001, 41234, n]                       # four files, one of them empty
+    tot = [int((types == t).sum()) for t in range(5)] + [0]
+    with HotPath(n, SofteningTable=[0, 0.3, 0.3, 0, 0.3, 0]) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.set_field("ptype", types)
+        hp.predict_collisionless_only(0.0)
+        seen = []
+        for f in range(4):
+            a, b = cuts[f], cuts[f + 1]
+            path = os.path.join(out, f"snap_007.{f}")
+            npart = hp.savepositions_part(path, a, b - a, 4, time=0.25, mass_table=mt, hubble_param=0.7)
+            assert npart.tolist() == [int((types[a:b] == t).sum()) for t in range(5)] + [0]
+            ref = oracle.snapshot_bytes(pos[a:b], vel[a:b], ids[a:b], mass[a:b], types[a:b], time=0.25, mass_table=mt, hubble_param=0.7,
+                                        omega0=1.0, npart_total=tot, num_files=4)
+            assert open(path, "rb").read() == ref
+            if b > a:
+                seen.append(oracle.read_snapshot(path)["ids"])
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(ids))
