@@ -304,7 +304,9 @@ int  b200_savepositions_part(const char *path, double time, const double *mass_t
  * into the device state: types from the header's block ranges, masses from MassTable or the mass block, PosPred = Pos,
  * VelPred = Vel, CurrentTime = header time, Accel = dVel = OldAcc = Potential = 0, GravCost = 1, Hsml = 0.  The file is
  * streamed through pinned buffers; the particle count becomes the file's (<= MaxPart).  Block markers are checked
- * (B200_ERR_IO).  time_out, mass_table_out[6], npart_out[6] may be NULL. */
+ * (B200_ERR_IO).  time_out, mass_table_out[6], npart_out[6] may be NULL.  A snapshot split over several files (NumFilesPerSnapshot
+ * > 1, read_ic.c:62-75) is read when `path` names no file but path.0 does: path.0 .. path.<num_files-1>, their particles one
+ * after the other. */
 int  b200_load_snapshot(const char *path, double *time_out, double *mass_table_out, int *npart_out);
 /* raw double potentials of the given targets as forcetree.c:1389 leaves them in GravDataPotential */
 int  b200_potential_raw(const int *targets, int n, double *pot_out);

@@ -1532,10 +1532,17 @@ extern "C" int b200_setup_smoothinglengths_sidm(int desired_ngb) {
   return repair_loop(0, 0.0, 0.0, nullptr, 60, g.iota, n);                   // init.c:453-509
 }
 
+#include <chrono>
 extern "C" int b200_compute_accelerations(int mode, const int *active, int nactive, double time, double vmax) {
   if (!g.ready || g.n <= 0) return B200_ERR_STATE;
+  static const bool timing = getenv("B200_TIMING") != nullptr;      // host clock at the points where the host has synchronised
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   B200_TRY(b200_predict(time));                    // gravtree.c:72 predict_collisionless_only(All.Time)
+  const auto t1 = now();
   B200_TRY(b200_tree_build());                     // gravtree.c:76 force_treebuild()
+  const auto t2 = now();
   if (mode != 0) return b200_gravity(active, nactive, time);     // accel.c:62: no SIDM in mode 1
   // gravity_tree() and sidm() + sidm_ensure_neighbours() (accel.c:39-65) are independent once the
   // tree exists: they read the same particles and tree and write disjoint fields (Accel, OldAcc,
@@ -1577,8 +1584,13 @@ extern "C" int b200_compute_accelerations(int mode, const int *active, int nacti
   if (rc != B200_OK) return rc;
   if (rs != B200_OK) return rs;
   if (rf != B200_OK) return rf;
-  if (omode == 2) return b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);   // on the main stream, the GPU to itself
-  return rf;
+  const auto t3 = now();
+  int re = B200_OK;
+  if (omode == 2) re = b200_sidm_ensure_neighbours(mode, time, vmax, nullptr);     // on the main stream, the GPU to itself
+  if (timing && g.shard_rank == 0)
+    fprintf(stderr, "libsidm_b200 timing: step of %d targets, mode %d: predict %.3f | build %.3f | walk || sidm (+ exchanges) %.3f | repair loop after it %.3f | total %.3f ms (walk kernel %.3f)\n",
+            active ? nactive : g.n, omode, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()), ms(t0, now()), g.cnt.ms_walk);
+  return re;
 }
 
 extern "C" int b200_ngb_treefind(const int *idx, int n, int desngb, float *h2_out) {

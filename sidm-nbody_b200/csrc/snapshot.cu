@@ -64,19 +64,21 @@ struct SnapTypes { int cum[7]; int moff[6]; float mtab[6]; };
 __global__ void k_snap_scatter(int n, SnapTypes T, const float *pos, const float *vel, const int *id, const float *mass, float time,
                                float4 *posm, float4 *velh, float *pos0, float *velpred, int *pid, int *ptype, float *accel, float *dvel,
                                float *curtime, float *oldacc, float *gravcost, float *left, float *right, int *ngb, float *maxpred,
-                               float *potential) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+                               float *potential, int dst0) {
+  const int jf = blockIdx.x * blockDim.x + threadIdx.x;      // particle of the file
+  if (jf >= n) return;
   int t = 0;
-  while (t < 5 && j >= T.cum[t + 1]) t++;
-  const float m = T.moff[t] >= 0 ? mass[T.moff[t] + (j - T.cum[t])] : T.mtab[t];
-  const float x = pos[3 * (size_t)j], y = pos[3 * (size_t)j + 1], z = pos[3 * (size_t)j + 2];
-  const float vx = vel[3 * (size_t)j], vy = vel[3 * (size_t)j + 1], vz = vel[3 * (size_t)j + 2];
+  while (t < 5 && jf >= T.cum[t + 1]) t++;
+  const float m = T.moff[t] >= 0 ? mass[T.moff[t] + (jf - T.cum[t])] : T.mtab[t];
+  const float x = pos[3 * (size_t)jf], y = pos[3 * (size_t)jf + 1], z = pos[3 * (size_t)jf + 2];
+  const float vx = vel[3 * (size_t)jf], vy = vel[3 * (size_t)jf + 1], vz = vel[3 * (size_t)jf + 2];
+  const int idj = id[jf];
+  const int j = dst0 + jf;                                   // its place in the particle order (files one after the other)
   posm[j] = make_float4(x, y, z, m); velh[j] = make_float4(vx, vy, vz, 0.f);
   pos0[3 * (size_t)j] = x; pos0[3 * (size_t)j + 1] = y; pos0[3 * (size_t)j + 2] = z;
   velpred[3 * (size_t)j] = vx; velpred[3 * (size_t)j + 1] = vy; velpred[3 * (size_t)j + 2] = vz;
   for (int k = 0; k < 3; k++) { accel[3 * (size_t)j + k] = 0.f; dvel[3 * (size_t)j + k] = 0.f; }
-  pid[j] = id[j]; ptype[j] = t;
+  pid[j] = idj; ptype[j] = t;
   curtime[j] = time; maxpred[j] = time; oldacc[j] = 0.f; gravcost[j] = 1.f; left[j] = 0.f; right[j] = 0.f; ngb[j] = 0; potential[j] = 0.f;
 }
 
@@ -236,9 +238,8 @@ extern "C" int b200_savepositions_part(const char *path, double time, const doub
   return B200_OK;
 }
 
-extern "C" int b200_load_snapshot(const char *path, double *time_out, double *mass_table_out, int *npart_out) {
-  if (!g.ready) return B200_ERR_STATE;
-  if (!path) return B200_ERR_ARG;
+// one file of the (possibly split) snapshot into the particle order at dst0; returns the header
+static int load_one_file(const char *path, int dst0, SnapHeader &h, int *n_file) {
   FileCloser fc{fopen(path, "r")};
   FILE *fd = fc.fd;
   if (!fd) return B200_ERR_IO;
@@ -247,11 +248,9 @@ extern "C" int b200_load_snapshot(const char *path, double *time_out, double *ma
     if (fread(&d, sizeof(d), 1, fd) != 1) return B200_ERR_IO;
     return d == (int)expect ? B200_OK : B200_ERR_IO;
   };
-  SnapHeader h;
   B200_TRY(marker(256));
   if (fread(&h, sizeof(h), 1, fd) != 1) return B200_ERR_IO;
   B200_TRY(marker(256));
-  if (h.num_files > 1) return B200_ERR_ARG;                 // one file per snapshot on this path
   if (h.npart[0] > 0) return B200_ERR_ARG;                  // gas blocks are not on this path
   SnapTypes T;
   long long ntot = 0, nmass = 0;
@@ -263,7 +262,9 @@ extern "C" int b200_load_snapshot(const char *path, double *time_out, double *ma
     ntot += h.npart[t];
   }
   T.cum[6] = (int)ntot;
-  if (ntot <= 0 || ntot > g.maxpart) return B200_ERR_ARG;
+  *n_file = (int)ntot;
+  if (ntot < 0 || dst0 + ntot > g.maxpart) return B200_ERR_ARG;
+  if (ntot == 0) return B200_OK;
   const int n = (int)ntot;
   float *d_pos = (float *)g.d_acc, *d_vel = d_pos + 3 * (size_t)n;
   int *d_id = g.d_cost; float *d_mass = (float *)(g.d_cost + n);
@@ -274,16 +275,45 @@ extern "C" int b200_load_snapshot(const char *path, double *time_out, double *ma
   B200_TRY(marker(12 * ntot)); B200_TRY(ld.read(fd, d_vel, 12 * (size_t)ntot)); B200_TRY(marker(12 * ntot));
   B200_TRY(marker(4 * ntot));  B200_TRY(ld.read(fd, d_id, 4 * (size_t)ntot));   B200_TRY(marker(4 * ntot));
   if (nmass > 0) { B200_TRY(marker(4 * nmass)); B200_TRY(ld.read(fd, d_mass, 4 * (size_t)nmass)); B200_TRY(marker(4 * nmass)); }
-  g.n = n;
   k_snap_scatter<<<cdiv(n, 256), 256, 0, g.stream>>>(n, T, d_pos, d_vel, d_id, d_mass, (float)h.time, g.posm, g.velh, g.pos0, g.velpred,
                                                      g.pid, g.ptype, g.accel, g.dvel, g.curtime, g.oldacc, g.gravcost, g.left, g.right,
-                                                     g.ngb, g.maxpred, g.potential);
+                                                     g.ngb, g.maxpred, g.potential, dst0);
   count_launch();
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));                // the staging scratch is reused by the next file
   CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// `path` itself, or - a snapshot split over several files (read_ic.c:62-75) - path.0, path.1, ... (header num_files), the
+// files' particles one after the other in the particle order (as the tasks of the reference hold them)
+extern "C" int b200_load_snapshot(const char *path, double *time_out, double *mass_table_out, int *npart_out) {
+  if (!g.ready) return B200_ERR_STATE;
+  if (!path) return B200_ERR_ARG;
+  SnapHeader h;
+  int ntot = 0, nf = 0, files = 1;
+  int npart[6] = {0, 0, 0, 0, 0, 0};
+  FILE *probe = fopen(path, "r");
+  if (probe) {
+    fclose(probe);
+    B200_TRY(load_one_file(path, 0, h, &nf));
+    if (h.num_files > 1) return B200_ERR_ARG;               // one part of a split snapshot: name the base path instead
+    ntot = nf;
+    for (int t = 0; t < 6; t++) npart[t] = h.npart[t];
+  } else {
+    for (int k = 0; k < files; k++) {
+      char name[1024];
+      if (snprintf(name, sizeof(name), "%s.%d", path, k) >= (int)sizeof(name)) return B200_ERR_ARG;
+      B200_TRY(load_one_file(name, ntot, h, &nf));
+      if (k == 0) files = h.num_files > 1 ? h.num_files : 1;
+      ntot += nf;
+      for (int t = 0; t < 6; t++) npart[t] += h.npart[t];
+    }
+  }
+  if (ntot <= 0) return B200_ERR_ARG;
+  g.n = ntot;
   g.tree_valid = false; g.types_dirty = true;
   if (time_out) *time_out = h.time;
   if (mass_table_out) for (int t = 0; t < 6; t++) mass_table_out[t] = h.mass[t];
-  if (npart_out) for (int t = 0; t < 6; t++) npart_out[t] = h.npart[t];
+  if (npart_out) for (int t = 0; t < 6; t++) npart_out[t] = npart[t];
   return B200_OK;
 }

@@ -224,3 +224,34 @@ def test_snapshot_split_over_files():
             if b > a:
                 seen.append(oracle.read_snapshot(path)["ids"])
         assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(ids))
+
+
+def test_read_ic_split_over_files():
+    """read_ic() of initial conditions split over files (read_ic.c:62-75): path.0 .. path.3 written by the part writer, read back
+    as one particle order; types, masses (mass block and MassTable), ids and positions as written"""
+    from sidm_b200 import HotPath, ic
+    n = 40000
+    pos, vel, mass, ids = ic.hernquist(n, seed=29)
+    types = np.random.default_rng(5).choice(np.array([1, 2, 3], np.int32), n, p=[0.5, 0.3, 0.2]).astype(np.int32)
+    mass = mass.copy(); mass[types == 2] = np.float32(mass[0] * 2)
+    mt = [0, 0, float(mass[0] * 2), 0, 0, 0]
+    out = tempfile.mkdtemp()
+    cuts = [0, 9000, 21000, 21000, n]
+    base = os.path.join(out, "ics")
+    with HotPath(n, SofteningTable=[0, 0.3, 0.3, 0.3, 0, 0]) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.set_field("ptype", types)
+        hp.predict_collisionless_only(0.0)
+        for f in range(4):
+            hp.savepositions_part(f"{base}.{f}", cuts[f], cuts[f + 1] - cuts[f], 4, time=0.5, mass_table=mt)
+    with HotPath(n, SofteningTable=[0, 0.3, 0.3, 0.3, 0, 0]) as hp:
+        t, mtab, npart = hp.read_ic(base)
+        assert t == 0.5 and hp.n == n and npart.tolist() == [int((types == k).sum()) for k in range(5)] + [0]
+        # expected order: file after file, inside a file type after type
+        order = np.concatenate([np.arange(cuts[f], cuts[f + 1])[np.argsort(types[cuts[f]:cuts[f + 1]], kind="stable")] for f in range(4)])
+        posm = hp.peek("posm", np.float32, (n, 4))
+        assert np.array_equal(posm[:, :3], pos[order]) and np.array_equal(posm[:, 3], mass[order])
+        assert np.array_equal(hp.peek("pid", np.int32, (n,)), ids[order]) and np.array_equal(hp.peek("ptype", np.int32, (n,)), types[order])
+        assert np.array_equal(hp.peek("velh", np.float32, (n, 4))[:, :3], vel[order])
+        hp.predict_collisionless_only(0.5)
+        hp.force_treebuild()                                 # the loaded state is usable
