@@ -180,7 +180,7 @@ int gravity_impl(const int *active, int nactive, double time, bool defer_sync = 
 int gravity_finish();
 inline cudaStream_t sidm_stream() { return g.overlap_now ? g.stream_sidm : g.stream; }
 int direct_impl(const int *targets, int n, double *acc_out);
-int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only);
+int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only, bool defer_final = false);
 int prepare_targets(const int *active_host, int nactive, int **d_sorted_out);
 void sidm_release();
 void snapshot_release();

@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
 
 // ------------------------------------------------------------------ pass 2
 struct Pass2 {
-  int np; const int *passlist; const int *slot_part; SearchCtx C;
+  int np; const int *np_dev; unsigned long long *ctr_pass1;   // np_dev != null: the number of slots is read on the device (np = upper bound)
+  const int *passlist; const int *slot_part; SearchCtx C;
   const float4 *posm, *velh; const float *dvel; const float *dt; const double *rnd;
   const double *replay_dir; double sigma, s_a_inverse; uint32_t k0, k1; int xs_type; double vc, pl_n, pl_v0;
   const double *extra; const int *extra_off;   // type 4: replayed (rand, cosO-uniform) pairs per slot
@@ -684,7 +685,10 @@ __device__ __forceinline__ void unit_vector(const Pass2 &P, int s, int i, double
 
 __global__ void __launch_bounds__(128) k_pass2(Pass2 P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = t < P.np;
+  const int np = P.np_dev ? *P.np_dev : P.np;
+  if ((int)(blockIdx.x * blockDim.x) >= np) return;                   // launched for the upper bound: nothing here
+  if (t == 0 && P.ctr_pass1) atomicAdd(P.ctr_pass1, (unsigned long long)np);
+  const bool valid = t < np;
   const int s = valid ? P.passlist[t] : 0;
   const int i = valid ? P.slot_part[s] : 0;
   const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
@@ -811,7 +815,7 @@ __global__ void k_resolve_own(int ns, const int *slot_part, const int *sngb, con
 }
 // sidm.c:559-601: partner gets -dv; several slots naming one partner: the last in buffer order wins
 __global__ void k_resolve_partner(int ns, const int *confirm, const int *partner, const float *dv, const unsigned long long *winner, unsigned long long wbase, float *dvel,
-                                  const int *logpos, b200_scatlog *log, int logcap, int logbase, const int *slot_part,
+                                  const int *logpos, b200_scatlog *log, int logcap, const int *logbase_dev, const int *slot_part,
                                   const float4 *posm, const float4 *velh, const int *pid, float time, int *kick_list, int *nkick, int kick_cap) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns || !confirm[s]) return;
@@ -821,7 +825,7 @@ __global__ void k_resolve_partner(int ns, const int *confirm, const int *partner
     const int at = atomicAdd(nkick, 1);                    // the partner need not be active: b200_download_active() sends it along
     if (at < kick_cap) kick_list[at] = j;
   }
-  const int lp = logbase + logpos[s];
+  const int lp = *logbase_dev + logpos[s];
   if (lp < logcap) {
     const int i = slot_part[s];
     b200_scatlog e;
@@ -833,6 +837,8 @@ __global__ void k_resolve_partner(int ns, const int *confirm, const int *partner
     log[lp] = e;
   }
 }
+
+__global__ void k_bump_logbase(int *logbase, const int *nlog) { if (threadIdx.x == 0 && blockIdx.x == 0) *logbase += *nlog; }
 
 // multi-GPU: per-slot results of this rank's share of the buffer -> all ranks
 struct __attribute__((aligned(16))) SlotRec { int ngb, partner; float dv[3]; int pass, pad0, pad1; };
@@ -1007,7 +1013,30 @@ int refresh_search_nodes() {
 
 // one sidm() call for a device-resident active list (d_active == nullptr: every particle in
 // index order).  replay arrays are host pointers indexed by buffer slot.
-int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only) {
+// device counters of the chain are cumulative since sidm_begin(); sidm_collect() brings them to the host (after a sync)
+static int sidm_begin(cudaStream_t st) {
+  CUDA_TRY(cudaMemsetAsync(g.d_ctr + CT_CAND, 0, (CT_COUNT - CT_CAND) * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_ERR_NGB, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(g.d_nkick + 1, 0, sizeof(int), st));          // scatter-log position
+  g.scatlog_n = 0;
+  return B200_OK;
+}
+static int sidm_collect(cudaStream_t st) {
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctr + CT_CAND, g.d_ctr + CT_CAND, (CT_COUNT - CT_CAND) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(g.h_flags + FL_COUNT, g.d_nkick + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  const int nlog = g.h_flags[FL_COUNT];
+  g.scatlog_n = nlog < g.scatlog_cap ? nlog : g.scatlog_cap;
+  g.cnt.sct_pass1 = (int)g.h_ctr[CT_PASS1];
+  g.cnt.sct_scattered = (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected = (int)g.h_ctr[CT_REJECTED];
+  g.cnt.ngb_candidates = (long long)g.h_ctr[CT_CAND];
+  if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
+  return B200_OK;
+}
+
+int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only, bool defer_final) {
   if (!g.tree_valid) return B200_ERR_STATE;
   B200_TRY(ensure_sidm_buffers());
   B200_TRY(refresh_search_nodes());
@@ -1036,8 +1065,6 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   const uint32_t k0 = (uint32_t)(g.par.Seed & 0xffffffffu) ^ (uint32_t)(g.sidm_calls * 0x9E3779B9u);
   const uint32_t k1 = (uint32_t)(g.par.Seed >> 32) ^ (uint32_t)(g.sidm_calls >> 32) ^ 0x5851F42Du;
 
-  CUDA_TRY(cudaMemsetAsync(g.d_ctr + CT_CAND, 0, 4 * sizeof(unsigned long long), st));
-  CUDA_TRY(cudaMemsetAsync(g.d_flags + FL_ERR_NGB, 0, sizeof(int), st));
   // B200_TIMING=1: device time of the phases of every large pass (development aid)
   static const bool timing = getenv("B200_TIMING") != nullptr;
   static cudaEvent_t tev[8]; static bool tev_ok = false;
@@ -1047,7 +1074,6 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
   mark(0);
 
   int bunch = g.par.BunchSizeSidm > 0 ? g.par.BunchSizeSidm : na;
-  int logbase = g.scatlog_n, tot_pass1 = 0;
   size_t replay_off = 0;
   for (int b0 = 0; b0 < na; b0 += bunch) {
     const int nb = (na - b0 < bunch) ? na - b0 : bunch;
@@ -1066,7 +1092,11 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
                                     g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags, g.s_partner, g.s_dv, g.s_prob, S.ptot);
     count_launch(4);
-    if (act) {
+    // explicit lists: slots sorted along the tree order, so that the queries of a warp are neighbours.  Small lists are searched
+    // one warp per query (k_pass1_warp), where the order of the queries does not matter: no sort (five launches less per repair pass)
+    const bool periodic_search = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+    const bool sort_slots = act && !(nb <= kWarpQueryMax && !periodic_search && g.opt_group_search && !(g.shard_world > 1 && na >= g.shard_min_work));
+    if (sort_slots) {
       size_t tb2 = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tb2, S.x_keys, S.x_keys2, S.x_vals, S.slot_of_sorted, nb, 0, 32, st);
       B200_TRY(cub_scratch(tb2));
@@ -1104,10 +1134,10 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       d_rx = S.rx; d_ro = S.ro;
     }
     // this rank's share of the buffer (all of it on one GPU)
-    const int *order = S.slot_of_sorted; int nord = nb;
+    const int *order = (act && !sort_slots) ? S.x_vals : S.slot_of_sorted; int nord = nb;
     const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
     const bool group_mode = !act && nb == g.n && !periodic_box && S.ngroups > 0 && g.opt_group_search;
-    const int *global_order = S.slot_of_sorted;      // all ranks' slots in processing order
+    const int *global_order = order;                 // all ranks' slots in processing order
     if (group_mode && sharded) {                     // sharded group search: processing order = leaf order
       k_order_leaf<<<G, B, 0, st>>>(nb, g.leaf_orig, slot_of_active, S.order_leaf);
       count_launch();
@@ -1148,12 +1178,16 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
         B200_TRY(cub_scratch(tb3));
         CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tb3, order, g.s_pass, S.passlist, g.d_flags + FL_NPASS, nord, st));
       }
-      CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      npass = g.h_flags[FL_NPASS];
-      count_launch(3);
-      tot_pass1 += npass;
       const bool ref_order = g.par.ReferenceNgbOrder != 0;
+      // the scan in tree order needs no scratch sized by the number of slots that passed: the pair kernel is launched for the
+      // upper bound and reads the count on the device (no host round trip); the reference-order mode sizes its candidate lists
+      const bool lean = !ref_order;
+      if (!lean) {
+        CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        npass = g.h_flags[FL_NPASS];
+      } else npass = nord;
+      count_launch(3);
       // reference-order mode: per-slot candidate lists in scratch (option "cand_cap" entries each), about 1.6 GB at most
       const int cand_cap = g.opt_cand_cap;
       const int chunk = ref_order ? (int)(((size_t)131072 * 1024 / cand_cap + 127) / 128 * 128) : npass;
@@ -1170,7 +1204,8 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       for (int c0 = 0; c0 < npass; c0 += chunk) {
         const int nc = (npass - c0 < chunk) ? npass - c0 : chunk;
         Pass2 P2;
-        P2.np = nc; P2.passlist = S.passlist + c0; P2.slot_part = g.s_slot_part; P2.C = search_ctx();
+        P2.np = nc; P2.np_dev = lean ? g.d_flags + FL_NPASS : nullptr; P2.passlist = S.passlist + c0; P2.slot_part = g.s_slot_part; P2.C = search_ctx();
+        P2.ctr_pass1 = sharded ? nullptr : g.d_ctr + CT_PASS1;       // sharded: the gathered headers carry the counts of all ranks
         P2.posm = g.posm; P2.velh = g.velh; P2.dvel = g.dvel; P2.dt = S.dt; P2.rnd = g.s_rand; P2.replay_dir = d_rd;
         P2.sigma = sigma; P2.s_a_inverse = sainv; P2.k0 = k0; P2.k1 = k1; P2.xs_type = T; P2.vc = vc;
         P2.pl_n = g.par.CrossSectionPowLaw; P2.pl_v0 = g.par.CrossSectionVelScale; P2.kernel = d_kernel_table;
@@ -1231,13 +1266,10 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       cub::DeviceScan::ExclusiveSum(nullptr, tb4, confirm, S.logpos, nb + 1, st);
       B200_TRY(cub_scratch(tb4));
       CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb4, confirm, S.logpos, nb + 1, st));
-      k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, wbase, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, logbase,
+      k_resolve_partner<<<G, B, 0, st>>>(nb, confirm, g.s_partner, g.s_dv, g.s_winner, wbase, g.dvel, S.logpos, g.d_scatlog, g.scatlog_cap, g.d_nkick + 1,
                                          g.s_slot_part, g.posm, g.velh, g.pid, (float)time, g.kick_list, g.d_nkick, g.maxpart);
-      int nlog = 0;
-      CUDA_TRY(cudaMemcpyAsync(&nlog, S.logpos + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      logbase += nlog;
-      count_launch(3);
+      k_bump_logbase<<<1, 32, 0, st>>>(g.d_nkick + 1, S.logpos + nb);      // the next bunch / pass appends (no host round trip)
+      count_launch(4);
     }
     g.last_nslot = nb;
     mark(5);
@@ -1249,28 +1281,20 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
               g.shard_rank, nb, nord, S.ngroups, t[0], t[1], t[2], t[3], t[4]);
     }
   }
-  g.scatlog_n = logbase < g.scatlog_cap ? logbase : g.scatlog_cap;
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctr + CT_CAND, g.d_ctr + CT_CAND, (CT_COUNT - CT_CAND) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  CUDA_TRY(cudaGetLastError());
-  if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
+  g.cnt.sct_ntot += na;
   // totals since the last b200_sidm(): the sum of the reference's SCT lines for this step
-  if (sharded) tot_pass1 = (int)g.h_ctr[CT_PASS1];
-  g.cnt.sct_ntot += na; g.cnt.sct_pass1 += tot_pass1;
-  g.cnt.sct_scattered += (int)g.h_ctr[CT_SCATTERED]; g.cnt.sct_rejected += (int)g.h_ctr[CT_REJECTED];
-  g.cnt.ngb_candidates += (long long)g.h_ctr[CT_CAND];
-  return B200_OK;
+  if (defer_final) return B200_OK;                           // the repair loop collects at its own synchronisation points
+  return sidm_collect(st);
 }
 
 // ------------------------------------------------------------------ k nearest (ngb_treefind)
-struct KnnParams { int nq; const int *idx; SearchCtx C; const float4 *posm; int k; float *h2; const SearchNode *snode; const float4 *geom; const uint64_t *shi, *slo;
+struct KnnParams { int nq; const int *idx; const int *want; SearchCtx C; const float4 *posm; int k; float *h2; const SearchNode *snode; const float4 *geom; const uint64_t *shi, *slo;
                    const int *nstart; const unsigned char *nlevel; const int *nend; };
 constexpr int kKnnMax = 64;
 
 __global__ void __launch_bounds__(128) k_knn(KnnParams P) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = t < P.nq;
+  const bool valid = t < P.nq && (!P.want || P.want[t]);           // want: only the flagged entries of the list
   const int i = valid ? P.idx[t] : 0;
   const float4 p = valid ? P.posm[i] : make_float4(0, 0, 0, 0);
   const int K = P.k;
@@ -1320,10 +1344,10 @@ __global__ void __launch_bounds__(128) k_knn(KnnParams P) {
   if (valid) P.h2[t] = h2max;
 }
 
-static int knn_device(const int *d_idx, int nq, int k, float *d_h2) {
+static int knn_device(const int *d_idx, int nq, int k, float *d_h2, const int *d_want = nullptr) {
   if (k < 1 || k > kKnnMax) return B200_ERR_ARG;
   B200_TRY(refresh_search_nodes());
-  KnnParams P; P.nq = nq; P.idx = d_idx; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode; P.geom = g.geom;
+  KnnParams P; P.nq = nq; P.idx = d_idx; P.want = d_want; P.C = search_ctx(); P.posm = g.posm; P.k = k; P.h2 = d_h2; P.snode = S.snode; P.geom = g.geom;
   P.shi = g.skey_hi; P.slo = g.skey_lo; P.nstart = g.nstart; P.nlevel = g.nlevel; P.nend = g.nend;
   k_knn<<<cdiv(nq, 128), 128, 0, sidm_stream()>>>(P);
   count_launch();
@@ -1373,9 +1397,9 @@ __global__ void k_new_hsml(int nr, const int *redo, const int *ngb, const float 
   velh[i] = v;
   want_knn[a] = knn;
 }
-__global__ void k_apply_knn(int nw, const int *wlist, const float *h2, float4 *velh) {
+__global__ void k_apply_knn(int nw, const int *wlist, const int *want, const float *h2, float4 *velh) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= nw) return;
+  if (a >= nw || !want[a]) return;
   velh[wlist[a]].w = (float)sqrt((double)h2[a]);
 }
 __global__ void k_zero_lr(int na, const int *active, float *left, float *right) {
@@ -1420,32 +1444,23 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     CUDA_TRY(cudaStreamSynchronize(st));
     count_launch(4);
     const int nr = g.h_flags[FL_NREPAIR];
+    if (g.h_flags[FL_ERR_NGB]) return B200_ERR_NGBOVERFLOW;
     if (nr == 0) break;
     TypeCount tc;
     for (int t = 0; t < 8; t++) tc.n[t] = t < 6 ? g.type_count[t] : 0;
     k_new_hsml<<<cdiv(nr, B), B, 0, st>>>(nr, redo, g.ngb, g.left, g.right, g.velh, g.par.DesNumNgb, ensure_variant, tc, g.ptype, want);
     count_launch();
     if (ensure_variant) {
-      // exact k-th neighbour distance where sidm.c:918-922 asks for it (rare: Ngb < 15 with no upper bracket)
-      int *wlist = S.x_keys;
-      size_t tbw = 0;
-      cub::DeviceSelect::Flagged(nullptr, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st);
-      B200_TRY(cub_scratch(tbw));
-      CUDA_TRY(cub::DeviceSelect::Flagged(S.cub_tmp, tbw, redo, want, wlist, g.d_flags + FL_NPASS, nr, st));
-      CUDA_TRY(cudaMemcpyAsync(g.h_flags, g.d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      count_launch(2);
-      const int nw = g.h_flags[FL_NPASS];
-      if (nw > 0) {
-        B200_TRY(knn_device(wlist, nw, g.par.DesNumNgb, h2));
-        k_apply_knn<<<cdiv(nw, B), B, 0, st>>>(nw, wlist, h2, g.velh);
-        count_launch();
-      }
+      // exact k-th neighbour distance where sidm.c:918-922 asks for it (rare: Ngb < 15 with no upper bracket): the search runs for
+      // the flagged entries of the list only - no compaction, no host round trip
+      B200_TRY(knn_device(redo, nr, g.par.DesNumNgb, h2, want));
+      k_apply_knn<<<cdiv(nr, B), B, 0, st>>>(nr, redo, want, h2, g.velh);
+      count_launch();
     }
     b200_replay rp; const b200_replay *rpp = nullptr;
     rp.extra = nullptr; rp.extra_off = nullptr;
     if (replay && replay->rand) { rp.rand = replay->rand + roff; rp.dir = replay->dir ? replay->dir + 3 * roff : nullptr; rpp = &rp; roff += nr; }
-    B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0));
+    B200_TRY(sidm_impl(redo, nr, time, vmax, rpp, ensure_variant == 0, true));      // collected with the next pass's count
     iter++;
     g.cnt.ensure_repaired += nr;
     list = redo; nlist = nr;                                    // the next pass looks at these only
@@ -1453,7 +1468,7 @@ static int repair_loop(int ensure_variant, double time, double vmax, const b200_
     if (iter > maxiter) { fprintf(stderr, "libsidm_b200: failed to converge in ensure_neighbours\n"); return B200_ERR_HSML; }
   }
   g.cnt.ensure_iterations = iter;
-  return B200_OK;
+  return sidm_collect(st);
 }
 
 }  // namespace b200
@@ -1473,11 +1488,11 @@ extern "C" int b200_sidm(const int *active, int nactive, double time, double vma
   if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
   const int *d; int na;
   B200_TRY(stage_active(active, nactive, &d, &na));
-  g.scatlog_n = 0;
   g.cnt.sct_ntot = g.cnt.sct_pass1 = g.cnt.sct_scattered = g.cnt.sct_rejected = 0; g.cnt.ngb_candidates = 0;
   g.cnt.ensure_iterations = 0; g.cnt.ensure_repaired = 0;
+  B200_TRY(sidm_begin(sidm_stream()));
   CUDA_TRY(cudaEventRecord(g.ev_s0, sidm_stream()));
-  int rc = sidm_impl(d, na, time, vmax, replay, false);
+  int rc = sidm_impl(d, na, time, vmax, replay, false, false);
   cudaEventRecord(g.ev_s1, sidm_stream()); cudaEventSynchronize(g.ev_s1);
   cudaEventElapsedTime(&g.cnt.ms_sidm, g.ev_s0, g.ev_s1);
   return rc;
@@ -1487,7 +1502,8 @@ extern "C" int b200_setup_nbr_sidm(const int *active, int nactive) {
   if (!g.ready || g.n <= 0 || !g.tree_valid) return B200_ERR_STATE;
   const int *d; int na;
   B200_TRY(stage_active(active, nactive, &d, &na));
-  return sidm_impl(d, na, 0.0, 0.0, nullptr, true);
+  B200_TRY(sidm_begin(sidm_stream()));
+  return sidm_impl(d, na, 0.0, 0.0, nullptr, true, false);
 }
 
 extern "C" int b200_sidm_ensure_neighbours(int mode, double time, double vmax, const b200_replay *replay) {
@@ -1528,7 +1544,8 @@ extern "C" int b200_setup_smoothinglengths_sidm(int desired_ngb) {
   k_set_hsml_from_h2<<<cdiv(n, 256), 256, 0, st>>>(n, h2, g.velh, g.left, g.right);
   count_launch(2);
   S.last_all = true; S.last_nactive = n;
-  B200_TRY(sidm_impl(nullptr, n, 0.0, 0.0, nullptr, true));                  // setup_nbr_sidm(), init.c:446
+  B200_TRY(sidm_begin(st));
+  B200_TRY(sidm_impl(nullptr, n, 0.0, 0.0, nullptr, true, false));           // setup_nbr_sidm(), init.c:446
   return repair_loop(0, 0.0, 0.0, nullptr, 60, g.iota, n);                   // init.c:453-509
 }
 

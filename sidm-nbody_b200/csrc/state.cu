@@ -180,7 +180,7 @@ extern "C" int b200_init(const b200_params *p) {
   g.winner_base = 1;
   int rc = alloc_all();
   if (rc != B200_OK) { b200_finalize(); return rc; }
-  CUDA_TRY(cudaMallocHost((void **)&g.h_flags, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMallocHost((void **)&g.h_flags, (FL_COUNT + 4) * sizeof(int)));   // + the scatter-log position (sidm_collect)
   CUDA_TRY(cudaMallocHost((void **)&g.h_ctr, CT_COUNT * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), g.stream));
   CUDA_TRY(cudaMemsetAsync(g.d_ctr, 0, CT_COUNT * sizeof(unsigned long long), g.stream));
