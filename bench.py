@@ -345,6 +345,8 @@ def main_b200(args, cfg):
     sh.compute_accelerations(1, time=T0, vmax=vmax)       # BH criterion (OldAcc = 0) -> OldAcc
 
     tl = Timeline(n, pos) if cfg.get("timeline") else None
+    reuse = max(args.tree_reuse, 0)
+    hp.set_option("tree_reuse", reuse)
     state = dict(t=T0, it=0, active=0)
 
     def step():
@@ -475,7 +477,8 @@ def main_b200(args, cfg):
                 "config": {"workload": workload_name(args, cfg), "config": args.config, "particles": n, "parallelism": sh.describe(),
                            "l2": "inputs larger than L2 (particle + node records per step vs 126 MB L2)" if n >= 1_000_000 else
                                  "inputs smaller than L2: 256 MB written to HBM between the timed steps (each step timed on its own with CUDA events)",
-                           "step": "compute_accelerations(0) + advance()" + (", all particles active" if tl is None else ", the time line's active particles")},
+                           "step": "compute_accelerations(0) + advance()" + (", all particles active" if tl is None else ", the time line's active particles"),
+                           "tree_reuse": reuse},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "phases": phases, "state_crc": crc}
         print(json.dumps(line))
@@ -608,6 +611,8 @@ def main():
     ap.add_argument("--n", type=lambda s: int(float(s)), default=0, help="particle number (default: the configuration's)")
     ap.add_argument("--ref-procs", type=int, default=0, help="host processes for the reference arm (0 = all that fit)")
     ap.add_argument("--ref-sample", type=int, default=60000, help="active particles per reference process per step")
+    ap.add_argument("--tree-reuse", type=int, default=0, help="option tree_reuse of the library: full build every k-th step, refits in between (default 0 = build at "
+                    "every step, the only setting whose forces are the reference's to 1e-4; see tests/test_gpu_reuse.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

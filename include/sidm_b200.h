@@ -141,7 +141,8 @@ int  b200_last_cuda_error(void);
 /* run on the caller's CUDA stream (a cudaStream_t); default is the legacy default stream */
 int  b200_set_stream(void *cuda_stream);
 const char *b200_version(void);
-/* run-time switches.  "overlap": how b200_compute_accelerations(0) uses its two CUDA streams: 0 = the phases one after the
+/* run-time switches of the current context: legal between b200_init and b200_finalize (B200_ERR_STATE otherwise), and every
+ * one returns to its default at the next b200_init.  "overlap": how b200_compute_accelerations(0) uses its two CUDA streams: 0 = the phases one after the
  * other as accel.c:39-65 does; 1 = gravity walk and the whole SIDM chain (pass + repair loop) next to each other; 2 = walk and
  * SIDM pass next to each other, the repair loop's many small launches after the walk.  Default (-1): 1 on one GPU, 2 when the
  * work is sharded over several (the repair loop would outlast a walk that is split N ways).
@@ -154,7 +155,15 @@ const char *b200_version(void);
  * ReferenceNgbOrder parity mode (the search cube of a particle in the outskirts can clip the dense centre);
  * more than that returns B200_ERR_NGBOVERFLOW like the reference's endrun(78).  "walk_pairs" (default 0): 1 selects the packed
  * sibling-pair form of the gravity walk (f32x2 arithmetic over two child cells at a time, same interaction lists; open boundaries,
- * one particle type), "walkp_minb" (8 / 6 / 4) its occupancy variant. */
+ * one particle type), "walkp_minb" (8 / 6 / 4) its occupancy variant.  "tree_reuse" (default 0 = a full build at every
+ * b200_tree_build / b200_compute_accelerations, i.e. the reference run with TreeUpdateFrequency 0): k > 1 builds the tree at
+ * every k-th request and REFITS it in between - same topology, leaves and all multipole moments from the current predicted
+ * positions (the counterpart of the reference's dynamic tree updates, gravtree.c:63-96, forcetree.c:935-954,2486-2549, which
+ * drift the cells instead).  Neighbour searches on a refitted tree are exact (cell tests widened by the largest displacement
+ * since the build); forces come from a different, equally valid tree: as close to direct summation as the fresh tree's, about
+ * 1e-3 relative rms away from them (tests/test_gpu_reuse.py) - outside the 1e-4 the default path keeps to the reference's tree,
+ * hence opt-in.  A refit needs an unchanged particle set: full uploads, new types or
+ * b200_set_soa positions force a build; one particle type, open boundaries, tree-order neighbour scans. */
 int  b200_set_option(const char *name, int value);
 /* Generator state for restarts ("next" row f3; the reference's restart files, restart.c:37-154, do not save its
  * MT19937 state, so a restarted reference run draws different scatterings).  Here every random number is a function

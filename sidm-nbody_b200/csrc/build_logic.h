@@ -28,6 +28,9 @@ struct BuildView {
   // leaf order
   float4 *leaf_posm; int *leaf_orig, *orig_leaf; int *krank; int *lrank; int *leaf_parent;
   int *flags;                 // device status words
+  // refit (tree reuse): extent of every cell's particles about the cell centre (largest coordinate distance), bottom-up;
+  // null in a fresh build, where every particle lies inside its cell
+  float *next = nullptr;
 };
 
 // ---- B1: shared levels with the next particle, and how many nodes start here
@@ -151,7 +154,24 @@ B200_HD void b5_body(const BuildView &v, int id) {
   v.nmom[id] = m;
   v.nminidx[id] = mn;
   NodeRec r = v.nodes[id];
-  moments_finish(m, gm.x, gm.y, gm.z, gm.w, r);
+  float len = gm.w;
+  if (v.next) {
+    // refitted tree: particles may have left the cell they are filed under.  The cell's size for the opening tests (len2, oc =
+    // mass len^4, bmax2) grows to cover them, like the reference's ngb_update_nodes() grows `len` (forcetree.c:2486-2549): a
+    // target always opens the cell it is filed under, and a spread-out cell is opened from further away.
+    float ext = 0.f;
+    for (int k = 0; k < np; k++) {
+      const float4 p = v.leaf_posm[ps + k];
+      ext = fmaxf(ext, fmaxf(fabsf(p.x - gm.x), fmaxf(fabsf(p.y - gm.y), fabsf(p.z - gm.z))));
+    }
+    for (int c = id + 1; c < end; c = v.nodes[c].skip) {
+      const float4 cg = v.geom[c];
+      ext = fmaxf(ext, v.next[c] + fmaxf(fabsf(cg.x - gm.x), fmaxf(fabsf(cg.y - gm.y), fabsf(cg.z - gm.z))));
+    }
+    v.next[id] = ext;
+    if (2.0f * ext > len) len = 2.0f * ext;
+  }
+  moments_finish(m, gm.x, gm.y, gm.z, len, r);
   v.nodes[id] = r;
 }
 

@@ -59,6 +59,10 @@ struct Ctx {
 
   // ---- tree (rebuilt by b200_tree_build)
   bool tree_valid = false;
+  // tree reuse (option "tree_reuse" = k > 0): a full build every k-th build request, in between a REFIT - same topology (order,
+  // cells, leaf order, level lists, search records), leaves and moments from the current positions (tree_build.cu tree_refit_impl)
+  bool topo_valid = false; int opt_tree_reuse = 0, refits_since_build = 0;
+  float *d_pad = nullptr;          // [2] largest coordinate displacement of a particle since the full build (searches inflate their cell tests by it), and the last refit's
   unsigned long long tree_epoch = 0, search_epoch = ~0ull;   // bumped by every tree build
   double *d_bbox = nullptr;        // [6] min xyz, max xyz (double), written by the bbox kernels
   RootBox *d_root = nullptr;       // root cell

@@ -78,7 +78,10 @@ struct SearchCtx {
   int M; const SearchNode *snode; const SearchNodeF *snodef; const float4 *leaf_posm; const int *leaf_orig;
   const int *nparent, *leaf_parent, *orig_leaf;
   double box;                      // > 0: periodic box (ngb_periodic(), forcetree.c:1999-2006)
+  const float *pad;                // refitted tree (option "tree_reuse"): the cells are as built, the particles have moved by at most
+                                   // *pad per coordinate since: every cell test is widened by it (null: a fresh build)
 };
+__device__ __forceinline__ float search_pad(const SearchCtx &C) { return C.pad ? __ldg(C.pad) : 0.0f; }
 
 // ngb_periodic(): float argument, wrapped with double Box / BoxHalf, rounded back to float
 __device__ __forceinline__ float ngb_periodic(float x, double box) {
@@ -106,7 +109,7 @@ __device__ __forceinline__ float dist2_ref(float px, float py, float pz, float x
 __device__ __forceinline__ int search_start(const SearchCtx &C, int i, float x, float y, float z, float h) {
   const double lox = (double)fadd(x, -h), loy = (double)fadd(y, -h), loz = (double)fadd(z, -h);
   const double hix = (double)fadd(x, h), hiy = (double)fadd(y, h), hiz = (double)fadd(z, h);
-  const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h);
+  const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h) + (double)search_pad(C);
   int no = C.leaf_parent[C.orig_leaf[i]];
   if (C.box > 0) { while (C.nparent[no] >= 0) no = C.nparent[no]; return no; }   // periodic: the root of the particle's own tree
   while (C.nparent[no] >= 0) {                 // stop at the root of the particle's tree (one tree per type)
@@ -161,7 +164,8 @@ __device__ __forceinline__ void range_search(const SearchCtx &C, bool valid, int
     }
     return;
   }
-  const double dlx = lox, dly = loy, dlz = loz, dhx = hix, dhy = hiy, dhz = hiz;
+  const double pd = (double)search_pad(C);
+  const double dlx = (double)lox - pd, dly = (double)loy - pd, dlz = (double)loz - pd, dhx = (double)hix + pd, dhy = (double)hiy + pd, dhz = (double)hiz + pd;
   // Flattened walk: every trip of the loop does ONE thing for this lane - test one pending
   // particle, or test one cell - so that the lanes of a warp, which are at different places of
   // different subtrees, diverge two ways per trip instead of nesting loops of different lengths
@@ -196,6 +200,11 @@ __device__ __forceinline__ void range_search_fast(const SearchCtx &C, bool valid
   if (C.box > 0) { range_search(C, valid, start, x, y, z, h, f); return; }
   const float lox = fadd(x, -h), loy = fadd(y, -h), loz = fadd(z, -h);
   const float hix = fadd(x, h), hiy = fadd(y, h), hiz = fadd(z, h);
+  // cell tests: the cube widened by the refit displacement bound (0 after a fresh build); "taken whole" needs the cell inside the
+  // cube even when its particles have moved by that much
+  const float pd = search_pad(C);
+  const float clx = lox - pd, cly = loy - pd, clz = loz - pd, chx = hix + pd, chy = hiy + pd, chz = hiz + pd;
+  const float wlx = lox + pd, wly = loy + pd, wlz = loz + pd, whx = hix - pd, why = hiy - pd, whz = hiz - pd;
   int no = start;
   const int stop = C.snodef[start].skip;
   int pk = 0, pe = 0, pnode = 0; bool bulk = false;
@@ -212,8 +221,8 @@ __device__ __forceinline__ void range_search_fast(const SearchCtx &C, bool valid
     const float4 a = __ldg(q), b = __ldg(q + 1);                  // lo.xyz hi.x | hi.yz skip pinfo
     const int skip = __float_as_int(b.z), pinfo = __float_as_int(b.w);
     asm volatile("prefetch.global.L1 [%0];" ::"l"(C.snodef + skip));     // the jump target, if this cell is skipped or taken whole
-    if (a.w < lox || a.x > hix || b.x < loy || a.y > hiy || b.y < loz || a.z > hiz) { no = skip; continue; }
-    bulk = (a.x >= lox) && (a.w <= hix) && (a.y >= loy) && (b.x <= hiy) && (a.z >= loz) && (b.y <= hiz);
+    if (a.w < clx || a.x > chx || b.x < cly || a.y > chy || b.y < clz || a.z > chz) { no = skip; continue; }
+    bulk = (a.x >= wlx) && (a.w <= whx) && (a.y >= wly) && (b.x <= why) && (a.z >= wlz) && (b.y <= whz);
     pnode = no; pk = pinfo >> 5;
     if (bulk) { pe = C.snodef[skip].pinfo >> 5; no = skip; } else { pe = pk + (pinfo & 15); no = (pinfo & 16) ? skip : no + 1; }
   }
@@ -458,6 +467,7 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   U.hx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.x, h) : -big)));
   U.hy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.y, h) : -big)));
   U.hz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.z, h) : -big)));
+  { const float pd = search_pad(P.C); U.lx -= pd; U.ly -= pd; U.lz -= pd; U.hx += pd; U.hy += pd; U.hz += pd; }   // refitted tree: cells as built
   // smallest ancestor cell that contains the union with a safety margin (cf. search_start)
   int A = P.gnode[w];
   {
@@ -574,6 +584,7 @@ __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
   Cube U;
   U.lx = fadd(p.x, -h); U.ly = fadd(p.y, -h); U.lz = fadd(p.z, -h);
   U.hx = fadd(p.x, h); U.hy = fadd(p.y, h); U.hz = fadd(p.z, h);
+  { const float pd = search_pad(P.C); U.lx -= pd; U.ly -= pd; U.lz -= pd; U.hx += pd; U.hy += pd; U.hz += pd; }   // refitted tree: cells as built
   const int A = search_start(P.C, i, p.x, p.y, p.z, h);
   const int stopA = P.C.snodef[A].skip;
   __shared__ int2 s_q[4][kQCap];
@@ -974,6 +985,7 @@ static SearchCtx search_ctx() {
   SearchCtx C; C.qcap = g.opt_queue_cap; C.M = g.num_nodes; C.snode = S.snode; C.snodef = S.snodef; C.leaf_posm = g.leaf_posm; C.leaf_orig = g.leaf_orig;
   C.nparent = g.nparent; C.leaf_parent = g.leaf_parent; C.orig_leaf = g.orig_leaf;
   C.box = (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? g.par.BoxSize : 0.0;
+  C.pad = g.refits_since_build > 0 ? g.d_pad : nullptr;
   return C;
 }
 

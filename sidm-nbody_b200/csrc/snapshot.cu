@@ -311,7 +311,7 @@ extern "C" int b200_load_snapshot(const char *path, double *time_out, double *ma
   }
   if (ntot <= 0) return B200_ERR_ARG;
   g.n = ntot;
-  g.tree_valid = false; g.types_dirty = true;
+  g.tree_valid = false; g.types_dirty = true; g.topo_valid = false;
   if (time_out) *time_out = h.time;
   if (mass_table_out) for (int t = 0; t < 6; t++) mass_table_out[t] = h.mass[t];
   if (npart_out) for (int t = 0; t < 6; t++) npart_out[t] = npart[t];

@@ -41,7 +41,7 @@ static int alloc_all() {
   B200_TRY(dalloc(&g.nlevel, m + 1)); B200_TRY(dalloc(&g.nnp, m + 1)); B200_TRY(dalloc(&g.nnchild, m + 1));
   B200_TRY(dalloc(&g.ndp, 8 * (m + 1))); B200_TRY(dalloc(&g.narrive, m + 1));
   B200_TRY(dalloc(&g.nminidx, m + 1)); B200_TRY(dalloc(&g.nlstart, m + 1));
-  B200_TRY(dalloc(&g.nmom, m + 1)); B200_TRY(dalloc(&g.lev_off, (size_t)72));
+  B200_TRY(dalloc(&g.nmom, m + 1)); B200_TRY(dalloc(&g.lev_off, (size_t)72)); B200_TRY(dalloc(&g.d_pad, (size_t)4));
   B200_TRY(dalloc(&g.pairs, m + 4)); B200_TRY(dalloc(&g.gbase, m + 2));
   B200_TRY(dalloc(&g.leaf_posm, n)); B200_TRY(dalloc(&g.leaf_orig, n)); B200_TRY(dalloc(&g.orig_leaf, n)); B200_TRY(dalloc(&g.leaf_parent, n));
   B200_TRY(dalloc(&g.lrank, n));
@@ -76,10 +76,12 @@ extern "C" int b200_shard_buffers(void **send, void **recv, long long *cap_bytes
 }
 extern "C" int b200_set_option(const char *name, int value) {
   if (!name) return B200_ERR_ARG;
+  if (!g.ready) return B200_ERR_STATE;          // options belong to a context: b200_init resets them to their defaults
   if (!strcmp(name, "overlap")) { g.opt_overlap = value < 0 ? -1 : (value > 2 ? 2 : value); return B200_OK; }
   if (!strcmp(name, "group_search")) { g.opt_group_search = value != 0; return B200_OK; }
   if (!strcmp(name, "walkp_minb")) { g.opt_walkp_minb = value; return B200_OK; }
-  if (!strcmp(name, "walk_pairs")) { g.opt_walk_pairs = value != 0; g.tree_valid = false; return B200_OK; }
+  if (!strcmp(name, "walk_pairs")) { g.opt_walk_pairs = value != 0; g.tree_valid = false; g.topo_valid = false; return B200_OK; }
+  if (!strcmp(name, "tree_reuse")) { g.opt_tree_reuse = value < 0 ? 0 : value; return B200_OK; }
   if (!strcmp(name, "shard_overlap")) { g.opt_shard_overlap = value != 0; return B200_OK; }
   if (!strcmp(name, "shard_min_work")) { g.shard_min_work = value; return B200_OK; }
   if (!strcmp(name, "compact_exchange")) { g.opt_compact_exchange = value != 0; return B200_OK; }
@@ -176,6 +178,10 @@ extern "C" int b200_init(const b200_params *p) {
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
     CUDA_TRY(cudaStreamCreateWithPriority(&g.stream_sidm, cudaStreamNonBlocking, phi));
   }
+  // every option starts from its default in a new context (b200_set_option is legal only between b200_init and b200_finalize's
+  // successor: a setting must not leak from one run of a process into the next)
+  g.opt_shard_overlap = false; g.shard_min_work = kShardMinWorkDefault; g.opt_compact_exchange = true; g.opt_queue_cap = 320;
+  g.opt_cand_cap = 1024; g.opt_group_search = true; g.opt_tree_reuse = 0; g.opt_walk_pairs = false; g.opt_walkp_minb = 6;
   g.opt_overlap = getenv("B200_NO_OVERLAP") ? 0 : (getenv("B200_OVERLAP") ? atoi(getenv("B200_OVERLAP")) : -1); g.overlap_now = false; g.walk_pending = false;
   g.winner_base = 1;
   int rc = alloc_all();
@@ -188,7 +194,7 @@ extern "C" int b200_init(const b200_params *p) {
   CUDA_TRY(cudaMemsetAsync(g.s_winner, 0, (size_t)g.maxpart * sizeof(unsigned long long), g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   memset(&g.cnt, 0, sizeof(g.cnt));
-  g.n = 0; g.tree_valid = false; g.sidm_calls = 0; g.ts_calls = 0;
+  g.n = 0; g.tree_valid = false; g.topo_valid = false; g.refits_since_build = 0; g.sidm_calls = 0; g.ts_calls = 0;
   g.ready = true;
   return B200_OK;
 }
@@ -210,7 +216,7 @@ extern "C" void b200_finalize(void) {
   dfree(&g.d_flags); dfree(&g.d_ctr);
   dfree(&g.nodes); dfree(&g.geom); dfree(&g.nstart); dfree(&g.nend); dfree(&g.nparent); dfree(&g.npstart);
   dfree(&g.nlevel); dfree(&g.nnp); dfree(&g.nnchild); dfree(&g.ndp); dfree(&g.narrive);
-  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.lev_off); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
+  dfree(&g.nminidx); dfree(&g.nlstart); dfree(&g.nmom); dfree(&g.lev_off); dfree(&g.d_pad); dfree(&g.pairs); dfree(&g.gbase); g.pairs_valid = false;
   dfree(&g.leaf_posm); dfree(&g.leaf_orig); dfree(&g.orig_leaf); dfree(&g.leaf_parent); dfree(&g.lrank);
   dfree(&g.d_shard_list);
   if (g.shard_own) { cudaFree(g.shard_send); cudaFree(g.shard_recv); g.shard_own = false; g.shard_send = g.shard_recv = nullptr; g.shard_world = 1; g.shard_rank = 0; }
@@ -236,7 +242,7 @@ extern "C" void b200_finalize(void) {
   if (g.stream_sidm) cudaStreamDestroy(g.stream_sidm); g.stream_sidm = nullptr;
   g.overlap_now = false; g.walk_pending = false;
   g.stream = nullptr;
-  g.ready = false; g.n = 0; g.tree_valid = false;
+  g.ready = false; g.n = 0; g.tree_valid = false; g.topo_valid = false;
 }
 
 // ----------------------------------------------------------------------------- SoA I/O
@@ -275,6 +281,7 @@ extern "C" int b200_set_soa(int n, const float *pos, const float *vel, const flo
   const bool fresh = (n != g.n);
   g.n = n;
   if (fresh || pos || mass) g.tree_valid = false;   // the tree depends on PosPred and Mass only
+  if (fresh || pos) g.topo_valid = false;           // new particles / arbitrary new positions: no refit of the old topology
   const int B = 256, G = cdiv(n, B);
   if (fresh) {   // start-up state of init.c:76-100
     CUDA_TRY(cudaMemsetAsync(g.posm, 0, n * sizeof(float4), g.stream));
@@ -349,6 +356,7 @@ extern "C" int b200_bind_particles(void *base, int num_part, const b200_layout *
   if (!g.ready) return B200_ERR_STATE;
   if (!base || !lay || num_part <= 0 || num_part > g.maxpart || lay->stride <= 0 || (lay->stride & 3) || lay->stride > 188) return B200_ERR_ARG;
   if (g.pinned && g.h_base && g.h_base != (char *)base) { cudaHostUnregister(g.h_base); g.pinned = false; }
+  if (num_part != g.n) g.topo_valid = false;
   g.h_base = (char *)base; g.lay = *lay; g.n = num_part; g.tree_valid = false; g.h_first = 0; g.h_count = num_part;
   const size_t bytes = (size_t)g.maxpart * lay->stride;
   if (g.aos_cap < bytes) {
@@ -371,6 +379,7 @@ extern "C" int b200_bind_rows(void *base, int first, int count, int n_global, co
   if (!g.ready) return B200_ERR_STATE;
   if (!base || !lay || count < 0 || first < 0 || n_global <= 0 || first + count > n_global || n_global > g.maxpart || lay->stride <= 0 || (lay->stride & 3) || lay->stride > 188) return B200_ERR_ARG;
   if (g.pinned && g.h_base && (g.h_base != (char *)base || g.h_count != count)) { cudaHostUnregister(g.h_base); g.pinned = false; }
+  g.topo_valid = false;
   g.h_base = (char *)base; g.lay = *lay; g.n = n_global; g.tree_valid = false; g.h_first = first; g.h_count = count;
   const size_t bytes = (size_t)g.maxpart * lay->stride;
   if (g.aos_cap < bytes) {
@@ -487,7 +496,7 @@ extern "C" int b200_upload(void) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
-  g.tree_valid = false; g.types_dirty = true;
+  g.tree_valid = false; g.types_dirty = true; g.topo_valid = false;
   return B200_OK;
 }
 
@@ -541,7 +550,7 @@ static int upload_rows_impl(const int *counts) {
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_upload, g.ev0, g.ev1);
-  g.tree_valid = false; g.types_dirty = true;
+  g.tree_valid = false; g.types_dirty = true; g.topo_valid = false;
   return B200_OK;
 }
 
@@ -799,7 +808,7 @@ extern "C" int b200_set_field(const char *name, const void *host, long long nbyt
   if (!host || nbytes <= 0 || nbytes > nb || !d) return B200_ERR_ARG;
   CUDA_TRY(cudaMemcpyAsync(d, host, (size_t)nbytes, cudaMemcpyHostToDevice, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
-  if (!strcmp(name, "ptype")) { g.types_dirty = true; g.tree_valid = false; }
+  if (!strcmp(name, "ptype")) { g.types_dirty = true; g.tree_valid = false; g.topo_valid = false; }
   return B200_OK;
 }
 

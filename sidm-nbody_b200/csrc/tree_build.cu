@@ -288,10 +288,86 @@ BuildView make_view() {
   return v;
 }
 
+// ------------------------------------------------------------------ refit (option "tree_reuse")
+// The reference does not rebuild its tree at every step either (gravtree.c:63-96, TreeUpdateFrequency): it lets the cells drift
+// with their centre-of-mass velocity and re-moments lazily (forcetree.c:935-954, 2486-2549).  Here: between two full builds the
+// topology stays (key order, cells, leaf order, level lists, search records, query groups) and the leaves and ALL moments are
+// recomputed from the current predicted positions, so every cell has its exact mass, centre of mass and quadrupole; what ages is
+// only which cell a particle is filed under.  Neighbour searches stay exact: they widen their cell tests by the largest coordinate
+// displacement since the full build (d_pad), the sphere test uses the current positions.
+__global__ void k_refit_leaves(int n, const int *leaf_orig, const float4 *posm, float4 *leaf_posm, float *padstep) {
+  __shared__ float sm[256];
+  float d = 0.f;
+  for (int L = blockIdx.x * blockDim.x + threadIdx.x; L < n; L += gridDim.x * blockDim.x) {
+    const float4 p = posm[leaf_orig[L]], o = leaf_posm[L];
+    d = fmaxf(d, fmaxf(fabsf(p.x - o.x), fmaxf(fabsf(p.y - o.y), fabsf(p.z - o.z))));
+    leaf_posm[L] = p;
+  }
+  sm[threadIdx.x] = d; __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<int *>(padstep), __float_as_int(sm[0]));     // non-negative floats order like ints
+}
+__global__ void k_pad_accumulate(float *pad) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { pad[0] = (pad[0] + pad[1]) * 1.000001f + 1.0e-30f; pad[1] = 0.f; }   // triangle inequality, rounded up
+}
+
+static int launch_moments(const BuildView &v, int m, cudaStream_t st, bool lists_ready) {
+  int *hist = g.lev_off, *lev_ids = g.sidx_tmp;             // sidx_tmp: scratch of the key sort, free between builds
+  if (!lists_ready) {
+    unsigned char *lkeys = (unsigned char *)g.key_tmp;
+    CUDA_TRY(cudaMemsetAsync(hist, 0, 72 * sizeof(int), st));
+    k_level_hist<<<cdiv(m, 256), 256, 0, st>>>(m, g.nlevel, hist);
+    k_level_offsets<<<1, 32, 0, st>>>(hist);
+    size_t tbl = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st);
+    B200_TRY(ensure_cub(tbl));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st));
+    count_launch(5);
+  }
+  static int coop_blocks = 0;
+  if (!coop_blocks) {
+    int per_sm = 0, dev = 0, sms = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels, 256, 0));
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    coop_blocks = per_sm * sms;
+  }
+  const int *cl = lev_ids, *co = hist;
+  void *args[] = {(void *)&v, (void *)&cl, (void *)&co};
+  CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_b5_levels, dim3(coop_blocks), dim3(256), args, 0, st));
+  count_launch();
+  return B200_OK;
+}
+
+static int tree_refit_impl() {
+  const int n = g.n;
+  cudaStream_t st = g.stream;
+  CUDA_TRY(cudaEventRecord(g.ev0, st));
+  // DomainMin/Max of the current positions (sidm.c:141-161 flags the particles near it); the root cell stays as built
+  k_bbox_partial<<<296, 256, 0, st>>>(n, g.posm, g.ptype, (float *)g.d_cost, g.d_flags, -1);
+  k_bbox_final<<<1, 32, 0, st>>>(296, (float *)g.d_cost, g.d_bbox, g.d_root + 7, g.d_domain);
+  k_refit_leaves<<<592, 256, 0, st>>>(n, g.leaf_orig, g.posm, g.leaf_posm, g.d_pad + 1);
+  k_pad_accumulate<<<1, 32, 0, st>>>(g.d_pad);
+  count_launch(4);
+  BuildView v = make_view();
+  v.next = (float *)g.narrive;                              // per-cell extent (scratch of the build's arrival counters)
+  B200_TRY(launch_moments(v, g.num_nodes, st, true));
+  CUDA_TRY(cudaEventRecord(g.ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&g.cnt.ms_build, g.ev0, g.ev1);
+  g.tree_valid = true; g.refits_since_build++;
+  return B200_OK;
+}
+
 int tree_build_impl() {
   const int n = g.n;
   const int B = 256, G = cdiv(n, B);
   cudaStream_t st = g.stream;
+  // tree reuse: a refit of the last topology instead of a build (one particle type, open boundaries, tree-order neighbour scans)
+  if (g.opt_tree_reuse > 1 && g.topo_valid && g.refits_since_build + 1 < g.opt_tree_reuse && g.ntypes == 1 && !g.types_dirty &&
+      !(g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) && !g.par.ReferenceNgbOrder && !g.opt_walk_pairs)
+    return tree_refit_impl();
   CUDA_TRY(cudaEventRecord(g.ev0, st));
   CUDA_TRY(cudaMemsetAsync(g.d_flags, 0, FL_COUNT * sizeof(int), st));
 
@@ -403,27 +479,7 @@ int tree_build_impl() {
   static const bool climb = getenv("B200_MOMENTS_CLIMB") != nullptr;             // the last-arriver climb of round 1, kept for A/B
   if (per_level) { for (int lev = g.max_level; lev >= 0; lev--) k_b5<<<GM, B, 0, st>>>(v, lev); count_launch(g.max_level + 1); }
   else if (!climb) {
-    int *hist = g.lev_off, *lev_ids = g.sidx_tmp;           // sidx_tmp: scratch of the key sort, free by now
-    unsigned char *lkeys = (unsigned char *)g.key_tmp;
-    CUDA_TRY(cudaMemsetAsync(hist, 0, 72 * sizeof(int), st));
-    k_level_hist<<<cdiv(m, 256), 256, 0, st>>>(m, g.nlevel, hist);
-    k_level_offsets<<<1, 32, 0, st>>>(hist);
-    size_t tbl = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st);
-    B200_TRY(ensure_cub(tbl));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st));
-    static int coop_blocks = 0;
-    if (!coop_blocks) {
-      int per_sm = 0, dev = 0, sms = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels, 256, 0));
-      CUDA_TRY(cudaGetDevice(&dev));
-      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      coop_blocks = per_sm * sms;
-    }
-    const int *cl = lev_ids, *co = hist;
-    void *args[] = {(void *)&v, (void *)&cl, (void *)&co};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_b5_levels, dim3(coop_blocks), dim3(256), args, 0, st));
-    count_launch(6);
+    B200_TRY(launch_moments(v, m, st, false));
   } else {
     CUDA_TRY(cudaMemsetAsync(g.narrive, 0, (size_t)(m + 1) * sizeof(int), st));
     k_b5_up<<<cdiv(m + 1, 128), 128, 0, st>>>(v);
@@ -452,6 +508,8 @@ int tree_build_impl() {
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&g.cnt.ms_build, g.ev0, g.ev1);
   g.tree_valid = true; g.tree_epoch++;
+  g.topo_valid = true; g.refits_since_build = 0;
+  CUDA_TRY(cudaMemsetAsync(g.d_pad, 0, 2 * sizeof(float), st));
   return B200_OK;
 }
 

