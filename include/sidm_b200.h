@@ -144,8 +144,8 @@ const char *b200_version(void);
 /* run-time switches of the current context: legal between b200_init and b200_finalize (B200_ERR_STATE otherwise), and every
  * one returns to its default at the next b200_init.  "overlap": how b200_compute_accelerations(0) uses its two CUDA streams: 0 = the phases one after the
  * other as accel.c:39-65 does; 1 = gravity walk and the whole SIDM chain (pass + repair loop) next to each other; 2 = walk and
- * SIDM pass next to each other, the repair loop's many small launches after the walk.  Default (-1): 1 on one GPU, 2 when the
- * work is sharded over several (the repair loop would outlast a walk that is split N ways).
+ * SIDM pass next to each other, the repair loop's many small launches after the walk.  Default (-1): 1; sharded over several
+ * GPUs the exchange of the gravity results is then issued behind the running walk and travels while the repair loop runs.
  * "shard_overlap" (default 0): see
  * b200_set_shard.  "group_search" (default 1): warp-shared neighbour search for all-active passes.  "shard_min_work"
  * (default 262144): work lists shorter than this are done completely by every rank instead of being sharded

@@ -24,7 +24,8 @@ struct Ctx {
   // while the gravity walk fills the machine on `stream` (both only read the tree)
   cudaStream_t stream_sidm = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
-  int opt_overlap = -1;            // b200_set_option("overlap", 0|1|2); -1 = default: 1 on one GPU, 2 when sharded (sidm.cu, b200_compute_accelerations)
+  int opt_overlap = -1;            // b200_set_option("overlap", 0|1|2); -1 = default = 1 (sidm.cu, b200_compute_accelerations)
+  bool shard_busy = false;         // the exchange buffers hold a collective that is still queued behind the walk: SIDM passes issued now run replicated
   bool opt_shard_overlap = false;  // b200_set_option("shard_overlap", 1): the host's all-gather callback runs on
                                    // b200_current_stream(), so the two-stream overlap is also safe when sharded
   int shard_min_work = kShardMinWorkDefault;
@@ -182,6 +183,7 @@ int tree_build_impl();
 int walk_impl(const int *d_targets_sorted, int nt, bool with_slots, bool defer_sync = false);
 int gravity_impl(const int *active, int nactive, double time, bool defer_sync = false);
 int gravity_finish();
+int gravity_exchange_early();     // sharded: issue the exchange of {Accel, OldAcc} behind the running walk; the buffers stay busy until gravity_finish()
 inline cudaStream_t sidm_stream() { return g.overlap_now ? g.stream_sidm : g.stream; }
 int direct_impl(const int *targets, int n, double *acc_out);
 int sidm_impl(const int *d_active, int nactive, double time, double vmax, const b200_replay *replay, bool count_only, bool defer_final = false);

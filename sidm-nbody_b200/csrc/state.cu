@@ -1076,7 +1076,7 @@ extern "C" int b200_device_buffer(const char *name, void **dptr, long long *nbyt
       {"oldacc", g.oldacc, n * 4}, {"ngb", g.ngb, n * 4}, {"acc_raw", g.d_acc, n * 24}, {"cost", g.d_cost, n * 8},
       {"velpred", g.velpred, n * 12}, {"pos0", g.pos0, n * 12}, {"curtime", g.curtime, n * 4},
       {"gravcost", g.gravcost, n * 4}, {"left", g.left, n * 4}, {"right", g.right, n * 4}, {"maxpred", g.maxpred, n * 4}, {"potential", g.potential, n * 4}, {"ptype", g.ptype, n * 4}, {"pid", g.pid, n * 4},
-      {"ewald", g.d_ewald, g.d_ewald ? 33LL * 33 * 33 * 16 : 0}};
+      {"sidx", g.sidx, n * 4}, {"ewald", g.d_ewald, g.d_ewald ? 33LL * 33 * 33 * 16 : 0}};
   for (auto &t : tab) if (!strcmp(t.nm, name)) { *dptr = t.p; *nbytes = t.b; return B200_OK; }
   return B200_ERR_ARG;
 }

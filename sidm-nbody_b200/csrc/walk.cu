@@ -600,6 +600,8 @@ __global__ void k_target_keys(int nt, const int *active, const int *krank, int *
 int prepare_targets(const int *active_host, int nactive, int **d_sorted_out) {
   if (!active_host) { *d_sorted_out = g.sidx; return B200_OK; }   // all particles, key order, slot == particle
   CUDA_TRY(cudaMemcpyAsync(g.d_active, active_host, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  static const bool keep_order = getenv("B200_KEEP_TARGET_ORDER") != nullptr;    // experiment: targets grouped into warps as listed
+  if (keep_order) { CUDA_TRY(cudaMemcpyAsync(g.d_tsorted, g.iota, (size_t)nactive * sizeof(int), cudaMemcpyDeviceToDevice, g.stream)); *d_sorted_out = g.d_tsorted; return B200_OK; }
   k_target_keys<<<cdiv(nactive, 256), 256, 0, g.stream>>>(nactive, g.d_active, g.krank, g.d_tkeys, g.d_tvals2);
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, g.d_tkeys, g.d_tkeys2, g.d_tvals2, g.d_tsorted, nactive, 0, 32, g.stream);
@@ -752,8 +754,15 @@ static int gravity_exchange() {
   return B200_OK;
 }
 
+int gravity_exchange_early() {
+  if (!GX.pending) return B200_OK;
+  g.shard_busy = true;
+  return gravity_exchange();
+}
+
 int gravity_finish() {
   B200_TRY(gravity_exchange());
+  g.shard_busy = false;
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
   if (g.walk_pending) { g.walk_pending = false; return walk_read_counters(); }
