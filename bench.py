@@ -571,16 +571,24 @@ def run_e2e(hp, sh, n, mass, ids, vmax, state, args, world, rank, step_fn, cfg, 
         rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
     hp.bind_particles(snaps[0], pin=False)
 
+    parts = [0.0, 0.0, 0.0]
+
     def one(k):
+        c0 = time.perf_counter()
         hp.bind_particles(snaps[k % nsnap], pin=False)
         sh.upload()                                  # own rows over PCIe (+ NVLink all-gather when sharded)
+        c1 = time.perf_counter()
         sh.compute_accelerations(0, time=times[k % nsnap], vmax=vmax)
+        c2 = time.perf_counter()
         sh.download(into=out)
+        c3 = time.perf_counter()                     # each of the three calls returns after its own stream synchronisation
+        parts[0] += c1 - c0; parts[1] += c2 - c1; parts[2] += c3 - c2
         return int(hp.counters().sct_scattered)
 
     steps = max(2, min(args.steps, 5))
     one(0)
     torch.cuda.synchronize()
+    parts[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for k in range(steps):
         one(k)
@@ -597,6 +605,7 @@ def run_e2e(hp, sh, n, mass, ids, vmax, state, args, world, rank, step_fn, cfg, 
     return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(rows * snaps[0].itemsize * world),
             "d2h_bytes_per_step": int(rows * out.itemsize * world),
             "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "ms_upload": parts[0] / steps * 1e3, "ms_compute": parts[1] / steps * 1e3, "ms_download": parts[2] / steps * 1e3,   # rank 0's
             "api": ("b200_bind_particles + b200_upload + b200_compute_accelerations(0) + b200_download_to on pinned 124-byte particle_data arrays (successive states of the run)"
                     if world == 1 else "b200_upload_shard (own rows over PCIe + NVLink all-gather) + b200_compute_accelerations(0) + b200_download_shard, pinned 124-byte particle_data rows per rank")}
 

@@ -451,11 +451,11 @@ __global__ void __launch_bounds__(kAosRows) k_unpack_aos(int n, const char *aos,
 }
 
 // the device image keeps the fields the path does not write (Pos Vel Mass ID Type CurrentTime ForceFlag) as uploaded
-__global__ void __launch_bounds__(kAosRows) k_pack_aos(int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
+__global__ void __launch_bounds__(kAosRows) k_pack_aos(int first, int n, char *aos, Lay L, const float4 *posm, const float4 *velh, const float *velpred,
                            const float *accel, const float *dvel, const float *oldacc, const float *gravcost,
                            const float *left, const float *right, const int *ngb, const float *maxpred, const float *potential) {
   extern __shared__ __align__(16) int sm_aos[];
-  const int r0 = blockIdx.x * kAosRows, nrec = min(kAosRows, n - r0);
+  const int r0 = first + blockIdx.x * kAosRows, nrec = min(kAosRows, first + n - r0);     // rows [first, first + n)
   aos_block_load(aos, L.stride, r0, nrec, sm_aos);
   __syncthreads();
   if ((int)threadIdx.x < nrec) {
@@ -513,7 +513,7 @@ extern "C" int b200_download(void) {
   if (!g.ready || !g.have_aos) return B200_ERR_STATE;
   const int n = g.n;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  k_pack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+  k_pack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(0, n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   CUDA_TRY(cudaMemcpyAsync(g.h_base, g.d_aos, (size_t)n * g.lay.stride, cudaMemcpyDeviceToHost, g.stream));
@@ -578,7 +578,10 @@ extern "C" int b200_download_shard(void *dst, int first, int count) {
   if (first < 0 || count < 0 || first + count > n) return B200_ERR_ARG;
   char *out = dst ? (char *)dst : g.h_base;
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  k_pack_aos<<<cdiv(n, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(n, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
+  // only the rows that go down are packed (1/world of the image); the range starts at a multiple of 4 rows so that the
+  // 16-byte accesses of aos_block_load/store stay aligned for every stride (packing a row more than once is harmless)
+  const int first_al = first & ~3, count_al = first + count - first_al;
+  if (count > 0) k_pack_aos<<<cdiv(count_al, kAosRows), kAosRows, (size_t)kAosRows * g.lay.stride, g.stream>>>(first_al, count_al, g.d_aos, to_lay(g.lay), g.posm, g.velh, g.velpred, g.accel, g.dvel,
                                                  g.oldacc, g.gravcost, g.left, g.right, g.ngb, g.maxpred, g.potential);
   count_launch();
   if (!dst && (first < g.h_first || first + count > g.h_first + g.h_count)) return B200_ERR_ARG;
