@@ -78,10 +78,24 @@ struct SearchCtx {
   int M; const SearchNode *snode; const SearchNodeF *snodef; const float4 *leaf_posm; const int *leaf_orig;
   const int *nparent, *leaf_parent, *orig_leaf;
   double box;                      // > 0: periodic box (ngb_periodic(), forcetree.c:1999-2006)
+  const float *domain;             // periodic box with one tree: float[6] DomainMin xyz, DomainMax xyz of the particles at the build (see box_interior)
   const float *pad;                // refitted tree (option "tree_reuse"): the cells are as built, the particles have moved by at most
                                    // *pad per coordinate since: every cell test is widened by it (null: a fresh build)
 };
 __device__ __forceinline__ float search_pad(const SearchCtx &C) { return C.pad ? __ldg(C.pad) : 0.0f; }
+// Periodic box, one tree: a search cube that keeps a distance from the faces of the box larger than any particle sticks out of
+// it (the reference wraps positions only at a domain decomposition, run.c:135) cannot contain a periodic image: ngb_periodic()
+// returns every coordinate difference unchanged, and the plain search - started at the enclosing ancestor cell, float records -
+// yields the same candidates in the same order with the same distances.  Only cubes near a face walk from the root with the
+// wrapped tests of forcetree.c:2228-2276.  `domain` = DomainMin / DomainMax of the last tree build (null: always wrapped).
+__device__ __forceinline__ bool box_interior(const SearchCtx &C, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+  if (!C.domain) return false;
+  const double box = C.box;
+  double e = 0.0;
+  for (int k = 0; k < 3; k++) { e = fmax(e, -(double)__ldg(C.domain + k)); e = fmax(e, (double)__ldg(C.domain + 3 + k) - box); }
+  e = e * 1.000001 + 1.0e-6 * box;
+  return (double)lox > e && (double)loy > e && (double)loz > e && (double)hix < box - e && (double)hiy < box - e && (double)hiz < box - e;
+}
 
 // ngb_periodic(): float argument, wrapped with double Box / BoxHalf, rounded back to float
 __device__ __forceinline__ float ngb_periodic(float x, double box) {
@@ -111,7 +125,10 @@ __device__ __forceinline__ int search_start(const SearchCtx &C, int i, float x, 
   const double hix = (double)fadd(x, h), hiy = (double)fadd(y, h), hiz = (double)fadd(z, h);
   const double m = 1.0e-5 * (fabs((double)x) + fabs((double)y) + fabs((double)z) + (double)h) + (double)search_pad(C);
   int no = C.leaf_parent[C.orig_leaf[i]];
-  if (C.box > 0) { while (C.nparent[no] >= 0) no = C.nparent[no]; return no; }   // periodic: the root of the particle's own tree
+  if (C.box > 0 && !box_interior(C, (float)lox, (float)loy, (float)loz, (float)hix, (float)hiy, (float)hiz)) {
+    while (C.nparent[no] >= 0) no = C.nparent[no];       // periodic, near a face: the root of the particle's own tree
+    return no;
+  }
   while (C.nparent[no] >= 0) {                 // stop at the root of the particle's tree (one tree per type)
     const SearchNode &nd = C.snode[no];
     if (nd.lo[0] + m <= lox && nd.lo[1] + m <= loy && nd.lo[2] + m <= loz && nd.hi[0] - m >= hix && nd.hi[1] - m >= hiy && nd.hi[2] - m >= hiz) break;
@@ -197,9 +214,9 @@ __device__ __forceinline__ void range_search(const SearchCtx &C, bool valid, int
 template <class F>
 __device__ __forceinline__ void range_search_fast(const SearchCtx &C, bool valid, int start, float x, float y, float z, float h, F &&f) {
   if (!valid) return;
-  if (C.box > 0) { range_search(C, valid, start, x, y, z, h, f); return; }
   const float lox = fadd(x, -h), loy = fadd(y, -h), loz = fadd(z, -h);
   const float hix = fadd(x, h), hiy = fadd(y, h), hiz = fadd(z, h);
+  if (C.box > 0 && !box_interior(C, lox, loy, loz, hix, hiy, hiz)) { range_search(C, valid, start, x, y, z, h, f); return; }
   // cell tests: the cube widened by the refit displacement bound (0 after a fresh build); "taken whole" needs the cell inside the
   // cube even when its particles have moved by that much
   const float pd = search_pad(C);
@@ -451,13 +468,13 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   // a few stray particles (direct particles of a big cell, far from each other): per-query tree walks, as k_pass1.  Short runs
   // inside a small cell (the 32-aligned cuts of sharded runs leave many) stay on the warp-shared search: their cubes overlap.
   const SearchNode &gn = P.C.snode[P.gnode[w]];
-  if (gr.y <= kGroupTiny && gn.pend - gn.pstart > kGroupCell) {
+  auto each_lane_alone = [&]() {
     int cnt = 0, cand = 0;
     const int start = valid ? search_start(P.C, i, p.x, p.y, p.z, h) : 0;
     range_search_fast(P.C, valid, start, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
     if (valid) { atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand); pass1_finish(P, L, i, p, h, cnt); }
-    return;
-  }
+  };
+  if (gr.y <= kGroupTiny && gn.pend - gn.pstart > kGroupCell) { each_lane_alone(); return; }
   // union of the group's search cubes
   const float big = 3.0e38f;
   Cube U;
@@ -467,6 +484,9 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   U.hx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.x, h) : -big)));
   U.hy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.y, h) : -big)));
   U.hz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? fadd(p.z, h) : -big)));
+  // periodic box: a group whose union cube comes near a face is searched lane by lane (wrapped tests from the root where
+  // needed, forcetree.c:2228-2276); everywhere else no periodic image can be a neighbour and the shared search applies as it is
+  if (P.C.box > 0 && !box_interior(P.C, U.lx, U.ly, U.lz, U.hx, U.hy, U.hz)) { each_lane_alone(); return; }
   { const float pd = search_pad(P.C); U.lx -= pd; U.ly -= pd; U.lz -= pd; U.hx += pd; U.hy += pd; U.hz += pd; }   // refitted tree: cells as built
   // smallest ancestor cell that contains the union with a safety margin (cf. search_start)
   int A = P.gnode[w];
@@ -591,7 +611,12 @@ __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
   int2 *q = s_q[threadIdx.x >> 5];
   const unsigned lt = (1u << lane) - 1u;
   int cnt = 0; unsigned cand = 0;
-  int qn = 1;
+  // periodic box, cube near a face (A is the root then): the wrapped walk of forcetree.c:2228-2276 by one lane; the few
+  // queries this concerns do not pay for a lane-parallel form of the wrapped tests
+  const bool wrapped = P.C.box > 0 && !box_interior(P.C, U.lx, U.ly, U.lz, U.hx, U.hy, U.hz);
+  if (wrapped && lane == 0)
+    range_search(P.C, true, A, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  int qn = wrapped ? 0 : 1;
   if (lane == 0) q[0] = make_int2(A, stopA);
   __syncwarp();
   bool overflow = false;
@@ -986,6 +1011,8 @@ static SearchCtx search_ctx() {
   C.nparent = g.nparent; C.leaf_parent = g.leaf_parent; C.orig_leaf = g.orig_leaf;
   C.box = (g.par.PeriodicBoundariesOn && g.par.BoxSize > 0) ? g.par.BoxSize : 0.0;
   C.pad = g.refits_since_build > 0 ? g.d_pad : nullptr;
+  static const bool wrapped_always = getenv("B200_PERIODIC_SEARCH_FROM_ROOT") != nullptr;        // A/B: round-1 behaviour
+  C.domain = (C.box > 0 && g.ntrees == 1 && !wrapped_always) ? g.d_domain : nullptr;
   return C;
 }
 
@@ -1106,7 +1133,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     count_launch(4);
     // explicit lists: slots sorted along the tree order, so that the queries of a warp are neighbours.  Small lists are searched
     // one warp per query (k_pass1_warp), where the order of the queries does not matter: no sort (five launches less per repair pass)
-    const bool periodic_search = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+    const bool periodic_search = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0 && search_ctx().domain == nullptr;
     const bool sort_slots = act && !(nb <= kWarpQueryMax && !periodic_search && g.opt_group_search && !sharded);
     if (sort_slots) {
       size_t tb2 = 0;
@@ -1148,7 +1175,8 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     // this rank's share of the buffer (all of it on one GPU)
     const int *order = (act && !sort_slots) ? S.x_vals : S.slot_of_sorted; int nord = nb;
     const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
-    const bool group_mode = !act && nb == g.n && !periodic_box && S.ngroups > 0 && g.opt_group_search;
+    const bool plain_search = !periodic_box || search_ctx().domain != nullptr;      // periodic: the shared searches need box_interior()
+    const bool group_mode = !act && nb == g.n && plain_search && S.ngroups > 0 && g.opt_group_search;
     const int *global_order = order;                 // all ranks' slots in processing order
     if (group_mode && sharded) {                     // sharded group search: processing order = leaf order
       k_order_leaf<<<G, B, 0, st>>>(nb, g.leaf_orig, slot_of_active, S.order_leaf);
@@ -1175,7 +1203,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       if (!sharded) order = S.order_leaf;                  // the pass flags are indexed by leaf position
     } else if (nord > 0) {
       // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
-      if (nord <= kWarpQueryMax && !periodic_box && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
+      if (nord <= kWarpQueryMax && plain_search && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
       else k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     }
     count_launch(2);
