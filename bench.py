@@ -481,7 +481,22 @@ def main_b200(args, cfg):
                            "tree_reuse": reuse},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "phases": phases, "state_crc": crc}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if args.overlap_sweep:
+        # A/B of the option "overlap" (0 = phases in sequence, 1 = SIDM chain next to the walk, 2 = SIDM pass next to the walk)
+        # on the state the run has reached, after the line above: 2 untimed + 6 timed steps per mode, stderr only
+        for m in (0, 1, 2, 1, 0):
+            hp.set_option("overlap", m)
+            for _ in range(2):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(6):
+                step()
+            barrier()
+            if rank == 0:
+                print(f"bench.py overlap sweep: mode {m}: {(time.perf_counter() - t0) / 6 * 1e3:.3f} ms per step on {world} GPU(s)", file=sys.stderr, flush=True)
+        hp.set_option("overlap", -1)
     hp.close()
     if world > 1:
         dist.destroy_process_group()
@@ -617,13 +632,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C3 = the one the metric is quoted on)")
-    ap.add_argument("--n", type=lambda s: int(float(s)), default=0, help="particle number (default: the configuration's)")
+    ap.add_argument("--n", "--particles", dest="n", type=lambda s: int(float(s)), default=0, help="particle number (default: the configuration's)")
     ap.add_argument("--ref-procs", type=int, default=0, help="host processes for the reference arm (0 = all that fit)")
     ap.add_argument("--ref-sample", type=int, default=60000, help="active particles per reference process per step")
     ap.add_argument("--tree-reuse", type=int, default=0, help="option tree_reuse of the library: full build every k-th step, refits in between (default 0 = build at "
                     "every step, the only setting whose forces are the reference's to 1e-4; see tests/test_gpu_reuse.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap-sweep", action="store_true", help="after the bench line: time the three values of the library option `overlap` (stderr)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if not args.n:
