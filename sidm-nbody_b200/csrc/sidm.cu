@@ -55,6 +55,7 @@ struct SidmState {
   void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
   // query groups of the warp-shared search (k_pass1_group): leaf range + tree node of each group
   int2 *groups = nullptr; int *gnode = nullptr, *gflag = nullptr, *gpos = nullptr, *order_leaf = nullptr; int ngroups = 0;
+  int *spart = nullptr;            // particle -> slot of the current pass, -1 = not a query (warp-shared search over a large explicit list)
   int *gown = nullptr, *gownflag = nullptr; int nown = 0;   // sharded: the groups this rank searches (compact list: no idle warps in k_pass1_group)
 } S;
 
@@ -287,7 +288,8 @@ __global__ void k_export_flag(int na, const int *active, const float4 *posm, con
 }
 __global__ void k_assign_slots(int na, const int *active, const int *flag, const int *scan, int *slot_part, int *slot_of_active,
                                const float *curtime, const float *dvel, double time, float *dt, unsigned char *already,
-                               const int *krank, int *keys, int *vals, int *flags_out, int *partner, float *dv, double *prob, double *ptot) {
+                               const int *krank, int *keys, int *vals, int *flags_out, int *partner, float *dv, double *prob, double *ptot,
+                               int *slot_of_part) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= na) return;
   partner[a] = -1; dv[3 * (size_t)a] = dv[3 * (size_t)a + 1] = dv[3 * (size_t)a + 2] = 0; prob[a] = 0; ptot[a] = 0;   // slot a's results
@@ -296,6 +298,7 @@ __global__ void k_assign_slots(int na, const int *active, const int *flag, const
   const int place = flag[a] ? scan[a] : nexport + (a - scan[a]);
   slot_part[place] = i;
   slot_of_active[a] = place;
+  if (slot_of_part) slot_of_part[i] = place;       // large explicit list on the warp-shared search: the array was filled with -1
   dt[place] = (float)(2 * (time - (double)curtime[i]));             // sidm.c:196
   already[place] = dvel[3 * (size_t)i] != 0.0f;                    // sidm.c:189-192 (ID = 0)
   if (active) { keys[a] = krank[i]; vals[a] = place; }
@@ -404,6 +407,7 @@ struct Pass1G {
   const float *dt; const unsigned char *already; const double *replay_rand; double C_Pmax, s_a_inverse; uint32_t k0, k1;
   int *ngb; double *pmax, *rnd; int *pass; int *order_leaf; int count_only; unsigned long long *ctr;
   int rank, world;     // sharded: this rank handles the groups of the 32-blocks b with b % world == rank
+  int masked;          // slot_of_part holds -1 for the particles that are not queries of this pass (large explicit lists, one rank)
 };
 constexpr int kGroupTiny = 4;
 constexpr int kWarpQueryMax = 1 << 14;   // up to this many queries a pass is served one warp per query (beyond, the
@@ -459,10 +463,16 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
   if (wi >= P.ng) return;                                  // warp-uniform
   const int w = P.own ? P.own[wi] : wi;                    // sharded: this rank's groups only
   const int2 gr = P.groups[w];
-  const bool valid = lane < gr.y;
+  bool valid = lane < gr.y;
   const int L = gr.x + (valid ? lane : 0);
   const float4 p = P.C.leaf_posm[L];
   const int i = P.C.leaf_orig[L];
+  if (P.masked) {
+    // a large explicit list (the repair passes of a step in which most particles left the neighbour window): the members of the
+    // group that are not queries sit out; their places in the leaf-ordered pass flags are cleared here
+    if (valid && P.slot_of_part[i] < 0) { valid = false; P.pass[L] = 0; P.order_leaf[L] = 0; }
+    if (!__any_sync(0xffffffffu, valid)) return;
+  }
   const float h = valid ? P.velh[i].w : 0.0f;
   const float sr2 = fmul(h, h);
   // a few stray particles (direct particles of a big cell, far from each other): per-query tree walks, as k_pass1.  Short runs
@@ -582,7 +592,8 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
     cnt = 0; cand = 0;
     group_walk_uniform(P.C, U, A, stopA, p, sr2, cnt, cand);
   }
-  if (lane == 0) atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand * (unsigned)gr.y);
+  const int nq = P.masked ? __popc(__ballot_sync(0xffffffffu, valid)) : gr.y;
+  if (lane == 0) atomicAdd(&P.ctr[CT_CAND], (unsigned long long)cand * (unsigned)nq);
   if (valid) pass1_finish(P, L, i, p, h, cnt);
 }
 
@@ -968,7 +979,7 @@ static int ensure_sidm_buffers() {
   B200_TRY(al((void **)&S.x_vals, n * sizeof(int))); B200_TRY(al((void **)&S.x_shard, (n + 64) * sizeof(int)));
   B200_TRY(al((void **)&S.groups, (n + m + 1) * sizeof(int2))); B200_TRY(al((void **)&S.gnode, (n + m + 1) * sizeof(int)));
   B200_TRY(al((void **)&S.gflag, (m + 2) * sizeof(int))); B200_TRY(al((void **)&S.gpos, (m + 2) * sizeof(int)));
-  B200_TRY(al((void **)&S.order_leaf, n * sizeof(int)));
+  B200_TRY(al((void **)&S.order_leaf, n * sizeof(int))); B200_TRY(al((void **)&S.spart, n * sizeof(int)));
   B200_TRY(al((void **)&S.gown, (n + m + 1) * sizeof(int))); B200_TRY(al((void **)&S.gownflag, (n + m + 1) * sizeof(int)));
   if (!d_kernel_table) {
     double K[1002];
@@ -989,7 +1000,7 @@ void sidm_release() {
   void **ptrs[] = {(void **)&S.snode, (void **)&S.snodef, (void **)&S.last_active, (void **)&S.slot_of_sorted, (void **)&S.passlist,
                    (void **)&S.logpos, (void **)&S.rr, (void **)&S.dt, (void **)&S.already, (void **)&S.ptot,
                    (void **)&S.x_redo, (void **)&S.x_redo2, (void **)&S.x_want, (void **)&S.x_keys, (void **)&S.x_keys2, (void **)&S.x_vals, (void **)&S.x_shard, &S.cub_tmp,
-                   (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf, (void **)&S.gown, (void **)&S.gownflag};
+                   (void **)&S.groups, (void **)&S.gnode, (void **)&S.gflag, (void **)&S.gpos, (void **)&S.order_leaf, (void **)&S.spart, (void **)&S.gown, (void **)&S.gownflag};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (S.rx) cudaFree(S.rx); if (S.ro) cudaFree(S.ro);
   S.rx = nullptr; S.ro = nullptr; S.rx_cap = S.ro_cap = 0;
@@ -1127,14 +1138,23 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     B200_TRY(cub_scratch(tb));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, g.s_flag, g.s_pos, nb + 1, st));
     int *slot_of_active = g.s_repair;     // scratch
+    // warp-shared search: when every particle is a query, and - on one rank - for explicit lists that hold a good part of the
+    // particles (repair passes after a long step: thread-per-query costs 4 ns per query, the shared search 0.6)
+    const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
+    const bool plain_search = !periodic_box || search_ctx().domain != nullptr;      // periodic: the shared searches need box_interior()
+    const bool group_ok = plain_search && S.ngroups > 0 && g.opt_group_search;
+    const bool group_all = !act && nb == g.n && group_ok;
+    const bool group_part = act && !sharded && group_ok && nb > kWarpQueryMax / 4 && (long long)nb * 8 >= g.n && g.par.BunchSizeSidm <= 0;
+    if (group_part) CUDA_TRY(cudaMemsetAsync(S.spart, 0xff, (size_t)g.n * sizeof(int), st));
     // processing order: slots sorted along the tree key order (spatial coherence inside a warp)
     k_assign_slots<<<G, B, 0, st>>>(nb, act, g.s_flag, g.s_pos, g.s_slot_part, slot_of_active, g.curtime, g.dvel, time, S.dt, S.already,
-                                    g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags, g.s_partner, g.s_dv, g.s_prob, S.ptot);
+                                    g.krank, S.x_keys, act ? S.x_vals : S.slot_of_sorted, g.d_flags, g.s_partner, g.s_dv, g.s_prob, S.ptot,
+                                    group_part ? S.spart : nullptr);
     count_launch(4);
     // explicit lists: slots sorted along the tree order, so that the queries of a warp are neighbours.  Small lists are searched
     // one warp per query (k_pass1_warp), where the order of the queries does not matter: no sort (five launches less per repair pass)
     const bool periodic_search = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0 && search_ctx().domain == nullptr;
-    const bool sort_slots = act && !(nb <= kWarpQueryMax && !periodic_search && g.opt_group_search && !sharded);
+    const bool sort_slots = act && !group_part && !(nb <= kWarpQueryMax && !periodic_search && g.opt_group_search && !sharded);
     if (sort_slots) {
       size_t tb2 = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tb2, S.x_keys, S.x_keys2, S.x_vals, S.slot_of_sorted, nb, 0, 32, st);
@@ -1174,9 +1194,7 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     }
     // this rank's share of the buffer (all of it on one GPU)
     const int *order = (act && !sort_slots) ? S.x_vals : S.slot_of_sorted; int nord = nb;
-    const bool periodic_box = g.par.PeriodicBoundariesOn && g.par.BoxSize > 0;
-    const bool plain_search = !periodic_box || search_ctx().domain != nullptr;      // periodic: the shared searches need box_interior()
-    const bool group_mode = !act && nb == g.n && plain_search && S.ngroups > 0 && g.opt_group_search;
+    const bool group_mode = group_all || group_part;
     const int *global_order = order;                 // all ranks' slots in processing order
     if (group_mode && sharded) {                     // sharded group search: processing order = leaf order
       k_order_leaf<<<G, B, 0, st>>>(nb, g.leaf_orig, slot_of_active, S.order_leaf);
@@ -1195,12 +1213,12 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
     const bool grouped = group_mode;
     if (grouped) {
       Pass1G PG;
-      PG.ng = sharded ? S.nown : S.ngroups; PG.own = sharded ? S.gown : nullptr; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = slot_of_active;
+      PG.ng = sharded ? S.nown : S.ngroups; PG.own = sharded ? S.gown : nullptr; PG.groups = S.groups; PG.gnode = S.gnode; PG.C = P1.C; PG.velh = g.velh; PG.slot_of_part = group_part ? S.spart : slot_of_active; PG.masked = group_part;
       PG.dt = S.dt; PG.already = S.already; PG.replay_rand = d_rr; PG.C_Pmax = C_Pmax; PG.s_a_inverse = sainv; PG.k0 = k0; PG.k1 = k1;
       PG.ngb = g.s_ngb; PG.pmax = g.s_pmax; PG.rnd = g.s_rand; PG.pass = g.s_pass; PG.order_leaf = S.order_leaf; PG.count_only = count_only; PG.ctr = g.d_ctr;
       PG.rank = sharded ? g.shard_rank : 0; PG.world = sharded ? g.shard_world : 1;
       if (PG.ng > 0) k_pass1_group<<<cdiv((long long)PG.ng * 32, 128), 128, 0, st>>>(PG);
-      if (!sharded) order = S.order_leaf;                  // the pass flags are indexed by leaf position
+      if (!sharded) { order = S.order_leaf; nord = g.n; }  // the pass flags are indexed by leaf position (of all particles)
     } else if (nord > 0) {
       // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
       if (nord <= kWarpQueryMax && plain_search && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
