@@ -91,20 +91,13 @@ __device__ __forceinline__ float search_pad(const SearchCtx &C) { return C.pad ?
 // wrapped tests of forcetree.c:2228-2276.  `domain` = DomainMin / DomainMax of the last tree build (null: always wrapped).
 __device__ __forceinline__ bool box_interior(const SearchCtx &C, float lox, float loy, float loz, float hix, float hiy, float hiz) {
   if (!C.domain) return false;
-  const double box = C.box;
-  double e = 0.0;
-  for (int k = 0; k < 3; k++) { e = fmax(e, -(double)__ldg(C.domain + k)); e = fmax(e, (double)__ldg(C.domain + 3 + k) - box); }
-  e = e * 1.000001 + 1.0e-6 * box;
-  return (double)lox > e && (double)loy > e && (double)loz > e && (double)hix < box - e && (double)hiy < box - e && (double)hiz < box - e;
+  float dom[6];
+  for (int k = 0; k < 6; k++) dom[k] = __ldg(C.domain + k);
+  return cube_clear_of_faces(dom, C.box, lox, loy, loz, hix, hiy, hiz);      // tree_logic.h (checked on the host: tests/test_hostcheck.py)
 }
 
-// ngb_periodic(): float argument, wrapped with double Box / BoxHalf, rounded back to float
-__device__ __forceinline__ float ngb_periodic(float x, double box) {
-  const double bh = 0.5 * box;
-  while ((double)x > bh) x = (float)((double)x - box);
-  while ((double)x < -bh) x = (float)((double)x + box);
-  return x;
-}
+// ngb_periodic(): float argument, wrapped with double Box / BoxHalf, rounded back to float (tree_logic.h)
+__device__ __forceinline__ float ngb_periodic(float x, double box) { return wrap_periodic(x, box); }
 __device__ __forceinline__ float dist2_per(float px, float py, float pz, float x, float y, float z, double box) {
   const float dx = ngb_periodic(fadd(px, -x), box), dy = ngb_periodic(fadd(py, -y), box), dz = ngb_periodic(fadd(pz, -z), box);
   return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));

@@ -47,6 +47,27 @@ B200_HD float fmul(float a, float b) {
 #endif
 }
 
+// ---- periodic boxes (neighbour searches, sidm.cu)
+// ngb_periodic(), forcetree.c:1999-2006: a float coordinate difference wrapped into [-Box/2, Box/2] with double Box / BoxHalf,
+// rounded back to float
+B200_HD float wrap_periodic(float x, double box) {
+  const double bh = 0.5 * box;
+  while ((double)x > bh) x = (float)((double)x - box);
+  while ((double)x < -bh) x = (float)((double)x + box);
+  return x;
+}
+// Is the search cube [lo, hi] so far from the faces of the box [0, Box)^3 that no periodic image of any particle can lie in it?
+// `dom` = min xyz, max xyz of the particle coordinates: between two do_box_wrapping() calls (run.c:135) particles may stick out
+// of the box by e = max(0, -min, max - Box); their images lie within e of the opposite face.  A cube that keeps more than e
+// (plus a rounding margin) from every face contains no image, every coordinate difference to a particle inside it is below
+// Box/2 in magnitude, and wrap_periodic() leaves it unchanged: the open-boundary search gives the wrapped search's result.
+B200_HD bool cube_clear_of_faces(const float dom[6], double box, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+  double e = 0.0;
+  for (int k = 0; k < 3; k++) { e = fmax(e, -(double)dom[k]); e = fmax(e, (double)dom[3 + k] - box); }
+  e = e * 1.000001 + 1.0e-6 * box;
+  return (double)lox > e && (double)loy > e && (double)loz > e && (double)hix < box - e && (double)hiy < box - e && (double)hiz < box - e;
+}
+
 // root box from the bounding box of float coordinates (forcetree.c:179-212)
 B200_HD RootBox make_root(const double mn[3], const double mx[3]) {
   double len = mx[0] - mn[0];

@@ -188,3 +188,18 @@ extern "C" void hc_walk_types(int nt, const int *targets, const float *oldacc, c
     acc[3 * t] = ax; acc[3 * t + 1] = ay; acc[3 * t + 2] = az; cost[2 * t] = npart; cost[2 * t + 1] = nnode;
   }
 }
+
+// ---- periodic neighbour searches: the classification that lets a search use the open-boundary kernels (tree_logic.h)
+extern "C" int hc_cube_clear_of_faces(const float *dom, double box, const float *cube) {
+  return b200::cube_clear_of_faces(dom, box, cube[0], cube[1], cube[2], cube[3], cube[4], cube[5]) ? 1 : 0;
+}
+// r^2 of the wrapped and of the plain float test (forcetree.c:2195-2206 with / without ngb_periodic) for n particles and one centre
+extern "C" void hc_dist2_both(int n, const float *pos, const float *c, double box, float *r2_wrapped, float *r2_plain) {
+  using namespace b200;
+  for (int i = 0; i < n; i++) {
+    const float dx = fadd(pos[3 * i], -c[0]), dy = fadd(pos[3 * i + 1], -c[1]), dz = fadd(pos[3 * i + 2], -c[2]);
+    const float wx = wrap_periodic(dx, box), wy = wrap_periodic(dy, box), wz = wrap_periodic(dz, box);
+    r2_wrapped[i] = fadd(fadd(fmul(wx, wx), fmul(wy, wy)), fmul(wz, wz));
+    r2_plain[i] = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+  }
+}

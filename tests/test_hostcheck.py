@@ -137,3 +137,47 @@ def test_forest_walk_matches_reference_golden(hc):
     hc.hc_walk_types(len(idx), idx.ctypes, oa.ctypes, types.ctypes, eps.ctypes, 1, C.c_float(0.5), C.c_float(0.005), acc.ctypes, cost.ctypes)
     assert (cost == t["cost_rel"]).all(axis=1).mean() > 0.995
     assert np.sqrt(((acc - t["acc_rel"]) ** 2).sum() / (t["acc_rel"] ** 2).sum()) < 1e-5
+
+
+def test_periodic_cubes_clear_of_the_faces_see_no_image(hc):
+    """sidm.cu box_interior(): a search cube classified `clear of the faces` must give the SAME neighbour set with the SAME float
+    r^2 through the plain distance test as through the wrapped one (ngb_periodic(), forcetree.c:1999-2006, 2195-2206) - also when
+    particles stick out of the box, as they do between two do_box_wrapping() calls (run.c:135).  Cubes near a face must not be
+    classified clear whenever an image would make a difference."""
+    rng = np.random.default_rng(3)
+    hc.hc_cube_clear_of_faces.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    hc.hc_dist2_both.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    n_clear = n_near = n_differs_near = 0
+    for box, stick in ((100.0, 0.0), (100.0, 1.5), (7.25, 0.3), (50000.0, 900.0)):
+        n = 4000
+        pos = (rng.random((n, 3)) * box).astype(np.float32)
+        out = rng.random(n) < 0.05                               # 5 % of the particles have drifted out of the box
+        pos[out, rng.integers(0, 3, out.sum())] = np.where(rng.random(out.sum()) < 0.5, -rng.random(out.sum()) * stick,
+                                                           box + rng.random(out.sum()) * stick).astype(np.float32)
+        dom = np.concatenate([pos.min(0), pos.max(0)]).astype(np.float32)
+        r2w, r2p = np.empty(n, np.float32), np.empty(n, np.float32)
+        for _ in range(400):
+            h = np.float32(box * (0.01 + 0.08 * rng.random()))
+            # half of the centres near a face, where the classification matters
+            c = (rng.random(3) * box).astype(np.float32)
+            if rng.random() < 0.5:
+                k = rng.integers(0, 3)
+                c[k] = np.float32(rng.choice([0.0, box]) + (rng.random() - 0.5) * 4 * (float(h) + stick))
+                c[k] = min(max(c[k], np.float32(-stick)), np.float32(box + stick))
+            cube = np.concatenate([c - h, c + h]).astype(np.float32)
+            clear = hc.hc_cube_clear_of_faces(dom.ctypes.data, box, cube.ctypes.data)
+            hc.hc_dist2_both(n, pos.ctypes.data, c.ctypes.data, box, r2w.ctypes.data, r2p.ctypes.data)
+            h2 = np.float32(h) * np.float32(h)
+            in_w, in_p = r2w < h2, r2p < h2
+            if clear:
+                n_clear += 1
+                assert np.array_equal(in_w, in_p)
+                assert np.array_equal(r2w[in_w].view(np.uint32), r2p[in_w].view(np.uint32))
+                # and inside the whole search cube no coordinate difference was wrapped (candidates are tested identically)
+                inside = np.all((pos >= cube[:3]) & (pos <= cube[3:]), axis=1)
+                assert np.array_equal(r2w[inside].view(np.uint32), r2p[inside].view(np.uint32))
+            else:
+                n_near += 1
+                n_differs_near += int(not np.array_equal(in_w, in_p))
+    assert n_clear > 400 and n_near > 200
+    assert n_differs_near > 20, "the fixture never exercised a periodic image"
