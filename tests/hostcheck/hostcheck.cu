@@ -25,6 +25,8 @@ struct Host {
   RootBox roots[8];                       // several particle types: one root cell per type
   std::vector<unsigned char> stype;       // type of every sorted particle (empty: one type)
   int flags[16];
+  BuildView v;                           // the views of the last build (hc_refit goes on with them)
+  std::vector<float> next;
 } H;
 }
 
@@ -61,7 +63,7 @@ static int hc_build_impl(int n, const float *pos, const float *mass, const int *
   H.narrive.assign(cap, 0); H.nminidx.assign(cap, 0); H.nlstart.assign(cap, 0); H.nmom.resize(cap);
   H.leaf_posm.resize(n); H.leaf_orig.assign(n, 0); H.orig_leaf.assign(n, 0); H.krank.assign(n, 0); H.lrank.assign(n, 0); H.leaf_parent.assign(n, 0);
   for (int k = 0; k < 16; k++) H.flags[k] = 0;
-  BuildView v;
+  BuildView &v = H.v; v = BuildView();
   v.n = n; v.maxnodes = cap; v.posm = H.posm.data(); v.shi = H.shi.data(); v.slo = H.slo.data(); v.sidx = H.sidx.data();
   v.clev = H.clev.data(); v.nodestart = H.nodestart.data(); v.root = types ? H.roots : &H.root;
   v.stype = types ? H.stype.data() : nullptr;
@@ -202,4 +204,35 @@ extern "C" void hc_dist2_both(int n, const float *pos, const float *c, double bo
     r2_wrapped[i] = fadd(fadd(fmul(wx, wx), fmul(wy, wy)), fmul(wz, wz));
     r2_plain[i] = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
   }
+}
+
+// ---- tree reuse: the refit of csrc/tree_build.cu tree_refit_impl() on the host - same topology, leaves from the new positions,
+// all moments and cell extents bottom-up (b5_body with BuildView::next set).  Returns the largest coordinate displacement.
+extern "C" float hc_refit(const float *pos_new) {
+  float pad = 0.f;
+  for (int i = 0; i < H.n; i++) { H.posm[i].x = pos_new[3 * i]; H.posm[i].y = pos_new[3 * i + 1]; H.posm[i].z = pos_new[3 * i + 2]; }
+  for (int L = 0; L < H.n; L++) {
+    const float4 p = H.posm[H.leaf_orig[L]], o = H.leaf_posm[L];
+    pad = std::max(pad, std::max(fabsf(p.x - o.x), std::max(fabsf(p.y - o.y), fabsf(p.z - o.z))));
+    H.leaf_posm[L] = p;
+  }
+  H.next.assign(H.m + 1, 0.f);
+  H.v.next = H.next.data();
+  for (int lev = H.maxlev; lev >= 0; lev--)
+    for (int id = 0; id < H.m; id++) if (H.nlevel[id] == lev) b5_body(H.v, id);
+  H.v.next = nullptr;
+  return pad;
+}
+// per node: len2 of the walk's record, the leaf range [first, end) of its subtree, the cell extent of the last refit
+extern "C" void hc_get_refit(float *len2, int *leaf_first, int *leaf_end, float *extent) {
+  for (int id = 0; id < H.m; id++) {
+    len2[id] = H.nodes[id].len2;
+    leaf_first[id] = H.npstart[id];
+    const int skip = H.nodes[id].skip;
+    leaf_end[id] = skip < H.m ? H.npstart[skip] : H.n;
+    extent[id] = H.next.empty() ? 0.f : H.next[id];
+  }
+}
+extern "C" void hc_get_leaves(float *leaf_pos, int *leaf_orig) {
+  for (int L = 0; L < H.n; L++) { leaf_pos[3 * L] = H.leaf_posm[L].x; leaf_pos[3 * L + 1] = H.leaf_posm[L].y; leaf_pos[3 * L + 2] = H.leaf_posm[L].z; leaf_orig[L] = H.leaf_orig[L]; }
 }

@@ -181,3 +181,71 @@ def test_periodic_cubes_clear_of_the_faces_see_no_image(hc):
                 n_differs_near += int(not np.array_equal(in_w, in_p))
     assert n_clear > 400 and n_near > 200
     assert n_differs_near > 20, "the fixture never exercised a periodic image"
+
+
+def _tree(hc):
+    m = hc.hc_num_nodes()
+    d = dict(center=np.empty((m, 3), np.float32), len=np.empty(m, np.float32), mass=np.empty(m, np.float32),
+             s=np.empty((m, 3), np.float32), Q=np.empty((m, 7), np.float32), oc=np.empty(m, np.float32),
+             bmax2=np.empty(m, np.float32), count=np.empty(m, np.int32), level=np.empty(m, np.int32),
+             skip=np.empty(m, np.int32), parent=np.empty(m, np.int32), minidx=np.empty(m, np.int32))
+    hc.hc_get_tree(*[d[k].ctypes for k in ("center", "len", "mass", "s", "Q", "oc", "bmax2", "count", "level", "skip",
+                                           "parent", "minidx")])
+    r = dict(len2=np.empty(m, np.float32), first=np.empty(m, np.int32), end=np.empty(m, np.int32), ext=np.empty(m, np.float32))
+    hc.hc_get_refit(*[r[k].ctypes for k in ("len2", "first", "end", "ext")])
+    d.update(r)
+    return d
+
+
+def test_refit_keeps_the_topology_and_recomputes_every_cell(hc):
+    """tree reuse (csrc/tree_build.cu tree_refit_impl, build_logic.h b5_body with BuildView::next): after the particles have
+    moved, a refit leaves the cells and their membership as built, recomputes mass / centre of mass / quadrupole of every cell
+    from the members' NEW positions, and grows the cell size used by the opening tests so that it covers every member - the
+    property that lets a target always open the cell it is filed under.  Nothing moved: bit-identical node records."""
+    g = np.load(GOLD)
+    pos, mass = np.ascontiguousarray(g["pos"]), np.ascontiguousarray(g["mass"])
+    n = len(mass)
+    hc.hc_refit.restype = C.c_float
+    assert hc.hc_build(n, pos.ctypes, mass.ctypes, 0) == 0
+    t0 = _tree(hc)
+    assert np.array_equal(t0["len2"], (t0["len"] * t0["len"]).astype(np.float32))
+    # nothing moved
+    assert hc.hc_refit(pos.ctypes) == 0.0
+    t1 = _tree(hc)
+    for k in ("mass", "s", "Q", "oc", "bmax2", "len2", "skip", "first", "end"):
+        assert np.array_equal(t0[k].view(np.uint32) if t0[k].dtype == np.float32 else t0[k], t1[k].view(np.uint32) if t1[k].dtype == np.float32 else t1[k]), k
+    # particles moved by up to 5 % of their radius
+    rng = np.random.default_rng(8)
+    r = np.sqrt((pos.astype(np.float64) ** 2).sum(1))
+    new = (pos + (rng.random((n, 3)) - 0.5) * 0.1 * r[:, None]).astype(np.float32)
+    pad = hc.hc_refit(new.ctypes)
+    assert pad == np.abs(new - pos).max()
+    t2 = _tree(hc)
+    for k in ("skip", "first", "end", "count", "parent", "center", "len"):
+        assert np.array_equal(t0[k], t2[k]), k                  # topology and geometry as built
+    assert np.array_equal(t0["mass"].view(np.uint32), t2["mass"].view(np.uint32))
+    lp, lo = np.empty((n, 3), np.float32), np.empty(n, np.int32)
+    hc.hc_get_leaves(lp.ctypes, lo.ctypes)
+    assert np.array_equal(lp, new[lo])
+    grown = 0
+    for id in rng.choice(len(t2["len"]), 600, replace=False):
+        mem = lo[t2["first"][id]:t2["end"][id]]
+        assert len(mem) == t2["count"][id]
+        x, w = new[mem].astype(np.float64), mass[mem].astype(np.float64)
+        com = (x * w[:, None]).sum(0) / w.sum()
+        L = float(t2["len"][id])
+        assert np.abs(t2["s"][id] - com).max() < 2e-6 * (np.abs(com).max() + L)
+        d = x - com
+        q = np.array([(w * d[:, 0] ** 2).sum(), (w * d[:, 1] ** 2).sum(), (w * d[:, 2] ** 2).sum(), (w * d[:, 0] * d[:, 1]).sum(),
+                      (w * d[:, 0] * d[:, 2]).sum(), (w * d[:, 1] * d[:, 2]).sum(), (w * (d ** 2).sum(1)).sum()])
+        assert np.abs(t2["Q"][id] - q).max() < 1e-5 * (w.sum() * max(L, float(np.abs(d).max())) ** 2)
+        ext = np.abs(x - t2["center"][id].astype(np.float64)).max()      # largest coordinate distance of a member from the cell centre
+        assert t2["ext"][id] >= ext * (1 - 1e-6)
+        side = np.sqrt(float(t2["len2"][id]))
+        assert side >= L * (1 - 1e-6) and side / 2 >= ext * (1 - 1e-6)    # the cell of the opening tests covers its members
+        if ext > L / 2:
+            grown += 1
+            assert abs(side - 2 * t2["ext"][id]) < 1e-5 * side
+        else:
+            assert t2["len2"][id] == t0["len2"][id] or side > L
+    assert grown > 20, "the fixture never moved a particle out of its cell"
