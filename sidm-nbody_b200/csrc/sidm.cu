@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(128) k_pass1_group(Pass1G P) {
 // queries or one).  Here a warp serves one query with the same lane-parallel cell walk as
 // k_pass1_group and tests 32 candidates per trip, one per lane: the dependent chain shrinks to a few
 // dozen trips.  Same neighbour set, same counts.
+template <bool PERIODIC>                                      // the open-boundary instantiation carries no wrapped-search code (40 registers)
 __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
   const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= P.ns) return;                                   // warp-uniform
@@ -617,9 +618,11 @@ __global__ void __launch_bounds__(128) k_pass1_warp(Pass1 P) {
   int cnt = 0; unsigned cand = 0;
   // periodic box, cube near a face (A is the root then): the wrapped walk of forcetree.c:2228-2276 by one lane; the few
   // queries this concerns do not pay for a lane-parallel form of the wrapped tests
-  const bool wrapped = P.C.box > 0 && !box_interior(P.C, U.lx, U.ly, U.lz, U.hx, U.hy, U.hz);
-  if (wrapped && lane == 0)
-    range_search(P.C, true, A, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  const bool wrapped = PERIODIC && P.C.box > 0 && !box_interior(P.C, U.lx, U.ly, U.lz, U.hx, U.hy, U.hz);
+  if (PERIODIC) {
+    if (wrapped && lane == 0)
+      range_search(P.C, true, A, p.x, p.y, p.z, h, [&](int, const float4 &, float r2, bool, int) { cand++; if (r2 < sr2) cnt++; });
+  }
   int qn = wrapped ? 0 : 1;
   if (lane == 0) q[0] = make_int2(A, stopA);
   __syncwarp();
@@ -1214,7 +1217,10 @@ int sidm_impl(const int *d_active, int nactive, double time, double vmax, const 
       if (!sharded) { order = S.order_leaf; nord = g.n; }  // the pass flags are indexed by leaf position (of all particles)
     } else if (nord > 0) {
       // small query sets: one warp per query (latency), large ones: one thread per query (throughput)
-      if (nord <= kWarpQueryMax && plain_search && g.opt_group_search) k_pass1_warp<<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
+      if (nord <= kWarpQueryMax && plain_search && g.opt_group_search) {
+        if (periodic_box) k_pass1_warp<true><<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
+        else k_pass1_warp<false><<<cdiv((long long)nord * 32, 128), 128, 0, st>>>(P1);
+      }
       else k_pass1<<<cdiv(nord, 128), 128, 0, st>>>(P1);
     }
     count_launch(2);
