@@ -135,8 +135,11 @@ B200_HD void b4_body(const BuildView &v, int id) {
   v.nodes[id].pinfo = (ps << 4) | np;
 }
 
-// ---- B5: moments of one node from its direct particles and its (finished) child nodes
-B200_HD void b5_body(const BuildView &v, int id) {
+// ---- B5: moments of one node from its direct particles and its (finished) child nodes.  REFIT (tree reuse): also the extent of
+// the cell's particles, see below; a compile-time switch so that the build's instantiation is exactly the code it was before
+// the refit existed (the run-time form cost k_b5_levels 0.4 ms at N = 1e7)
+template <bool REFIT>
+B200_HD void b5_body_t(const BuildView &v, int id) {
   const float4 gm = v.geom[id];
   Moments m; moments_zero(m);
   const int np = v.nnp[id], ps = v.npstart[id];
@@ -155,7 +158,7 @@ B200_HD void b5_body(const BuildView &v, int id) {
   v.nminidx[id] = mn;
   NodeRec r = v.nodes[id];
   float len = gm.w;
-  if (v.next) {
+  if (REFIT) {
     // refitted tree: particles may have left the cell they are filed under.  The cell's size for the opening tests (len2, oc =
     // mass len^4, bmax2) grows to cover them, like the reference's ngb_update_nodes() grows `len` (forcetree.c:2486-2549): a
     // target always opens the cell it is filed under, and a spread-out cell is opened from further away.
@@ -174,6 +177,7 @@ B200_HD void b5_body(const BuildView &v, int id) {
   moments_finish(m, gm.x, gm.y, gm.z, len, r);
   v.nodes[id] = r;
 }
+B200_HD void b5_body(const BuildView &v, int id) { if (v.next) b5_body_t<true>(v, id); else b5_body_t<false>(v, id); }
 
 // ---- B6: position of every node / particle in the reference's next[] chain.
 // forcetree.c:274-279 appends a particle at the end of the deepest existing node's chain, so

@@ -227,13 +227,14 @@ __global__ void k_level_offsets(int *hist) {          // counts [64] -> exclusiv
   for (int l = 0; l < 64; l++) { const int c = hist[l]; hist[l] = at; at += c; }
   hist[64] = at;
 }
+template <bool REFIT>
 __global__ void __launch_bounds__(256) k_b5_levels(BuildView v, const int *lev_ids, const int *lev_off) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
   for (int lev = kMaxLevels; lev >= 0; lev--) {
     const int a = lev_off[lev], b = lev_off[lev + 1];
     if (b == a) continue;                                   // the same for every thread: no barrier needed
-    for (int k = a + gt; k < b; k += gs) b5_body(v, lev_ids[k]);
+    for (int k = a + gt; k < b; k += gs) b5_body_t<REFIT>(v, lev_ids[k]);
     grid.sync();
   }
 }
@@ -335,17 +336,20 @@ static int launch_moments(const BuildView &v, int m, cudaStream_t st, bool lists
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_tmp, tbl, g.nlevel, lkeys, g.iota, lev_ids, m, 0, 6, st));
     count_launch(5);
   }
-  static int coop_blocks = 0;
-  if (!coop_blocks) {
+  const bool refit = v.next != nullptr;
+  void *kernel = refit ? (void *)k_b5_levels<true> : (void *)k_b5_levels<false>;
+  static int coop_blocks[2] = {0, 0};
+  if (!coop_blocks[refit]) {
     int per_sm = 0, dev = 0, sms = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels, 256, 0));
+    if (refit) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels<true>, 256, 0));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_b5_levels<false>, 256, 0));
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    coop_blocks = per_sm * sms;
+    coop_blocks[refit] = per_sm * sms;
   }
   const int *cl = lev_ids, *co = hist;
   void *args[] = {(void *)&v, (void *)&cl, (void *)&co};
-  CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_b5_levels, dim3(coop_blocks), dim3(256), args, 0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(coop_blocks[refit]), dim3(256), args, 0, st));
   count_launch();
   return B200_OK;
 }
